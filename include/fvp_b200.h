@@ -1,0 +1,165 @@
+/*
+ * fvp_b200.h - C ABI of libfvp_b200.so: the B200-native (sm_100a) inference hot path of
+ * Faster-VoxelPose (AlvinYH/Faster-VoxelPose @ 733aa98).
+ *
+ * The reference is pure Python/PyTorch and has no FFI; the native boundary it *would* bind is the
+ * set of nn.Module.forward() calls on the hot path.  Each entry point below
+ * names the reference interface it replaces.  All pointers are plain host or device pointers, all
+ * sizes are explicit, no torch types appear.  Every function returns 0 on success or a negative
+ * FVP_E_* code; fvp_last_error() gives the message (the Python host layer turns it into the
+ * exception the reference would have raised: AssertionError for calibration mismatches,
+ * RuntimeError otherwise).
+ *
+ * Tensor layouts are the reference's (row-major, fp32) unless a name ends in _cl (channel-last,
+ * channels padded to a multiple of 4).  "d_" = device pointer, "h_" = host pointer.
+ * All device work is enqueued on the cudaStream_t passed as `stream` (a CUstream handle as
+ * uintptr; 0 = legacy default stream) and is CUDA-graph capturable unless stated otherwise.
+ */
+#ifndef FVP_B200_H_
+#define FVP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVP_ABI_VERSION 1
+
+enum {
+  FVP_OK = 0,
+  FVP_E_INVALID = -1,   /* bad argument / shape                                   */
+  FVP_E_CUDA = -2,      /* CUDA runtime error (message has cudaGetErrorString)    */
+  FVP_E_STATE = -3,     /* call order (e.g. forward before finalize_params)       */
+  FVP_E_NOTFOUND = -4,  /* unknown parameter / sequence slot                      */
+  FVP_E_CALIB = -5      /* calibration missing / wrong camera count (reference: AssertionError,
+                           lib/models/project_whole.py:73-74)                     */
+};
+
+/* Geometry + network constants: the keys FasterVoxelPoseNet reads from cfg (SURVEY.md section 5,
+ * lib/models/project_whole.py:16-23, project_individual.py:17-33, human_detection_net.py:19-23,
+ * joint_localization_net.py:18, weight_net.py:51-54). */
+typedef struct fvp_config {
+  int32_t num_views;          /* DATASET.CAMERA_NUM                         */
+  int32_t num_joints;         /* DATASET.NUM_JOINTS                         */
+  int32_t hm_w, hm_h;         /* DATASET.HEATMAP_SIZE  (w, h)               */
+  float image_w, image_h;     /* DATASET.IMAGE_SIZE                         */
+  float ori_w, ori_h;         /* DATASET.ORI_IMAGE_SIZE                     */
+  float space_size[3];        /* CAPTURE_SPEC.SPACE_SIZE                    */
+  float space_center[3];      /* CAPTURE_SPEC.SPACE_CENTER                  */
+  int32_t voxels[3];          /* CAPTURE_SPEC.VOXELS_PER_AXIS               */
+  float ind_space_size[3];    /* INDIVIDUAL_SPEC.SPACE_SIZE                 */
+  int32_t ind_voxels[3];      /* INDIVIDUAL_SPEC.VOXELS_PER_AXIS (64,64,64) */
+  int32_t max_people;         /* CAPTURE_SPEC.MAX_PEOPLE                    */
+  float min_score;            /* CAPTURE_SPEC.MIN_SCORE                     */
+  float beta;                 /* NETWORK.BETA                               */
+  int32_t feat_channels;      /* NETWORK.NUM_CHANNEL_JOINT_FEAT   (32)      */
+  int32_t hidden_channels;    /* NETWORK.NUM_CHANNEL_JOINT_HIDDEN (64)      */
+  int32_t max_batch;          /* frames per forward call the workspaces are sized for */
+  int32_t max_sequences;      /* distinct calibrations kept resident        */
+} fvp_config;
+
+typedef struct fvp_ctx fvp_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* replaces models.faster_voxelpose.get(cfg) (lib/models/faster_voxelpose.py:108-110) */
+int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out);
+void fvp_destroy(fvp_ctx* ctx);
+const char* fvp_last_error(const fvp_ctx* ctx);   /* ctx may be NULL: error of the last failed fvp_create */
+int fvp_abi_version(void);
+
+/* ---- parameters: replaces nn.Module.load_state_dict (run/validate.py:78-81) ------------------ */
+/* The table lists the reference's 485 state_dict keys in order (SURVEY.md section 5 "checkpoint"). */
+int fvp_param_count(const fvp_ctx* ctx);
+const char* fvp_param_name(const fvp_ctx* ctx, int index);
+int64_t fvp_param_numel(const fvp_ctx* ctx, int index);
+/* copy one fp32 state_dict tensor (host memory, contiguous, reference shape); the int64
+ * num_batches_tracked entries are accepted and ignored (numel 1, pass NULL or anything). */
+int fvp_set_param(fvp_ctx* ctx, const char* name, const float* h_data, int64_t numel);
+/* fold eval-mode BatchNorm (eps 1e-5) into the convolutions, repack for the kernels, upload.
+ * Must be called after all parameters were set and again after any later fvp_set_param. */
+int fvp_finalize_params(fvp_ctx* ctx);
+
+/* ---- geometry tables (optional) ---------------------------------------------------------------
+ * The reference builds voxel coordinates with torch.linspace (project_whole.py:34-40), whose fp32
+ * values are not exactly start+i*step.  By default the library uses the symmetric scalar formula of
+ * ATen's CUDA linspace; a host that wants bit-parity with a particular CPU run passes the exact
+ * tables: coarse axes (X+Y+Z floats), fine axes (fineX+fineY+fineZ floats, project_individual.py:41)
+ * and individual axes (64+64+64 floats: the center_grid of project_individual.py:37-40). */
+int fvp_set_axes(fvp_ctx* ctx, const float* h_coarse, const float* h_fine, const float* h_individual);
+int fvp_fine_voxels(const fvp_ctx* ctx, int32_t out[3]);
+
+/* ---- calibration: replaces the per-sequence sample-grid caches (project_whole.py:75-80,
+ *      project_individual.py:104-106) by a 21-float camera block per view ---------------------- */
+/* h_cameras: [num_views][21] fp32 = R(9 row-major) T(3) fx fy cx cy k(3) p(2)
+ * h_resize : [6] fp32 resize_transform (2x3 row-major)                       */
+int fvp_set_sequence(fvp_ctx* ctx, int slot, const float* h_cameras, int num_views, const float* h_resize);
+
+/* ---- whole forward: replaces FasterVoxelPoseNet.forward, eval branch
+ *      (lib/models/faster_voxelpose.py:34-48,99-105) ------------------------------------------- */
+/* d_heatmaps        [batch][V][J][H][W] fp32 (input_heatmaps)
+ * h_seq_slots       [batch] calibration slot of every frame (meta['seq'] -> slot)
+ * d_fused_poses     [batch][P][J][5]   (x,y,z mm, flag, conf)
+ * d_plane_poses     [3][batch][P][J][2]
+ * d_proposal_centers[batch][P][7]
+ * Any output pointer may be NULL. */
+int fvp_forward(fvp_ctx* ctx, const float* d_heatmaps, int batch, const int32_t* h_seq_slots,
+                float* d_fused_poses, float* d_plane_poses, float* d_proposal_centers, uintptr_t stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D of the heatmaps, forward, D2H of the
+ * outputs, all on `stream`, followed by a stream synchronise.  This is the end-to-end entry the
+ * benchmark's `e2e` figure times. */
+int fvp_forward_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int32_t* h_seq_slots,
+                     float* h_fused_poses, float* h_plane_poses, float* h_proposal_centers, uintptr_t stream);
+
+/* Capture the forward for (batch, seq slots) into a CUDA graph bound to fixed internal I/O buffers
+ * and replay it on later fvp_forward* calls with the same signature (1 = on, 0 = off). */
+int fvp_use_cuda_graph(fvp_ctx* ctx, int enable);
+
+/* ---- stage entry points (parity tests + profiling; same kernels fvp_forward launches) -------- */
+/* K0: [batch][V][J][H][W] -> internal channel-last, zero-bordered copy */
+int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr_t stream);
+/* K1: ProjectLayer(whole).forward + CenterNet's z-max (project_whole.py:62-88, cnns_2d.py:174)
+ * -> d_plane [batch][J][X][Y] (reference layout).  Requires fvp_stage_heatmaps. */
+int fvp_hdn_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, float* d_plane, uintptr_t stream);
+/* CenterNet trunk + heads on the internal plane (cnns_2d.py:173-178)
+ * d_plane_in may be NULL (use K1's result) or [batch][J][X][Y]; outputs hm [batch][X][Y], size [batch][2][X][Y] */
+int fvp_center_net(fvp_ctx* ctx, const float* d_plane_in, int batch, float* d_hm, float* d_size, uintptr_t stream);
+/* nms2D + top-k (core/proposal.py:13-33): d_hm [batch][X][Y] -> conf [batch][P], flat index [batch][P] (int32) */
+int fvp_nms_topk(fvp_ctx* ctx, const float* d_hm, int batch, float* d_conf2d, int32_t* d_flat, uintptr_t stream);
+/* K2 + C2CNet + ProposalLayer (human_detection_net.py:88-102): given top-k (conf, flat) and the size
+ * map -> z-columns [batch*P][J][Z], 1-D heatmaps [batch*P][Z], proposal_centers [batch][P][7] */
+int fvp_proposals(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const float* d_conf2d,
+                  const int32_t* d_flat, const float* d_size, float* d_cols, float* d_hm1d,
+                  float* d_centers, uintptr_t stream);
+/* K3: ProjectLayer(individual).forward + three-plane max (project_individual.py:96-136,
+ * joint_localization_net.py:80-81): d_centers [batch][P][7] -> d_planes [3][batch*P][J][64][64],
+ * d_offset [batch*P][3]; invalid slots (flag < 0) give zero planes. */
+int fvp_jln_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const float* d_centers,
+                    float* d_planes, float* d_offset, uintptr_t stream);
+/* P2PNet (cnns_2d.py:131-135) on planes [n][J][64][64] (NULL = K3's internal result) -> [n][J][64][64];
+ * d_valid [n] int32 (NULL = all) selects images to compute */
+int fvp_p2p_net(fvp_ctx* ctx, const float* d_planes, int n, const int32_t* d_valid, float* d_feat, uintptr_t stream);
+/* SoftArgmaxLayer + WeightNet + fuse_pose_preds (joint_localization_net.py:20-62, weight_net.py:69-80):
+ * d_feat [3][n][J][64][64], d_offset [n][3] -> pose [3][n][J][2] (offset added), conf [n],
+ * weights [3][n][J], fused [n][J][3] */
+int fvp_pose_head(fvp_ctx* ctx, const float* d_feat, const float* d_offset, int n, float* d_pose,
+                  float* d_conf, float* d_weights, float* d_fused, uintptr_t stream);
+/* C2CNet alone (cnns_1d.py:128-132): [n][J][Z] -> [n][Z] */
+int fvp_c2c_net(fvp_ctx* ctx, const float* d_cols, int n, float* d_hm1d, uintptr_t stream);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+/* number of kernel launches the last fvp_forward enqueued (graph replay counts its kernel nodes) */
+int fvp_last_launch_count(const fvp_ctx* ctx);
+/* CUDA-event time (ms) of named stages of the last forward run with fvp_set_profiling(ctx,1):
+ * 0 stage-heatmaps, 1 hdn-project, 2 center-net, 3 nms, 4 proposals(c2c), 5 jln-project, 6 p2p-net,
+ * 7 pose-head, 8 total */
+int fvp_set_profiling(fvp_ctx* ctx, int enable);
+int fvp_stage_times_ms(const fvp_ctx* ctx, float out[9]);
+/* algorithmic HBM bytes per frame of K0+K1 and K3 for the current config */
+int fvp_algorithmic_bytes(const fvp_ctx* ctx, int num_valid_people, double* k1_bytes, double* k3_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVP_B200_H_ */
