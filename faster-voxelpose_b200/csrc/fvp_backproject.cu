@@ -1,0 +1,355 @@
+// fvp_backproject.cu - the fused back-projection kernels.
+//
+//   K0  stage heat maps : [B][V][J][H][W] -> channel-last [B][V][HP][WP][JP] with a zero border wide
+//                         enough for every tap of a clamped (|g|<=1.1) sample -> no bounds tests later.
+//   K1  HDN            : ProjectLayer(whole).forward (project_whole.py:62-88) + CenterNet's z-max
+//                         (cnns_2d.py:174): plane[b,j,x,y] = max_z clamp(mean_v bilinear(hm[b,v,j], proj_v(x,y,z)))
+//                         The [B,J,X,Y,Z] volume never exists.
+//   K3  JLN            : ProjectLayer(individual).forward (project_individual.py:96-136) + the three
+//                         orthographic max planes (joint_localization_net.py:80-81).  The [N,J,64^3] cubes
+//                         never exist; the 164 MB cached fine sample grid is replaced by in-kernel projection.
+//
+// Lane layout of K1/K3: CG consecutive lanes own one voxel column, lane s of the group holds channel
+// group s (4 joints, one float4).  One tap of one voxel is therefore a single contiguous 16*JG byte
+// record and a warp-wide LDG.128 touches 32/CG records -> fully used sectors.  The CG lanes of a column
+// split the (z, view) projection work between them and exchange tap descriptors by shuffle.
+#include "fvp_kernels.h"
+#include "fvp_project.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// K0
+// ------------------------------------------------------------------------------------------------
+template <int JG>
+__global__ void __launch_bounds__(256) k0_stage_heatmaps(const float* __restrict__ hm, float4* __restrict__ out,
+                                                          int J, int H, int W, int WP, int PADX, int PADY,
+                                                          size_t view_stride4) {
+  const int bv = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= H * W) return;
+  const float* src = hm + (size_t)bv * J * H * W + pix;
+  float v[JG * 4];
+#pragma unroll
+  for (int j = 0; j < JG * 4; ++j) v[j] = (j < J) ? __ldg(src + (size_t)j * H * W) : 0.0f;
+  const int y = pix / W, x = pix - y * W;
+  float4* dst = out + (size_t)bv * view_stride4 + ((size_t)(y + PADY) * WP + (x + PADX)) * JG;
+#pragma unroll
+  for (int g = 0; g < JG; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+}
+
+void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_cl, int batch, cudaStream_t st) {
+  const FvpProj& P = g.proj;
+  dim3 grid(fvp_cdiv(P.H * P.W, 256), batch * g.V);
+  if (g.JG == 4)
+    k0_stage_heatmaps<4><<<grid, 256, 0, st>>>(d_hm, (float4*)d_hm_cl, g.J, P.H, P.W, P.WP, P.PADX, P.PADY, g.view_stride4);
+  else
+    k0_stage_heatmaps<5><<<grid, 256, 0, st>>>(d_hm, (float4*)d_hm_cl, g.J, P.H, P.W, P.WP, P.PADX, P.PADY, g.view_stride4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------------
+template <int CG>
+__global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const float4* __restrict__ hm_cl,
+                                                            const int* __restrict__ frame_seq,
+                                                            float4* __restrict__ plane_cl) {
+  extern __shared__ float smem_f[];
+  __shared__ FvpSeq s_seq;
+  const int b = blockIdx.y;
+  const FvpProj& P = g.proj;
+  // calibration + z axis into shared memory
+  {
+    const int* src = (const int*)(g.seqs + frame_seq[b]);
+    int* dst = (int*)&s_seq;
+    for (int i = threadIdx.x; i < (int)(sizeof(FvpSeq) / 4); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < g.Z; i += blockDim.x) smem_f[i] = g.coarse_axes[g.X + g.Y + i];
+  }
+  __syncthreads();
+
+  constexpr int COLS_PER_WARP = 32 / CG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = lane % CG;                       // channel group / projection sub-lane
+  const int group_base = lane - s;               // first lane of my column
+  const int ncols = g.X * g.Y;
+  int col = (blockIdx.x * (blockDim.x >> 5) + warp) * COLS_PER_WARP + lane / CG;
+  const bool col_ok = col < ncols;
+  if (!col_ok) col = ncols - 1;                  // keep the warp convergent for the shuffles
+  const int cx = col / g.Y, cy = col - cx * g.Y;
+  const float wx = g.coarse_axes[cx], wy = g.coarse_axes[g.X + cy];
+
+  const int V = g.V, Z = g.Z, npairs = Z * V;
+  const float fV = (float)V, rV = 1.0f / fV;
+  const int row4 = P.WP * g.JG, px4 = g.JG;
+  const float4* hm_b = hm_cl + (size_t)b * V * g.view_stride4 + (s < g.JG ? s : 0);
+  const bool ch_ok = s < g.JG;
+
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), zmax = acc;
+  for (int base = 0; base < npairs; base += CG) {
+    // my (z, view) pair of this round
+    const int idx = base + s;
+    FvpTaps t;
+    t.off = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+    if (idx < npairs) {
+      const int z = idx / V, v = idx - z * V;
+      float ix, iy;
+      fvp_project(s_seq.cam[v], s_seq.A, P, wx, wy, smem_f[z], ix, iy);
+      t = fvp_taps(P, ix, iy);
+    }
+#pragma unroll
+    for (int k = 0; k < CG; ++k) {
+      const int ik = base + k;
+      if (ik >= npairs) break;                   // warp-uniform
+      const int off = __shfl_sync(0xffffffffu, t.off, group_base + k);
+      const float w00 = __shfl_sync(0xffffffffu, t.w00, group_base + k);
+      const float w01 = __shfl_sync(0xffffffffu, t.w01, group_base + k);
+      const float w10 = __shfl_sync(0xffffffffu, t.w10, group_base + k);
+      const float w11 = __shfl_sync(0xffffffffu, t.w11, group_base + k);
+      const int zk = ik / V, vk = ik - zk * V;
+      if (ch_ok) fvp_tap_accumulate(acc, hm_b + (size_t)vk * g.view_stride4, off, row4, px4, w00, w01, w10, w11);
+      if (vk == V - 1) {                         // last view of this z: mean, clamp, running z-max
+        zmax = fvp_max4(zmax, fvp_mean_clamp4(acc, fV, rV));
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  if (col_ok && ch_ok) plane_cl[((size_t)b * ncols + col) * g.JG + s] = zmax;
+}
+
+void fvp_launch_hdn_project(const FvpGeom& g, const float* d_hm_cl, const int* d_frame_seq, float* d_plane_cl,
+                            int batch, cudaStream_t st) {
+  const int ncols = g.X * g.Y;
+  const size_t smem = g.Z * sizeof(float);
+  if (g.JG <= 4) {
+    dim3 grid(fvp_cdiv(ncols, 4 * 8), batch);
+    k1_hdn_project_zmax<4><<<grid, 128, smem, st>>>(g, (const float4*)d_hm_cl, d_frame_seq, (float4*)d_plane_cl);
+  } else {
+    dim3 grid(fvp_cdiv(ncols, 4 * 4), batch);
+    k1_hdn_project_zmax<8><<<grid, 128, smem, st>>>(g, (const float4*)d_hm_cl, d_frame_seq, (float4*)d_plane_cl);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void k_nhwc_to_nchw(const float* __restrict__ in, float* __restrict__ out, int hw, int cp, int c) {
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hw * c) return;
+  const int ch = i / hw, p = i - ch * hw;
+  out[(size_t)n * c * hw + i] = in[((size_t)n * hw + p) * cp + ch];
+}
+__global__ void k_nchw_to_nhwc(const float* __restrict__ in, float* __restrict__ out, int hw, int cp, int c) {
+  const int n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hw * cp) return;
+  const int p = i / cp, ch = i - p * cp;
+  out[(size_t)n * hw * cp + i] = ch < c ? in[((size_t)n * c + ch) * hw + p] : 0.0f;
+}
+void fvp_launch_nhwc_to_nchw(const float* d_in, float* d_out, int n, int hw, int cp, int c, cudaStream_t st) {
+  dim3 grid(fvp_cdiv(hw * c, 256), n);
+  k_nhwc_to_nchw<<<grid, 256, 0, st>>>(d_in, d_out, hw, cp, c);
+}
+void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int cp, int c, cudaStream_t st) {
+  dim3 grid(fvp_cdiv(hw * cp, 256), n);
+  k_nchw_to_nhwc<<<grid, 256, 0, st>>>(d_in, d_out, hw, cp, c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------
+// One CTA = one person x one slab of TA consecutive cube rows (index a, world x).  Threads = 64 cube
+// columns b (world y) x CG lanes.  Loop: 8 chunks of 8 cube depths c (world z); inside a chunk, for
+// every a of the slab and every view, the CG lanes of a column project the chunk's 8 depths (one or two
+// each), exchange tap descriptors by shuffle and accumulate into 8 statically indexed registers; after
+// the last view: mean, clamp and
+//   xy[a][b] = max_c   : max of the 8 values, folded into a per-thread shared-memory slot per a
+//   yz[b][c] = max_a   : register running max over the slab; slab partials are combined by k3b
+//   xz[a][c] = max_b   : REDUX.MAX over the lanes of the warp that share a channel group (values are
+//                        >= 0, so their bit patterns order like unsigned ints), then a shared-memory
+//                        max over the warps (double-buffered: one barrier per a).
+constexpr int K3_CCH = 8;     // depths per chunk
+
+template <int CG, int TA>
+__global__ void __launch_bounds__(64 * CG) k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl,
+                                                           const FvpPerson* __restrict__ people,
+                                                           float4* __restrict__ planes_cl,
+                                                           float4* __restrict__ yz_scratch, int n_people) {
+  constexpr int NT = 64 * CG;                    // threads
+  constexpr int NW = NT / 32;                    // warps
+  constexpr int BPW = 32 / CG;                   // columns b per warp
+  constexpr int ROUNDS = K3_CCH / CG;            // projection rounds per (a, view)
+  static_assert(K3_CCH % CG == 0, "chunk must be a multiple of the lane group");
+  __shared__ FvpSeq s_seq;
+  __shared__ float s_fz[64];
+  __shared__ float s_fx[TA];
+  constexpr int NBUF = (CG == 4) ? 2 : 1;        // double buffer when it fits the 48 KB static limit
+  __shared__ float4 s_xz[NBUF][K3_CCH][NW][CG];  // per-warp partial maxima
+  __shared__ float4 s_xy[TA][NT];                // per-thread running max over c for every a of the slab
+
+  const int person = blockIdx.y, slab = blockIdx.x, nslab = gridDim.x;
+  const FvpPerson pd = people[person];
+  const FvpProj& P = g.proj;
+  const int JG = g.JG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = lane % CG, group_base = lane - s;
+  const int b = warp * BPW + lane / CG;          // cube column (world y index within the cube)
+  const bool ch_ok = s < JG;
+  const size_t img4 = (size_t)64 * 64 * JG;      // float4 per plane image
+  float4* xy_img = planes_cl + ((size_t)0 * n_people + person) * img4;
+  float4* xz_img = planes_cl + ((size_t)1 * n_people + person) * img4;
+  float4* yz_part = yz_scratch + ((size_t)person * nslab + slab) * img4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int a0 = slab * TA;
+
+  const bool live = pd.valid && !pd.empty;
+  const int alo = max(a0, pd.lo[0]), ahi = min(a0 + TA, pd.hi[0]);   // active rows of this slab
+  const bool any = live && alo < ahi && pd.lo[1] < pd.hi[1] && pd.lo[2] < pd.hi[2];
+
+  if (!any) {                                    // nothing to sample: this CTA's outputs are zero
+    if (ch_ok) {
+      for (int a = 0; a < TA; ++a) xy_img[((size_t)(a0 + a) * 64 + b) * JG + s] = zero4;
+      for (int c = 0; c < 64; ++c) yz_part[((size_t)b * 64 + c) * JG + s] = zero4;
+    }
+    for (int i = tid; i < TA * 64 * JG; i += NT) xz_img[(size_t)a0 * 64 * JG + i] = zero4;
+    return;
+  }
+
+  {
+    const int* src = (const int*)(g.seqs + pd.seq);
+    int* dst = (int*)&s_seq;
+    for (int i = tid; i < (int)(sizeof(FvpSeq) / 4); i += NT) dst[i] = src[i];
+    if (tid < 64) {
+      const int gz = pd.tl[2] + tid;
+      s_fz[tid] = (gz >= 0 && gz < g.fine[2]) ? g.fine_axes[g.fine[0] + g.fine[1] + gz] : 0.f;
+    }
+    if (tid < TA) {
+      const int gx = pd.tl[0] + a0 + tid;
+      s_fx[tid] = (gx >= 0 && gx < g.fine[0]) ? g.fine_axes[gx] : 0.f;
+    }
+#pragma unroll
+    for (int a = 0; a < TA; ++a) s_xy[a][tid] = zero4;
+  }
+  __syncthreads();
+
+  const bool b_ok = b >= pd.lo[1] && b < pd.hi[1];
+  const int gy = pd.tl[1] + b;
+  const float wy = (gy >= 0 && gy < g.fine[1]) ? g.fine_axes[g.fine[0] + gy] : 0.f;
+  const int V = g.V;
+  const float fV = (float)V, rV = 1.0f / fV;
+  const int row4 = P.WP * JG, px4 = JG;
+  const float4* hm_b = hm_cl + (size_t)(person / g.P) * V * g.view_stride4 + (ch_ok ? s : 0);
+  const bool sample_ok = ch_ok && b_ok;
+  unsigned rmask = 0;                            // lanes of this warp that hold my channel group
+#pragma unroll
+  for (int i = 0; i < BPW; ++i) rmask |= 1u << (i * CG + s);
+
+  int it = 0;                                    // (chunk, a) iteration counter -> xz buffer parity
+  for (int cc = 0; cc < 64; cc += K3_CCH) {
+    float4 yz_acc[K3_CCH];
+#pragma unroll
+    for (int c = 0; c < K3_CCH; ++c) yz_acc[c] = zero4;
+    const bool chunk_live = max(cc, pd.lo[2]) < min(cc + K3_CCH, pd.hi[2]);
+
+    for (int a = 0; a < TA; ++a, ++it) {
+      float4 acc[K3_CCH];
+#pragma unroll
+      for (int c = 0; c < K3_CCH; ++c) acc[c] = zero4;
+      const bool row_live = chunk_live && (a0 + a) >= alo && (a0 + a) < ahi;     // uniform
+      if (row_live) {
+        const float wx = s_fx[a];
+        for (int v = 0; v < V; ++v) {
+          const float4* hm_v = hm_b + (size_t)v * g.view_stride4;
+#pragma unroll
+          for (int r = 0; r < ROUNDS; ++r) {
+            float ix, iy;
+            fvp_project(s_seq.cam[v], s_seq.A, P, wx, wy, s_fz[cc + r * CG + s], ix, iy);
+            const FvpTaps t = fvp_taps(P, ix, iy);
+#pragma unroll
+            for (int k = 0; k < CG; ++k) {
+              const int c = r * CG + k;          // compile-time depth index within the chunk
+              const int off = __shfl_sync(0xffffffffu, t.off, group_base + k);
+              const float w00 = __shfl_sync(0xffffffffu, t.w00, group_base + k);
+              const float w01 = __shfl_sync(0xffffffffu, t.w01, group_base + k);
+              const float w10 = __shfl_sync(0xffffffffu, t.w10, group_base + k);
+              const float w11 = __shfl_sync(0xffffffffu, t.w11, group_base + k);
+              const bool c_ok = (cc + c) >= pd.lo[2] && (cc + c) < pd.hi[2];     // uniform
+              if (sample_ok && c_ok) fvp_tap_accumulate(acc[c], hm_v, off, row4, px4, w00, w01, w10, w11);
+            }
+          }
+        }
+      }
+      // mean + clamp + the three running maxima
+      float4 xy_m = zero4;
+      float4(*xzb)[NW][CG] = s_xz[NBUF == 2 ? (it & 1) : 0];
+#pragma unroll
+      for (int c = 0; c < K3_CCH; ++c) {
+        const float4 val = row_live ? fvp_mean_clamp4(acc[c], fV, rV) : zero4;   // untouched acc -> 0
+        xy_m = fvp_max4(xy_m, val);
+        yz_acc[c] = fvp_max4(yz_acc[c], val);
+        float4 m;
+        m.x = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.x)));
+        m.y = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.y)));
+        m.z = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.z)));
+        m.w = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.w)));
+        if (lane < CG) xzb[c][warp][s] = m;
+      }
+      s_xy[a][tid] = fvp_max4(s_xy[a][tid], xy_m);
+      __syncthreads();
+      // xz[a][cc..cc+7]: max over warps, one float4 per (c, channel group)
+      if (tid < K3_CCH * CG) {
+        const int ss = tid % CG, c = tid / CG;
+        if (ss < JG) {
+          float4 m = xzb[c][0][ss];
+#pragma unroll
+          for (int w = 1; w < NW; ++w) m = fvp_max4(m, xzb[c][w][ss]);
+          xz_img[((size_t)(a0 + a) * 64 + (cc + c)) * JG + ss] = m;
+        }
+      }
+      if (NBUF == 1) __syncthreads();
+    }
+    if (ch_ok) {                                 // yz partial of this slab for the chunk's depths
+#pragma unroll
+      for (int c = 0; c < K3_CCH; ++c) yz_part[((size_t)b * 64 + cc + c) * JG + s] = yz_acc[c];
+    }
+  }
+  if (ch_ok) {
+#pragma unroll
+    for (int a = 0; a < TA; ++a) xy_img[((size_t)(a0 + a) * 64 + b) * JG + s] = s_xy[a][tid];
+  }
+}
+
+// K3b: yz plane = max over the slab partials
+__global__ void __launch_bounds__(256) k3b_yz_reduce(const float4* __restrict__ yz_scratch,
+                                                      float4* __restrict__ planes_cl, int n_people, int nslab,
+                                                      int img4) {
+  const int person = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= img4) return;
+  const float4* src = yz_scratch + (size_t)person * nslab * img4 + i;
+  float4 m = src[0];
+  for (int sl = 1; sl < nslab; ++sl) m = fvp_max4(m, src[(size_t)sl * img4]);
+  planes_cl[((size_t)2 * n_people + person) * img4 + i] = m;
+}
+
+void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
+                            float* d_yz_scratch, int batch, int slab, cudaStream_t st) {
+  const int n_people = batch * g.P;
+  const int img4 = 64 * 64 * g.JG;
+  if (g.JG <= 4) {
+    if (slab == 4) {
+      dim3 grid(16, n_people);
+      k3_jln_project<4, 4><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                 (float4*)d_yz_scratch, n_people);
+    } else {
+      dim3 grid(8, n_people);
+      k3_jln_project<4, 8><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                 (float4*)d_yz_scratch, n_people);
+    }
+  } else {
+    slab = 2;
+    dim3 grid(32, n_people);
+    k3_jln_project<8, 2><<<grid, 512, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                               (float4*)d_yz_scratch, n_people);
+  }
+  dim3 grid2(fvp_cdiv(img4, 256), n_people);
+  k3b_yz_reduce<<<grid2, 256, 0, st>>>((const float4*)d_yz_scratch, (float4*)d_planes_cl, n_people, 64 / slab, img4);
+}

@@ -1,0 +1,88 @@
+// fvp_ctx.h - the context object behind the C ABI (host only).
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "fvp_kernels.h"
+
+struct FvpLayer {
+  std::string key, bn;
+  int cin, cout, k, ndim;
+  bool transposed;
+};
+struct FvpParam {
+  std::string name;
+  int64_t numel;
+  bool is_int;
+  bool set;
+  std::vector<float> data;
+};
+
+struct fvp_ctx {
+  fvp_config cfg;
+  int device;
+  std::string err;
+
+  // parameters
+  std::vector<FvpLayer> layers;
+  std::vector<FvpParam> params;
+  std::map<std::string, int> param_index;
+  bool params_ready = false;
+  float* d_weights = nullptr;
+  FvpTrunkW w_center, w_p2p;
+  FvpC2CW w_c2c;
+  FvpPoseW w_pose;
+
+  // geometry
+  FvpGeom geom;
+  float* d_axes = nullptr;            // coarse | fine | individual
+  FvpSeq* d_seqs = nullptr;
+  std::vector<int> seq_set;           // which calibration slots are populated
+  FvpPropArgs prop;                   // constants of the proposal kernel (pointers filled per call)
+
+  // workspaces (sized for cfg.max_batch)
+  float* d_hm_in = nullptr;           // [MB][V][J][H][W] staging for the host entry point
+  float* d_hm_cl = nullptr;
+  float* d_plane_cl = nullptr;        // [MB][X][Y][JP]
+  float* d_hmsize = nullptr;          // [MB][3][X][Y]  (hm, size_w, size_h)
+  float* d_conf2d = nullptr;          // [MB*P]
+  int* d_flat = nullptr;              // [MB*P]
+  float* d_centers = nullptr;         // [MB*P][7]
+  FvpPerson* d_people = nullptr;      // [MB*P]
+  int* d_img_valid = nullptr;         // [3*MB*P]
+  float* d_planes_cl = nullptr;       // [3][MB*P][64][64][JP]
+  float* d_yz_scratch = nullptr;
+  float* d_feat = nullptr;            // [3][MB*P][J][64][64]
+  float* d_pose = nullptr;            // [3][MB*P][J][2]
+  float* d_maxw = nullptr;            // [3][MB*P][J]
+  float* d_wts = nullptr;             // [3][MB*P][J]
+  float* d_fused = nullptr;           // [MB*P][J][3]
+  float* d_conf = nullptr;            // [MB*P]
+  float* d_out_fused = nullptr;       // [MB][P][J][5]   (graph / host entry outputs)
+  float* d_out_plane = nullptr;       // [3][MB][P][J][2]
+  float* d_out_centers = nullptr;     // [MB][P][7]
+  float* d_tmp = nullptr;             // scratch for stage-API layout conversions
+  size_t tmp_floats = 0;
+  float* cn_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* p2p_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* d_frame_seq = nullptr;         // [MB]
+  int* h_frame_seq = nullptr;         // pinned
+  int k3_slab = 8;
+
+  // cuda graph
+  bool use_graph = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_batch = 0;
+  std::vector<int> graph_seqs;
+  int graph_launches = 0;
+
+  // introspection
+  int last_launches = 0;
+  bool profiling = false;
+  cudaEvent_t ev[10] = {nullptr};
+  float stage_ms[9] = {0};
+};
+
+void fvp_build_param_table(fvp_ctx* ctx);
+int fvp_pack_params(fvp_ctx* ctx);

@@ -1,0 +1,125 @@
+// fvp_kernels.h - host-side launchers of every kernel in libfvp_b200 (all enqueue on `st`).
+#pragma once
+#include "fvp_common.cuh"
+
+// ---- geometry tables resident on the device ---------------------------------------------------
+struct FvpGeom {
+  FvpProj proj;
+  int V, J, JG;              // views, joints, channel groups (JP/4)
+  int X, Y, Z;               // coarse grid
+  int fine[3];               // fine whole-space grid (project_individual.py:25)
+  int P;                     // max people
+  const float* coarse_axes;  // [X+Y+Z]
+  const float* fine_axes;    // [fine0+fine1+fine2]
+  const float* ind_axes;     // [64*3] individual-space axes incl. space centre (center_grid)
+  const FvpSeq* seqs;        // [max_sequences]
+  size_t view_stride4;       // float4 per view of the channel-last heat map (HP*WP*JG)
+};
+
+// K0: [B][V][J][H][W] -> channel-last, zero-bordered [B][V][HP][WP][JP]
+void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_cl, int batch, cudaStream_t st);
+
+// K1: fused back-projection + view mean + clamp + z-max -> plane_cl [B][X][Y][JP]
+void fvp_launch_hdn_project(const FvpGeom& g, const float* d_hm_cl, const int* d_frame_seq, float* d_plane_cl,
+                            int batch, cudaStream_t st);
+
+// layout helpers (stage API / tests): NHWC(JP) <-> NCHW(J)
+void fvp_launch_nhwc_to_nchw(const float* d_in, float* d_out, int n, int hw, int cp, int c, cudaStream_t st);
+void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int cp, int c, cudaStream_t st);
+
+// K3: per-person back-projection + three-plane max.
+//   planes_cl [3][B*P][64][64][JP]; yz partial scratch [B*P][nslab][64][64][JP]
+void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
+                            float* d_yz_scratch, int batch, int slab, cudaStream_t st);
+
+// ---- convolutions (fp32 CUDA-core implicit GEMM, NHWC) ----------------------------------------
+struct FvpConvArgs {
+  const float* in;    // [n][H][W][Cin]
+  int H, W, Cin;
+  const float* in2;   // optional second source for a fused 1x1 (skip_con), same H,W
+  int Cin2;
+  const float* w;     // packed [(taps*CinP + Cin2P)][CoutP], CinP = round_up(Cin,16)
+  const float* bias;  // [CoutP]
+  float* out;         // NHWC [n][Ho][Wo][CoutS]  or NCHW [n][CoutReal][Ho][Wo]
+  int CoutP;          // GEMM N (multiple of 4); for upsample = 4*Co
+  int CoutS;          // channel stride of the NHWC output
+  int CoutReal;       // channels stored when nchw
+  const float* res;   // residual, same layout as out (NHWC)
+  int res_mode;       // 0 none, 1 add before ReLU, 2 add after ReLU
+  int relu;
+  int ksize;          // 1, 3, 7
+  int upsample;       // ConvTranspose k2 s2 expressed as 1x1 conv to 4*Co + pixel shuffle
+  int nchw;
+  int n;
+  const int* valid;   // optional per-image gate
+};
+void fvp_launch_conv(const FvpConvArgs& a, cudaStream_t st);
+void fvp_launch_maxpool2(const float* in, float* out, int n, int H, int W, int C, const int* valid, cudaStream_t st);
+
+// ---- 2-D trunk program (CenterNet / P2PNet) ------------------------------------------------------
+struct FvpConvW {         // one packed conv
+  const float* w;
+  const float* b;
+  int cin, cin2, coutp, k;
+};
+struct FvpTrunkW {
+  FvpConvW front, r1a, r1b, s1a, s1b, e1a, e1b, s2a, s2b, e2a, e2b, ma, mb, d2a, d2b, up2, d1a, d1b, up1;
+  FvpConvW head_a, head_b;   // CenterNet: merged 3x3 (32->64) + block-diagonal 1x1 (64->3); P2PNet: head_b only
+};
+// buf[6]: scratch units of n*H*W*64 floats each
+void fvp_run_trunk2d(const FvpTrunkW& t, const float* d_in, int cin, int n, int H, int W, float* const buf[6],
+                     const int* valid, bool center_heads, float* d_out, int out_real, int* launches, cudaStream_t st);
+
+// ---- proposals -------------------------------------------------------------------------------
+// nms2D + top-k: hm planar with image stride `img_stride` floats -> conf [B][P], flat [B][P]
+void fvp_launch_nms_topk(const float* d_hm, size_t img_stride, int X, int Y, int P, int batch, float* d_conf,
+                         int* d_flat, cudaStream_t st);
+
+struct FvpC2CW {            // packed 1-D trunk, weights [tap][ci][co] per conv
+  const float* w[24];
+  const float* b[24];
+};
+struct FvpPropArgs {
+  FvpGeom g;
+  const float* hm_cl;
+  const int* frame_seq;
+  const float* conf2d;      // [B*P]
+  const int* flat;          // [B*P]
+  const float* size;        // planar: size_w at size[b*img_stride + (X*Y)*0 + flat], size_h at +X*Y
+  size_t size_img_stride;
+  const float* cols_in;     // optional [n][J][Z] columns (c2c stage API); else sampled from hm_cl
+  float* cols_out;          // optional [n][J][Z]
+  float* hm1d_out;          // optional [n][Z]
+  float* centers;           // optional [B][P][7]
+  FvpPerson* people;        // optional [B*P]
+  int* img_valid;           // optional [3][n_slots]: gate of the three plane images of every slot
+  int n_slots;
+  float min_score;
+  float hdn_scale[3], hdn_bias[3];                 // human_detection_net.py:22-23
+  float jln_scale[3], jln_bias[3];                 // project_individual.py:27-29
+  float whole[3], ind[3];
+  int ind_vox[3];
+  int mode;                 // 0 full (sample + c2c + proposal), 1 c2c only on cols_in
+};
+void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, cudaStream_t st);
+// proposal_centers [B][P][7] -> FvpPerson (stage API for K3)
+void fvp_launch_people_from_centers(const FvpPropArgs& a, const float* d_centers, int n, cudaStream_t st);
+
+// ---- pose head ----------------------------------------------------------------------------------
+struct FvpPoseW {
+  const float* conv_w;   // [32][9] BN-folded
+  const float* conv_b;   // [32]
+  const float* fc1_w;    // [hidden][feat]
+  const float* fc1_b;
+  const float* fc2_w;    // [hidden]
+  const float* fc2_b;    // [1]
+  int feat, hidden;
+};
+// feat planar [3][n][J][64][64]; people may be NULL (then offsets from d_offset [n][3], all valid)
+void fvp_launch_pose_head(const FvpGeom& g, const FvpPoseW& w, const float* d_feat, const FvpPerson* d_people,
+                          const float* d_offset, int n, float beta, float* d_pose, float* d_maxw, float* d_weights,
+                          float* d_fused, cudaStream_t st);
+// conf[n] = mean over (plane, joint) of max softmax; writes fused_poses/plane_poses/centers col 4 (final pack)
+void fvp_launch_finalize(const FvpGeom& g, const FvpPerson* d_people, const float* d_maxw, const float* d_pose,
+                         const float* d_fused, float* d_centers, int batch, float* d_conf, float* d_fused_poses,
+                         float* d_plane_poses, float* d_centers_out, cudaStream_t st);

@@ -1,0 +1,323 @@
+// fvp_params.cu - the reference's state_dict as a parameter table, eval-mode BatchNorm folding and
+// repacking for the kernels.  Table order == nn.Module.state_dict() order of FasterVoxelPoseNet
+// (485 entries for J=15; SURVEY.md section 5 "checkpoint"); tests/test_netspec.py checks it against
+// the Python enumeration (fvp/netspec.py), which itself was checked against the reference.
+#include <cmath>
+#include <cstring>
+
+#include "fvp_ctx.h"
+
+namespace {
+
+void add_res(std::vector<FvpLayer>& L, const std::string& p, int cin, int cout, int nd) {
+  L.push_back({p + ".res_branch.0", p + ".res_branch.1", cin, cout, 3, nd, false});
+  L.push_back({p + ".res_branch.3", p + ".res_branch.4", cout, cout, 3, nd, false});
+  if (cin != cout) L.push_back({p + ".skip_con.0", p + ".skip_con.1", cin, cout, 1, nd, false});
+}
+
+// front_layers + EncoderDecorder in registration order (cnns_2d.py:78-92,150-155)
+void add_trunk(std::vector<FvpLayer>& L, const std::string& p, int cin, int nd) {
+  const std::string ed = p + ".encoder_decoder";
+  L.push_back({p + ".front_layers.0.block.0", p + ".front_layers.0.block.1", cin, 16, 7, nd, false});
+  add_res(L, p + ".front_layers.1", 16, 32, nd);
+  add_res(L, ed + ".encoder_res1", 32, 64, nd);
+  add_res(L, ed + ".encoder_res2", 64, 128, nd);
+  add_res(L, ed + ".mid_res", 128, 128, nd);
+  add_res(L, ed + ".decoder_res2", 128, 128, nd);
+  L.push_back({ed + ".decoder_upsample2.block.0", ed + ".decoder_upsample2.block.1", 128, 64, 2, nd, true});
+  add_res(L, ed + ".decoder_res1", 64, 64, nd);
+  L.push_back({ed + ".decoder_upsample1.block.0", ed + ".decoder_upsample1.block.1", 64, 32, 2, nd, true});
+  add_res(L, ed + ".skip_res1", 32, 32, nd);
+  add_res(L, ed + ".skip_res2", 64, 64, nd);
+}
+
+int64_t ipow(int b, int e) {
+  int64_t r = 1;
+  for (int i = 0; i < e; ++i) r *= b;
+  return r;
+}
+
+}  // namespace
+
+void fvp_build_param_table(fvp_ctx* ctx) {
+  const int J = ctx->cfg.num_joints;
+  std::vector<FvpLayer>& L = ctx->layers;
+  L.clear();
+  add_trunk(L, "pose_net.center_net", J, 2);
+  L.push_back({"pose_net.center_net.output_hm.0", "", 32, 32, 3, 2, false});
+  L.push_back({"pose_net.center_net.output_hm.2", "", 32, 1, 1, 2, false});
+  L.push_back({"pose_net.center_net.output_size.0", "", 32, 32, 3, 2, false});
+  L.push_back({"pose_net.center_net.output_size.2", "", 32, 2, 1, 2, false});
+  add_trunk(L, "pose_net.c2c_net", J, 1);
+  L.push_back({"pose_net.c2c_net.output_hm", "", 32, 1, 1, 1, false});
+  add_trunk(L, "joint_net.conv_net", J, 2);
+  L.push_back({"joint_net.conv_net.output_layer", "", 32, J, 1, 2, false});
+  const int F = ctx->cfg.feat_channels, Hd = ctx->cfg.hidden_channels;
+  L.push_back({"joint_net.weight_net.heatmap_feature_net.0", "joint_net.weight_net.heatmap_feature_net.1", 1, F, 3, 2, false});
+  L.push_back({"joint_net.weight_net.output.0", "", F, Hd, 1, 0, false});
+  L.push_back({"joint_net.weight_net.output.2", "", Hd, 1, 1, 0, false});
+
+  ctx->params.clear();
+  ctx->param_index.clear();
+  auto add = [&](const std::string& name, int64_t numel, bool is_int) {
+    FvpParam p;
+    p.name = name;
+    p.numel = numel;
+    p.is_int = is_int;
+    p.set = is_int;  // num_batches_tracked is optional
+    if (!is_int) p.data.assign((size_t)numel, 0.f);
+    ctx->param_index[name] = (int)ctx->params.size();
+    ctx->params.push_back(std::move(p));
+  };
+  for (const FvpLayer& l : L) {
+    const int64_t kk = l.ndim ? ipow(l.k, l.ndim) : 1;
+    add(l.key + ".weight", (int64_t)l.cin * l.cout * kk, false);
+    add(l.key + ".bias", l.cout, false);
+    if (!l.bn.empty()) {
+      add(l.bn + ".weight", l.cout, false);
+      add(l.bn + ".bias", l.cout, false);
+      add(l.bn + ".running_mean", l.cout, false);
+      add(l.bn + ".running_var", l.cout, false);
+      add(l.bn + ".num_batches_tracked", 1, true);
+    }
+  }
+}
+
+namespace {
+
+const FvpLayer* find_layer(const fvp_ctx* ctx, const std::string& key) {
+  for (const FvpLayer& l : ctx->layers)
+    if (l.key == key) return &l;
+  return nullptr;
+}
+const std::vector<float>& P(const fvp_ctx* ctx, const std::string& name) {
+  return ctx->params[ctx->param_index.at(name)].data;
+}
+
+// BN scale / shift of a layer's output channels (identity when no BN): y = s*conv + t,
+// s = gamma / sqrt(var + 1e-5), t = (bias - mean) * s + beta        (F.batch_norm, eval)
+void bn_affine(const fvp_ctx* ctx, const FvpLayer& l, std::vector<double>& s, std::vector<double>& t) {
+  const std::vector<float>& b = P(ctx, l.key + ".bias");
+  s.assign(l.cout, 1.0);
+  t.assign(l.cout, 0.0);
+  for (int c = 0; c < l.cout; ++c) t[c] = b[c];
+  if (l.bn.empty()) return;
+  const std::vector<float>&g = P(ctx, l.bn + ".weight"), &be = P(ctx, l.bn + ".bias"),
+                    &m = P(ctx, l.bn + ".running_mean"), &v = P(ctx, l.bn + ".running_var");
+  for (int c = 0; c < l.cout; ++c) {
+    s[c] = (double)g[c] / std::sqrt((double)v[c] + 1e-5);
+    t[c] = ((double)b[c] - (double)m[c]) * s[c] + (double)be[c];
+  }
+}
+
+struct Packed {
+  std::vector<float> w, b;
+  int cin, cin2, coutp, k;
+};
+
+// regular conv (2-D or 1-D), optional fused 1x1 skip conv as extra K rows
+Packed pack_conv(const fvp_ctx* ctx, const std::string& key, const std::string& skip_key = "") {
+  const FvpLayer& l = *find_layer(ctx, key);
+  const int nd = l.ndim, K = l.k, taps = (int)ipow(K, nd);
+  const int cinP = fvp_round_up(l.cin, 16), coutP = fvp_round_up(l.cout, 4);
+  const FvpLayer* sk = skip_key.empty() ? nullptr : find_layer(ctx, skip_key);
+  const int cin2 = sk ? sk->cin : 0, cin2P = sk ? fvp_round_up(cin2, 16) : 0;
+  Packed p;
+  p.cin = l.cin; p.cin2 = cin2; p.coutp = coutP; p.k = K;
+  p.w.assign((size_t)(taps * cinP + cin2P) * coutP, 0.f);
+  p.b.assign(coutP, 0.f);
+  std::vector<double> s, t;
+  bn_affine(ctx, l, s, t);
+  const std::vector<float>& w = P(ctx, key + ".weight");      // [co][ci][taps]
+  for (int co = 0; co < l.cout; ++co)
+    for (int ci = 0; ci < l.cin; ++ci)
+      for (int tp = 0; tp < taps; ++tp)
+        p.w[(size_t)(tp * cinP + ci) * coutP + co] = (float)((double)w[((size_t)co * l.cin + ci) * taps + tp] * s[co]);
+  std::vector<double> bias(t);
+  if (sk) {
+    std::vector<double> s2, t2;
+    bn_affine(ctx, *sk, s2, t2);
+    const std::vector<float>& w2 = P(ctx, skip_key + ".weight");   // [co][ci][1]
+    for (int co = 0; co < l.cout; ++co) {
+      for (int ci = 0; ci < cin2; ++ci)
+        p.w[(size_t)(taps * cinP + ci) * coutP + co] = (float)((double)w2[(size_t)co * cin2 + ci] * s2[co]);
+      bias[co] += t2[co];
+    }
+  }
+  for (int co = 0; co < l.cout; ++co) p.b[co] = (float)bias[co];
+  return p;
+}
+
+// ConvTranspose(k=2,s=2): [ci][co][q] -> GEMM columns q*Co + co, q = dy*2+dx (2-D) or d (1-D)
+Packed pack_convT(const fvp_ctx* ctx, const std::string& key) {
+  const FvpLayer& l = *find_layer(ctx, key);
+  const int Q = (int)ipow(2, l.ndim);
+  const int cinP = fvp_round_up(l.cin, 16), coutP = Q * l.cout;
+  Packed p;
+  p.cin = l.cin; p.cin2 = 0; p.coutp = coutP; p.k = 1;
+  p.w.assign((size_t)cinP * coutP, 0.f);
+  p.b.assign(coutP, 0.f);
+  std::vector<double> s, t;
+  bn_affine(ctx, l, s, t);
+  const std::vector<float>& w = P(ctx, key + ".weight");      // [ci][co][Q]
+  for (int ci = 0; ci < l.cin; ++ci)
+    for (int co = 0; co < l.cout; ++co)
+      for (int q = 0; q < Q; ++q)
+        p.w[(size_t)ci * coutP + q * l.cout + co] = (float)((double)w[((size_t)ci * l.cout + co) * Q + q] * s[co]);
+  for (int q = 0; q < Q; ++q)
+    for (int co = 0; co < l.cout; ++co) p.b[q * l.cout + co] = (float)t[co];
+  return p;
+}
+
+struct Arena {
+  std::vector<float> host;
+  size_t put(const std::vector<float>& v) {
+    const size_t off = (host.size() + 63) & ~(size_t)63;     // 256-byte aligned
+    host.resize(off + v.size());
+    std::memcpy(host.data() + off, v.data(), v.size() * sizeof(float));
+    return off;
+  }
+};
+
+struct PendingConv {
+  size_t w_off, b_off;
+  int cin, cin2, coutp, k;
+};
+
+PendingConv stash(Arena& A, const Packed& p) {
+  PendingConv pc;
+  pc.w_off = A.put(p.w);
+  pc.b_off = A.put(p.b);
+  pc.cin = p.cin; pc.cin2 = p.cin2; pc.coutp = p.coutp; pc.k = p.k;
+  return pc;
+}
+
+// the 19 trunk convs in execution order (see fvp_run_trunk2d / c2c_forward)
+void pack_trunk(const fvp_ctx* ctx, const std::string& p, Arena& A, std::vector<PendingConv>& out) {
+  const std::string ed = p + ".encoder_decoder";
+  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.0.block.0")));
+  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.1.res_branch.0")));
+  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.1.res_branch.3", p + ".front_layers.1.skip_con.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res1.res_branch.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res1.res_branch.3")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res1.res_branch.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res1.res_branch.3", ed + ".encoder_res1.skip_con.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res2.res_branch.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res2.res_branch.3")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res2.res_branch.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res2.res_branch.3", ed + ".encoder_res2.skip_con.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".mid_res.res_branch.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".mid_res.res_branch.3")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res2.res_branch.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res2.res_branch.3")));
+  out.push_back(stash(A, pack_convT(ctx, ed + ".decoder_upsample2.block.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res1.res_branch.0")));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res1.res_branch.3")));
+  out.push_back(stash(A, pack_convT(ctx, ed + ".decoder_upsample1.block.0")));
+}
+
+FvpConvW bind(const float* base, const PendingConv& pc) {
+  FvpConvW w;
+  w.w = base + pc.w_off;
+  w.b = base + pc.b_off;
+  w.cin = pc.cin; w.cin2 = pc.cin2; w.coutp = pc.coutp; w.k = pc.k;
+  return w;
+}
+
+void bind_trunk(const float* base, const std::vector<PendingConv>& v, FvpTrunkW& t) {
+  FvpConvW* slots[19] = {&t.front, &t.r1a, &t.r1b, &t.s1a, &t.s1b, &t.e1a, &t.e1b, &t.s2a, &t.s2b, &t.e2a,
+                         &t.e2b,   &t.ma,  &t.mb,  &t.d2a, &t.d2b, &t.up2, &t.d1a, &t.d1b, &t.up1};
+  for (int i = 0; i < 19; ++i) *slots[i] = bind(base, v[i]);
+}
+
+}  // namespace
+
+int fvp_pack_params(fvp_ctx* ctx) {
+  for (const FvpParam& p : ctx->params)
+    if (!p.set) return fvp_fail(ctx, FVP_E_STATE, "parameter '%s' was never set", p.name.c_str());
+  Arena A;
+  std::vector<PendingConv> cn, c2c, p2p;
+  // ---- CenterNet -----------------------------------------------------------------------------
+  pack_trunk(ctx, "pose_net.center_net", A, cn);
+  {
+    // both 3x3 heads as one 32->64 conv (+ReLU), both 1x1 heads as one block-diagonal 64->4 conv
+    const Packed a = pack_conv(ctx, "pose_net.center_net.output_hm.0");
+    const Packed b = pack_conv(ctx, "pose_net.center_net.output_size.0");
+    Packed m;
+    m.cin = 32; m.cin2 = 0; m.coutp = 64; m.k = 3;
+    m.w.assign((size_t)9 * 32 * 64, 0.f);
+    m.b.assign(64, 0.f);
+    for (int r = 0; r < 9 * 32; ++r)
+      for (int c = 0; c < 32; ++c) {
+        m.w[(size_t)r * 64 + c] = a.w[(size_t)r * 32 + c];
+        m.w[(size_t)r * 64 + 32 + c] = b.w[(size_t)r * 32 + c];
+      }
+    for (int c = 0; c < 32; ++c) { m.b[c] = a.b[c]; m.b[32 + c] = b.b[c]; }
+    cn.push_back(stash(A, m));
+    const std::vector<float>&wh = P(ctx, "pose_net.center_net.output_hm.2.weight"),
+                      &bh = P(ctx, "pose_net.center_net.output_hm.2.bias"),
+                      &ws = P(ctx, "pose_net.center_net.output_size.2.weight"),
+                      &bs = P(ctx, "pose_net.center_net.output_size.2.bias");
+    Packed h;
+    h.cin = 64; h.cin2 = 0; h.coutp = 4; h.k = 1;
+    h.w.assign((size_t)64 * 4, 0.f);
+    h.b.assign(4, 0.f);
+    for (int ci = 0; ci < 32; ++ci) {
+      h.w[(size_t)ci * 4 + 0] = wh[ci];
+      h.w[(size_t)(32 + ci) * 4 + 1] = ws[ci];
+      h.w[(size_t)(32 + ci) * 4 + 2] = ws[32 + ci];
+    }
+    h.b[0] = bh[0]; h.b[1] = bs[0]; h.b[2] = bs[1];
+    cn.push_back(stash(A, h));
+  }
+  // ---- C2CNet --------------------------------------------------------------------------------
+  pack_trunk(ctx, "pose_net.c2c_net", A, c2c);
+  c2c.push_back(stash(A, pack_conv(ctx, "pose_net.c2c_net.output_hm")));
+  // ---- P2PNet --------------------------------------------------------------------------------
+  pack_trunk(ctx, "joint_net.conv_net", A, p2p);
+  p2p.push_back(stash(A, pack_conv(ctx, "joint_net.conv_net.output_layer")));
+  // ---- WeightNet -----------------------------------------------------------------------------
+  const std::string wn = "joint_net.weight_net";
+  const FvpLayer& wl = *find_layer(ctx, wn + ".heatmap_feature_net.0");
+  std::vector<double> s, t;
+  bn_affine(ctx, wl, s, t);
+  const int F = ctx->cfg.feat_channels;
+  std::vector<float> cw((size_t)F * 9), cb(F);
+  {
+    const std::vector<float>& w = P(ctx, wn + ".heatmap_feature_net.0.weight");
+    for (int c = 0; c < F; ++c) {
+      for (int i = 0; i < 9; ++i) cw[(size_t)c * 9 + i] = (float)((double)w[(size_t)c * 9 + i] * s[c]);
+      cb[c] = (float)t[c];
+    }
+  }
+  const size_t o_cw = A.put(cw), o_cb = A.put(cb);
+  const size_t o_f1w = A.put(P(ctx, wn + ".output.0.weight")), o_f1b = A.put(P(ctx, wn + ".output.0.bias"));
+  const size_t o_f2w = A.put(P(ctx, wn + ".output.2.weight")), o_f2b = A.put(P(ctx, wn + ".output.2.bias"));
+
+  // ---- upload --------------------------------------------------------------------------------
+  if (ctx->d_weights) cudaFree(ctx->d_weights);
+  ctx->d_weights = nullptr;
+  FVP_CUDA_OK(cudaMalloc(&ctx->d_weights, A.host.size() * sizeof(float)));
+  FVP_CUDA_OK(cudaMemcpy(ctx->d_weights, A.host.data(), A.host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  const float* base = ctx->d_weights;
+  bind_trunk(base, cn, ctx->w_center);
+  ctx->w_center.head_a = bind(base, cn[19]);
+  ctx->w_center.head_b = bind(base, cn[20]);
+  bind_trunk(base, p2p, ctx->w_p2p);
+  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0};
+  ctx->w_p2p.head_b = bind(base, p2p[19]);
+  for (int i = 0; i < 20; ++i) {
+    ctx->w_c2c.w[i] = base + c2c[i].w_off;
+    ctx->w_c2c.b[i] = base + c2c[i].b_off;
+  }
+  ctx->w_pose.conv_w = base + o_cw;
+  ctx->w_pose.conv_b = base + o_cb;
+  ctx->w_pose.fc1_w = base + o_f1w;
+  ctx->w_pose.fc1_b = base + o_f1b;
+  ctx->w_pose.fc2_w = base + o_f2w;
+  ctx->w_pose.fc2_b = base + o_f2b;
+  ctx->w_pose.feat = F;
+  ctx->w_pose.hidden = ctx->cfg.hidden_channels;
+  ctx->params_ready = true;
+  return FVP_OK;
+}

@@ -1,0 +1,341 @@
+// fvp_proposal.cu - everything between the CenterNet output and the JLN crops:
+//   * nms2D + top-k                       (lib/core/proposal.py:13-33)
+//   * z-column re-sampling (K2)           (replaces the torch.gather on the never-materialised volume,
+//                                          lib/models/human_detection_net.py:92-93)
+//   * C2CNet, whole net in one CTA        (lib/models/cnns_1d.py:10-132)
+//   * z arg-max, ProposalLayer assembly   (human_detection_net.py:44-65,95-102)
+//   * JLN crop parameters                 (lib/models/project_individual.py:110-121)
+#include "fvp_kernels.h"
+#include "fvp_project.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// NMS + top-k: one CTA per frame.  nms = (hm == maxpool3x3(hm)) ? hm : 0 ; P rounds of block arg-max.
+// Ties (only possible among exact duplicates, e.g. the zeros of suppressed cells) resolve to the
+// lowest flat index - torch.topk leaves that order unspecified.
+// ------------------------------------------------------------------------------------------------
+struct ValIdx {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ValIdx vi_best(ValIdx a, ValIdx b) {
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+
+__global__ void __launch_bounds__(1024) k_nms_topk(const float* __restrict__ hm, size_t img_stride, int X, int Y,
+                                                   int P, float* __restrict__ conf, int* __restrict__ flat) {
+  extern __shared__ float s_nms[];               // [X*Y]
+  __shared__ ValIdx s_red[32];
+  __shared__ ValIdx s_win;
+  const int b = blockIdx.x, n = X * Y, tid = threadIdx.x;
+  const float* h = hm + (size_t)b * img_stride;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int x = i / Y, y = i - x * Y;
+    const float v = h[i];
+    float m = v;
+    for (int dx = -1; dx <= 1; ++dx)
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int xx = x + dx, yy = y + dy;
+        if (xx >= 0 && xx < X && yy >= 0 && yy < Y) m = fmaxf(m, h[xx * Y + yy]);
+      }
+    s_nms[i] = (v == m) ? v : 0.0f;
+  }
+  __syncthreads();
+  for (int r = 0; r < P; ++r) {
+    ValIdx best = {-INFINITY, 0x7fffffff};
+    for (int i = tid; i < n; i += blockDim.x) best = vi_best(best, ValIdx{s_nms[i], i});
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ValIdx other;
+      other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+      other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+      best = vi_best(best, other);
+    }
+    if ((tid & 31) == 0) s_red[tid >> 5] = best;
+    __syncthreads();
+    if (tid < 32) {
+      ValIdx v2 = tid < (int)(blockDim.x >> 5) ? s_red[tid] : ValIdx{-INFINITY, 0x7fffffff};
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ValIdx other;
+        other.v = __shfl_xor_sync(0xffffffffu, v2.v, o);
+        other.i = __shfl_xor_sync(0xffffffffu, v2.i, o);
+        v2 = vi_best(v2, other);
+      }
+      if (tid == 0) {
+        s_win = v2;
+        conf[b * P + r] = v2.v;
+        flat[b * P + r] = v2.i;
+        s_nms[v2.i] = -INFINITY;                 // remove from later rounds
+      }
+    }
+    __syncthreads();
+  }
+}
+
+void fvp_launch_nms_topk(const float* d_hm, size_t img_stride, int X, int Y, int P, int batch, float* d_conf,
+                         int* d_flat, cudaStream_t st) {
+  const size_t smem = (size_t)X * Y * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaFuncSetAttribute(k_nms_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  k_nms_topk<<<batch, 1024, smem, st>>>(d_hm, img_stride, X, Y, P, d_conf, d_flat);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1-D trunk in shared memory.  Activations [C][L] fp32; weights packed [(tap*CinP + ci) (+ CinP2 rows)][Cout].
+// ------------------------------------------------------------------------------------------------
+constexpr int C2C_THREADS = 512;
+constexpr int C2C_MAXZ = 40;
+constexpr int C2C_BUF = 32 * C2C_MAXZ;   // floats per activation buffer: 32xZ = 64xZ/2 = 128xZ/4
+
+struct C2CLayer {
+  const float* w;
+  const float* b;
+};
+struct C2CNet {
+  C2CLayer l[20];
+};
+
+// out[co][l] = epilogue( sum_{tap,ci} w[tap*CinP+ci][co] * in[ci][l+tap-pad]  (+ sum_ci w2[ci][co]*in2[ci][l]) + b[co] )
+// upsample: GEMM columns co' = d*Co + co  ->  out[co][2l+d]
+__device__ void c2c_conv(const float* __restrict__ in, int Cin, int L, const float* __restrict__ in2, int Cin2,
+                         C2CLayer ly, int K, float* __restrict__ out, int CoutG, const float* __restrict__ res,
+                         int res_mode, bool relu, bool upsample) {
+  const int tid = threadIdx.x;
+  const int CinP = (Cin + 15) & ~15;
+  const int groups = C2C_THREADS / CoutG > 0 ? C2C_THREADS / CoutG : 1;
+  const int co = tid % CoutG, lg = tid / CoutG;
+  const int pad = (K - 1) / 2;
+  if (lg < groups && tid < CoutG * groups) {
+    for (int l0 = lg; l0 < L; l0 += 2 * groups) {
+      const int l1 = l0 + groups;
+      const bool has1 = l1 < L;
+      float a0 = 0.f, a1 = 0.f;
+      for (int tap = 0; tap < K; ++tap) {
+        const int p0 = l0 + tap - pad, p1 = l1 + tap - pad;
+        const bool ok0 = p0 >= 0 && p0 < L, ok1 = has1 && p1 >= 0 && p1 < L;
+        const float* wr = ly.w + (size_t)(tap * CinP) * CoutG + co;
+#pragma unroll 4
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float wv = __ldg(wr + (size_t)ci * CoutG);
+          const float x0 = ok0 ? in[ci * L + p0] : 0.f;
+          const float x1 = ok1 ? in[ci * L + p1] : 0.f;
+          a0 = fmaf(wv, x0, a0);
+          a1 = fmaf(wv, x1, a1);
+        }
+      }
+      if (in2) {
+        const float* wr = ly.w + (size_t)(K * CinP) * CoutG + co;
+#pragma unroll 4
+        for (int ci = 0; ci < Cin2; ++ci) {
+          const float wv = __ldg(wr + (size_t)ci * CoutG);
+          a0 = fmaf(wv, in2[ci * L + l0], a0);
+          if (has1) a1 = fmaf(wv, in2[ci * L + l1], a1);
+        }
+      }
+      const float bias = __ldg(ly.b + co);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (e == 1 && !has1) break;
+        float v = (e == 0 ? a0 : a1) + bias;
+        const int l = e == 0 ? l0 : l1;
+        int oc = co, ol = l, Lo = L;
+        if (upsample) {
+          const int Co = CoutG >> 1;
+          const int d = co / Co;
+          oc = co - d * Co;
+          ol = 2 * l + d;
+          Lo = 2 * L;
+        }
+        if (res_mode == 1) v += res[oc * Lo + ol];
+        if (relu) v = fmaxf(v, 0.f);
+        if (res_mode == 2) v += res[oc * Lo + ol];
+        out[oc * Lo + ol] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ void c2c_pool(const float* __restrict__ in, int C, int L, float* __restrict__ out) {
+  const int Lo = L >> 1;
+  for (int i = threadIdx.x; i < C * Lo; i += C2C_THREADS) {
+    const int c = i / Lo, l = i - c * Lo;
+    out[i] = fmaxf(in[c * L + 2 * l], in[c * L + 2 * l + 1]);
+  }
+  __syncthreads();
+}
+
+// x0: [>=J][Z] input columns; result hm1d[Z] lands in `out` (smem)
+__device__ void c2c_forward(const C2CNet& net, const float* x0, int J, int Z, float* buf, float* out) {
+  float *B0 = buf, *B1 = buf + C2C_BUF, *B2 = buf + 2 * C2C_BUF, *B3 = buf + 3 * C2C_BUF, *B4 = buf + 4 * C2C_BUF,
+        *B5 = buf + 5 * C2C_BUF;
+  const int L = Z, L2 = Z / 2, L4 = Z / 4;
+  c2c_conv(x0, J, L, nullptr, 0, net.l[0], 7, B0, 16, nullptr, 0, true, false);
+  c2c_conv(B0, 16, L, nullptr, 0, net.l[1], 3, B1, 32, nullptr, 0, true, false);
+  c2c_conv(B1, 32, L, B0, 16, net.l[2], 3, B2, 32, nullptr, 0, true, false);
+  c2c_conv(B2, 32, L, nullptr, 0, net.l[3], 3, B0, 32, nullptr, 0, true, false);
+  c2c_conv(B0, 32, L, nullptr, 0, net.l[4], 3, B3, 32, B2, 1, true, false);          // skip1
+  c2c_pool(B2, 32, L, B0);
+  c2c_conv(B0, 32, L2, nullptr, 0, net.l[5], 3, B1, 64, nullptr, 0, true, false);
+  c2c_conv(B1, 64, L2, B0, 32, net.l[6], 3, B4, 64, nullptr, 0, true, false);         // e1
+  c2c_conv(B4, 64, L2, nullptr, 0, net.l[7], 3, B0, 64, nullptr, 0, true, false);
+  c2c_conv(B0, 64, L2, nullptr, 0, net.l[8], 3, B5, 64, B4, 1, true, false);          // skip2
+  c2c_pool(B4, 64, L2, B0);
+  c2c_conv(B0, 64, L4, nullptr, 0, net.l[9], 3, B1, 128, nullptr, 0, true, false);
+  c2c_conv(B1, 128, L4, B0, 64, net.l[10], 3, B2, 128, nullptr, 0, true, false);      // e2
+  c2c_conv(B2, 128, L4, nullptr, 0, net.l[11], 3, B0, 128, nullptr, 0, true, false);
+  c2c_conv(B0, 128, L4, nullptr, 0, net.l[12], 3, B1, 128, B2, 1, true, false);       // m
+  c2c_conv(B1, 128, L4, nullptr, 0, net.l[13], 3, B0, 128, nullptr, 0, true, false);
+  c2c_conv(B0, 128, L4, nullptr, 0, net.l[14], 3, B2, 128, B1, 1, true, false);       // d2
+  c2c_conv(B2, 128, L4, nullptr, 0, net.l[15], 1, B0, 128, B5, 2, true, true);        // u2 = relu(convT)+skip2
+  c2c_conv(B0, 64, L2, nullptr, 0, net.l[16], 3, B1, 64, nullptr, 0, true, false);
+  c2c_conv(B1, 64, L2, nullptr, 0, net.l[17], 3, B2, 64, B0, 1, true, false);         // d1
+  c2c_conv(B2, 64, L2, nullptr, 0, net.l[18], 1, B0, 64, B3, 2, true, true);          // u1 = relu(convT)+skip1
+  c2c_conv(B0, 32, L, nullptr, 0, net.l[19], 1, out, 4, nullptr, 0, false, false);    // head (row 0 of 4)
+}
+
+// ------------------------------------------------------------------------------------------------
+// crop parameters of one proposal (project_individual.py:110-121), exact fp32 op order
+// ------------------------------------------------------------------------------------------------
+__device__ void fvp_make_person(const FvpPropArgs& a, const float* c7, int seq, FvpPerson& pd) {
+  pd.valid = c7[3] >= 0.0f;
+  pd.seq = seq;
+  pd.pad = 0;
+  bool empty = false;
+  for (int d = 0; d < 3; ++d) {
+    const int fine = a.g.fine[d];
+    const int tl = (int)rintf(__fadd_rn(__fmul_rn(c7[d], a.jln_scale[d]), a.jln_bias[d]));
+    float off = __fdiv_rn((float)tl, (float)(fine - 1));
+    off = __fmul_rn(off, a.whole[d]);
+    off = __fsub_rn(off, __fmul_rn(a.whole[d], 0.5f));
+    off = __fadd_rn(off, __fmul_rn(a.ind[d], 0.5f));
+    int m = 0;
+    if (d < 2) {
+      m = (int)__fmul_rn(__fmul_rn(__fsub_rn(1.0f, c7[5 + d]), 0.5f), (float)(a.ind_vox[d] - 1));
+      if (m < 0) m = 0;
+    }
+    const int start = tl + m >= 0 ? tl + m : 0;
+    const int end = tl + a.ind_vox[d] - m <= fine ? tl + a.ind_vox[d] - m : fine;
+    if (start >= end) empty = true;
+    pd.tl[d] = tl;
+    pd.offset[d] = off;
+    pd.lo[d] = start - tl;
+    pd.hi[d] = end - tl;
+  }
+  pd.empty = empty;
+}
+
+// one CTA per proposal slot
+__global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet net) {
+  __shared__ float s_buf[6 * C2C_BUF];
+  __shared__ float s_x0[24 * C2C_MAXZ];          // [JP][Z] input columns
+  __shared__ float s_out[4 * C2C_MAXZ];
+  __shared__ FvpSeq s_seq;
+  const FvpGeom& g = a.g;
+  const int slot = blockIdx.x, b = slot / g.P;
+  const int tid = threadIdx.x;
+  const int J = g.J, Z = g.Z, JP = g.proj.JP;
+  int flat = 0;
+
+  if (a.mode == 0) {
+    // ---- K2: sample the z column of the selected (x,y) cell straight from the heat maps ----------
+    flat = a.flat[slot];
+    const int seq = a.frame_seq[b];
+    {
+      const int* src = (const int*)(g.seqs + seq);
+      int* dst = (int*)&s_seq;
+      for (int i = tid; i < (int)(sizeof(FvpSeq) / 4); i += C2C_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int cx = flat / g.Y, cy = flat - cx * g.Y;       // true layout of the flattened (X,Y) map
+    const float wx = g.coarse_axes[cx], wy = g.coarse_axes[g.X + cy];
+    const int V = g.V;
+    const float fV = (float)V, rV = 1.0f / fV;
+    const int row4 = g.proj.WP * g.JG, px4 = g.JG;
+    for (int i = tid; i < Z * g.JG; i += C2C_THREADS) {
+      const int z = i / g.JG, s = i - z * g.JG;
+      const float wz = g.coarse_axes[g.X + g.Y + z];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* hm_b = (const float4*)a.hm_cl + (size_t)b * V * g.view_stride4 + s;
+      for (int v = 0; v < V; ++v) {
+        float ix, iy;
+        fvp_project(s_seq.cam[v], s_seq.A, g.proj, wx, wy, wz, ix, iy);
+        const FvpTaps t = fvp_taps(g.proj, ix, iy);
+        fvp_tap_accumulate(acc, hm_b + (size_t)v * g.view_stride4, t.off, row4, px4, t.w00, t.w01, t.w10, t.w11);
+      }
+      const float4 val = fvp_mean_clamp4(acc, fV, rV);
+      s_x0[(4 * s + 0) * Z + z] = val.x;
+      s_x0[(4 * s + 1) * Z + z] = val.y;
+      s_x0[(4 * s + 2) * Z + z] = val.z;
+      s_x0[(4 * s + 3) * Z + z] = val.w;
+    }
+  } else {
+    for (int i = tid; i < J * Z; i += C2C_THREADS) s_x0[i] = a.cols_in[(size_t)slot * J * Z + i];
+  }
+  __syncthreads();
+  if (a.cols_out)
+    for (int i = tid; i < J * Z; i += C2C_THREADS) a.cols_out[(size_t)slot * J * Z + i] = s_x0[i];
+  (void)JP;
+
+  c2c_forward(net, s_x0, J, Z, s_buf, s_out);    // s_out[0..Z) = 1-D heat map
+
+  if (a.hm1d_out)
+    for (int i = tid; i < Z; i += C2C_THREADS) a.hm1d_out[(size_t)slot * Z + i] = s_out[i];
+  if (a.mode != 0 || tid != 0) return;
+
+  // ---- topk(1) over z, ProposalLayer (human_detection_net.py:44-65,95-102) -----------------------
+  int iz = 0;
+  float c1 = s_out[0];
+  for (int z = 1; z < Z; ++z)
+    if (s_out[z] > c1) { c1 = s_out[z]; iz = z; }
+  const float c2 = a.conf2d[slot];
+  const float conf = __fmul_rn(c2, c1);
+  // get_index2D divides by shape[1] of the [1,X,Y] map, i.e. X (core/proposal.py:16-17,32)
+  const int ixq = flat / g.X, iyq = flat - ixq * g.X;
+  float c7[7];
+  c7[0] = __fadd_rn(__fmul_rn((float)ixq, a.hdn_scale[0]), a.hdn_bias[0]);
+  c7[1] = __fadd_rn(__fmul_rn((float)iyq, a.hdn_scale[1]), a.hdn_bias[1]);
+  c7[2] = __fadd_rn(__fmul_rn((float)iz, a.hdn_scale[2]), a.hdn_bias[2]);
+  c7[3] = (conf > a.min_score) ? 0.0f : -1.0f;
+  c7[4] = conf;
+  const float* sz = a.size + (size_t)b * a.size_img_stride + flat;
+  c7[5] = sz[0];
+  c7[6] = sz[(size_t)g.X * g.Y];
+  if (a.centers)
+    for (int i = 0; i < 7; ++i) a.centers[(size_t)slot * 7 + i] = c7[i];
+  if (a.people) {
+    FvpPerson pd;
+    fvp_make_person(a, c7, a.frame_seq[b], pd);
+    a.people[slot] = pd;
+  }
+  if (a.img_valid)
+    for (int q = 0; q < 3; ++q) a.img_valid[q * a.n_slots + slot] = c7[3] >= 0.0f;
+}
+
+__global__ void k_people_from_centers(FvpPropArgs a, const float* __restrict__ centers, int n) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n) return;
+  float c7[7];
+  for (int i = 0; i < 7; ++i) c7[i] = centers[(size_t)slot * 7 + i];
+  FvpPerson pd;
+  fvp_make_person(a, c7, a.frame_seq[slot / a.g.P], pd);
+  a.people[slot] = pd;
+  if (a.img_valid)
+    for (int q = 0; q < 3; ++q) a.img_valid[q * a.n_slots + slot] = pd.valid;
+}
+
+void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, cudaStream_t st) {
+  C2CNet net;
+  for (int i = 0; i < 20; ++i) {
+    net.l[i].w = w.w[i];
+    net.l[i].b = w.b[i];
+  }
+  k_proposals<<<n, C2C_THREADS, 0, st>>>(a, net);
+}
+
+void fvp_launch_people_from_centers(const FvpPropArgs& a, const float* d_centers, int n, cudaStream_t st) {
+  k_people_from_centers<<<fvp_cdiv(n, 64), 64, 0, st>>>(a, d_centers, n);
+}

@@ -1,0 +1,295 @@
+"""Host-side engine over the C ABI: owns one ``fvp_ctx`` on one GPU.
+
+PyTorch is used for what the task allows it for - device memory, streams, ``torch.distributed`` -
+never for arithmetic on the hot path.  Every compute call goes through ``libfvp_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+from typing import Dict, List, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import capi
+
+
+def _f32_ptr(a: np.ndarray) -> int:
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def camera_rows(cams: Sequence[Mapping]) -> np.ndarray:
+    """[V,21] fp32 = R(9) T(3) fx fy cx cy k(3) p(2): float64 calibration rounded to fp32 exactly as
+    ``unfold_camera_param`` does (lib/utils/cameras.py:11-18)."""
+    out = np.zeros((len(cams), 21), np.float32)
+    for i, c in enumerate(cams):
+        out[i, 0:9] = np.asarray(c["R"], np.float64).reshape(9).astype(np.float32)
+        out[i, 9:12] = np.asarray(c["T"], np.float64).reshape(3).astype(np.float32)
+        out[i, 12:16] = np.array([c["fx"], c["fy"], c["cx"], c["cy"]], np.float64).astype(np.float32)
+        out[i, 16:19] = np.asarray(c["k"], np.float64).reshape(3).astype(np.float32)
+        out[i, 19:21] = np.asarray(c["p"], np.float64).reshape(2).astype(np.float32)
+    return out
+
+
+def reference_axes(cfg) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Voxel-centre tables with the reference's own expression ``torch.linspace(-S/2, S/2, N) + centre``
+    (project_whole.py:34-40, project_individual.py:25,37-41), evaluated by this host's PyTorch.  Passing
+    them to the library makes the in-kernel projection bit-identical to a CPU run of the reference on
+    the same host (torch's vectorised CPU linspace is not the scalar start+i*step formula)."""
+    whole = [float(v) for v in cfg.CAPTURE_SPEC.SPACE_SIZE]
+    ctr = [float(v) for v in cfg.CAPTURE_SPEC.SPACE_CENTER]
+    ind = [float(v) for v in cfg.INDIVIDUAL_SPEC.SPACE_SIZE]
+    nb = [int(v) for v in cfg.CAPTURE_SPEC.VOXELS_PER_AXIS]
+    iv = [int(v) for v in cfg.INDIVIDUAL_SPEC.VOXELS_PER_AXIS]
+    whole_t, ind_t = torch.tensor(whole), torch.tensor(ind)
+    fine = ((whole_t / ind_t * (torch.tensor(iv, dtype=torch.int32) - 1)).int() + 1).tolist()
+
+    def ax(size, c, n):
+        return (torch.linspace(-size / 2, size / 2, int(n)) + c).numpy().astype(np.float32)
+
+    coarse = np.concatenate([ax(whole[d], ctr[d], nb[d]) for d in range(3)])
+    fine_a = np.concatenate([ax(whole[d], ctr[d], fine[d]) for d in range(3)])
+    indiv = np.concatenate([ax(ind[d], ctr[d], iv[d]) for d in range(3)])
+    return coarse, fine_a, indiv
+
+
+class Engine:
+    def __init__(self, cfg, device: Optional[torch.device] = None, max_batch: int = 8, max_sequences: int = 8,
+                 axes: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None):
+        self.lib = capi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("faster-voxelpose_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+        self.device = torch.device(device if device is not None else getattr(cfg, "DEVICE", "cuda:0"))
+        if self.device.type != "cuda":
+            raise RuntimeError("DEVICE must be a cuda device, got %s" % self.device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        self.cfg = cfg
+        c = capi.FvpConfig()
+        ds, cs, isp = cfg.DATASET, cfg.CAPTURE_SPEC, cfg.INDIVIDUAL_SPEC
+        c.num_views, c.num_joints = int(ds.CAMERA_NUM), int(ds.NUM_JOINTS)
+        c.hm_w, c.hm_h = int(ds.HEATMAP_SIZE[0]), int(ds.HEATMAP_SIZE[1])
+        c.image_w, c.image_h = float(ds.IMAGE_SIZE[0]), float(ds.IMAGE_SIZE[1])
+        c.ori_w, c.ori_h = float(ds.ORI_IMAGE_SIZE[0]), float(ds.ORI_IMAGE_SIZE[1])
+        for d in range(3):
+            c.space_size[d] = float(cs.SPACE_SIZE[d])
+            c.space_center[d] = float(cs.SPACE_CENTER[d])
+            c.voxels[d] = int(cs.VOXELS_PER_AXIS[d])
+            c.ind_space_size[d] = float(isp.SPACE_SIZE[d])
+            c.ind_voxels[d] = int(isp.VOXELS_PER_AXIS[d])
+        c.max_people, c.min_score = int(cs.MAX_PEOPLE), float(cs.MIN_SCORE)
+        c.beta = float(cfg.NETWORK.BETA)
+        c.feat_channels = int(cfg.NETWORK.NUM_CHANNEL_JOINT_FEAT)
+        c.hidden_channels = int(cfg.NETWORK.NUM_CHANNEL_JOINT_HIDDEN)
+        c.max_batch, c.max_sequences = int(max_batch), int(max_sequences)
+        self.c = c
+        self.V, self.J, self.P = c.num_views, c.num_joints, c.max_people
+        self.H, self.W = c.hm_h, c.hm_w
+        self.X, self.Y, self.Z = c.voxels[0], c.voxels[1], c.voxels[2]
+        self.max_batch, self.max_sequences = int(max_batch), int(max_sequences)
+        ctx = C.c_void_p()
+        rc = self.lib.fvp_create(C.byref(c), idx, C.byref(ctx))
+        if rc != capi.FVP_OK:
+            raise capi.FvpError(rc, (self.lib.fvp_last_error(None) or b"?").decode())
+        self.ctx = ctx
+        coarse, fine, indiv = axes if axes is not None else reference_axes(cfg)
+        fv = (C.c_int32 * 3)()
+        self._ck(self.lib.fvp_fine_voxels(self.ctx, C.byref(fv)))
+        self.fine = [int(v) for v in fv]
+        assert coarse.size == self.X + self.Y + self.Z and fine.size == sum(self.fine) and indiv.size == 192
+        self._ck(self.lib.fvp_set_axes(self.ctx, _f32_ptr(np.ascontiguousarray(coarse, np.float32)),
+                                       _f32_ptr(np.ascontiguousarray(fine, np.float32)),
+                                       _f32_ptr(np.ascontiguousarray(indiv, np.float32))))
+        self._seq_slots: Dict[str, int] = {}     # calibration fingerprint -> slot
+        self._seq_lru: List[str] = []
+        self._params_loaded = False
+
+    # ------------------------------------------------------------------------------------------
+    def _ck(self, rc: int) -> None:
+        capi.check(self.lib, self.ctx, rc)
+
+    def close(self) -> None:
+        if getattr(self, "ctx", None):
+            self.lib.fvp_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return int(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- parameters --------------------------------------------------------------------------
+    def param_names(self) -> List[str]:
+        n = self.lib.fvp_param_count(self.ctx)
+        return [self.lib.fvp_param_name(self.ctx, i).decode() for i in range(n)]
+
+    def load_state_dict(self, sd: Mapping[str, object]) -> None:
+        """Reference ``state_dict`` (torch tensors or numpy arrays, any device) -> folded, packed, uploaded."""
+        names = self.param_names()
+        missing = [k for k in names if k not in sd]
+        unexpected = [k for k in sd if k not in set(names)]
+        if missing or unexpected:
+            raise RuntimeError("Error(s) in loading state_dict: missing %s unexpected %s" % (missing[:5], unexpected[:5]))
+        for k in names:
+            v = sd[k]
+            if isinstance(v, torch.Tensor):
+                v = v.detach().cpu().numpy()
+            v = np.asarray(v)
+            if k.endswith("num_batches_tracked"):
+                continue
+            a = np.ascontiguousarray(v, np.float32)
+            self._ck(self.lib.fvp_set_param(self.ctx, k.encode(), _f32_ptr(a), a.size))
+        self._ck(self.lib.fvp_finalize_params(self.ctx))
+        self._params_loaded = True
+
+    # ---- calibration -------------------------------------------------------------------------
+    def sequence_slot(self, cams: Sequence[Mapping], resize) -> int:
+        """Slot of a calibration; uploads it on first use.  Keyed on the calibration *values* (the
+        reference keys its grid cache on the sequence name only, SURVEY.md 3.3 - a stale-cache hazard)."""
+        rows = camera_rows(cams)
+        rz = np.ascontiguousarray(np.asarray(resize.detach().cpu() if isinstance(resize, torch.Tensor) else resize,
+                                             np.float64).astype(np.float32).reshape(6))
+        key = hashlib.sha1(rows.tobytes() + rz.tobytes()).hexdigest()
+        if key in self._seq_slots:
+            self._seq_lru.remove(key)
+            self._seq_lru.append(key)
+            return self._seq_slots[key]
+        if len(self._seq_slots) < self.max_sequences:
+            slot = len(self._seq_slots)
+        else:
+            old = self._seq_lru.pop(0)
+            slot = self._seq_slots.pop(old)
+        self._ck(self.lib.fvp_set_sequence(self.ctx, slot, _f32_ptr(rows), rows.shape[0], _f32_ptr(rz)))
+        self._seq_slots[key] = slot
+        self._seq_lru.append(key)
+        return slot
+
+    # ---- forward -----------------------------------------------------------------------------
+    def _slots_arr(self, slots: Sequence[int]):
+        return (C.c_int32 * len(slots))(*[int(s) for s in slots])
+
+    def _check_hm(self, hm: torch.Tensor) -> int:
+        if hm.dim() != 5 or tuple(hm.shape[1:]) != (self.V, self.J, self.H, self.W):
+            raise ValueError("input_heatmaps must be [B,%d,%d,%d,%d], got %s" % (self.V, self.J, self.H, self.W, tuple(hm.shape)))
+        if hm.shape[0] > self.max_batch:
+            raise ValueError("batch %d exceeds max_batch %d" % (hm.shape[0], self.max_batch))
+        return int(hm.shape[0])
+
+    def forward(self, heatmaps: torch.Tensor, slots: Sequence[int]):
+        """[B,V,J,H,W] fp32 on this device -> (fused_poses [B,P,J,5], plane_poses [3,B,P,J,2], proposal_centers [B,P,7])."""
+        B = self._check_hm(heatmaps)
+        hm = heatmaps.to(device=self.device, dtype=torch.float32).contiguous()
+        fused = torch.empty((B, self.P, self.J, 5), device=self.device, dtype=torch.float32)
+        plane = torch.empty((3, B, self.P, self.J, 2), device=self.device, dtype=torch.float32)
+        centers = torch.empty((B, self.P, 7), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.fvp_forward(self.ctx, hm.data_ptr(), B, self._slots_arr(slots), fused.data_ptr(),
+                                          plane.data_ptr(), centers.data_ptr(), self._stream()))
+        return fused, plane, centers
+
+    def forward_host(self, heatmaps: torch.Tensor, slots: Sequence[int], out: Optional[Tuple[torch.Tensor, ...]] = None):
+        """Same through host buffers (H2D + forward + D2H inside the call, synchronous)."""
+        B = self._check_hm(heatmaps)
+        assert heatmaps.device.type == "cpu" and heatmaps.dtype == torch.float32 and heatmaps.is_contiguous()
+        if out is None:
+            out = (torch.empty((B, self.P, self.J, 5)).pin_memory(), torch.empty((3, B, self.P, self.J, 2)).pin_memory(),
+                   torch.empty((B, self.P, 7)).pin_memory())
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.fvp_forward_host(self.ctx, heatmaps.data_ptr(), B, self._slots_arr(slots),
+                                               out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), self._stream()))
+        return out
+
+    def use_cuda_graph(self, on: bool = True) -> None:
+        self._ck(self.lib.fvp_use_cuda_graph(self.ctx, 1 if on else 0))
+
+    def set_profiling(self, on: bool) -> None:
+        self._ck(self.lib.fvp_set_profiling(self.ctx, 1 if on else 0))
+
+    def stage_times_ms(self) -> List[float]:
+        t = (C.c_float * 9)()
+        self._ck(self.lib.fvp_stage_times_ms(self.ctx, C.byref(t)))
+        return [float(v) for v in t]
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.fvp_last_launch_count(self.ctx))
+
+    def algorithmic_bytes(self, num_valid: int) -> Tuple[float, float]:
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.fvp_algorithmic_bytes(self.ctx, int(num_valid), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ---- stage entry points (tests / profiling) -------------------------------------------------
+    def _new(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, device=self.device, dtype=dtype)
+
+    def stage_heatmaps(self, hm: torch.Tensor) -> None:
+        B = self._check_hm(hm)
+        self._keep = hm.to(self.device, torch.float32).contiguous()
+        self._ck(self.lib.fvp_stage_heatmaps(self.ctx, self._keep.data_ptr(), B, self._stream()))
+
+    def hdn_project(self, B: int, slots) -> torch.Tensor:
+        out = self._new(B, self.J, self.X, self.Y)
+        self._ck(self.lib.fvp_hdn_project(self.ctx, B, self._slots_arr(slots), out.data_ptr(), self._stream()))
+        return out
+
+    def center_net(self, plane: Optional[torch.Tensor], B: int):
+        hm, size = self._new(B, self.X, self.Y), self._new(B, 2, self.X, self.Y)
+        p = plane.to(self.device, torch.float32).contiguous() if plane is not None else None
+        self._ck(self.lib.fvp_center_net(self.ctx, p.data_ptr() if p is not None else None, B, hm.data_ptr(),
+                                         size.data_ptr(), self._stream()))
+        return hm, size
+
+    def nms_topk(self, hm: torch.Tensor):
+        B = hm.shape[0]
+        h = hm.to(self.device, torch.float32).contiguous()
+        conf, flat = self._new(B, self.P), self._new(B, self.P, dtype=torch.int32)
+        self._ck(self.lib.fvp_nms_topk(self.ctx, h.data_ptr(), B, conf.data_ptr(), flat.data_ptr(), self._stream()))
+        return conf, flat
+
+    def proposals(self, B: int, slots, conf2d: torch.Tensor, flat: torch.Tensor, size: torch.Tensor):
+        c = conf2d.to(self.device, torch.float32).contiguous()
+        f = flat.to(self.device, torch.int32).contiguous()
+        s = size.to(self.device, torch.float32).contiguous()
+        cols, hm1d = self._new(B * self.P, self.J, self.Z), self._new(B * self.P, self.Z)
+        centers = self._new(B, self.P, 7)
+        self._ck(self.lib.fvp_proposals(self.ctx, B, self._slots_arr(slots), c.data_ptr(), f.data_ptr(), s.data_ptr(),
+                                        cols.data_ptr(), hm1d.data_ptr(), centers.data_ptr(), self._stream()))
+        return cols, hm1d, centers
+
+    def c2c_net(self, cols: torch.Tensor) -> torch.Tensor:
+        x = cols.to(self.device, torch.float32).contiguous()
+        out = self._new(x.shape[0], self.Z)
+        self._ck(self.lib.fvp_c2c_net(self.ctx, x.data_ptr(), x.shape[0], out.data_ptr(), self._stream()))
+        return out
+
+    def jln_project(self, B: int, slots, centers: torch.Tensor):
+        c = centers.to(self.device, torch.float32).contiguous()
+        n = B * self.P
+        planes, off = self._new(3, n, self.J, 64, 64), self._new(n, 3)
+        self._ck(self.lib.fvp_jln_project(self.ctx, B, self._slots_arr(slots), c.data_ptr(), planes.data_ptr(),
+                                          off.data_ptr(), self._stream()))
+        return planes, off
+
+    def p2p_net(self, planes: torch.Tensor, valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = planes.to(self.device, torch.float32).contiguous().view(-1, self.J, 64, 64)
+        v = valid.to(self.device, torch.int32).contiguous() if valid is not None else None
+        out = torch.zeros_like(x)
+        self._ck(self.lib.fvp_p2p_net(self.ctx, x.data_ptr(), x.shape[0], v.data_ptr() if v is not None else None,
+                                      out.data_ptr(), self._stream()))
+        return out
+
+    def pose_head(self, feat: torch.Tensor, offset: torch.Tensor):
+        f = feat.to(self.device, torch.float32).contiguous()          # [3,n,J,64,64]
+        n = f.shape[1]
+        o = offset.to(self.device, torch.float32).contiguous()
+        pose, conf = self._new(3, n, self.J, 2), self._new(n)
+        w, fused = self._new(3, n, self.J), self._new(n, self.J, 3)
+        self._ck(self.lib.fvp_pose_head(self.ctx, f.data_ptr(), o.data_ptr(), n, pose.data_ptr(), conf.data_ptr(),
+                                        w.data_ptr(), fused.data_ptr(), self._stream()))
+        return pose, conf, w, fused

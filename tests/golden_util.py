@@ -1,0 +1,54 @@
+"""Load tests/golden/*.npz (written by oracle/gen_golden.py from the unmodified reference)."""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "faster-voxelpose_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from fvp import config as fcfg, synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+CASES = ["panoptic_b2", "panoptic_mixed", "panoptic_none_valid", "panoptic_256x192", "campus_b1", "shelf_crowd"]
+
+
+def weights_sha(sd) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k]).tobytes())
+    return h.hexdigest()
+
+
+class Golden:
+    def __init__(self, name: str):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        z = self.z
+        self.cfg = fcfg.preset(str(z["preset"]))
+        self.cfg.CAPTURE_SPEC.MIN_SCORE = float(z["min_score"])
+        self.J = int(self.cfg.DATASET.NUM_JOINTS)
+        self.P = int(self.cfg.CAPTURE_SPEC.MAX_PEOPLE)
+        self.heatmaps = synth.dequantise_u16(z["heatmaps_u16"])          # [B,V,J,H,W]
+        self.B = self.heatmaps.shape[0]
+        self.cams = synth.cameras_from_array(z["cameras"])
+        self.resize = z["resize"]
+        self.weights = synth.make_weights(self.J, seed=int(z["weight_seed"]))
+        assert weights_sha(self.weights) == str(z["weights_sha256"]), "weight generator drifted from the golden"
+        X, Y, Zc = [int(v) for v in self.cfg.CAPTURE_SPEC.VOXELS_PER_AXIS]
+        self.axes = (z["axes_coarse"], z["axes_fine"], z["axes_ind"])
+        self.seq = "seq0"
+        self.cameras = {self.seq: self.cams}
+
+    def __getitem__(self, k):
+        return self.z[k]
+
+    def has(self, k):
+        return k in self.z.files
