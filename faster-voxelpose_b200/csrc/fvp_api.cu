@@ -47,12 +47,19 @@ int check_stage_ready(fvp_ctx* ctx, int batch) {
 }
 
 int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaStream_t st) {
+  bool same = true;
+  std::vector<int> want(batch);
   for (int b = 0; b < batch; ++b) {
     const int s = h_seq_slots ? h_seq_slots[b] : 0;
     if (s < 0 || s >= ctx->cfg.max_sequences || !ctx->seq_set[s])
       return fvp_fail(ctx, FVP_E_CALIB, "missing camera parameters for the current sequence (slot %d of frame %d)", s, b);
-    ctx->h_frame_seq[b] = s;
+    if (ctx->h_frame_seq[b] != s || b >= ctx->frame_seq_uploaded) same = false;
+    want[b] = s;
   }
+  if (same) return FVP_OK;                       // device copy already holds these slots
+  FVP_CUDA_OK(cudaStreamSynchronize(st));        // the pinned staging buffer may still be in flight
+  for (int b = 0; b < batch; ++b) ctx->h_frame_seq[b] = want[b];
+  ctx->frame_seq_uploaded = batch;
   FVP_CUDA_OK(cudaMemcpyAsync(ctx->d_frame_seq, ctx->h_frame_seq, batch * sizeof(int), cudaMemcpyHostToDevice, st));
   return FVP_OK;
 }
@@ -236,6 +243,7 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   A(dalloc(&ctx->d_frame_seq, (size_t)MB));
   A(cudaMallocHost((void**)&ctx->h_frame_seq, MB * sizeof(int)));
   for (int i = 0; i < 10; ++i) A(cudaEventCreate(&ctx->ev[i]));
+  A(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   if (ok) {
     A(cudaMemset(ctx->d_hm_cl, 0, (size_t)MB * g.V * g.view_stride4 * 16));   // zero borders (never written again)
     A(cudaMemset(ctx->d_seqs, 0, (size_t)c.max_sequences * sizeof(FvpSeq)));
@@ -280,6 +288,7 @@ void fvp_destroy(fvp_ctx* ctx) {
     if (ctx->p2p_buf[i]) cudaFree(ctx->p2p_buf[i]);
   }
   if (ctx->h_frame_seq) cudaFreeHost(ctx->h_frame_seq);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   for (int i = 0; i < 10; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   delete ctx;
@@ -425,6 +434,15 @@ static int forward_device(fvp_ctx* ctx, const float* d_heatmaps, int batch, cons
   T.mark(0);
   fvp_launch_stage_heatmaps(g, d_heatmaps, ctx->d_hm_cl, batch, st); ++launches;
 
+  // Stream capture is illegal on the legacy default stream: in graph mode run on the context's own
+  // stream, ordered after / before the caller's stream with events.
+  cudaStream_t caller = st;
+  const bool reroute = ctx->use_graph && !ctx->profiling && (st == nullptr || st == cudaStreamLegacy);
+  if (reroute) {
+    FVP_CUDA_OK(cudaEventRecord(ctx->ev[9], caller));
+    st = ctx->own_stream;
+    FVP_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev[9], 0));
+  }
   bool sig_same = ctx->graph_exec && ctx->graph_batch == batch && (int)ctx->graph_seqs.size() == batch;
   if (sig_same)
     for (int b = 0; b < batch; ++b) sig_same = sig_same && ctx->graph_seqs[b] == ctx->h_frame_seq[b];
@@ -455,6 +473,10 @@ static int forward_device(fvp_ctx* ctx, const float* d_heatmaps, int batch, cons
   } else {
     rc = run_pipeline(ctx, batch, d_fused, d_plane, d_centers, st, &launches);
     if (rc != FVP_OK) return rc;
+  }
+  if (reroute) {
+    FVP_CUDA_OK(cudaEventRecord(ctx->ev[9], st));
+    FVP_CUDA_OK(cudaStreamWaitEvent(caller, ctx->ev[9], 0));
   }
   ctx->last_launches = launches;
   FVP_CUDA_OK(cudaGetLastError());

@@ -68,10 +68,12 @@ struct fvp_ctx {
   float* p2p_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int* d_frame_seq = nullptr;         // [MB]
   int* h_frame_seq = nullptr;         // pinned
+  int frame_seq_uploaded = 0;         // how many leading entries of d_frame_seq mirror h_frame_seq
   int k3_slab = 8;
 
   // cuda graph
   bool use_graph = false;
+  cudaStream_t own_stream = nullptr;  // used for graph capture/replay when the caller passes the legacy stream
   cudaGraphExec_t graph_exec = nullptr;
   int graph_batch = 0;
   std::vector<int> graph_seqs;

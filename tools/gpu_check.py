@@ -57,6 +57,7 @@ def run_case(name):
     rep["e2e plane_poses"] = err(plane_poses.cpu(), g["plane_poses"])
     rep["e2e flag equal"] = bool(np.array_equal(fused.cpu().numpy()[..., 3], g["fused_poses"][..., 3]))
     rep["launches"] = eng.last_launch_count()
+    print(name, "PARTIAL", json.dumps(rep)); sys.stdout.flush()
     # graph replay equals eager
     eng.use_cuda_graph(True)
     for _ in range(3):
