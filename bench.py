@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the Faster-VoxelPose hot path on B200 (contract: see the task brief / DESIGN.md "measurement").
+
+    python bench.py --gpus N --steps K --warmup W          # ours, one rank per GPU (torchrun for N>1)
+    python bench.py --impl reference ...                   # the reference's CPU path (oracle port) on host cores
+
+One *step* = one forward of the whole hot path (K0..finalize) over one batch of synthetic frames per rank
+(default batch 1 = BASELINE.json configs[1]: Panoptic 5-view jln64, 80x80x20 voxel, batch=1), followed for N>1 by
+the single all_gather of the final pose tensor.  `value` = frames/s of the whole job with the inputs already in HBM;
+`e2e` = the same through the host-buffer C-ABI entry (fvp_forward_host: H2D of the step's heat maps from pinned
+memory + forward + D2H of the three result tensors inside the timed region).
+Prints exactly ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "faster-voxelpose_b200")
+for p in (PKG, os.path.join(PKG, "lib"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "3D-pose FPS (5-view->80x80x20 voxel)"
+UNIT = "frames/s"
+POOL = 12                # distinct input frames rotated through: 12 x 14.7 MB = 177 MB > 126 MB L2
+
+
+def workload(preset: str):
+    from fvp import config as fcfg, synth
+    cfg = fcfg.preset(preset)
+    cfg.CAPTURE_SPEC.MIN_SCORE = -1.0e30          # every proposal slot valid: worst case N = P persons
+    if preset.startswith("ring8"):
+        cams = synth.ring_cameras(8, cfg.CAPTURE_SPEC.SPACE_CENTER)
+    else:
+        cal = os.path.join(ROOT, "tests", "golden", "panoptic_256x192.npz")
+        cams = synth.cameras_from_array(np.load(cal)["cameras"])       # Panoptic HD cameras (demo/calibration.json)
+    resize = synth.resize_transform(cfg.DATASET.ORI_IMAGE_SIZE, cfg.DATASET.IMAGE_SIZE)
+    return cfg, cams, resize
+
+
+def make_frames(cfg, cams, count: int, seed0: int) -> np.ndarray:
+    """[count,V,J,H,W] Gaussian-blob heat maps of P synthetic people per frame (seed = seed0 + frame)."""
+    from fvp import synth
+    P = int(cfg.CAPTURE_SPEC.MAX_PEOPLE)
+    out = []
+    for i in range(count):
+        sk = synth.make_skeletons(cfg, P, seed=seed0 + i)
+        out.append(synth.render_heatmaps(cfg, cams, sk, sigma=float(cfg.NETWORK.SIGMA)))
+    return np.stack(out)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_fps(cfg, cams, resize, frames: np.ndarray, sd_np, warm: int, steps: int):
+    """The reference's CPU path (oracle port: the same PyTorch-CPU ops in the same order as the reference,
+    pinned bit-exact to it by oracle/gen_golden.py) on this host's cores, one frame per step."""
+    from oracle import fvp_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}
+    rz = torch.as_tensor(resize, dtype=torch.float)
+    cameras = {"s": cams}
+    ts = []
+    with torch.no_grad():
+        for i in range(warm + steps):
+            hm = torch.from_numpy(frames[i % frames.shape[0]][None])
+            t0 = time.perf_counter()
+            O.forward(cfg, sd, hm, ["s"], cameras, rz, taps=False)
+            ts.append(time.perf_counter() - t0)
+    ts = ts[warm:]
+    return len(ts) / sum(ts), torch.get_num_threads(), float(np.median(ts)) * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--batch", type=int, default=1, help="frames per rank per step (1 = BASELINE configs[1])")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preset", default="panoptic_256x192")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg, cams, resize = workload(args.preset)
+    from fvp import synth
+    J, P, V = int(cfg.DATASET.NUM_JOINTS), int(cfg.CAPTURE_SPEC.MAX_PEOPLE), int(cfg.DATASET.CAMERA_NUM)
+    W, H = [int(v) for v in cfg.DATASET.HEATMAP_SIZE]
+    sd_np = synth.make_weights(J, seed=2024)
+    conf = {"workload": "Panoptic 5-view jln64 geometry, %dx%d synthetic heat maps, 80x80x20 coarse grid, batch=%d per GPU, "
+                        "P=%d people all valid (worst case), random-conditioned weights" % (W, H, args.batch, P),
+            "preset": args.preset, "batch_per_gpu": args.batch, "people": P, "views": V,
+            "l2": "inputs rotate through %d distinct frames (%.0f MB) > 126 MB L2" % (POOL, POOL * 4.0 * V * J * H * W / 1e6),
+            "parallelism": "frame-sharded x%d" % world}
+
+    # ------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = min(args.steps, 20)
+        warm = min(args.warmup, 3)
+        frames = make_frames(cfg, cams, 4, seed0=5000)
+        fps, cores, med_ms = cpu_reference_fps(cfg, cams, resize, frames, sd_np, warm, steps)
+        sample = "%d forwards of one frame each (after %d warm-up), all %d host threads" % (steps, warm, cores)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": conf,
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is pure Python and cannot travel to the GPU box: timed is the oracle port (oracle/fvp_oracle.py)"}))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    import torch.distributed as dist
+    from fvp import dist as fdist
+    from fvp.engine import Engine
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        fdist.init_from_env("nccl")
+    B = args.batch
+    eng = Engine(cfg, dev, max_batch=B, max_sequences=1)
+    eng.load_state_dict(sd_np)
+    slot = eng.sequence_slot(cams, resize)
+    slots = [slot] * B
+    frames = make_frames(cfg, cams, POOL, seed0=1000 + 100 * rank)           # distinct frames per rank
+    pool_dev = [torch.from_numpy(np.stack([frames[(i + b) % POOL] for b in range(B)])).to(dev) for i in range(POOL)]
+    pool_host = [torch.from_numpy(np.stack([frames[(i + b) % POOL] for b in range(B)])).pin_memory() for i in range(POOL)]
+    if not args.no_graph:
+        eng.use_cuda_graph(True)
+    gather_buf = [torch.empty((B, P, J, 5), device=dev) for _ in range(world)] if world > 1 else None
+
+    def step(i):
+        fused, plane, centers = eng.forward(pool_dev[i % POOL], slots)
+        if world > 1:
+            dist.all_gather(gather_buf, fused)       # the single collective of the path (run/validate.py:114)
+        return fused
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    launches_per_step = eng.last_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for i in range(args.steps):
+        out = step(i)
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    n_valid = int((out[..., 0, 3] >= 0).sum().item())
+
+    # ---- e2e through the host-buffer entry point -----------------------------------------------------
+    host_out = (torch.empty((B, P, J, 5)).pin_memory(), torch.empty((3, B, P, J, 2)).pin_memory(), torch.empty((B, P, 7)).pin_memory())
+    for i in range(3):
+        eng.forward_host(pool_host[i % POOL], slots, host_out)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(10, args.steps // 2)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(e2e_steps):
+        eng.forward_host(pool_host[i % POOL], slots, host_out)
+        if world > 1:
+            dist.all_gather(gather_buf, host_out[0].to(dev, non_blocking=True))
+    e1.record()
+    sync_all()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = int(B * V * J * H * W * 4)
+    d2h = int(sum(t.numel() for t in host_out) * 4)
+
+    # ---- per-stage CUDA-event times (same stream, graph off) -> roofline of the back-projection ----
+    eng.use_cuda_graph(False)
+    eng.set_profiling(True)
+    acc = np.zeros(9)
+    prof_steps = min(args.steps, 50)
+    for i in range(3 + prof_steps):
+        eng.forward(pool_dev[i % POOL], slots)
+        if i >= 3:
+            acc += np.array(eng.stage_times_ms())
+    eng.set_profiling(False)
+    stage = acc / prof_steps
+    k1_bytes, k3_bytes = eng.algorithmic_bytes(max(1, n_valid // B))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    k3_ms = stage[5] / 1.0
+    k3_gbs = B * k3_bytes / (k3_ms * 1e-3) / 1e9
+    k1_ms = stage[0] + stage[1]
+    k1_gbs = B * k1_bytes / (k1_ms * 1e-3) / 1e9
+    samples = B * max(1, n_valid // B) * V * J * 64 ** 3
+    roofline = {"kernel": "k3_jln_project (+k3b): fused per-person back-projection + 3-plane max", "bound": "hbm",
+                "achieved": k3_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k3_gbs / hbm_peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": B * k3_bytes, "ms_per_launch": k3_ms,
+                "traffic": (traffic or {}).get("k3_dram_bytes_per_launch"),
+                "bilinear_samples_per_s": samples / (k3_ms * 1e-3),
+                "note": "K3 is on-chip-gather/ALU bound on its compulsory bytes (SURVEY.md H2); see also k1 below"}
+    extra_kernels = {
+        "k0+k1_hdn_project": {"ms": k1_ms, "algorithmic_bytes": B * k1_bytes, "achieved_gbs": k1_gbs, "frac_hbm": k1_gbs / hbm_peak},
+        "stage_ms": {n: float(v) for n, v in zip(["k0_stage", "k1_hdn_project", "center_net", "nms_topk", "proposals_c2c",
+                                                  "k3_jln_project", "p2p_net", "pose_head", "total"], stage)},
+    }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        fps_c, cores, med = cpu_reference_fps(cfg, cams, resize, frames[:4], sd_np, 2, 12)
+        cpu_base = {"value": fps_c, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "12 single-frame forwards of the oracle port after 2 warm-ups (median %.0f ms)" % med}
+    fps = world * B * args.steps / (ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": conf, "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": launches_per_step,
+        "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+        "roofline": roofline, "cpu_baseline": cpu_base, "kernels": extra_kernels, "valid_people_last_step": n_valid,
+        "cuda_graph": not args.no_graph,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
