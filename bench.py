@@ -106,10 +106,26 @@ def cpu_reference_fps(cfg, cams, resize, frames: np.ndarray, sd_np, warm: int, s
     """The reference's CPU path (oracle port: the same PyTorch-CPU ops in the same order as the reference,
     pinned bit-exact to it by oracle/gen_golden.py) on this host's cores, one frame per step."""
     from oracle import fvp_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}
     rz = torch.as_tensor(resize, dtype=torch.float)
     cameras = {"s": cams}
+    # the tiny per-person convolutions of this path scale badly past a few dozen threads (128 threads are ~20x
+    # slower than 16 on the B200 host): give the baseline its best thread count among {8,16,32,all}
+    ncpu = os.cpu_count() or 1
+    best = (None, 1e30)
+    with torch.no_grad():
+        for nt in sorted({min(8, ncpu), min(16, ncpu), min(32, ncpu), ncpu}):
+            torch.set_num_threads(nt)
+            hm = torch.from_numpy(frames[0][None])
+            O.forward(cfg, sd, hm, ["s"], cameras, rz, taps=False)
+            t0 = time.perf_counter()
+            O.forward(cfg, sd, hm, ["s"], cameras, rz, taps=False)
+            dt = time.perf_counter() - t0
+            if dt < best[1]:
+                best = (nt, dt)
+            if dt > 4 * best[1]:
+                break
+    torch.set_num_threads(best[0])
     ts = []
     with torch.no_grad():
         for i in range(warm + steps):
@@ -156,7 +172,7 @@ def main():
         warm = min(args.warmup, 3)
         frames = make_frames(cfg, cams, 4, seed0=5000)
         fps, cores, med_ms = cpu_reference_fps(cfg, cams, resize, frames, sd_np, warm, steps)
-        sample = "%d forwards of one frame each (after %d warm-up), all %d host threads" % (steps, warm, cores)
+        sample = "%d forwards of one frame each (after %d warm-up), best of {8,16,32,all} = %d host threads" % (steps, warm, cores)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
