@@ -64,6 +64,14 @@ int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaSt
   return FVP_OK;
 }
 
+// depth parts per person for K3: enough CTAs for ~3 waves of (3 CTAs/SM) at small batch
+int fvp_k3_parts(const fvp_ctx* ctx, int batch) {
+  const int base = 16 * batch * ctx->geom.P;                 // slabs x persons
+  int parts = 1;
+  while (parts < 8 && base * parts < 9 * ctx->num_sms) parts *= 2;
+  return parts;
+}
+
 FvpPropArgs prop_args(fvp_ctx* ctx) {
   FvpPropArgs a = ctx->prop;
   a.g = ctx->geom;
@@ -109,7 +117,7 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
     fvp_launch_proposals(a, ctx->w_c2c, n, st); ++*launches;
   }
   T.mark(5);
-  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, ctx->d_yz_scratch, batch, ctx->k3_slab, st);
+  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, ctx->d_yz_scratch, ctx->d_xy_scratch, batch, fvp_k3_parts(ctx, batch), st);
   *launches += 2;
   T.mark(6);
   fvp_run_trunk2d(ctx->w_p2p, ctx->d_planes_cl, g.proj.JP, 3 * n, 64, 64, ctx->p2p_buf, ctx->d_img_valid, false,
@@ -183,6 +191,8 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   P.hm_w = (float)c.hm_w; P.hm_h = (float)c.hm_h;
   P.img_w = c.image_w; P.img_h = c.image_h;
   P.wm1 = (float)(c.hm_w - 1); P.hm1 = (float)(c.hm_h - 1);
+  P.r_img_w = (float)(1.0 / (double)P.img_w); P.r_img_h = (float)(1.0 / (double)P.img_h);
+  P.r_wm1 = (float)(1.0 / (double)P.wm1); P.r_hm1 = (float)(1.0 / (double)P.hm1);
   g.view_stride4 = (size_t)P.HP * P.WP * g.JG;
 
   FvpPropArgs& pa = ctx->prop;
@@ -224,6 +234,7 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   A(dalloc(&ctx->d_img_valid, (size_t)3 * n));
   A(dalloc(&ctx->d_planes_cl, (size_t)3 * n * 4096 * JP));
   A(dalloc(&ctx->d_yz_scratch, (size_t)n * 32 * 4096 * JP));
+  A(dalloc(&ctx->d_xy_scratch, (size_t)n * 8 * 4096 * JP));
   A(dalloc(&ctx->d_feat, (size_t)3 * n * g.J * 4096));
   A(dalloc(&ctx->d_pose, (size_t)3 * n * g.J * 2));
   A(dalloc(&ctx->d_maxw, (size_t)3 * n * g.J));
@@ -261,8 +272,7 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   g.fine_axes = ctx->d_axes + g.X + g.Y + g.Z;
   g.ind_axes = g.fine_axes + g.fine[0] + g.fine[1] + g.fine[2];
   g.seqs = ctx->d_seqs;
-  // batch-1 latency wants more CTAs (slab 4 -> 16 CTAs / person), throughput wants fewer partials
-  ctx->k3_slab = (MB * g.P * 8 < 2 * prop.multiProcessorCount) ? 4 : 8;
+  ctx->num_sms = prop.multiProcessorCount;
   int rc = fvp_set_axes(ctx, nullptr, nullptr, nullptr);
   if (rc != FVP_OK) {
     g_create_error = ctx->err;
@@ -279,7 +289,7 @@ void fvp_destroy(fvp_ctx* ctx) {
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   void* ptrs[] = {ctx->d_weights, ctx->d_axes, ctx->d_seqs, ctx->d_hm_in, ctx->d_hm_cl, ctx->d_plane_cl, ctx->d_hmsize,
                   ctx->d_conf2d, ctx->d_flat, ctx->d_centers, ctx->d_people, ctx->d_img_valid, ctx->d_planes_cl,
-                  ctx->d_yz_scratch, ctx->d_feat, ctx->d_pose, ctx->d_maxw, ctx->d_wts, ctx->d_fused, ctx->d_conf,
+                  ctx->d_yz_scratch, ctx->d_xy_scratch, ctx->d_feat, ctx->d_pose, ctx->d_maxw, ctx->d_wts, ctx->d_fused, ctx->d_conf,
                   ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -524,6 +534,16 @@ int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr
   return FVP_OK;
 }
 
+int fvp_debug_project(fvp_ctx* ctx, int slot, const float* d_points, int n, float* d_ix, float* d_iy, uintptr_t stream) {
+  if (!ctx || !d_points || !d_ix || !d_iy || n < 1) return FVP_E_INVALID;
+  if (slot < 0 || slot >= ctx->cfg.max_sequences || !ctx->seq_set[slot])
+    return fvp_fail(ctx, FVP_E_CALIB, "missing camera parameters for the current sequence (slot %d)", slot);
+  cudaSetDevice(ctx->device);
+  fvp_launch_debug_project(ctx->geom, slot, d_points, n, d_ix, d_iy, (cudaStream_t)stream);
+  FVP_CUDA_OK(cudaGetLastError());
+  return FVP_OK;
+}
+
 int fvp_hdn_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, float* d_plane, uintptr_t stream) {
   int rc = check_stage_ready(ctx, batch);
   if (rc != FVP_OK) return rc;
@@ -620,7 +640,7 @@ int fvp_jln_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const f
   FvpPropArgs a = prop_args(ctx);
   a.people = ctx->d_people; a.img_valid = ctx->d_img_valid; a.n_slots = n;
   fvp_launch_people_from_centers(a, d_centers, n, st);
-  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, ctx->d_yz_scratch, batch, ctx->k3_slab, st);
+  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, ctx->d_yz_scratch, ctx->d_xy_scratch, batch, fvp_k3_parts(ctx, batch), st);
   if (d_planes) fvp_launch_nhwc_to_nchw(ctx->d_planes_cl, d_planes, 3 * n, 4096, g.proj.JP, g.J, st);
   if (d_offset) {
     FVP_CUDA_OK(cudaMemcpy2DAsync(d_offset, 3 * sizeof(float), (const char*)ctx->d_people + offsetof(FvpPerson, offset),

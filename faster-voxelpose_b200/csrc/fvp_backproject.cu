@@ -48,15 +48,17 @@ void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
+// CTA = 4 warps that all own the same 32/CG voxel columns; warp w takes the z range [w*Z/4, (w+1)*Z/4) so a
+// batch-1 launch still puts ~5 CTAs on every SM; the four partial z-maxima meet in shared memory.
 template <int CG>
 __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const float4* __restrict__ hm_cl,
                                                             const int* __restrict__ frame_seq,
                                                             float4* __restrict__ plane_cl) {
   extern __shared__ float smem_f[];
   __shared__ FvpSeq s_seq;
+  __shared__ float4 s_part[4][32];
   const int b = blockIdx.y;
   const FvpProj& P = g.proj;
-  // calibration + z axis into shared memory
   {
     const int* src = (const int*)(g.seqs + frame_seq[b]);
     int* dst = (int*)&s_seq;
@@ -70,13 +72,13 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
   const int s = lane % CG;                       // channel group / projection sub-lane
   const int group_base = lane - s;               // first lane of my column
   const int ncols = g.X * g.Y;
-  int col = (blockIdx.x * (blockDim.x >> 5) + warp) * COLS_PER_WARP + lane / CG;
+  int col = blockIdx.x * COLS_PER_WARP + lane / CG;
   const bool col_ok = col < ncols;
   if (!col_ok) col = ncols - 1;                  // keep the warp convergent for the shuffles
   const int cx = col / g.Y, cy = col - cx * g.Y;
   const float wx = g.coarse_axes[cx], wy = g.coarse_axes[g.X + cy];
 
-  const int V = g.V, Z = g.Z, npairs = Z * V;
+  const int V = g.V, ZW = g.Z >> 2, z0 = warp * ZW, npairs = ZW * V;
   const float fV = (float)V, rV = 1.0f / fV;
   const int row4 = P.WP * g.JG, px4 = g.JG;
   const float4* hm_b = hm_cl + (size_t)b * V * g.view_stride4 + (s < g.JG ? s : 0);
@@ -84,14 +86,13 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), zmax = acc;
   for (int base = 0; base < npairs; base += CG) {
-    // my (z, view) pair of this round
-    const int idx = base + s;
+    const int idx = base + s;                    // my (z, view) pair of this round
     FvpTaps t;
     t.off = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
     if (idx < npairs) {
       const int z = idx / V, v = idx - z * V;
       float ix, iy;
-      fvp_project(s_seq.cam[v], s_seq.A, P, wx, wy, smem_f[z], ix, iy);
+      fvp_project(s_seq.cam[v], s_seq.A, P, wx, wy, smem_f[z0 + z], ix, iy);
       t = fvp_taps(P, ix, iy);
     }
 #pragma unroll
@@ -111,7 +112,12 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
       }
     }
   }
-  if (col_ok && ch_ok) plane_cl[((size_t)b * ncols + col) * g.JG + s] = zmax;
+  s_part[warp][lane] = zmax;
+  __syncthreads();
+  if (warp == 0 && col_ok && ch_ok) {
+    const float4 m = fvp_max4(fvp_max4(s_part[0][lane], s_part[1][lane]), fvp_max4(s_part[2][lane], s_part[3][lane]));
+    plane_cl[((size_t)b * ncols + col) * g.JG + s] = m;
+  }
 }
 
 void fvp_launch_hdn_project(const FvpGeom& g, const float* d_hm_cl, const int* d_frame_seq, float* d_plane_cl,
@@ -119,10 +125,10 @@ void fvp_launch_hdn_project(const FvpGeom& g, const float* d_hm_cl, const int* d
   const int ncols = g.X * g.Y;
   const size_t smem = g.Z * sizeof(float);
   if (g.JG <= 4) {
-    dim3 grid(fvp_cdiv(ncols, 4 * 8), batch);
+    dim3 grid(fvp_cdiv(ncols, 8), batch);
     k1_hdn_project_zmax<4><<<grid, 128, smem, st>>>(g, (const float4*)d_hm_cl, d_frame_seq, (float4*)d_plane_cl);
   } else {
-    dim3 grid(fvp_cdiv(ncols, 4 * 4), batch);
+    dim3 grid(fvp_cdiv(ncols, 4), batch);
     k1_hdn_project_zmax<8><<<grid, 128, smem, st>>>(g, (const float4*)d_hm_cl, d_frame_seq, (float4*)d_plane_cl);
   }
 }
@@ -166,13 +172,12 @@ void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int
 //   xz[a][c] = max_b   : REDUX.MAX over the lanes of the warp that share a channel group (values are
 //                        >= 0, so their bit patterns order like unsigned ints), then a shared-memory
 //                        max over the warps (double-buffered: one barrier per a).
-constexpr int K3_CCH = 8;     // depths per chunk
 
-template <int CG, int TA>
-__global__ void __launch_bounds__(64 * CG) k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl,
-                                                           const FvpPerson* __restrict__ people,
-                                                           float4* __restrict__ planes_cl,
-                                                           float4* __restrict__ yz_scratch, int n_people) {
+template <int CG, int TA, int K3_CCH>
+__global__ void __launch_bounds__(64 * CG, (CG == 4) ? 3 : 1)
+k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __restrict__ people,
+               float4* __restrict__ planes_cl, float4* __restrict__ yz_scratch, float4* __restrict__ xy_scratch,
+               int n_people, int nslab, int ncpart) {
   constexpr int NT = 64 * CG;                    // threads
   constexpr int NW = NT / 32;                    // warps
   constexpr int BPW = 32 / CG;                   // columns b per warp
@@ -185,7 +190,10 @@ __global__ void __launch_bounds__(64 * CG) k3_jln_project(FvpGeom g, const float
   __shared__ float4 s_xz[NBUF][K3_CCH][NW][CG];  // per-warp partial maxima
   __shared__ float4 s_xy[TA][NT];                // per-thread running max over c for every a of the slab
 
-  const int person = blockIdx.y, slab = blockIdx.x, nslab = gridDim.x;
+  // blockIdx.x = slab + nslab * cpart : the cube's depth range is split into ncpart parts handled by different
+  // CTAs (more CTAs at small batch); xz columns of a part are complete, xy becomes a partial over the parts.
+  const int person = blockIdx.y, slab = blockIdx.x % nslab, cpart = blockIdx.x / nslab;
+  const int c_begin = cpart * (64 / ncpart), c_end = c_begin + 64 / ncpart;
   const FvpPerson pd = people[person];
   const FvpProj& P = g.proj;
   const int JG = g.JG;
@@ -194,7 +202,8 @@ __global__ void __launch_bounds__(64 * CG) k3_jln_project(FvpGeom g, const float
   const int b = warp * BPW + lane / CG;          // cube column (world y index within the cube)
   const bool ch_ok = s < JG;
   const size_t img4 = (size_t)64 * 64 * JG;      // float4 per plane image
-  float4* xy_img = planes_cl + ((size_t)0 * n_people + person) * img4;
+  float4* xy_img = ncpart == 1 ? planes_cl + ((size_t)0 * n_people + person) * img4
+                               : xy_scratch + ((size_t)person * ncpart + cpart) * img4;
   float4* xz_img = planes_cl + ((size_t)1 * n_people + person) * img4;
   float4* yz_part = yz_scratch + ((size_t)person * nslab + slab) * img4;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -202,14 +211,16 @@ __global__ void __launch_bounds__(64 * CG) k3_jln_project(FvpGeom g, const float
 
   const bool live = pd.valid && !pd.empty;
   const int alo = max(a0, pd.lo[0]), ahi = min(a0 + TA, pd.hi[0]);   // active rows of this slab
-  const bool any = live && alo < ahi && pd.lo[1] < pd.hi[1] && pd.lo[2] < pd.hi[2];
+  const bool any = live && alo < ahi && pd.lo[1] < pd.hi[1] && max(c_begin, pd.lo[2]) < min(c_end, pd.hi[2]);
 
   if (!any) {                                    // nothing to sample: this CTA's outputs are zero
     if (ch_ok) {
       for (int a = 0; a < TA; ++a) xy_img[((size_t)(a0 + a) * 64 + b) * JG + s] = zero4;
-      for (int c = 0; c < 64; ++c) yz_part[((size_t)b * 64 + c) * JG + s] = zero4;
+      for (int c = c_begin; c < c_end; ++c) yz_part[((size_t)b * 64 + c) * JG + s] = zero4;
     }
-    for (int i = tid; i < TA * 64 * JG; i += NT) xz_img[(size_t)a0 * 64 * JG + i] = zero4;
+    const int ncol = (c_end - c_begin) * JG;
+    for (int i = tid; i < TA * ncol; i += NT)
+      xz_img[((size_t)(a0 + i / ncol) * 64 + c_begin) * JG + i % ncol] = zero4;
     return;
   }
 
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(64 * CG) k3_jln_project(FvpGeom g, const float
   for (int i = 0; i < BPW; ++i) rmask |= 1u << (i * CG + s);
 
   int it = 0;                                    // (chunk, a) iteration counter -> xz buffer parity
-  for (int cc = 0; cc < 64; cc += K3_CCH) {
+  for (int cc = c_begin; cc < c_end; cc += K3_CCH) {
     float4 yz_acc[K3_CCH];
 #pragma unroll
     for (int c = 0; c < K3_CCH; ++c) yz_acc[c] = zero4;
@@ -319,8 +330,9 @@ __global__ void __launch_bounds__(64 * CG) k3_jln_project(FvpGeom g, const float
 
 // K3b: yz plane = max over the slab partials
 __global__ void __launch_bounds__(256) k3b_yz_reduce(const float4* __restrict__ yz_scratch,
+                                                      const float4* __restrict__ xy_scratch,
                                                       float4* __restrict__ planes_cl, int n_people, int nslab,
-                                                      int img4) {
+                                                      int ncpart, int img4) {
   const int person = blockIdx.y;
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= img4) return;
@@ -328,28 +340,50 @@ __global__ void __launch_bounds__(256) k3b_yz_reduce(const float4* __restrict__ 
   float4 m = src[0];
   for (int sl = 1; sl < nslab; ++sl) m = fvp_max4(m, src[(size_t)sl * img4]);
   planes_cl[((size_t)2 * n_people + person) * img4 + i] = m;
+  if (ncpart > 1) {                              // xy plane = max over the depth parts
+    const float4* sx = xy_scratch + (size_t)person * ncpart * img4 + i;
+    float4 mx = sx[0];
+    for (int cp = 1; cp < ncpart; ++cp) mx = fvp_max4(mx, sx[(size_t)cp * img4]);
+    planes_cl[((size_t)0 * n_people + person) * img4 + i] = mx;
+  }
 }
 
 void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
-                            float* d_yz_scratch, int batch, int slab, cudaStream_t st) {
+                            float* d_yz_scratch, float* d_xy_scratch, int batch, int ncpart, cudaStream_t st) {
   const int n_people = batch * g.P;
   const int img4 = 64 * 64 * g.JG;
+  int nslab;
   if (g.JG <= 4) {
-    if (slab == 4) {
-      dim3 grid(16, n_people);
-      k3_jln_project<4, 4><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                 (float4*)d_yz_scratch, n_people);
-    } else {
-      dim3 grid(8, n_people);
-      k3_jln_project<4, 8><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                 (float4*)d_yz_scratch, n_people);
-    }
+    nslab = 16;                                  // TA = 4 rows per slab
+    dim3 grid(nslab * ncpart, n_people);
+    k3_jln_project<4, 4, 4><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                               (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
   } else {
-    slab = 2;
-    dim3 grid(32, n_people);
-    k3_jln_project<8, 2><<<grid, 512, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                               (float4*)d_yz_scratch, n_people);
+    nslab = 32;                                  // TA = 2
+    dim3 grid(nslab * ncpart, n_people);
+    k3_jln_project<8, 2, 8><<<grid, 512, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                               (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
   }
   dim3 grid2(fvp_cdiv(img4, 256), n_people);
-  k3b_yz_reduce<<<grid2, 256, 0, st>>>((const float4*)d_yz_scratch, (float4*)d_planes_cl, n_people, 64 / slab, img4);
+  k3b_yz_reduce<<<grid2, 256, 0, st>>>((const float4*)d_yz_scratch, (const float4*)d_xy_scratch, (float4*)d_planes_cl,
+                                       n_people, nslab, ncpart, img4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hook: the in-kernel projection chain on arbitrary world points (bit-parity test vs project_chain_np)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_debug_project(FvpGeom g, int seq, const float* __restrict__ pts, int n, float* __restrict__ ix,
+                                float* __restrict__ iy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (i >= n) return;
+  const FvpSeq& sq = g.seqs[seq];
+  float x, y;
+  fvp_project(sq.cam[v], sq.A, g.proj, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], x, y);
+  ix[(size_t)v * n + i] = x;
+  iy[(size_t)v * n + i] = y;
+}
+void fvp_launch_debug_project(const FvpGeom& g, int seq, const float* d_pts, int n, float* d_ix, float* d_iy,
+                              cudaStream_t st) {
+  dim3 grid(fvp_cdiv(n, 128), g.V);
+  k_debug_project<<<grid, 128, 0, st>>>(g, seq, d_pts, n, d_ix, d_iy);
 }

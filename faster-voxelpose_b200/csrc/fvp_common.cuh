@@ -33,6 +33,7 @@ struct FvpProj {
   float hm_w, hm_h;    // float(w), float(h)
   float img_w, img_h;
   float wm1, hm1;      // w-1, h-1
+  float r_img_w, r_img_h, r_wm1, r_hm1;   // correctly rounded reciprocals of the four constant divisors
   int W, H;            // heat-map size
   int WP, HP;          // zero-bordered size
   int PADX, PADY;

@@ -53,6 +53,7 @@ struct fvp_ctx {
   int* d_img_valid = nullptr;         // [3*MB*P]
   float* d_planes_cl = nullptr;       // [3][MB*P][64][64][JP]
   float* d_yz_scratch = nullptr;
+  float* d_xy_scratch = nullptr;
   float* d_feat = nullptr;            // [3][MB*P][J][64][64]
   float* d_pose = nullptr;            // [3][MB*P][J][2]
   float* d_maxw = nullptr;            // [3][MB*P][J]
@@ -69,7 +70,7 @@ struct fvp_ctx {
   int* d_frame_seq = nullptr;         // [MB]
   int* h_frame_seq = nullptr;         // pinned
   int frame_seq_uploaded = 0;         // how many leading entries of d_frame_seq mirror h_frame_seq
-  int k3_slab = 8;
+  int num_sms = 148;
 
   // cuda graph
   bool use_graph = false;

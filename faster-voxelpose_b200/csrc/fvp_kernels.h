@@ -23,14 +23,18 @@ void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_
 void fvp_launch_hdn_project(const FvpGeom& g, const float* d_hm_cl, const int* d_frame_seq, float* d_plane_cl,
                             int batch, cudaStream_t st);
 
+void fvp_launch_debug_project(const FvpGeom& g, int seq, const float* d_pts, int n, float* d_ix, float* d_iy,
+                              cudaStream_t st);
+
 // layout helpers (stage API / tests): NHWC(JP) <-> NCHW(J)
 void fvp_launch_nhwc_to_nchw(const float* d_in, float* d_out, int n, int hw, int cp, int c, cudaStream_t st);
 void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int cp, int c, cudaStream_t st);
 
 // K3: per-person back-projection + three-plane max.
 //   planes_cl [3][B*P][64][64][JP]; yz partial scratch [B*P][nslab][64][64][JP]
+//   xy partial scratch [B*P][ncpart][64][64][JP] (used when the depth range is split, ncpart in {1,2,4,8})
 void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
-                            float* d_yz_scratch, int batch, int slab, cudaStream_t st);
+                            float* d_yz_scratch, float* d_xy_scratch, int batch, int ncpart, cudaStream_t st);
 
 // ---- convolutions (fp32 CUDA-core implicit GEMM, NHWC) ----------------------------------------
 struct FvpConvArgs {

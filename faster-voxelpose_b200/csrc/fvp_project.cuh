@@ -9,6 +9,16 @@
 #pragma once
 #include "fvp_common.cuh"
 
+// Correctly rounded x / d from a correctly rounded reciprocal r = RN(1/d): q = RN(x*r); rem = x - q*d (exact, FMA);
+// q' = RN(q + rem*r) (Markstein).  Three FMA-pipe instructions instead of the ~10 of __fdiv_rn's slow path; valid for
+// the normal-range operands of this chain (pixel / millimetre magnitudes) - tests/test_gpu_parity.py checks the whole
+// chain bit-for-bit against oracle.project_chain_np on random points.
+__device__ __forceinline__ float fvp_div_by(float x, float d, float r) {
+  const float q = __fmul_rn(x, r);
+  const float rem = __fmaf_rn(-q, d, x);
+  return __fmaf_rn(rem, r, q);
+}
+
 __device__ __forceinline__ void fvp_project(const FvpCam& c, const float* __restrict__ A, const FvpProj& P,
                                             float px, float py, float pz, float& ix, float& iy) {
   const float dx = __fsub_rn(px, c.T[0]);
@@ -19,8 +29,18 @@ __device__ __forceinline__ void fvp_project(const FvpCam& c, const float* __rest
   const float q1 = __fmaf_rn(c.R[5], dz, __fmaf_rn(c.R[4], dy, __fmul_rn(c.R[3], dx)));
   const float q2 = __fmaf_rn(c.R[8], dz, __fmaf_rn(c.R[7], dy, __fmul_rn(c.R[6], dx)));
   const float den = __fadd_rn(q2, 1e-5f);                 // no cheirality test (cameras.py:44)
-  const float y0 = __fdiv_rn(q0, den);
-  const float y1 = __fdiv_rn(q1, den);
+  float y0, y1;
+  {
+    const float aden = fabsf(den);
+    if (aden > 1e-3f && aden < 1e9f) {                    // common case: shared correctly-rounded reciprocal
+      const float rden = __frcp_rn(den);
+      y0 = fvp_div_by(q0, den, rden);
+      y1 = fvp_div_by(q1, den, rden);
+    } else {                                              // grazing the camera plane: full IEEE division
+      y0 = __fdiv_rn(q0, den);
+      y1 = __fdiv_rn(q1, den);
+    }
+  }
   const float r2 = __fadd_rn(__fmul_rn(y0, y0), __fmul_rn(y1, y1));
   float d = __fadd_rn(1.0f, __fmul_rn(c.k[0], r2));
   d = __fadd_rn(d, __fmul_rn(__fmul_rn(c.k[1], r2), r2));
@@ -36,10 +56,10 @@ __device__ __forceinline__ void fvp_project(const FvpCam& c, const float* __rest
   // torch.mm(A[2x3], [X;Y;1])
   const float ax = __fadd_rn(__fmaf_rn(A[1], Y, __fmul_rn(A[0], X)), A[2]);
   const float ay = __fadd_rn(__fmaf_rn(A[4], Y, __fmul_rn(A[3], X)), A[5]);
-  const float sx = __fdiv_rn(__fmul_rn(ax, P.hm_w), P.img_w);
-  const float sy = __fdiv_rn(__fmul_rn(ay, P.hm_h), P.img_h);
-  float gx = __fsub_rn(__fmul_rn(__fdiv_rn(sx, P.wm1), 2.0f), 1.0f);
-  float gy = __fsub_rn(__fmul_rn(__fdiv_rn(sy, P.hm1), 2.0f), 1.0f);
+  const float sx = fvp_div_by(__fmul_rn(ax, P.hm_w), P.img_w, P.r_img_w);
+  const float sy = fvp_div_by(__fmul_rn(ay, P.hm_h), P.img_h, P.r_img_h);
+  float gx = __fsub_rn(__fmul_rn(fvp_div_by(sx, P.wm1, P.r_wm1), 2.0f), 1.0f);
+  float gy = __fsub_rn(__fmul_rn(fvp_div_by(sy, P.hm1, P.r_hm1), 2.0f), 1.0f);
   gx = fminf(fmaxf(gx, -1.1f), 1.1f);
   gy = fminf(fmaxf(gy, -1.1f), 1.1f);
   ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), P.wm1);   // ((g+1)/2)*(size-1), /2 is exact

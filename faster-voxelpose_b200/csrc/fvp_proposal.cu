@@ -100,60 +100,101 @@ struct C2CNet {
 
 // out[co][l] = epilogue( sum_{tap,ci} w[tap*CinP+ci][co] * in[ci][l+tap-pad]  (+ sum_ci w2[ci][co]*in2[ci][l]) + b[co] )
 // upsample: GEMM columns co' = d*Co + co  ->  out[co][2l+d]
+// The layer's packed weights are streamed global(L2) -> shared in 32 KB chunks with cp.async, double buffered, so the
+// inner loop reads only shared memory (round 1 read every weight straight from L2 inside the FMA loop: 0.45 ms).
+constexpr int C2C_WCHUNK = 8192;    // floats per weight buffer (32 KB)
+
+__device__ __forceinline__ void c2c_cp16(float* dst_smem, const float* src_gmem) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem));
+}
+
 __device__ void c2c_conv(const float* __restrict__ in, int Cin, int L, const float* __restrict__ in2, int Cin2,
                          C2CLayer ly, int K, float* __restrict__ out, int CoutG, const float* __restrict__ res,
-                         int res_mode, bool relu, bool upsample) {
+                         int res_mode, bool relu, bool upsample, float* __restrict__ wbuf) {
   const int tid = threadIdx.x;
-  const int CinP = (Cin + 15) & ~15;
-  const int groups = C2C_THREADS / CoutG > 0 ? C2C_THREADS / CoutG : 1;
+  const int CinP = (Cin + 15) & ~15;                 // 16, 32, 64 or 128: a power of two
+  const int cin_shift = 31 - __clz(CinP);
+  const int Cin2P = in2 ? ((Cin2 + 15) & ~15) : 0;
+  const int main_rows = K * CinP, rows = main_rows + Cin2P;
+  const int rpc = C2C_WCHUNK / CoutG;                 // rows per chunk
+  const int nchunks = (rows + rpc - 1) / rpc;
+  const int groups = C2C_THREADS / CoutG;
   const int co = tid % CoutG, lg = tid / CoutG;
   const int pad = (K - 1) / 2;
-  if (lg < groups && tid < CoutG * groups) {
-    for (int l0 = lg; l0 < L; l0 += 2 * groups) {
-      const int l1 = l0 + groups;
-      const bool has1 = l1 < L;
-      float a0 = 0.f, a1 = 0.f;
-      for (int tap = 0; tap < K; ++tap) {
-        const int p0 = l0 + tap - pad, p1 = l1 + tap - pad;
-        const bool ok0 = p0 >= 0 && p0 < L, ok1 = has1 && p1 >= 0 && p1 < L;
-        const float* wr = ly.w + (size_t)(tap * CinP) * CoutG + co;
-#pragma unroll 4
-        for (int ci = 0; ci < Cin; ++ci) {
-          const float wv = __ldg(wr + (size_t)ci * CoutG);
-          const float x0 = ok0 ? in[ci * L + p0] : 0.f;
-          const float x1 = ok1 ? in[ci * L + p1] : 0.f;
-          a0 = fmaf(wv, x0, a0);
-          a1 = fmaf(wv, x1, a1);
-        }
-      }
-      if (in2) {
-        const float* wr = ly.w + (size_t)(K * CinP) * CoutG + co;
-#pragma unroll 4
-        for (int ci = 0; ci < Cin2; ++ci) {
-          const float wv = __ldg(wr + (size_t)ci * CoutG);
-          a0 = fmaf(wv, in2[ci * L + l0], a0);
-          if (has1) a1 = fmaf(wv, in2[ci * L + l1], a1);
-        }
-      }
-      const float bias = __ldg(ly.b + co);
+  const bool worker = lg < groups;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int lpos[4];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (e == 1 && !has1) break;
-        float v = (e == 0 ? a0 : a1) + bias;
-        const int l = e == 0 ? l0 : l1;
-        int oc = co, ol = l, Lo = L;
-        if (upsample) {
-          const int Co = CoutG >> 1;
-          const int d = co / Co;
-          oc = co - d * Co;
-          ol = 2 * l + d;
-          Lo = 2 * L;
+  for (int k = 0; k < 4; ++k) lpos[k] = lg + k * groups;
+
+  auto issue = [&](int ch) {
+    const int r0 = ch * rpc, nr = min(rpc, rows - r0);
+    const float* src = ly.w + (size_t)r0 * CoutG;
+    float* dst = wbuf + (ch & 1) * C2C_WCHUNK;
+    for (int i = tid * 4; i < nr * CoutG; i += C2C_THREADS * 4) c2c_cp16(dst + i, src + i);
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  issue(0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    if (ch + 1 < nchunks) {
+      issue(ch + 1);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    if (worker) {
+      const float* wb = wbuf + (ch & 1) * C2C_WCHUNK + co;
+      const int r0 = ch * rpc, nr = min(rpc, rows - r0);
+#pragma unroll 4
+      for (int rr = 0; rr < nr; ++rr) {
+        const int r = r0 + rr;
+        const float* src;
+        int ci, shift;
+        if (r < main_rows) {
+          const int tap = r >> cin_shift;
+          ci = r - (tap << cin_shift);
+          if (ci >= Cin) continue;                  // zero padding rows
+          shift = tap - pad;
+          src = in;
+        } else {
+          ci = r - main_rows;
+          if (ci >= Cin2) continue;
+          shift = 0;
+          src = in2;
         }
-        if (res_mode == 1) v += res[oc * Lo + ol];
-        if (relu) v = fmaxf(v, 0.f);
-        if (res_mode == 2) v += res[oc * Lo + ol];
-        out[oc * Lo + ol] = v;
+        const float wv = wb[rr * CoutG];
+        const float* xr = src + ci * L;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int p = lpos[k] + shift;
+          const float x = (lpos[k] < L && p >= 0 && p < L) ? xr[p] : 0.f;
+          acc[k] = fmaf(wv, x, acc[k]);
+        }
       }
+    }
+    __syncthreads();                                   // buffer (ch&1) may be refilled by chunk ch+2
+  }
+  if (worker) {
+    const float bias = __ldg(ly.b + co);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int l = lpos[k];
+      if (l >= L) continue;
+      float v = acc[k] + bias;
+      int oc = co, ol = l, Lo = L;
+      if (upsample) {
+        const int Co = CoutG >> 1;
+        const int d = co / Co;
+        oc = co - d * Co;
+        ol = 2 * l + d;
+        Lo = 2 * L;
+      }
+      if (res_mode == 1) v += res[oc * Lo + ol];
+      if (relu) v = fmaxf(v, 0.f);
+      if (res_mode == 2) v += res[oc * Lo + ol];
+      out[oc * Lo + ol] = v;
     }
   }
   __syncthreads();
@@ -169,32 +210,32 @@ __device__ void c2c_pool(const float* __restrict__ in, int C, int L, float* __re
 }
 
 // x0: [>=J][Z] input columns; result hm1d[Z] lands in `out` (smem)
-__device__ void c2c_forward(const C2CNet& net, const float* x0, int J, int Z, float* buf, float* out) {
+__device__ void c2c_forward(const C2CNet& net, const float* x0, int J, int Z, float* buf, float* out, float* wbuf) {
   float *B0 = buf, *B1 = buf + C2C_BUF, *B2 = buf + 2 * C2C_BUF, *B3 = buf + 3 * C2C_BUF, *B4 = buf + 4 * C2C_BUF,
         *B5 = buf + 5 * C2C_BUF;
   const int L = Z, L2 = Z / 2, L4 = Z / 4;
-  c2c_conv(x0, J, L, nullptr, 0, net.l[0], 7, B0, 16, nullptr, 0, true, false);
-  c2c_conv(B0, 16, L, nullptr, 0, net.l[1], 3, B1, 32, nullptr, 0, true, false);
-  c2c_conv(B1, 32, L, B0, 16, net.l[2], 3, B2, 32, nullptr, 0, true, false);
-  c2c_conv(B2, 32, L, nullptr, 0, net.l[3], 3, B0, 32, nullptr, 0, true, false);
-  c2c_conv(B0, 32, L, nullptr, 0, net.l[4], 3, B3, 32, B2, 1, true, false);          // skip1
+  c2c_conv(x0, J, L, nullptr, 0, net.l[0], 7, B0, 16, nullptr, 0, true, false, wbuf);
+  c2c_conv(B0, 16, L, nullptr, 0, net.l[1], 3, B1, 32, nullptr, 0, true, false, wbuf);
+  c2c_conv(B1, 32, L, B0, 16, net.l[2], 3, B2, 32, nullptr, 0, true, false, wbuf);
+  c2c_conv(B2, 32, L, nullptr, 0, net.l[3], 3, B0, 32, nullptr, 0, true, false, wbuf);
+  c2c_conv(B0, 32, L, nullptr, 0, net.l[4], 3, B3, 32, B2, 1, true, false, wbuf);          // skip1
   c2c_pool(B2, 32, L, B0);
-  c2c_conv(B0, 32, L2, nullptr, 0, net.l[5], 3, B1, 64, nullptr, 0, true, false);
-  c2c_conv(B1, 64, L2, B0, 32, net.l[6], 3, B4, 64, nullptr, 0, true, false);         // e1
-  c2c_conv(B4, 64, L2, nullptr, 0, net.l[7], 3, B0, 64, nullptr, 0, true, false);
-  c2c_conv(B0, 64, L2, nullptr, 0, net.l[8], 3, B5, 64, B4, 1, true, false);          // skip2
+  c2c_conv(B0, 32, L2, nullptr, 0, net.l[5], 3, B1, 64, nullptr, 0, true, false, wbuf);
+  c2c_conv(B1, 64, L2, B0, 32, net.l[6], 3, B4, 64, nullptr, 0, true, false, wbuf);         // e1
+  c2c_conv(B4, 64, L2, nullptr, 0, net.l[7], 3, B0, 64, nullptr, 0, true, false, wbuf);
+  c2c_conv(B0, 64, L2, nullptr, 0, net.l[8], 3, B5, 64, B4, 1, true, false, wbuf);          // skip2
   c2c_pool(B4, 64, L2, B0);
-  c2c_conv(B0, 64, L4, nullptr, 0, net.l[9], 3, B1, 128, nullptr, 0, true, false);
-  c2c_conv(B1, 128, L4, B0, 64, net.l[10], 3, B2, 128, nullptr, 0, true, false);      // e2
-  c2c_conv(B2, 128, L4, nullptr, 0, net.l[11], 3, B0, 128, nullptr, 0, true, false);
-  c2c_conv(B0, 128, L4, nullptr, 0, net.l[12], 3, B1, 128, B2, 1, true, false);       // m
-  c2c_conv(B1, 128, L4, nullptr, 0, net.l[13], 3, B0, 128, nullptr, 0, true, false);
-  c2c_conv(B0, 128, L4, nullptr, 0, net.l[14], 3, B2, 128, B1, 1, true, false);       // d2
-  c2c_conv(B2, 128, L4, nullptr, 0, net.l[15], 1, B0, 128, B5, 2, true, true);        // u2 = relu(convT)+skip2
-  c2c_conv(B0, 64, L2, nullptr, 0, net.l[16], 3, B1, 64, nullptr, 0, true, false);
-  c2c_conv(B1, 64, L2, nullptr, 0, net.l[17], 3, B2, 64, B0, 1, true, false);         // d1
-  c2c_conv(B2, 64, L2, nullptr, 0, net.l[18], 1, B0, 64, B3, 2, true, true);          // u1 = relu(convT)+skip1
-  c2c_conv(B0, 32, L, nullptr, 0, net.l[19], 1, out, 4, nullptr, 0, false, false);    // head (row 0 of 4)
+  c2c_conv(B0, 64, L4, nullptr, 0, net.l[9], 3, B1, 128, nullptr, 0, true, false, wbuf);
+  c2c_conv(B1, 128, L4, B0, 64, net.l[10], 3, B2, 128, nullptr, 0, true, false, wbuf);      // e2
+  c2c_conv(B2, 128, L4, nullptr, 0, net.l[11], 3, B0, 128, nullptr, 0, true, false, wbuf);
+  c2c_conv(B0, 128, L4, nullptr, 0, net.l[12], 3, B1, 128, B2, 1, true, false, wbuf);       // m
+  c2c_conv(B1, 128, L4, nullptr, 0, net.l[13], 3, B0, 128, nullptr, 0, true, false, wbuf);
+  c2c_conv(B0, 128, L4, nullptr, 0, net.l[14], 3, B2, 128, B1, 1, true, false, wbuf);       // d2
+  c2c_conv(B2, 128, L4, nullptr, 0, net.l[15], 1, B0, 128, B5, 2, true, true, wbuf);        // u2 = relu(convT)+skip2
+  c2c_conv(B0, 64, L2, nullptr, 0, net.l[16], 3, B1, 64, nullptr, 0, true, false, wbuf);
+  c2c_conv(B1, 64, L2, nullptr, 0, net.l[17], 3, B2, 64, B0, 1, true, false, wbuf);         // d1
+  c2c_conv(B2, 64, L2, nullptr, 0, net.l[18], 1, B0, 64, B3, 2, true, true, wbuf);          // u1 = relu(convT)+skip1
+  c2c_conv(B0, 32, L, nullptr, 0, net.l[19], 1, out, 4, nullptr, 0, false, false, wbuf);    // head (row 0 of 4)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -230,9 +271,11 @@ __device__ void fvp_make_person(const FvpPropArgs& a, const float* c7, int seq, 
 
 // one CTA per proposal slot
 __global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet net) {
-  __shared__ float s_buf[6 * C2C_BUF];
-  __shared__ float s_x0[24 * C2C_MAXZ];          // [JP][Z] input columns
-  __shared__ float s_out[4 * C2C_MAXZ];
+  extern __shared__ __align__(16) float c2c_smem[];
+  float* s_wbuf = c2c_smem;                       // 2 x C2C_WCHUNK weight staging
+  float* s_buf = s_wbuf + 2 * C2C_WCHUNK;         // 6 activation buffers
+  float* s_x0 = s_buf + 6 * C2C_BUF;              // [JP][Z] input columns
+  float* s_out = s_x0 + 24 * C2C_MAXZ;            // [4][Z] head output
   __shared__ FvpSeq s_seq;
   const FvpGeom& g = a.g;
   const int slot = blockIdx.x, b = slot / g.P;
@@ -280,7 +323,7 @@ __global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet
     for (int i = tid; i < J * Z; i += C2C_THREADS) a.cols_out[(size_t)slot * J * Z + i] = s_x0[i];
   (void)JP;
 
-  c2c_forward(net, s_x0, J, Z, s_buf, s_out);    // s_out[0..Z) = 1-D heat map
+  c2c_forward(net, s_x0, J, Z, s_buf, s_out, s_wbuf);    // s_out[0..Z) = 1-D heat map
 
   if (a.hm1d_out)
     for (int i = tid; i < Z; i += C2C_THREADS) a.hm1d_out[(size_t)slot * Z + i] = s_out[i];
@@ -333,7 +376,13 @@ void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, cudaStr
     net.l[i].w = w.w[i];
     net.l[i].b = w.b[i];
   }
-  k_proposals<<<n, C2C_THREADS, 0, st>>>(a, net);
+  const size_t smem = (size_t)(2 * C2C_WCHUNK + 6 * C2C_BUF + 24 * C2C_MAXZ + 4 * C2C_MAXZ) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_proposals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  k_proposals<<<n, C2C_THREADS, smem, st>>>(a, net);
 }
 
 void fvp_launch_people_from_centers(const FvpPropArgs& a, const float* d_centers, int n, cudaStream_t st) {

@@ -228,6 +228,13 @@ class Engine:
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(shape, device=self.device, dtype=dtype)
 
+    def debug_project(self, slot: int, points: torch.Tensor):
+        p = points.to(self.device, torch.float32).contiguous()
+        n = p.shape[0]
+        ix, iy = self._new(self.V, n), self._new(self.V, n)
+        self._ck(self.lib.fvp_debug_project(self.ctx, int(slot), p.data_ptr(), n, ix.data_ptr(), iy.data_ptr(), self._stream()))
+        return ix, iy
+
     def stage_heatmaps(self, hm: torch.Tensor) -> None:
         B = self._check_hm(hm)
         self._keep = hm.to(self.device, torch.float32).contiguous()

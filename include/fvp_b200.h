@@ -117,6 +117,9 @@ int fvp_forward_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int
 int fvp_use_cuda_graph(fvp_ctx* ctx, int enable);
 
 /* ---- stage entry points (parity tests + profiling; same kernels fvp_forward launches) -------- */
+/* test hook: the in-kernel voxel -> heat-map-pixel chain (project_whole.py:49-60 + grid_sample un-normalise) on
+ * arbitrary world points d_points [n][3] -> d_ix, d_iy [V][n]; bit-identical to oracle.project_chain_np */
+int fvp_debug_project(fvp_ctx* ctx, int slot, const float* d_points, int n, float* d_ix, float* d_iy, uintptr_t stream);
 /* K0: [batch][V][J][H][W] -> internal channel-last, zero-bordered copy */
 int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr_t stream);
 /* K1: ProjectLayer(whole).forward + CenterNet's z-max (project_whole.py:62-88, cnns_2d.py:174)

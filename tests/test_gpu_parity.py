@@ -43,6 +43,33 @@ def test_param_table_matches_python_enumeration(built_library, golden):
     eng.close()
 
 
+def test_inkernel_projection_chain_is_bit_identical(case):
+    """fvp_project (csrc/fvp_project.cuh) == oracle.project_chain_np == the reference's cached sample grid, bit for
+    bit, on the coarse voxel centres plus random points in and around the capture space (incl. behind cameras)."""
+    from oracle import fvp_oracle as O
+    g, eng, slots = case
+    cfg = g.cfg
+    rng = np.random.default_rng(7)
+    size = np.asarray(cfg.CAPTURE_SPEC.SPACE_SIZE, np.float64)
+    ctr = np.asarray(cfg.CAPTURE_SPEC.SPACE_CENTER, np.float64)
+    rnd = (rng.uniform(-1.5, 1.5, (200000, 3)) * size / 2 + ctr).astype(np.float32)
+    vox = O.voxel_grid(cfg.CAPTURE_SPEC.SPACE_SIZE, cfg.CAPTURE_SPEC.SPACE_CENTER, cfg.CAPTURE_SPEC.VOXELS_PER_AXIS).numpy()[::3]
+    pts = np.concatenate([vox, rnd]).astype(np.float32)
+    ix, iy = eng.debug_project(slots[0], torch.from_numpy(pts))
+    ix, iy = ix.cpu().numpy(), iy.cpu().numpy()
+    W, H = [int(v) for v in cfg.DATASET.HEATMAP_SIZE]
+    ori, img = cfg.DATASET.ORI_IMAGE_SIZE, cfg.DATASET.IMAGE_SIZE
+    rz = np.asarray(g.resize, np.float64).astype(np.float32).reshape(6)
+    for v, cam in enumerate(g.cams):
+        with np.errstate(all="ignore"):
+            ex, ey = O.project_chain_np(pts[:, 0], pts[:, 1], pts[:, 2], O.cam21_f32(cam), rz, float(max(ori)), (W, H),
+                                        (float(img[0]), float(img[1])))
+        ok = np.isfinite(ex) & np.isfinite(ey)
+        assert ok.mean() > 0.999
+        assert np.array_equal(ix[v][ok].view(np.int32), ex[ok].view(np.int32))
+        assert np.array_equal(iy[v][ok].view(np.int32), ey[ok].view(np.int32))
+
+
 def test_k1_hdn_backprojection_zmax(case):
     """K0+K1 vs ProjectLayer(whole)+z-max of the reference: <= 1e-6 abs on values in [0,1]."""
     g, eng, slots = case
