@@ -98,7 +98,7 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
   fvp_launch_hdn_project(g, ctx->d_hm_cl, ctx->d_frame_seq, ctx->d_plane_cl, batch, st); ++*launches;
   T.mark(2);
   fvp_run_trunk2d(ctx->w_center, ctx->d_plane_cl, g.proj.JP, batch, g.X, g.Y, ctx->cn_buf, nullptr, true,
-                  ctx->d_hmsize, 3, launches, st);
+                  ctx->d_hmsize, 3, launches, st, ctx->conv_mode);
   T.mark(3);
   fvp_launch_nms_topk(ctx->d_hmsize, (size_t)3 * XY, g.X, g.Y, g.P, batch, ctx->d_conf2d, ctx->d_flat, st); ++*launches;
   T.mark(4);
@@ -121,7 +121,7 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
   *launches += 2;
   T.mark(6);
   fvp_run_trunk2d(ctx->w_p2p, ctx->d_planes_cl, g.proj.JP, 3 * n, 64, 64, ctx->p2p_buf, ctx->d_img_valid, false,
-                  ctx->d_feat, g.J, launches, st);
+                  ctx->d_feat, g.J, launches, st, ctx->conv_mode);
   T.mark(7);
   fvp_launch_pose_head(g, ctx->w_pose, ctx->d_feat, ctx->d_people, nullptr, n, ctx->cfg.beta, ctx->d_pose,
                        ctx->d_maxw, ctx->d_wts, ctx->d_fused, st); ++*launches;
@@ -404,6 +404,13 @@ int fvp_use_cuda_graph(fvp_ctx* ctx, int enable) {
   return FVP_OK;
 }
 
+int fvp_set_conv_mode(fvp_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return FVP_E_INVALID;
+  if (mode != ctx->conv_mode && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+  ctx->conv_mode = mode;
+  return FVP_OK;
+}
+
 int fvp_set_profiling(fvp_ctx* ctx, int enable) {
   if (!ctx) return FVP_E_INVALID;
   ctx->profiling = enable != 0;
@@ -569,7 +576,7 @@ int fvp_center_net(fvp_ctx* ctx, const float* d_plane_in, int batch, float* d_hm
   if (d_plane_in) fvp_launch_nchw_to_nhwc(d_plane_in, ctx->d_plane_cl, batch, XY, g.proj.JP, g.J, st);
   int launches = 0;
   fvp_run_trunk2d(ctx->w_center, ctx->d_plane_cl, g.proj.JP, batch, g.X, g.Y, ctx->cn_buf, nullptr, true,
-                  ctx->d_hmsize, 3, &launches, st);
+                  ctx->d_hmsize, 3, &launches, st, ctx->conv_mode);
   for (int b = 0; b < batch; ++b) {
     if (d_hm) FVP_CUDA_OK(cudaMemcpyAsync(d_hm + (size_t)b * XY, ctx->d_hmsize + (size_t)b * 3 * XY, XY * 4, cudaMemcpyDeviceToDevice, st));
     if (d_size) FVP_CUDA_OK(cudaMemcpyAsync(d_size + (size_t)b * 2 * XY, ctx->d_hmsize + (size_t)b * 3 * XY + XY, 2 * XY * 4, cudaMemcpyDeviceToDevice, st));
@@ -663,7 +670,7 @@ int fvp_p2p_net(fvp_ctx* ctx, const float* d_planes, int n, const int32_t* d_val
     in = ctx->d_tmp;
   }
   int launches = 0;
-  fvp_run_trunk2d(ctx->w_p2p, in, g.proj.JP, n, 64, 64, ctx->p2p_buf, d_valid, false, d_feat, g.J, &launches, st);
+  fvp_run_trunk2d(ctx->w_p2p, in, g.proj.JP, n, 64, 64, ctx->p2p_buf, d_valid, false, d_feat, g.J, &launches, st, ctx->conv_mode);
   FVP_CUDA_OK(cudaGetLastError());
   return FVP_OK;
 }

@@ -206,6 +206,7 @@ void fvp_launch_maxpool2(const float* in, float* out, int n, int H, int W, int C
 // ------------------------------------------------------------------------------------------------
 // trunk program: front_layers + EncoderDecorder (+ heads), cnns_2d.py:94-135,173-178
 // ------------------------------------------------------------------------------------------------
+static int g_tc = 0;   // set by fvp_run_trunk2d for the duration of one (single-threaded) trunk enqueue
 static void conv(const FvpConvW& w, const float* in, int H, int W, const float* in2, float* out, int couts,
                  const float* res, int res_mode, int relu, int upsample, int n, const int* valid, int* launches,
                  cudaStream_t st, int nchw = 0, int cout_real = 0) {
@@ -216,13 +217,16 @@ static void conv(const FvpConvW& w, const float* in, int H, int W, const float* 
   a.out = out; a.CoutP = w.coutp; a.CoutS = couts; a.CoutReal = cout_real;
   a.res = res; a.res_mode = res_mode; a.relu = relu; a.ksize = w.k; a.upsample = upsample;
   a.nchw = nchw; a.n = n; a.valid = valid;
-  fvp_launch_conv(a, st);
+  if (g_tc && w.wtc) fvp_launch_conv_tc(a, w.wtc, st);
+  else fvp_launch_conv(a, st);
   if (launches) ++*launches;
 }
 
 void fvp_run_trunk2d(const FvpTrunkW& t, const float* d_in, int cin, int n, int H, int W, float* const buf[6],
-                     const int* valid, bool center_heads, float* d_out, int out_real, int* launches, cudaStream_t st) {
+                     const int* valid, bool center_heads, float* d_out, int out_real, int* launches, cudaStream_t st,
+                     int tensor_cores) {
   (void)cin;
+  g_tc = tensor_cores;
   float *B0 = buf[0], *B1 = buf[1], *B2 = buf[2], *B3 = buf[3], *B4 = buf[4], *B5 = buf[5];
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
   // front_layers

@@ -1,0 +1,332 @@
+// fvp_conv_tc.cu - tcgen05 / TMEM implicit-GEMM convolution for the CenterNet / P2PNet trunks
+// (cnns_2d.py:12-178), same fused epilogues and NHWC fp32 interface as fvp_conv.cu (k_conv_nhwc).
+//
+// Precision: "3xTF32" error-compensated split.  Every fp32 operand x is split on the fly into
+// hi = tf32(x) (round-to-nearest) and lo = tf32(x - hi); D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulates
+// in fp32 in tensor memory.  A single kind::tf32 pass moves joints by 1.33 mm; the split keeps
+// the convolution at ~1e-6 relative of the exact-fp32 kernel (tests/test_gpu_parity.py compares both).
+//
+// GEMM view per CTA: M = 128 output pixels (tile 16 rows x 8 cols), N = N_TILE <= 128 output channels,
+// K = taps x Cin (+ Cin2 of the fused 1x1 skip conv).
+//   * A (activations): the (16+k-1)x(8+k-1) input halo of a 32-channel K-block is staged ONCE in shared memory
+//     as [channel-quad][halo pixel][4 floats] (the canonical K-major / no-swizzle UMMA layout: core matrix =
+//     8 pixels x 16 B contiguous).  Because the tile is 8 pixels wide, the operand of tap (dy,dx) is the same
+//     buffer with start address + (dy*HW+dx)*16 B and stride-byte-offset HW*16 B: nine taps = nine descriptors.
+//   * B (weights): pre-split hi/lo and pre-tiled on the host into the exact shared-memory image of each
+//     (K-block, tap, N-tile): a stage is one contiguous copy.
+//   * D: 128 lanes x N_TILE fp32 columns of TMEM; epilogue = tcgen05.ld 32x32b, bias/residual/ReLU, NHWC store
+//     (or pixel-shuffle for ConvTranspose k2s2, or planar store for the final layers).
+// Warp roles: warps 0-3 stage operands (A ring of 2, B ring of 3, mbarrier full/empty pairs; MMA completion
+// frees a slot through tcgen05.commit) and run the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4
+// allocates TMEM and one elected lane issues every tcgen05.mma.
+#include "fvp_kernels.h"
+
+namespace {
+
+constexpr int TC_TH = 16, TC_TW = 8;       // output tile (pixels)
+constexpr int TC_LOADERS = 128;            // warps 0..3
+constexpr int TC_THREADS = 160;            // + warp 4 (MMA issuer, TMEM owner)
+constexpr int TC_A_STAGES = 2, TC_B_STAGES = 3;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 28)) {        // watchdog: a protocol bug must abort the kernel, never hang the GPU
+      printf("k_conv_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4, [16,30) leading byte offset>>4 (stride between the two 16-B K chunks),
+//   [32,46) stride byte offset>>4 (stride between 8-row groups), [46,48) version = 1, layout type [61,64) = 0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N>>3, M>>4
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcArgs {
+  FvpConvArgs c;
+  const float* wtc;      // tiled hi/lo weights (see fvp_pack_tc in fvp_params.cu)
+  int n_tile;            // GEMM N of this launch (multiple of 16, <= 128)
+  int n_tiles;           // CoutPad / n_tile
+  int cib0, cib1;        // channels per K-block of the main / fused-skip phase (16 or 32)
+  uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  __shared__ uint64_t s_bar[2 * TC_A_STAGES + 2 * TC_B_STAGES + 1];
+  __shared__ uint32_t s_tmem;
+  const FvpConvArgs& a = t.c;
+  const int img = blockIdx.z;
+  if (a.valid && !a.valid[img]) return;
+
+  uint8_t* sA = tc_smem;                                           // [TC_A_STAGES][a_stage_bytes] (hi then lo)
+  uint8_t* sB = tc_smem + TC_A_STAGES * t.a_stage_bytes;           // [TC_B_STAGES][b_stage_bytes] (hi then lo)
+  uint64_t* a_full = s_bar;
+  uint64_t* a_empty = s_bar + TC_A_STAGES;
+  uint64_t* b_full = s_bar + 2 * TC_A_STAGES;
+  uint64_t* b_empty = b_full + TC_B_STAGES;
+  uint64_t* acc_full = b_empty + TC_B_STAGES;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tiles_x = (a.W + TC_TW - 1) / TC_TW;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int y0 = ty * TC_TH, x0 = tx * TC_TW;
+  const int nt = blockIdx.y;                                       // N tile
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(a_full + i, TC_LOADERS); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < TC_B_STAGES; ++i) { mbar_init(b_full + i, TC_LOADERS); mbar_init(b_empty + i, 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 4) {                                                 // TMEM allocation (power of two >= 32 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(t.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+
+  // K-block schedule shared by both roles: phase 0 = main conv (k x k taps), phase 1 = fused 1x1 skip conv
+  const int nph = a.in2 ? 2 : 1;
+
+  if (warp < 4) {
+    // =============================== operand staging ================================================
+    int a_it = 0, b_it = 0;
+    const float* wsrc = t.wtc;
+    for (int ph = 0; ph < nph; ++ph) {
+      const float* src = ph == 0 ? a.in : a.in2;
+      const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
+      const int CinP = (Cin + 15) & ~15, pad = (K - 1) / 2;
+      const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
+      const float* img_in = src + (size_t)img * a.H * a.W * Cin;
+      const size_t wblk = (size_t)cib * t.n_tile * 2;            // floats of one (K-block, tap, N-tile): hi + lo
+      for (int c0 = 0; c0 < CinP; c0 += cib) {
+        // ---- A: halo of channels [c0, c0+cib), split into tf32 hi / lo ----
+        const int as = a_it % TC_A_STAGES;
+        if (a_it >= TC_A_STAGES) mbar_wait(a_empty + as, ((a_it / TC_A_STAGES) - 1) & 1);
+        float4* hi = (float4*)(sA + (size_t)as * t.a_stage_bytes);
+        float4* lo = hi + nq * npix;
+        for (int i = tid; i < nq * npix; i += TC_LOADERS) {
+          const int q = i / npix, pix = i - q * npix;            // pixel fastest: conflict-free 16-B stores
+          const int hy = pix / HW, hx = pix - hy * HW;
+          const int gy = y0 + hy - pad, gx = x0 + hx - pad, c = c0 + q * 4;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < Cin)
+            v = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
+          float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+          hi[i] = h;
+          lo[i] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+        }
+        fence_proxy_async();
+        mbar_arrive(a_full + as);
+        ++a_it;
+        // ---- B: one stage per tap (pre-tiled image, contiguous) ----
+        for (int tap = 0; tap < K * K; ++tap) {
+          const int bs = b_it % TC_B_STAGES;
+          if (b_it >= TC_B_STAGES) mbar_wait(b_empty + bs, ((b_it / TC_B_STAGES) - 1) & 1);
+          const float4* g = (const float4*)(wsrc + ((size_t)tap * t.n_tiles + nt) * wblk);
+          float4* d = (float4*)(sB + (size_t)bs * t.b_stage_bytes);
+          const int n4 = (int)(wblk >> 2);
+          for (int i = tid; i < n4; i += TC_LOADERS) d[i] = __ldg(g + i);
+          fence_proxy_async();
+          mbar_arrive(b_full + bs);
+          ++b_it;
+        }
+        wsrc += (size_t)K * K * t.n_tiles * wblk;
+      }
+    }
+  } else if (tid == TC_LOADERS) {
+    // =============================== MMA issue (one thread) =========================================
+    const uint32_t idesc = umma_idesc_tf32(128, t.n_tile);
+    int a_it = 0, b_it = 0;
+    uint32_t accumulate = 0;
+    for (int ph = 0; ph < nph; ++ph) {
+      const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
+      const int CinP = (Cin + 15) & ~15;
+      const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
+      const uint32_t a_plane = (uint32_t)npix * 16, a_lo_off = (uint32_t)nq * a_plane;
+      const uint32_t b_plane = (uint32_t)t.n_tile * 16, b_lo_off = (uint32_t)nq * b_plane;
+      for (int c0 = 0; c0 < CinP; c0 += cib) {
+        const int as = a_it % TC_A_STAGES;
+        mbar_wait(a_full + as, (a_it / TC_A_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + (size_t)as * t.a_stage_bytes);
+        for (int tap = 0; tap < K * K; ++tap) {
+          const int bs = b_it % TC_B_STAGES;
+          mbar_wait(b_full + bs, (b_it / TC_B_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(sB + (size_t)bs * t.b_stage_bytes);
+          const int dy = tap / K, dx = tap - dy * K;
+          const uint32_t a_tap = a_base + (uint32_t)(dy * HW + dx) * 16;
+          // three passes: lo*hi, hi*lo, hi*hi (small terms first), K = 8 (two 16-B chunks) per instruction
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t ao = pass == 0 ? a_lo_off : 0u, bo = pass == 1 ? b_lo_off : 0u;
+            for (int kc = 0; kc < nq; kc += 2) {
+              const uint64_t ad = umma_desc(a_tap + ao + (uint32_t)kc * a_plane, a_plane, (uint32_t)HW * 16);
+              const uint64_t bd = umma_desc(b_base + bo + (uint32_t)kc * b_plane, b_plane, 128);
+              umma_tf32(tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(b_empty + bs);                               // B slot reusable when these MMAs retire
+          ++b_it;
+        }
+        umma_commit(a_empty + as);
+        ++a_it;
+      }
+    }
+    umma_commit(acc_full);
+  }
+
+  // =================================== epilogue (warps 0-3) ===========================================
+  if (warp < 4) {
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int r = tid;                                             // accumulator row = TMEM lane
+    const int oy = y0 + (r >> 3), ox = x0 + (r & 7);
+    const bool px_ok = oy < a.H && ox < a.W;
+    const int co_base = nt * t.n_tile;
+    for (int cb = 0; cb < t.n_tile; cb += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
+      if (!px_ok) continue;
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) {
+        const int co = co_base + cb + g4 * 4;
+        if (co >= a.CoutP) break;
+        const float4 bias = __ldg((const float4*)(a.bias + co));
+        float4 o = make_float4(v[g4 * 4] + bias.x, v[g4 * 4 + 1] + bias.y, v[g4 * 4 + 2] + bias.z, v[g4 * 4 + 3] + bias.w);
+        int Y = oy, X = ox, Ho = a.H, Wo = a.W, ch = co;
+        if (a.upsample) {                                          // co' = q*Co + c, q = dy*2+dx (ConvTranspose k2 s2)
+          const int Co = a.CoutP >> 2, q = co / Co;
+          ch = co - q * Co;
+          Y = 2 * oy + (q >> 1);
+          X = 2 * ox + (q & 1);
+          Ho = 2 * a.H;
+          Wo = 2 * a.W;
+        }
+        const size_t opix = ((size_t)img * Ho + Y) * Wo + X;
+        if (a.res_mode == 1) {
+          const float4 rr = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (a.res_mode == 2) {
+          const float4 rr = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        if (!a.nchw) {
+          *(float4*)(a.out + opix * a.CoutS + ch) = o;
+        } else {
+          const size_t plane = (size_t)Ho * Wo;
+          float* op = a.out + (size_t)img * a.CoutReal * plane + (size_t)Y * Wo + X;
+          const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (ch + e < a.CoutReal) op[(size_t)(ch + e) * plane] = ov[e];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(t.tmem_cols));
+  }
+}
+
+}  // namespace
+
+// host: geometry of the tiled weight image (must match fvp_pack_tc in fvp_params.cu)
+void fvp_tc_geometry(int cin, int cin2, int coutp, int* n_tile, int* n_tiles, int* cib0, int* cib1) {
+  const int npad = fvp_round_up(coutp, 16);
+  *n_tile = npad <= 128 ? npad : 128;
+  *n_tiles = fvp_cdiv(npad, *n_tile);
+  const int cinp = fvp_round_up(cin, 16);
+  *cib0 = cinp >= 32 ? 32 : 16;
+  const int cin2p = cin2 ? fvp_round_up(cin2, 16) : 0;
+  *cib1 = cin2p >= 32 ? 32 : 16;
+}
+
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc, cudaStream_t st) {
+  TcArgs t;
+  t.c = a;
+  t.wtc = wtc;
+  fvp_tc_geometry(a.Cin, a.in2 ? a.Cin2 : 0, a.CoutP, &t.n_tile, &t.n_tiles, &t.cib0, &t.cib1);
+  const int k = a.ksize;
+  const uint32_t a0 = (uint32_t)(t.cib0 / 4) * (TC_TW + k - 1) * (TC_TH + k - 1) * 16 * 2;
+  const uint32_t a1 = a.in2 ? (uint32_t)(t.cib1 / 4) * TC_TW * TC_TH * 16 * 2 : 0;
+  t.a_stage_bytes = (a0 > a1 ? a0 : a1);
+  t.a_stage_bytes = (t.a_stage_bytes + 127) & ~127u;
+  const int cibm = t.cib0 > t.cib1 && a.in2 ? t.cib0 : (a.in2 ? (t.cib1 > t.cib0 ? t.cib1 : t.cib0) : t.cib0);
+  t.b_stage_bytes = (uint32_t)cibm * t.n_tile * 4 * 2;
+  t.tmem_cols = 32;
+  while ((int)t.tmem_cols < t.n_tile) t.tmem_cols <<= 1;
+  const size_t smem = (size_t)TC_A_STAGES * t.a_stage_bytes + (size_t)TC_B_STAGES * t.b_stage_bytes;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr = true;
+  }
+  dim3 grid(fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW), t.n_tiles, a.n);
+  k_conv_tc<<<grid, TC_THREADS, smem, st>>>(t);
+}

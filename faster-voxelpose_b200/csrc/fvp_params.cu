@@ -180,40 +180,79 @@ struct Arena {
 };
 
 struct PendingConv {
-  size_t w_off, b_off;
+  size_t w_off, b_off, tc_off;
   int cin, cin2, coutp, k;
 };
 
-PendingConv stash(Arena& A, const Packed& p) {
+// cvt.rna.tf32.f32 on the host: round to nearest (ties away), keep 10 mantissa bits
+float tf32_rna(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+
+// Tiled tf32 hi/lo image of a packed conv for k_conv_tc: [phase][K-block][tap][N-tile]{hi[cib/4][n_tile][4], lo[...]}
+// (cin_act = channels of the activation tensor the kernel will see: JP for the first layer)
+std::vector<float> pack_tc(const Packed& p, int cin_act) {
+  int n_tile, n_tiles, cib0, cib1;
+  fvp_tc_geometry(cin_act, p.cin2, p.coutp, &n_tile, &n_tiles, &cib0, &cib1);
+  const int taps = p.k * p.k, cinP = fvp_round_up(p.cin, 16), cin2P = p.cin2 ? fvp_round_up(p.cin2, 16) : 0;
+  std::vector<float> out;
+  for (int ph = 0; ph < (p.cin2 ? 2 : 1); ++ph) {
+    const int K2 = ph == 0 ? taps : 1, CP = ph == 0 ? cinP : cin2P, cib = ph == 0 ? cib0 : cib1;
+    const int rowbase = ph == 0 ? 0 : taps * cinP;
+    for (int c0 = 0; c0 < CP; c0 += cib)
+      for (int tap = 0; tap < K2; ++tap)
+        for (int nt = 0; nt < n_tiles; ++nt)
+          for (int part = 0; part < 2; ++part)
+            for (int q = 0; q < cib / 4; ++q)
+              for (int n = 0; n < n_tile; ++n)
+                for (int e = 0; e < 4; ++e) {
+                  const int col = nt * n_tile + n, ci = c0 + q * 4 + e;
+                  float w = 0.f;
+                  if (col < p.coutp && ci < CP) w = p.w[(size_t)(rowbase + tap * CP + ci) * p.coutp + col];
+                  const float hi = tf32_rna(w);
+                  out.push_back(part == 0 ? hi : tf32_rna(w - hi));
+                }
+  }
+  return out;
+}
+
+PendingConv stash(Arena& A, const Packed& p, bool tc = false, int cin_act = 0) {
   PendingConv pc;
   pc.w_off = A.put(p.w);
   pc.b_off = A.put(p.b);
+  pc.tc_off = tc ? A.put(pack_tc(p, cin_act ? cin_act : p.cin)) : (size_t)-1;
   pc.cin = p.cin; pc.cin2 = p.cin2; pc.coutp = p.coutp; pc.k = p.k;
   return pc;
 }
 
 // the 19 trunk convs in execution order (see fvp_run_trunk2d / c2c_forward)
-void pack_trunk(const fvp_ctx* ctx, const std::string& p, Arena& A, std::vector<PendingConv>& out) {
+void pack_trunk(const fvp_ctx* ctx, const std::string& p, Arena& A, std::vector<PendingConv>& out, bool tc) {
   const std::string ed = p + ".encoder_decoder";
-  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.0.block.0")));
-  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.1.res_branch.0")));
-  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.1.res_branch.3", p + ".front_layers.1.skip_con.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res1.res_branch.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res1.res_branch.3")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res1.res_branch.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res1.res_branch.3", ed + ".encoder_res1.skip_con.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res2.res_branch.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res2.res_branch.3")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res2.res_branch.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res2.res_branch.3", ed + ".encoder_res2.skip_con.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".mid_res.res_branch.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".mid_res.res_branch.3")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res2.res_branch.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res2.res_branch.3")));
-  out.push_back(stash(A, pack_convT(ctx, ed + ".decoder_upsample2.block.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res1.res_branch.0")));
-  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res1.res_branch.3")));
-  out.push_back(stash(A, pack_convT(ctx, ed + ".decoder_upsample1.block.0")));
+  const int JP = ctx->geom.proj.JP;
+  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.0.block.0"), tc, JP));
+  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.1.res_branch.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, p + ".front_layers.1.res_branch.3", p + ".front_layers.1.skip_con.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res1.res_branch.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res1.res_branch.3"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res1.res_branch.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res1.res_branch.3", ed + ".encoder_res1.skip_con.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res2.res_branch.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".skip_res2.res_branch.3"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res2.res_branch.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".encoder_res2.res_branch.3", ed + ".encoder_res2.skip_con.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".mid_res.res_branch.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".mid_res.res_branch.3"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res2.res_branch.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res2.res_branch.3"), tc));
+  out.push_back(stash(A, pack_convT(ctx, ed + ".decoder_upsample2.block.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res1.res_branch.0"), tc));
+  out.push_back(stash(A, pack_conv(ctx, ed + ".decoder_res1.res_branch.3"), tc));
+  out.push_back(stash(A, pack_convT(ctx, ed + ".decoder_upsample1.block.0"), tc));
 }
 
 FvpConvW bind(const float* base, const PendingConv& pc) {
@@ -221,6 +260,7 @@ FvpConvW bind(const float* base, const PendingConv& pc) {
   w.w = base + pc.w_off;
   w.b = base + pc.b_off;
   w.cin = pc.cin; w.cin2 = pc.cin2; w.coutp = pc.coutp; w.k = pc.k;
+  w.wtc = pc.tc_off == (size_t)-1 ? nullptr : base + pc.tc_off;
   return w;
 }
 
@@ -238,7 +278,7 @@ int fvp_pack_params(fvp_ctx* ctx) {
   Arena A;
   std::vector<PendingConv> cn, c2c, p2p;
   // ---- CenterNet -----------------------------------------------------------------------------
-  pack_trunk(ctx, "pose_net.center_net", A, cn);
+  pack_trunk(ctx, "pose_net.center_net", A, cn, true);
   {
     // both 3x3 heads as one 32->64 conv (+ReLU), both 1x1 heads as one block-diagonal 64->4 conv
     const Packed a = pack_conv(ctx, "pose_net.center_net.output_hm.0");
@@ -253,7 +293,7 @@ int fvp_pack_params(fvp_ctx* ctx) {
         m.w[(size_t)r * 64 + 32 + c] = b.w[(size_t)r * 32 + c];
       }
     for (int c = 0; c < 32; ++c) { m.b[c] = a.b[c]; m.b[32 + c] = b.b[c]; }
-    cn.push_back(stash(A, m));
+    cn.push_back(stash(A, m, true));
     const std::vector<float>&wh = P(ctx, "pose_net.center_net.output_hm.2.weight"),
                       &bh = P(ctx, "pose_net.center_net.output_hm.2.bias"),
                       &ws = P(ctx, "pose_net.center_net.output_size.2.weight"),
@@ -268,14 +308,14 @@ int fvp_pack_params(fvp_ctx* ctx) {
       h.w[(size_t)(32 + ci) * 4 + 2] = ws[32 + ci];
     }
     h.b[0] = bh[0]; h.b[1] = bs[0]; h.b[2] = bs[1];
-    cn.push_back(stash(A, h));
+    cn.push_back(stash(A, h, true));
   }
   // ---- C2CNet --------------------------------------------------------------------------------
-  pack_trunk(ctx, "pose_net.c2c_net", A, c2c);
+  pack_trunk(ctx, "pose_net.c2c_net", A, c2c, false);
   c2c.push_back(stash(A, pack_conv(ctx, "pose_net.c2c_net.output_hm")));
   // ---- P2PNet --------------------------------------------------------------------------------
-  pack_trunk(ctx, "joint_net.conv_net", A, p2p);
-  p2p.push_back(stash(A, pack_conv(ctx, "joint_net.conv_net.output_layer")));
+  pack_trunk(ctx, "joint_net.conv_net", A, p2p, true);
+  p2p.push_back(stash(A, pack_conv(ctx, "joint_net.conv_net.output_layer"), true));
   // ---- WeightNet -----------------------------------------------------------------------------
   const std::string wn = "joint_net.weight_net";
   const FvpLayer& wl = *find_layer(ctx, wn + ".heatmap_feature_net.0");
@@ -304,7 +344,7 @@ int fvp_pack_params(fvp_ctx* ctx) {
   ctx->w_center.head_a = bind(base, cn[19]);
   ctx->w_center.head_b = bind(base, cn[20]);
   bind_trunk(base, p2p, ctx->w_p2p);
-  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0};
+  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0, nullptr};
   ctx->w_p2p.head_b = bind(base, p2p[19]);
   for (int i = 0; i < 20; ++i) {
     ctx->w_c2c.w[i] = base + c2c[i].w_off;

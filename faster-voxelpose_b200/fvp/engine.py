@@ -208,6 +208,10 @@ class Engine:
     def use_cuda_graph(self, on: bool = True) -> None:
         self._ck(self.lib.fvp_use_cuda_graph(self.ctx, 1 if on else 0))
 
+    def set_conv_mode(self, mode: int) -> None:
+        """0 = fp32 CUDA-core convolutions, 1 = tcgen05 3xTF32 convolutions."""
+        self._ck(self.lib.fvp_set_conv_mode(self.ctx, int(mode)))
+
     def set_profiling(self, on: bool) -> None:
         self._ck(self.lib.fvp_set_profiling(self.ctx, 1 if on else 0))
 

@@ -151,6 +151,10 @@ int fvp_pose_head(fvp_ctx* ctx, const float* d_feat, const float* d_offset, int 
 /* C2CNet alone (cnns_1d.py:128-132): [n][J][Z] -> [n][Z] */
 int fvp_c2c_net(fvp_ctx* ctx, const float* d_cols, int n, float* d_hm1d, uintptr_t stream);
 
+/* convolution engine of CenterNet / P2PNet: 0 = exact-fp32 CUDA-core implicit GEMM, 1 = tcgen05/TMEM implicit GEMM with
+ * the error-compensated 3xTF32 split (default set at build time) */
+int fvp_set_conv_mode(fvp_ctx* ctx, int mode);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* number of kernel launches the last fvp_forward enqueued (graph replay counts its kernel nodes) */
 int fvp_last_launch_count(const fvp_ctx* ctx);
