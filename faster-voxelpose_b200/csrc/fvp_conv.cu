@@ -217,7 +217,7 @@ static void conv(const FvpConvW& w, const float* in, int H, int W, const float* 
   a.out = out; a.CoutP = w.coutp; a.CoutS = couts; a.CoutReal = cout_real;
   a.res = res; a.res_mode = res_mode; a.relu = relu; a.ksize = w.k; a.upsample = upsample;
   a.nchw = nchw; a.n = n; a.valid = valid;
-  if (g_tc && w.wtc) fvp_launch_conv_tc(a, w.wtc, st);
+  if (g_tc && w.wtc) fvp_launch_conv_tc(a, w.wtc, w.wtc_narrow, 148, st);
   else fvp_launch_conv(a, st);
   if (launches) ++*launches;
 }

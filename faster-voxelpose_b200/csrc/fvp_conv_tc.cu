@@ -24,9 +24,9 @@
 namespace {
 
 constexpr int TC_TH = 16, TC_TW = 8;       // output tile (pixels)
-constexpr int TC_LOADERS = 128;            // warps 0..3
-constexpr int TC_THREADS = 160;            // + warp 4 (MMA issuer, TMEM owner)
-constexpr int TC_A_STAGES = 2, TC_B_STAGES = 3;
+constexpr int TC_LOADERS = 128;            // warps 0..3: A staging + epilogue
+constexpr int TC_THREADS = 192;            // + warp 4 (MMA issuer, TMEM owner) + warp 5 (weight TMA producer)
+constexpr int TC_MAX_A = 2, TC_MAX_B = 4;  // ring depths are chosen per launch (a_stages, b_stages)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -36,6 +36,15 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared by the TMA engine (SASS UBLKCP), completion signalled on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -104,23 +113,25 @@ struct TcArgs {
   int n_tiles;           // CoutPad / n_tile
   int cib0, cib1;        // channels per K-block of the main / fused-skip phase (16 or 32)
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+  int a_stages, b_stages;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
+__global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs t) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
-  __shared__ uint64_t s_bar[2 * TC_A_STAGES + 2 * TC_B_STAGES + 1];
+  __shared__ uint64_t s_bar[2 * TC_MAX_A + 2 * TC_MAX_B + 1];
   __shared__ uint32_t s_tmem;
   const FvpConvArgs& a = t.c;
   const int img = blockIdx.z;
   if (a.valid && !a.valid[img]) return;
 
   uint8_t* sA = tc_smem;                                           // [TC_A_STAGES][a_stage_bytes] (hi then lo)
+  const int TC_A_STAGES = t.a_stages, TC_B_STAGES = t.b_stages;
   uint8_t* sB = tc_smem + TC_A_STAGES * t.a_stage_bytes;           // [TC_B_STAGES][b_stage_bytes] (hi then lo)
   uint64_t* a_full = s_bar;
-  uint64_t* a_empty = s_bar + TC_A_STAGES;
-  uint64_t* b_full = s_bar + 2 * TC_A_STAGES;
-  uint64_t* b_empty = b_full + TC_B_STAGES;
-  uint64_t* acc_full = b_empty + TC_B_STAGES;
+  uint64_t* a_empty = s_bar + TC_MAX_A;
+  uint64_t* b_full = s_bar + 2 * TC_MAX_A;
+  uint64_t* b_empty = b_full + TC_MAX_B;
+  uint64_t* acc_full = b_empty + TC_MAX_B;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tiles_x = (a.W + TC_TW - 1) / TC_TW;
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
 
   if (tid == 0) {
     for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(a_full + i, TC_LOADERS); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < TC_B_STAGES; ++i) { mbar_init(b_full + i, TC_LOADERS); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < TC_B_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -147,46 +158,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   const int nph = a.in2 ? 2 : 1;
 
   if (warp < 4) {
-    // =============================== operand staging ================================================
-    int a_it = 0, b_it = 0;
-    const float* wsrc = t.wtc;
+    // =============================== A staging (128 threads) ========================================
+    int a_it = 0;
     for (int ph = 0; ph < nph; ++ph) {
       const float* src = ph == 0 ? a.in : a.in2;
       const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
       const int CinP = (Cin + 15) & ~15, pad = (K - 1) / 2;
       const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
+      const int plane4 = npix + 1;                               // +16 B: the nq planes land on distinct banks
       const float* img_in = src + (size_t)img * a.H * a.W * Cin;
-      const size_t wblk = (size_t)cib * t.n_tile * 2;            // floats of one (K-block, tap, N-tile): hi + lo
       for (int c0 = 0; c0 < CinP; c0 += cib) {
-        // ---- A: halo of channels [c0, c0+cib), split into tf32 hi / lo ----
         const int as = a_it % TC_A_STAGES;
         if (a_it >= TC_A_STAGES) mbar_wait(a_empty + as, ((a_it / TC_A_STAGES) - 1) & 1);
         float4* hi = (float4*)(sA + (size_t)as * t.a_stage_bytes);
-        float4* lo = hi + nq * npix;
+        float4* lo = hi + nq * plane4;
         for (int i = tid; i < nq * npix; i += TC_LOADERS) {
-          const int q = i / npix, pix = i - q * npix;            // pixel fastest: conflict-free 16-B stores
+          const int pix = i / nq, q = i - pix * nq;              // channel quad fastest: 16*nq-byte coalesced reads
           const int hy = pix / HW, hx = pix - hy * HW;
           const int gy = y0 + hy - pad, gx = x0 + hx - pad, c = c0 + q * 4;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < Cin)
             v = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
           float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-          hi[i] = h;
-          lo[i] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+          hi[q * plane4 + pix] = h;
+          lo[q * plane4 + pix] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
         }
         fence_proxy_async();
         mbar_arrive(a_full + as);
         ++a_it;
-        // ---- B: one stage per tap (pre-tiled image, contiguous) ----
+      }
+    }
+  } else if (tid == TC_LOADERS + 32) {
+    // =============================== B producer: one TMA bulk copy per (K-block, tap) ================
+    int b_it = 0;
+    const float* wsrc = t.wtc;
+    for (int ph = 0; ph < nph; ++ph) {
+      const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
+      const int CinP = (Cin + 15) & ~15;
+      const size_t wblk = (size_t)cib * t.n_tile * 2;            // floats of one (K-block, tap, N-tile): hi + lo
+      for (int c0 = 0; c0 < CinP; c0 += cib) {
         for (int tap = 0; tap < K * K; ++tap) {
           const int bs = b_it % TC_B_STAGES;
           if (b_it >= TC_B_STAGES) mbar_wait(b_empty + bs, ((b_it / TC_B_STAGES) - 1) & 1);
-          const float4* g = (const float4*)(wsrc + ((size_t)tap * t.n_tiles + nt) * wblk);
-          float4* d = (float4*)(sB + (size_t)bs * t.b_stage_bytes);
-          const int n4 = (int)(wblk >> 2);
-          for (int i = tid; i < n4; i += TC_LOADERS) d[i] = __ldg(g + i);
-          fence_proxy_async();
-          mbar_arrive(b_full + bs);
+          mbar_arrive_expect_tx(b_full + bs, (uint32_t)(wblk * 4));
+          tma_bulk_g2s(sB + (size_t)bs * t.b_stage_bytes, wsrc + ((size_t)tap * t.n_tiles + nt) * wblk, (uint32_t)(wblk * 4),
+                       b_full + bs);
           ++b_it;
         }
         wsrc += (size_t)K * K * t.n_tiles * wblk;
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
       const int CinP = (Cin + 15) & ~15;
       const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
-      const uint32_t a_plane = (uint32_t)npix * 16, a_lo_off = (uint32_t)nq * a_plane;
+      const uint32_t a_plane = (uint32_t)(npix + 1) * 16, a_lo_off = (uint32_t)nq * a_plane;
       const uint32_t b_plane = (uint32_t)t.n_tile * 16, b_lo_off = (uint32_t)nq * b_plane;
       for (int c0 = 0; c0 < CinP; c0 += cib) {
         const int as = a_it % TC_A_STAGES;
@@ -296,10 +312,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
 
 }  // namespace
 
-// host: geometry of the tiled weight image (must match fvp_pack_tc in fvp_params.cu)
-void fvp_tc_geometry(int cin, int cin2, int coutp, int* n_tile, int* n_tiles, int* cib0, int* cib1) {
+// host: geometry of the tiled weight image (must match pack_tc in fvp_params.cu).  narrow = 32-column N tiles
+// (more CTAs for small launches), otherwise up to 128 columns per CTA.
+void fvp_tc_geometry(int cin, int cin2, int coutp, int narrow, int* n_tile, int* n_tiles, int* cib0, int* cib1) {
   const int npad = fvp_round_up(coutp, 16);
-  *n_tile = npad <= 128 ? npad : 128;
+  const int cap = narrow ? 32 : 128;
+  *n_tile = npad <= cap ? npad : cap;
   *n_tiles = fvp_cdiv(npad, *n_tile);
   const int cinp = fvp_round_up(cin, 16);
   *cib0 = cinp >= 32 ? 32 : 16;
@@ -307,21 +325,27 @@ void fvp_tc_geometry(int cin, int cin2, int coutp, int* n_tile, int* n_tiles, in
   *cib1 = cin2p >= 32 ? 32 : 16;
 }
 
-void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc, cudaStream_t st) {
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int num_sms, cudaStream_t st) {
   TcArgs t;
   t.c = a;
-  t.wtc = wtc;
-  fvp_tc_geometry(a.Cin, a.in2 ? a.Cin2 : 0, a.CoutP, &t.n_tile, &t.n_tiles, &t.cib0, &t.cib1);
+  const int tiles = fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW) * a.n;
+  int n_tile, n_tiles, cib0, cib1;
+  fvp_tc_geometry(a.Cin, a.in2 ? a.Cin2 : 0, a.CoutP, 0, &n_tile, &n_tiles, &cib0, &cib1);
+  const int narrow = (wtc_narrow != nullptr && n_tile > 32 && tiles * n_tiles < 2 * num_sms) ? 1 : 0;
+  fvp_tc_geometry(a.Cin, a.in2 ? a.Cin2 : 0, a.CoutP, narrow, &t.n_tile, &t.n_tiles, &t.cib0, &t.cib1);
+  t.wtc = narrow ? wtc_narrow : wtc_wide;
   const int k = a.ksize;
-  const uint32_t a0 = (uint32_t)(t.cib0 / 4) * (TC_TW + k - 1) * (TC_TH + k - 1) * 16 * 2;
-  const uint32_t a1 = a.in2 ? (uint32_t)(t.cib1 / 4) * TC_TW * TC_TH * 16 * 2 : 0;
-  t.a_stage_bytes = (a0 > a1 ? a0 : a1);
-  t.a_stage_bytes = (t.a_stage_bytes + 127) & ~127u;
-  const int cibm = t.cib0 > t.cib1 && a.in2 ? t.cib0 : (a.in2 ? (t.cib1 > t.cib0 ? t.cib1 : t.cib0) : t.cib0);
+  const uint32_t a0 = (uint32_t)(t.cib0 / 4) * ((TC_TW + k - 1) * (TC_TH + k - 1) + 1) * 16 * 2;
+  const uint32_t a1 = a.in2 ? (uint32_t)(t.cib1 / 4) * (TC_TW * TC_TH + 1) * 16 * 2 : 0;
+  t.a_stage_bytes = ((a0 > a1 ? a0 : a1) + 127) & ~127u;
+  const int cibm = a.in2 && t.cib1 > t.cib0 ? t.cib1 : t.cib0;
   t.b_stage_bytes = (uint32_t)cibm * t.n_tile * 4 * 2;
+  const int kblocks = fvp_round_up(a.Cin, 16) / t.cib0 + (a.in2 ? fvp_round_up(a.Cin2, 16) / t.cib1 : 0);
+  t.b_stages = t.n_tile > 64 ? 3 : 4;
+  t.a_stages = (kblocks > 1 && t.n_tile > 64) ? 2 : 1;          // wide tiles run 1 CTA/SM: keep the MMA stream fed
   t.tmem_cols = 32;
   while ((int)t.tmem_cols < t.n_tile) t.tmem_cols <<= 1;
-  const size_t smem = (size_t)TC_A_STAGES * t.a_stage_bytes + (size_t)TC_B_STAGES * t.b_stage_bytes;
+  const size_t smem = (size_t)t.a_stages * t.a_stage_bytes + (size_t)t.b_stages * t.b_stage_bytes;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

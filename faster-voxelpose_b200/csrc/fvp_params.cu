@@ -180,7 +180,7 @@ struct Arena {
 };
 
 struct PendingConv {
-  size_t w_off, b_off, tc_off;
+  size_t w_off, b_off, tc_off, tcn_off;
   int cin, cin2, coutp, k;
 };
 
@@ -196,9 +196,9 @@ float tf32_rna(float x) {
 
 // Tiled tf32 hi/lo image of a packed conv for k_conv_tc: [phase][K-block][tap][N-tile]{hi[cib/4][n_tile][4], lo[...]}
 // (cin_act = channels of the activation tensor the kernel will see: JP for the first layer)
-std::vector<float> pack_tc(const Packed& p, int cin_act) {
+std::vector<float> pack_tc(const Packed& p, int cin_act, int narrow) {
   int n_tile, n_tiles, cib0, cib1;
-  fvp_tc_geometry(cin_act, p.cin2, p.coutp, &n_tile, &n_tiles, &cib0, &cib1);
+  fvp_tc_geometry(cin_act, p.cin2, p.coutp, narrow, &n_tile, &n_tiles, &cib0, &cib1);
   const int taps = p.k * p.k, cinP = fvp_round_up(p.cin, 16), cin2P = p.cin2 ? fvp_round_up(p.cin2, 16) : 0;
   std::vector<float> out;
   for (int ph = 0; ph < (p.cin2 ? 2 : 1); ++ph) {
@@ -225,7 +225,8 @@ PendingConv stash(Arena& A, const Packed& p, bool tc = false, int cin_act = 0) {
   PendingConv pc;
   pc.w_off = A.put(p.w);
   pc.b_off = A.put(p.b);
-  pc.tc_off = tc ? A.put(pack_tc(p, cin_act ? cin_act : p.cin)) : (size_t)-1;
+  pc.tc_off = tc ? A.put(pack_tc(p, cin_act ? cin_act : p.cin, 0)) : (size_t)-1;
+  pc.tcn_off = (tc && fvp_round_up(p.coutp, 16) > 32) ? A.put(pack_tc(p, cin_act ? cin_act : p.cin, 1)) : (size_t)-1;
   pc.cin = p.cin; pc.cin2 = p.cin2; pc.coutp = p.coutp; pc.k = p.k;
   return pc;
 }
@@ -261,6 +262,7 @@ FvpConvW bind(const float* base, const PendingConv& pc) {
   w.b = base + pc.b_off;
   w.cin = pc.cin; w.cin2 = pc.cin2; w.coutp = pc.coutp; w.k = pc.k;
   w.wtc = pc.tc_off == (size_t)-1 ? nullptr : base + pc.tc_off;
+  w.wtc_narrow = pc.tcn_off == (size_t)-1 ? nullptr : base + pc.tcn_off;
   return w;
 }
 
@@ -344,7 +346,7 @@ int fvp_pack_params(fvp_ctx* ctx) {
   ctx->w_center.head_a = bind(base, cn[19]);
   ctx->w_center.head_b = bind(base, cn[20]);
   bind_trunk(base, p2p, ctx->w_p2p);
-  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0, nullptr};
+  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr};
   ctx->w_p2p.head_b = bind(base, p2p[19]);
   for (int i = 0; i < 20; ++i) {
     ctx->w_c2c.w[i] = base + c2c[i].w_off;
