@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--preset", default="panoptic_256x192")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--conv-mode", type=int, default=-1, help="-1 library default, 0 fp32 CUDA cores, 1 tcgen05 3xTF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -195,6 +196,8 @@ def main():
     B = args.batch
     eng = Engine(cfg, dev, max_batch=B, max_sequences=1)
     eng.load_state_dict(sd_np)
+    if args.conv_mode >= 0:
+        eng.set_conv_mode(args.conv_mode)
     slot = eng.sequence_slot(cams, resize)
     slots = [slot] * B
     frames = make_frames(cfg, cams, POOL, seed0=1000 + 100 * rank)           # distinct frames per rank

@@ -25,7 +25,8 @@ namespace {
 
 constexpr int TC_TH = 16, TC_TW = 8;       // output tile (pixels)
 constexpr int TC_LOADERS = 128;            // warps 0..3: A staging + epilogue
-constexpr int TC_THREADS = 192;            // + warp 4 (MMA issuer, TMEM owner) + warp 5 (weight TMA producer)
+constexpr int TC_THREADS = 320;            // + warp 4 (MMA issuer, TMEM owner), warp 5 (weight TMA producer), warps 6-9 (epilogue)
+constexpr int TC_EPI = 128;
 constexpr int TC_MAX_A = 2, TC_MAX_B = 4;  // ring depths are chosen per launch (a_stages, b_stages)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -108,41 +109,57 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 struct TcArgs {
   FvpConvArgs c;
-  const float* wtc;      // tiled hi/lo weights (see fvp_pack_tc in fvp_params.cu)
+  const float* wtc;      // tiled hi/lo weights (see pack_tc in fvp_params.cu)
   int n_tile;            // GEMM N of this launch (multiple of 16, <= 128)
   int n_tiles;           // CoutPad / n_tile
   int cib0, cib1;        // channels per K-block of the main / fused-skip phase (16 or 32)
-  uint32_t a_stage_bytes, b_stage_bytes, tmem_cols;
+  uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, acc_stride;
   int a_stages, b_stages;
+  int tiles_x, tiles_per_img, total_items;   // work item = (image, tile, N tile)
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs t) {
+struct TcItem {
+  int img, y0, x0, nt;
+};
+__device__ __forceinline__ bool tc_decode(const TcArgs& t, int item, TcItem& w) {
+  const int nt = item % t.n_tiles, r = item / t.n_tiles;
+  w.nt = nt;
+  w.img = r / t.tiles_per_img;
+  const int tile = r - w.img * t.tiles_per_img;
+  const int ty = tile / t.tiles_x;
+  w.y0 = ty * TC_TH;
+  w.x0 = (tile - ty * t.tiles_x) * TC_TW;
+  return !(t.c.valid && !t.c.valid[w.img]);
+}
+
+// Persistent CTA (one per SM), 10 warps:
+//   warps 0-3  A staging   : halo of the next K-block -> tf32 hi/lo planes            (a_full / a_empty ring)
+//   warp  4    MMA issue   : one lane issues every tcgen05.mma; owns the TMEM allocation
+//   warp  5    B producer  : one lane issues one TMA bulk copy per (K-block, tap)       (b_full / b_empty ring)
+//   warps 6-9  epilogue    : tcgen05.ld of the finished accumulator, bias/residual/ReLU, stores
+// Two accumulator buffers in TMEM (acc_full / acc_empty) let the MMAs of tile i+1 run under the epilogue of
+// tile i, and the staging of tile i+1 under the MMAs of tile i.
+__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
-  __shared__ uint64_t s_bar[2 * TC_MAX_A + 2 * TC_MAX_B + 1];
+  __shared__ uint64_t s_bar[2 * TC_MAX_A + 2 * TC_MAX_B + 4];
   __shared__ uint32_t s_tmem;
   const FvpConvArgs& a = t.c;
-  const int img = blockIdx.z;
-  if (a.valid && !a.valid[img]) return;
 
-  uint8_t* sA = tc_smem;                                           // [TC_A_STAGES][a_stage_bytes] (hi then lo)
-  const int TC_A_STAGES = t.a_stages, TC_B_STAGES = t.b_stages;
-  uint8_t* sB = tc_smem + TC_A_STAGES * t.a_stage_bytes;           // [TC_B_STAGES][b_stage_bytes] (hi then lo)
+  const int A_ST = t.a_stages, B_ST = t.b_stages;
+  uint8_t* sA = tc_smem;                                           // [A_ST][a_stage_bytes] (hi then lo)
+  uint8_t* sB = tc_smem + A_ST * t.a_stage_bytes;                  // [B_ST][b_stage_bytes] (hi then lo)
   uint64_t* a_full = s_bar;
   uint64_t* a_empty = s_bar + TC_MAX_A;
   uint64_t* b_full = s_bar + 2 * TC_MAX_A;
   uint64_t* b_empty = b_full + TC_MAX_B;
-  uint64_t* acc_full = b_empty + TC_MAX_B;
+  uint64_t* acc_full = b_empty + TC_MAX_B;                         // [2]
+  uint64_t* acc_empty = acc_full + 2;                              // [2]
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tiles_x = (a.W + TC_TW - 1) / TC_TW;
-  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int y0 = ty * TC_TH, x0 = tx * TC_TW;
-  const int nt = blockIdx.y;                                       // N tile
-
   if (tid == 0) {
-    for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(a_full + i, TC_LOADERS); mbar_init(a_empty + i, 1); }
-    for (int i = 0; i < TC_B_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < A_ST; ++i) { mbar_init(a_full + i, TC_LOADERS); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < B_ST; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 4) {                                                 // TMEM allocation (power of two >= 32 columns)
@@ -153,153 +170,179 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs t) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
-
-  // K-block schedule shared by both roles: phase 0 = main conv (k x k taps), phase 1 = fused 1x1 skip conv
   const int nph = a.in2 ? 2 : 1;
 
   if (warp < 4) {
     // =============================== A staging (128 threads) ========================================
     int a_it = 0;
-    for (int ph = 0; ph < nph; ++ph) {
-      const float* src = ph == 0 ? a.in : a.in2;
-      const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
-      const int CinP = (Cin + 15) & ~15, pad = (K - 1) / 2;
-      const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
-      const int plane4 = npix + 1;                               // +16 B: the nq planes land on distinct banks
-      const float* img_in = src + (size_t)img * a.H * a.W * Cin;
-      for (int c0 = 0; c0 < CinP; c0 += cib) {
-        const int as = a_it % TC_A_STAGES;
-        if (a_it >= TC_A_STAGES) mbar_wait(a_empty + as, ((a_it / TC_A_STAGES) - 1) & 1);
-        float4* hi = (float4*)(sA + (size_t)as * t.a_stage_bytes);
-        float4* lo = hi + nq * plane4;
-        for (int i = tid; i < nq * npix; i += TC_LOADERS) {
-          const int pix = i / nq, q = i - pix * nq;              // channel quad fastest: 16*nq-byte coalesced reads
-          const int hy = pix / HW, hx = pix - hy * HW;
-          const int gy = y0 + hy - pad, gx = x0 + hx - pad, c = c0 + q * 4;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < Cin)
-            v = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
-          float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-          hi[q * plane4 + pix] = h;
-          lo[q * plane4 + pix] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+    for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
+      TcItem w;
+      if (!tc_decode(t, item, w)) continue;
+      for (int ph = 0; ph < nph; ++ph) {
+        const float* src = ph == 0 ? a.in : a.in2;
+        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
+        const int CinP = (Cin + 15) & ~15, pad = (K - 1) / 2;
+        const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
+        const int plane4 = npix + 1;                             // +16 B: the nq planes land on distinct banks
+        const float* img_in = src + (size_t)w.img * a.H * a.W * Cin;
+        for (int c0 = 0; c0 < CinP; c0 += cib) {
+          const int as = a_it % A_ST;
+          if (a_it >= A_ST) mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1);
+          float4* hi = (float4*)(sA + (size_t)as * t.a_stage_bytes);
+          float4* lo = hi + nq * plane4;
+          for (int i = tid; i < nq * npix; i += TC_LOADERS) {
+            const int pix = i / nq, q = i - pix * nq;            // channel quad fastest: coalesced reads
+            const int hy = pix / HW, hx = pix - hy * HW;
+            const int gy = w.y0 + hy - pad, gx = w.x0 + hx - pad, c = c0 + q * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < Cin)
+              v = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
+            float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            hi[q * plane4 + pix] = h;
+            lo[q * plane4 + pix] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+          }
+          fence_proxy_async();
+          mbar_arrive(a_full + as);
+          ++a_it;
         }
-        fence_proxy_async();
-        mbar_arrive(a_full + as);
-        ++a_it;
       }
     }
   } else if (tid == TC_LOADERS + 32) {
     // =============================== B producer: one TMA bulk copy per (K-block, tap) ================
     int b_it = 0;
-    const float* wsrc = t.wtc;
-    for (int ph = 0; ph < nph; ++ph) {
-      const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
-      const int CinP = (Cin + 15) & ~15;
-      const size_t wblk = (size_t)cib * t.n_tile * 2;            // floats of one (K-block, tap, N-tile): hi + lo
-      for (int c0 = 0; c0 < CinP; c0 += cib) {
-        for (int tap = 0; tap < K * K; ++tap) {
-          const int bs = b_it % TC_B_STAGES;
-          if (b_it >= TC_B_STAGES) mbar_wait(b_empty + bs, ((b_it / TC_B_STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(b_full + bs, (uint32_t)(wblk * 4));
-          tma_bulk_g2s(sB + (size_t)bs * t.b_stage_bytes, wsrc + ((size_t)tap * t.n_tiles + nt) * wblk, (uint32_t)(wblk * 4),
-                       b_full + bs);
-          ++b_it;
+    for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
+      TcItem w;
+      if (!tc_decode(t, item, w)) continue;
+      const float* wsrc = t.wtc;
+      for (int ph = 0; ph < nph; ++ph) {
+        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
+        const int CinP = (Cin + 15) & ~15;
+        const size_t wblk = (size_t)cib * t.n_tile * 2;          // floats of one (K-block, tap, N-tile): hi + lo
+        for (int c0 = 0; c0 < CinP; c0 += cib) {
+          for (int tap = 0; tap < K * K; ++tap) {
+            const int bs = b_it % B_ST;
+            if (b_it >= B_ST) mbar_wait(b_empty + bs, ((b_it / B_ST) - 1) & 1);
+            mbar_arrive_expect_tx(b_full + bs, (uint32_t)(wblk * 4));
+            tma_bulk_g2s(sB + (size_t)bs * t.b_stage_bytes, wsrc + ((size_t)tap * t.n_tiles + w.nt) * wblk,
+                         (uint32_t)(wblk * 4), b_full + bs);
+            ++b_it;
+          }
+          wsrc += (size_t)K * K * t.n_tiles * wblk;
         }
-        wsrc += (size_t)K * K * t.n_tiles * wblk;
       }
     }
   } else if (tid == TC_LOADERS) {
     // =============================== MMA issue (one thread) =========================================
     const uint32_t idesc = umma_idesc_tf32(128, t.n_tile);
-    int a_it = 0, b_it = 0;
-    uint32_t accumulate = 0;
-    for (int ph = 0; ph < nph; ++ph) {
-      const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
-      const int CinP = (Cin + 15) & ~15;
-      const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
-      const uint32_t a_plane = (uint32_t)(npix + 1) * 16, a_lo_off = (uint32_t)nq * a_plane;
-      const uint32_t b_plane = (uint32_t)t.n_tile * 16, b_lo_off = (uint32_t)nq * b_plane;
-      for (int c0 = 0; c0 < CinP; c0 += cib) {
-        const int as = a_it % TC_A_STAGES;
-        mbar_wait(a_full + as, (a_it / TC_A_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + (size_t)as * t.a_stage_bytes);
-        for (int tap = 0; tap < K * K; ++tap) {
-          const int bs = b_it % TC_B_STAGES;
-          mbar_wait(b_full + bs, (b_it / TC_B_STAGES) & 1);
+    int a_it = 0, b_it = 0, it = 0;
+    for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
+      TcItem w;
+      if (!tc_decode(t, item, w)) continue;
+      const int buf = it & 1;
+      if (it >= 2) mbar_wait(acc_empty + buf, ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem + (uint32_t)buf * t.acc_stride;
+      uint32_t accumulate = 0;
+      for (int ph = 0; ph < nph; ++ph) {
+        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
+        const int CinP = (Cin + 15) & ~15;
+        const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
+        const uint32_t a_plane = (uint32_t)(npix + 1) * 16, a_lo_off = (uint32_t)nq * a_plane;
+        const uint32_t b_plane = (uint32_t)t.n_tile * 16, b_lo_off = (uint32_t)nq * b_plane;
+        for (int c0 = 0; c0 < CinP; c0 += cib) {
+          const int as = a_it % A_ST;
+          mbar_wait(a_full + as, (a_it / A_ST) & 1);
           tc_fence_after();
-          const uint32_t b_base = smem_u32(sB + (size_t)bs * t.b_stage_bytes);
-          const int dy = tap / K, dx = tap - dy * K;
-          const uint32_t a_tap = a_base + (uint32_t)(dy * HW + dx) * 16;
-          // three passes: lo*hi, hi*lo, hi*hi (small terms first), K = 8 (two 16-B chunks) per instruction
+          const uint32_t a_base = smem_u32(sA + (size_t)as * t.a_stage_bytes);
+          for (int tap = 0; tap < K * K; ++tap) {
+            const int bs = b_it % B_ST;
+            mbar_wait(b_full + bs, (b_it / B_ST) & 1);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(sB + (size_t)bs * t.b_stage_bytes);
+            const int dy = tap / K, dx = tap - dy * K;
+            const uint32_t a_tap = a_base + (uint32_t)(dy * HW + dx) * 16;
+            // three passes: lo*hi, hi*lo, hi*hi (small terms first), K = 8 (two 16-B chunks) per instruction
 #pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t ao = pass == 0 ? a_lo_off : 0u, bo = pass == 1 ? b_lo_off : 0u;
-            for (int kc = 0; kc < nq; kc += 2) {
-              const uint64_t ad = umma_desc(a_tap + ao + (uint32_t)kc * a_plane, a_plane, (uint32_t)HW * 16);
-              const uint64_t bd = umma_desc(b_base + bo + (uint32_t)kc * b_plane, b_plane, 128);
-              umma_tf32(tmem, ad, bd, idesc, accumulate);
-              accumulate = 1;
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t ao = pass == 0 ? a_lo_off : 0u, bo = pass == 1 ? b_lo_off : 0u;
+              for (int kc = 0; kc < nq; kc += 2) {
+                const uint64_t ad = umma_desc(a_tap + ao + (uint32_t)kc * a_plane, a_plane, (uint32_t)HW * 16);
+                const uint64_t bd = umma_desc(b_base + bo + (uint32_t)kc * b_plane, b_plane, 128);
+                umma_tf32(d_tmem, ad, bd, idesc, accumulate);
+                accumulate = 1;
+              }
             }
+            umma_commit(b_empty + bs);                             // B slot reusable when these MMAs retire
+            ++b_it;
           }
-          umma_commit(b_empty + bs);                               // B slot reusable when these MMAs retire
-          ++b_it;
+          umma_commit(a_empty + as);
+          ++a_it;
         }
-        umma_commit(a_empty + as);
-        ++a_it;
       }
+      umma_commit(acc_full + buf);
+      ++it;
     }
-    umma_commit(acc_full);
-  }
-
-  // =================================== epilogue (warps 0-3) ===========================================
-  if (warp < 4) {
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int r = tid;                                             // accumulator row = TMEM lane
-    const int oy = y0 + (r >> 3), ox = x0 + (r & 7);
-    const bool px_ok = oy < a.H && ox < a.W;
-    const int co_base = nt * t.n_tile;
-    for (int cb = 0; cb < t.n_tile; cb += 16) {
-      float v[16];
-      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);
-      if (!px_ok) continue;
+  } else if (warp >= 6) {
+    // =================================== epilogue (warps 6-9) =========================================
+    const int quarter = warp & 3;                                  // TMEM lanes this warp may read
+    const int r = quarter * 32 + (tid & 31);                       // accumulator row = output pixel of the tile
+    int it = 0;
+    for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
+      TcItem w;
+      if (!tc_decode(t, item, w)) continue;
+      const int buf = it & 1;
+      mbar_wait(acc_full + buf, (it >> 1) & 1);
+      tc_fence_after();
+      const int oy = w.y0 + (r >> 3), ox = w.x0 + (r & 7);
+      const bool px_ok = oy < a.H && ox < a.W;
+      const int co_base = w.nt * t.n_tile;
+      const uint32_t t_row = tmem + (uint32_t)buf * t.acc_stride + ((uint32_t)(quarter * 32) << 16);
+      for (int cb = 0; cb < t.n_tile; cb += 16) {
+        float v[16];
+        tmem_ld16(t_row + (uint32_t)cb, v);
+        if (cb + 16 >= t.n_tile) {                                 // last chunk read: hand the accumulator back
+          tc_fence_before();
+          mbar_arrive(acc_empty + buf);
+        }
+        if (!px_ok) continue;
 #pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const int co = co_base + cb + g4 * 4;
-        if (co >= a.CoutP) break;
-        const float4 bias = __ldg((const float4*)(a.bias + co));
-        float4 o = make_float4(v[g4 * 4] + bias.x, v[g4 * 4 + 1] + bias.y, v[g4 * 4 + 2] + bias.z, v[g4 * 4 + 3] + bias.w);
-        int Y = oy, X = ox, Ho = a.H, Wo = a.W, ch = co;
-        if (a.upsample) {                                          // co' = q*Co + c, q = dy*2+dx (ConvTranspose k2 s2)
-          const int Co = a.CoutP >> 2, q = co / Co;
-          ch = co - q * Co;
-          Y = 2 * oy + (q >> 1);
-          X = 2 * ox + (q & 1);
-          Ho = 2 * a.H;
-          Wo = 2 * a.W;
-        }
-        const size_t opix = ((size_t)img * Ho + Y) * Wo + X;
-        if (a.res_mode == 1) {
-          const float4 rr = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
-          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-        }
-        if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (a.res_mode == 2) {
-          const float4 rr = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
-          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-        }
-        if (!a.nchw) {
-          *(float4*)(a.out + opix * a.CoutS + ch) = o;
-        } else {
-          const size_t plane = (size_t)Ho * Wo;
-          float* op = a.out + (size_t)img * a.CoutReal * plane + (size_t)Y * Wo + X;
-          const float ov[4] = {o.x, o.y, o.z, o.w};
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const int co = co_base + cb + g4 * 4;
+          if (co >= a.CoutP) break;
+          const float4 bias = __ldg((const float4*)(a.bias + co));
+          float4 o = make_float4(v[g4 * 4] + bias.x, v[g4 * 4 + 1] + bias.y, v[g4 * 4 + 2] + bias.z, v[g4 * 4 + 3] + bias.w);
+          int Y = oy, X = ox, Ho = a.H, Wo = a.W, ch = co;
+          if (a.upsample) {                                        // co' = q*Co + c, q = dy*2+dx (ConvTranspose k2 s2)
+            const int Co = a.CoutP >> 2, q = co / Co;
+            ch = co - q * Co;
+            Y = 2 * oy + (q >> 1);
+            X = 2 * ox + (q & 1);
+            Ho = 2 * a.H;
+            Wo = 2 * a.W;
+          }
+          const size_t opix = ((size_t)w.img * Ho + Y) * Wo + X;
+          if (a.res_mode == 1) {
+            const float4 rr = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+          }
+          if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          if (a.res_mode == 2) {
+            const float4 rr = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+          }
+          if (!a.nchw) {
+            *(float4*)(a.out + opix * a.CoutS + ch) = o;
+          } else {
+            const size_t plane = (size_t)Ho * Wo;
+            float* op = a.out + (size_t)w.img * a.CoutReal * plane + (size_t)Y * Wo + X;
+            const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (ch + e < a.CoutReal) op[(size_t)(ch + e) * plane] = ov[e];
+            for (int e = 0; e < 4; ++e)
+              if (ch + e < a.CoutReal) op[(size_t)(ch + e) * plane] = ov[e];
+          }
         }
       }
+      ++it;
     }
   }
   tc_fence_before();
@@ -341,16 +384,21 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float
   const int cibm = a.in2 && t.cib1 > t.cib0 ? t.cib1 : t.cib0;
   t.b_stage_bytes = (uint32_t)cibm * t.n_tile * 4 * 2;
   const int kblocks = fvp_round_up(a.Cin, 16) / t.cib0 + (a.in2 ? fvp_round_up(a.Cin2, 16) / t.cib1 : 0);
+  (void)kblocks;
   t.b_stages = t.n_tile > 64 ? 3 : 4;
-  t.a_stages = (kblocks > 1 && t.n_tile > 64) ? 2 : 1;          // wide tiles run 1 CTA/SM: keep the MMA stream fed
+  t.a_stages = 2;
+  t.acc_stride = (uint32_t)fvp_round_up(t.n_tile, 32);          // two accumulators side by side in TMEM
   t.tmem_cols = 32;
-  while ((int)t.tmem_cols < t.n_tile) t.tmem_cols <<= 1;
+  while (t.tmem_cols < 2 * t.acc_stride) t.tmem_cols <<= 1;
+  t.tiles_x = fvp_cdiv(a.W, TC_TW);
+  t.tiles_per_img = t.tiles_x * fvp_cdiv(a.H, TC_TH);
+  t.total_items = t.tiles_per_img * a.n * t.n_tiles;
   const size_t smem = (size_t)t.a_stages * t.a_stage_bytes + (size_t)t.b_stages * t.b_stage_bytes;
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr = true;
   }
-  dim3 grid(fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW), t.n_tiles, a.n);
+  const int grid = t.total_items < num_sms ? t.total_items : num_sms;   // persistent: one CTA per SM
   k_conv_tc<<<grid, TC_THREADS, smem, st>>>(t);
 }
