@@ -184,22 +184,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         const int CinP = (Cin + 15) & ~15, pad = (K - 1) / 2;
         const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
         const int plane4 = npix + 1;                             // +16 B: the nq planes land on distinct banks
+        const int nq_shift = nq == 8 ? 3 : 2;
+        const int hw_magic = 65536 / HW + 1;                     // pix / HW for pix < 512 (HW in {8,10,14})
         const float* img_in = src + (size_t)w.img * a.H * a.W * Cin;
         for (int c0 = 0; c0 < CinP; c0 += cib) {
           const int as = a_it % A_ST;
           if (a_it >= A_ST) mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1);
           float4* hi = (float4*)(sA + (size_t)as * t.a_stage_bytes);
           float4* lo = hi + nq * plane4;
-          for (int i = tid; i < nq * npix; i += TC_LOADERS) {
-            const int pix = i / nq, q = i - pix * nq;            // channel quad fastest: coalesced reads
-            const int hy = pix / HW, hx = pix - hy * HW;
-            const int gy = w.y0 + hy - pad, gx = w.x0 + hx - pad, c = c0 + q * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < Cin)
-              v = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
-            float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-            hi[q * plane4 + pix] = h;
-            lo[q * plane4 + pix] = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+          // 8 loads in flight per thread (one L2 round trip per batch instead of one per element)
+          constexpr int UNR = 8;
+          const int total = nq * npix;
+          for (int base = tid; base < total; base += TC_LOADERS * UNR) {
+            float4 v[UNR];
+            int dst[UNR];
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+              const int i = base + j * TC_LOADERS;
+              const int pix = i >> nq_shift, q = i & (nq - 1);     // channel quad fastest: coalesced reads
+              const int hy = (pix * hw_magic) >> 16, hx = pix - hy * HW;
+              const int gy = w.y0 + hy - pad, gx = w.x0 + hx - pad, c = c0 + q * 4;
+              v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              dst[j] = i < total ? q * plane4 + pix : -1;
+              if (i < total && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < Cin)
+                v[j] = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
+            }
+#pragma unroll
+            for (int j = 0; j < UNR; ++j) {
+              if (dst[j] < 0) continue;
+              const float4 h = make_float4(to_tf32(v[j].x), to_tf32(v[j].y), to_tf32(v[j].z), to_tf32(v[j].w));
+              hi[dst[j]] = h;
+              lo[dst[j]] = make_float4(to_tf32(v[j].x - h.x), to_tf32(v[j].y - h.y), to_tf32(v[j].z - h.z),
+                                       to_tf32(v[j].w - h.w));
+            }
           }
           fence_proxy_async();
           mbar_arrive(a_full + as);
@@ -297,7 +314,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       const bool px_ok = oy < a.H && ox < a.W;
       const int co_base = w.nt * t.n_tile;
       const uint32_t t_row = tmem + (uint32_t)buf * t.acc_stride + ((uint32_t)(quarter * 32) << 16);
+      // output location of a 4-channel group (NHWC, pixel-shuffled for ConvTranspose k2s2)
+      auto locate = [&](int co, size_t& opix, int& ch, int& Y, int& X, int& Ho, int& Wo) {
+        Y = oy; X = ox; Ho = a.H; Wo = a.W; ch = co;
+        if (a.upsample) {                                          // co' = q*Co + c, q = dy*2+dx
+          const int Co = a.CoutP >> 2, q = co / Co;
+          ch = co - q * Co;
+          Y = 2 * oy + (q >> 1);
+          X = 2 * ox + (q & 1);
+          Ho = 2 * a.H;
+          Wo = 2 * a.W;
+        }
+        opix = ((size_t)w.img * Ho + Y) * Wo + X;
+      };
+      auto fetch_res = [&](int cb, float4* rr) {                   // residuals of one 16-column chunk, issued early
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const int co = co_base + cb + g4 * 4;
+          rr[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.res_mode && px_ok && co < a.CoutP && cb < t.n_tile) {
+            size_t opix; int ch, Y, X, Ho, Wo;
+            locate(co, opix, ch, Y, X, Ho, Wo);
+            rr[g4] = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
+          }
+        }
+      };
+      float4 rnext[4];
+      fetch_res(0, rnext);
       for (int cb = 0; cb < t.n_tile; cb += 16) {
+        float4 rcur[4];
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) rcur[g4] = rnext[g4];
+        fetch_res(cb + 16, rnext);                                 // next chunk's residuals fly under this chunk
         float v[16];
         tmem_ld16(t_row + (uint32_t)cb, v);
         if (cb + 16 >= t.n_tile) {                                 // last chunk read: hand the accumulator back
@@ -311,25 +359,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
           if (co >= a.CoutP) break;
           const float4 bias = __ldg((const float4*)(a.bias + co));
           float4 o = make_float4(v[g4 * 4] + bias.x, v[g4 * 4 + 1] + bias.y, v[g4 * 4 + 2] + bias.z, v[g4 * 4 + 3] + bias.w);
-          int Y = oy, X = ox, Ho = a.H, Wo = a.W, ch = co;
-          if (a.upsample) {                                        // co' = q*Co + c, q = dy*2+dx (ConvTranspose k2 s2)
-            const int Co = a.CoutP >> 2, q = co / Co;
-            ch = co - q * Co;
-            Y = 2 * oy + (q >> 1);
-            X = 2 * ox + (q & 1);
-            Ho = 2 * a.H;
-            Wo = 2 * a.W;
-          }
-          const size_t opix = ((size_t)w.img * Ho + Y) * Wo + X;
-          if (a.res_mode == 1) {
-            const float4 rr = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
-            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-          }
+          size_t opix; int ch, Y, X, Ho, Wo;
+          locate(co, opix, ch, Y, X, Ho, Wo);
+          const float4 rr = rcur[g4];
+          if (a.res_mode == 1) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
           if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          if (a.res_mode == 2) {
-            const float4 rr = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
-            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-          }
+          if (a.res_mode == 2) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
           if (!a.nchw) {
             *(float4*)(a.out + opix * a.CoutS + ch) = o;
           } else {
