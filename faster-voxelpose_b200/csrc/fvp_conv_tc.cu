@@ -27,7 +27,7 @@ constexpr int TC_TH = 16, TC_TW = 8;       // output tile (pixels)
 constexpr int TC_LOADERS = 128;            // warps 0..3: A staging + epilogue
 constexpr int TC_THREADS = 320;            // + warp 4 (MMA issuer, TMEM owner), warp 5 (weight TMA producer), warps 6-9 (epilogue)
 constexpr int TC_EPI = 128;
-constexpr int TC_MAX_A = 2, TC_MAX_B = 4;  // ring depths are chosen per launch (a_stages, b_stages)
+constexpr int TC_MAX_A = 2, TC_MAX_B = 8;  // ring depths are chosen per launch (a_stages, b_stages)
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,12 +74,16 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4, [16,30) leading byte offset>>4 (stride between the two 16-B K chunks),
-//   [32,46) stride byte offset>>4 (stride between 8-row groups), [46,48) version = 1, layout type [61,64) = 0.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         ((uint64_t)1 << 46);
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B (32 tf32), 16-B
+// chunks XOR-swizzled with the row index mod 8.
+//   [0,14) start>>4, [16,30) leading byte offset>>4 (unused for swizzled K-major: 1), [32,46) stride byte offset>>4
+//   (stride between 8-row groups), [46,48) version = 1, [49,52) base offset = swizzle phase of the first row
+//   ((start >> 7) & 7 when the start is not 1024-B aligned), [61,64) layout type = 2 (SWIZZLE_128B).
+// (Round-1 note: the un-swizzled "interleave" layout computes correctly but the tensor core then fetches one 16-B row
+//  per cycle: ~(128+N)*2 cycles per MMA, 13x below peak - measured in profiles/r01_launches_tc_noswizzle.csv.)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)(base_offset & 7) << 49) | ((uint64_t)2 << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N>>3, M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
@@ -112,9 +116,10 @@ struct TcArgs {
   const float* wtc;      // tiled hi/lo weights (see pack_tc in fvp_params.cu)
   int n_tile;            // GEMM N of this launch (multiple of 16, <= 128)
   int n_tiles;           // CoutPad / n_tile
-  int cib0, cib1;        // channels per K-block of the main / fused-skip phase (16 or 32)
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, acc_stride;
   int a_stages, b_stages;
+  int resident;          // 1: the whole weight image is loaded once per CTA (b_stage_bytes = its size)
+  uint32_t blk_bytes;    // bytes of one (K-block, tap, N-tile) weight block = n_tile*128*2
   int tiles_x, tiles_per_img, total_items;   // work item = (image, tile, N tile)
 };
 
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   const FvpConvArgs& a = t.c;
 
   const int A_ST = t.a_stages, B_ST = t.b_stages;
-  uint8_t* sA = tc_smem;                                           // [A_ST][a_stage_bytes] (hi then lo)
+  uint8_t* sA = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
   uint8_t* sB = tc_smem + A_ST * t.a_stage_bytes;                  // [B_ST][b_stage_bytes] (hi then lo)
   uint64_t* a_full = s_bar;
   uint64_t* a_empty = s_bar + TC_MAX_A;
@@ -180,32 +185,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       if (!tc_decode(t, item, w)) continue;
       for (int ph = 0; ph < nph; ++ph) {
         const float* src = ph == 0 ? a.in : a.in2;
-        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
-        const int CinP = (Cin + 15) & ~15, pad = (K - 1) / 2;
-        const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
-        const int plane4 = npix + 1;                             // +16 B: the nq planes land on distinct banks
-        const int nq_shift = nq == 8 ? 3 : 2;
+        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
+        const int CinP = (Cin + 31) & ~31, pad = (K - 1) / 2;
+        const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH;
+        const int HWP = K == 1 ? 8 : 16;                         // halo row pitch (pixels): group stride = HWP*128 B
         const int hw_magic = 65536 / HW + 1;                     // pix / HW for pix < 512 (HW in {8,10,14})
+        const uint32_t lo_off = (uint32_t)HH * HWP * 128;
         const float* img_in = src + (size_t)w.img * a.H * a.W * Cin;
-        for (int c0 = 0; c0 < CinP; c0 += cib) {
+        for (int c0 = 0; c0 < CinP; c0 += 32) {
           const int as = a_it % A_ST;
           if (a_it >= A_ST) mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1);
-          float4* hi = (float4*)(sA + (size_t)as * t.a_stage_bytes);
-          float4* lo = hi + nq * plane4;
-          // 8 loads in flight per thread (one L2 round trip per batch instead of one per element)
+          uint8_t* hi = sA + (size_t)as * t.a_stage_bytes;
+          // 8 loads in flight per thread; pixel rows of 128 B (32 channels), chunk q stored at q ^ (hx & 7)
           constexpr int UNR = 8;
-          const int total = nq * npix;
+          const int total = 8 * npix;
           for (int base = tid; base < total; base += TC_LOADERS * UNR) {
             float4 v[UNR];
             int dst[UNR];
 #pragma unroll
             for (int j = 0; j < UNR; ++j) {
               const int i = base + j * TC_LOADERS;
-              const int pix = i >> nq_shift, q = i & (nq - 1);     // channel quad fastest: coalesced reads
+              const int pix = i >> 3, q = i & 7;                   // channel quad fastest: coalesced 128-B reads
               const int hy = (pix * hw_magic) >> 16, hx = pix - hy * HW;
               const int gy = w.y0 + hy - pad, gx = w.x0 + hx - pad, c = c0 + q * 4;
               v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-              dst[j] = i < total ? q * plane4 + pix : -1;
+              dst[j] = i < total ? (hy * HWP + hx) * 128 + ((q ^ (hx & 7)) << 4) : -1;
               if (i < total && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < Cin)
                 v[j] = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
             }
@@ -213,9 +217,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
             for (int j = 0; j < UNR; ++j) {
               if (dst[j] < 0) continue;
               const float4 h = make_float4(to_tf32(v[j].x), to_tf32(v[j].y), to_tf32(v[j].z), to_tf32(v[j].w));
-              hi[dst[j]] = h;
-              lo[dst[j]] = make_float4(to_tf32(v[j].x - h.x), to_tf32(v[j].y - h.y), to_tf32(v[j].z - h.z),
-                                       to_tf32(v[j].w - h.w));
+              *(float4*)(hi + dst[j]) = h;
+              *(float4*)(hi + lo_off + dst[j]) = make_float4(to_tf32(v[j].x - h.x), to_tf32(v[j].y - h.y),
+                                                             to_tf32(v[j].z - h.z), to_tf32(v[j].w - h.w));
             }
           }
           fence_proxy_async();
@@ -225,26 +229,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       }
     }
   } else if (tid == TC_LOADERS + 32) {
-    // =============================== B producer: one TMA bulk copy per (K-block, tap) ================
-    int b_it = 0;
-    for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
-      TcItem w;
-      if (!tc_decode(t, item, w)) continue;
-      const float* wsrc = t.wtc;
-      for (int ph = 0; ph < nph; ++ph) {
-        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
-        const int CinP = (Cin + 15) & ~15;
-        const size_t wblk = (size_t)cib * t.n_tile * 2;          // floats of one (K-block, tap, N-tile): hi + lo
-        for (int c0 = 0; c0 < CinP; c0 += cib) {
-          for (int tap = 0; tap < K * K; ++tap) {
-            const int bs = b_it % B_ST;
-            if (b_it >= B_ST) mbar_wait(b_empty + bs, ((b_it / B_ST) - 1) & 1);
-            mbar_arrive_expect_tx(b_full + bs, (uint32_t)(wblk * 4));
-            tma_bulk_g2s(sB + (size_t)bs * t.b_stage_bytes, wsrc + ((size_t)tap * t.n_tiles + w.nt) * wblk,
-                         (uint32_t)(wblk * 4), b_full + bs);
-            ++b_it;
+    // =============================== B producer (TMA bulk copies) =====================================
+    if (t.resident) {                                             // whole weight image once per CTA
+      mbar_arrive_expect_tx(b_full, t.b_stage_bytes);
+      for (uint32_t off = 0; off < t.b_stage_bytes; off += 32768) {
+        const uint32_t n = t.b_stage_bytes - off < 32768 ? t.b_stage_bytes - off : 32768;
+        tma_bulk_g2s(sB + off, (const uint8_t*)t.wtc + off, n, b_full);
+      }
+    } else {
+      int b_it = 0;
+      for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
+        TcItem w;
+        if (!tc_decode(t, item, w)) continue;
+        const uint8_t* wsrc = (const uint8_t*)t.wtc;
+        for (int ph = 0; ph < nph; ++ph) {
+          const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
+          const int CinP = (Cin + 31) & ~31;
+          for (int c0 = 0; c0 < CinP; c0 += 32) {
+            for (int tap = 0; tap < K * K; ++tap) {
+              const int bs = b_it % B_ST;
+              if (b_it >= B_ST) mbar_wait(b_empty + bs, ((b_it / B_ST) - 1) & 1);
+              mbar_arrive_expect_tx(b_full + bs, t.blk_bytes);
+              tma_bulk_g2s(sB + (size_t)bs * t.b_stage_bytes, wsrc + ((size_t)tap * t.n_tiles + w.nt) * t.blk_bytes,
+                           t.blk_bytes, b_full + bs);
+              ++b_it;
+            }
+            wsrc += (size_t)K * K * t.n_tiles * t.blk_bytes;
           }
-          wsrc += (size_t)K * K * t.n_tiles * wblk;
         }
       }
     }
@@ -252,6 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
     // =============================== MMA issue (one thread) =========================================
     const uint32_t idesc = umma_idesc_tf32(128, t.n_tile);
     int a_it = 0, b_it = 0, it = 0;
+    bool b_ready = false;
     for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
       TcItem w;
       if (!tc_decode(t, item, w)) continue;
@@ -260,38 +272,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       tc_fence_after();
       const uint32_t d_tmem = tmem + (uint32_t)buf * t.acc_stride;
       uint32_t accumulate = 0;
+      uint32_t blk = 0;                                            // running weight block index (resident image)
       for (int ph = 0; ph < nph; ++ph) {
-        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2, cib = ph == 0 ? t.cib0 : t.cib1;
-        const int CinP = (Cin + 15) & ~15;
-        const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH, nq = cib >> 2;
-        const uint32_t a_plane = (uint32_t)(npix + 1) * 16, a_lo_off = (uint32_t)nq * a_plane;
-        const uint32_t b_plane = (uint32_t)t.n_tile * 16, b_lo_off = (uint32_t)nq * b_plane;
-        for (int c0 = 0; c0 < CinP; c0 += cib) {
+        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
+        const int CinP = (Cin + 31) & ~31;
+        const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
+        const uint32_t a_lo_off = (uint32_t)HH * HWP * 128, b_lo_off = (uint32_t)t.n_tile * 128;
+        for (int c0 = 0; c0 < CinP; c0 += 32) {
           const int as = a_it % A_ST;
           mbar_wait(a_full + as, (a_it / A_ST) & 1);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + (size_t)as * t.a_stage_bytes);
           for (int tap = 0; tap < K * K; ++tap) {
-            const int bs = b_it % B_ST;
-            mbar_wait(b_full + bs, (b_it / B_ST) & 1);
+            uint32_t b_base;
+            int bs = 0;
+            if (t.resident) {
+              if (!b_ready) { mbar_wait(b_full, 0); b_ready = true; }
+              b_base = smem_u32(sB) + (blk + (uint32_t)tap * t.n_tiles + w.nt) * t.blk_bytes;
+            } else {
+              bs = b_it % B_ST;
+              mbar_wait(b_full + bs, (b_it / B_ST) & 1);
+              b_base = smem_u32(sB + (size_t)bs * t.b_stage_bytes);
+            }
             tc_fence_after();
-            const uint32_t b_base = smem_u32(sB + (size_t)bs * t.b_stage_bytes);
             const int dy = tap / K, dx = tap - dy * K;
-            const uint32_t a_tap = a_base + (uint32_t)(dy * HW + dx) * 16;
-            // three passes: lo*hi, hi*lo, hi*hi (small terms first), K = 8 (two 16-B chunks) per instruction
+            const uint32_t a_tap = a_base + (uint32_t)(dy * HWP + dx) * 128;
+            // three passes: lo*hi, hi*lo, hi*hi (small terms first); one instruction = K 8 = 32 B of every row
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
               const uint32_t ao = pass == 0 ? a_lo_off : 0u, bo = pass == 1 ? b_lo_off : 0u;
-              for (int kc = 0; kc < nq; kc += 2) {
-                const uint64_t ad = umma_desc(a_tap + ao + (uint32_t)kc * a_plane, a_plane, (uint32_t)HW * 16);
-                const uint64_t bd = umma_desc(b_base + bo + (uint32_t)kc * b_plane, b_plane, 128);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ad = umma_desc(a_tap + ao + ks * 32, (uint32_t)HWP * 128, (uint32_t)dx);
+                const uint64_t bd = umma_desc(b_base + bo + ks * 32, 1024, 0);
                 umma_tf32(d_tmem, ad, bd, idesc, accumulate);
                 accumulate = 1;
               }
             }
-            umma_commit(b_empty + bs);                             // B slot reusable when these MMAs retire
-            ++b_it;
+            if (!t.resident) {
+              umma_commit(b_empty + bs);                           // B slot reusable when these MMAs retire
+              ++b_it;
+            }
           }
+          blk += (uint32_t)K * K * t.n_tiles;
           umma_commit(a_empty + as);
           ++a_it;
         }
@@ -391,47 +414,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
 }  // namespace
 
 // host: geometry of the tiled weight image (must match pack_tc in fvp_params.cu).  narrow = 32-column N tiles
-// (more CTAs for small launches), otherwise up to 128 columns per CTA.
-void fvp_tc_geometry(int cin, int cin2, int coutp, int narrow, int* n_tile, int* n_tiles, int* cib0, int* cib1) {
+// (more CTAs for small launches), otherwise up to 128 columns per CTA.  K-blocks are always 32 channels.
+void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
   const int npad = fvp_round_up(coutp, 16);
   const int cap = narrow ? 32 : 128;
   *n_tile = npad <= cap ? npad : cap;
   *n_tiles = fvp_cdiv(npad, *n_tile);
-  const int cinp = fvp_round_up(cin, 16);
-  *cib0 = cinp >= 32 ? 32 : 16;
-  const int cin2p = cin2 ? fvp_round_up(cin2, 16) : 0;
-  *cib1 = cin2p >= 32 ? 32 : 16;
 }
 
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int num_sms, cudaStream_t st) {
   TcArgs t;
   t.c = a;
   const int tiles = fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW) * a.n;
-  int n_tile, n_tiles, cib0, cib1;
-  fvp_tc_geometry(a.Cin, a.in2 ? a.Cin2 : 0, a.CoutP, 0, &n_tile, &n_tiles, &cib0, &cib1);
+  int n_tile, n_tiles;
+  fvp_tc_geometry(a.CoutP, 0, &n_tile, &n_tiles);
   const int narrow = (wtc_narrow != nullptr && n_tile > 32 && tiles * n_tiles < 2 * num_sms) ? 1 : 0;
-  fvp_tc_geometry(a.Cin, a.in2 ? a.Cin2 : 0, a.CoutP, narrow, &t.n_tile, &t.n_tiles, &t.cib0, &t.cib1);
+  fvp_tc_geometry(a.CoutP, narrow, &t.n_tile, &t.n_tiles);
   t.wtc = narrow ? wtc_narrow : wtc_wide;
   const int k = a.ksize;
-  const uint32_t a0 = (uint32_t)(t.cib0 / 4) * ((TC_TW + k - 1) * (TC_TH + k - 1) + 1) * 16 * 2;
-  const uint32_t a1 = a.in2 ? (uint32_t)(t.cib1 / 4) * (TC_TW * TC_TH + 1) * 16 * 2 : 0;
-  t.a_stage_bytes = ((a0 > a1 ? a0 : a1) + 127) & ~127u;
-  const int cibm = a.in2 && t.cib1 > t.cib0 ? t.cib1 : t.cib0;
-  t.b_stage_bytes = (uint32_t)cibm * t.n_tile * 4 * 2;
-  const int kblocks = fvp_round_up(a.Cin, 16) / t.cib0 + (a.in2 ? fvp_round_up(a.Cin2, 16) / t.cib1 : 0);
-  (void)kblocks;
-  t.b_stages = t.n_tile > 64 ? 3 : 4;
-  t.a_stages = 2;
+  const uint32_t a0 = (uint32_t)(TC_TH + k - 1) * (k == 1 ? 8 : 16) * 128 * 2;
+  const uint32_t a1 = a.in2 ? (uint32_t)TC_TH * 8 * 128 * 2 : 0;
+  t.a_stage_bytes = a0 > a1 ? a0 : a1;                            // multiples of 1024
+  t.blk_bytes = (uint32_t)t.n_tile * 128 * 2;
+  const int nblocks = k * k * (fvp_round_up(a.Cin, 32) / 32) + (a.in2 ? fvp_round_up(a.Cin2, 32) / 32 : 0);
+  const uint32_t image_bytes = (uint32_t)nblocks * t.n_tiles * t.blk_bytes;
+  const uint32_t budget = 224 * 1024 - 1024;                       // dynamic smem we may use (1 KB alignment slack)
+  const int stream2 = (2 * t.a_stage_bytes + 4 * t.blk_bytes <= budget) ? (int)((budget - 2 * t.a_stage_bytes) / t.blk_bytes) : 0;
+  if (image_bytes + 2 * t.a_stage_bytes <= budget) {              // weights resident, double-buffered halo
+    t.resident = 1; t.a_stages = 2; t.b_stages = 1; t.b_stage_bytes = image_bytes;
+  } else if (stream2 >= 4) {                                       // streamed weights, double-buffered halo
+    t.resident = 0; t.a_stages = 2; t.b_stage_bytes = t.blk_bytes;
+    t.b_stages = stream2 > TC_MAX_B ? TC_MAX_B : stream2;
+  } else if (image_bytes + t.a_stage_bytes <= budget) {
+    t.resident = 1; t.a_stages = 1; t.b_stages = 1; t.b_stage_bytes = image_bytes;
+  } else {
+    t.resident = 0; t.a_stages = 1; t.b_stage_bytes = t.blk_bytes;
+    const int bs = (int)((budget - t.a_stage_bytes) / t.blk_bytes);
+    t.b_stages = bs > TC_MAX_B ? TC_MAX_B : bs;
+  }
   t.acc_stride = (uint32_t)fvp_round_up(t.n_tile, 32);          // two accumulators side by side in TMEM
   t.tmem_cols = 32;
   while (t.tmem_cols < 2 * t.acc_stride) t.tmem_cols <<= 1;
   t.tiles_x = fvp_cdiv(a.W, TC_TW);
   t.tiles_per_img = t.tiles_x * fvp_cdiv(a.H, TC_TH);
   t.total_items = t.tiles_per_img * a.n * t.n_tiles;
-  const size_t smem = (size_t)t.a_stages * t.a_stage_bytes + (size_t)t.b_stages * t.b_stage_bytes;
+  const size_t smem = 1024 + (size_t)t.a_stages * t.a_stage_bytes + (size_t)t.b_stages * t.b_stage_bytes;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr = true;
   }
   const int grid = t.total_items < num_sms ? t.total_items : num_sms;   // persistent: one CTA per SM

@@ -70,7 +70,7 @@ struct FvpConvW {         // one packed conv
 };
 // tcgen05 / TMEM implicit-GEMM conv (fvp_conv_tc.cu); same arguments as fvp_launch_conv plus the tiled weights
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int num_sms, cudaStream_t st);
-void fvp_tc_geometry(int cin, int cin2, int coutp, int narrow, int* n_tile, int* n_tiles, int* cib0, int* cib1);
+void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles);
 struct FvpTrunkW {
   FvpConvW front, r1a, r1b, s1a, s1b, e1a, e1b, s2a, s2b, e2a, e2b, ma, mb, d2a, d2b, up2, d1a, d1b, up1;
   FvpConvW head_a, head_b;   // CenterNet: merged 3x3 (32->64) + block-diagonal 1x1 (64->3); P2PNet: head_b only

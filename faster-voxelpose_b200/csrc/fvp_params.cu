@@ -194,29 +194,35 @@ float tf32_rna(float x) {
   return r;
 }
 
-// Tiled tf32 hi/lo image of a packed conv for k_conv_tc: [phase][K-block][tap][N-tile]{hi[cib/4][n_tile][4], lo[...]}
+// Tiled tf32 hi/lo image of a packed conv for k_conv_tc: blocks [phase][32-channel K-block][tap][N-tile], each block =
+// hi[n_tile rows][128 B] then lo[...], rows K-major with the 16-B chunks XOR-swizzled by (row & 7) (SWIZZLE_128B).
 // (cin_act = channels of the activation tensor the kernel will see: JP for the first layer)
 std::vector<float> pack_tc(const Packed& p, int cin_act, int narrow) {
-  int n_tile, n_tiles, cib0, cib1;
-  fvp_tc_geometry(cin_act, p.cin2, p.coutp, narrow, &n_tile, &n_tiles, &cib0, &cib1);
+  int n_tile, n_tiles;
+  fvp_tc_geometry(p.coutp, narrow, &n_tile, &n_tiles);
+  (void)cin_act;
   const int taps = p.k * p.k, cinP = fvp_round_up(p.cin, 16), cin2P = p.cin2 ? fvp_round_up(p.cin2, 16) : 0;
   std::vector<float> out;
   for (int ph = 0; ph < (p.cin2 ? 2 : 1); ++ph) {
-    const int K2 = ph == 0 ? taps : 1, CP = ph == 0 ? cinP : cin2P, cib = ph == 0 ? cib0 : cib1;
+    const int K2 = ph == 0 ? taps : 1, CP = ph == 0 ? cinP : cin2P;
     const int rowbase = ph == 0 ? 0 : taps * cinP;
-    for (int c0 = 0; c0 < CP; c0 += cib)
+    const int CP32 = fvp_round_up(CP, 32);
+    for (int c0 = 0; c0 < CP32; c0 += 32)
       for (int tap = 0; tap < K2; ++tap)
         for (int nt = 0; nt < n_tiles; ++nt)
-          for (int part = 0; part < 2; ++part)
-            for (int q = 0; q < cib / 4; ++q)
-              for (int n = 0; n < n_tile; ++n)
-                for (int e = 0; e < 4; ++e) {
-                  const int col = nt * n_tile + n, ci = c0 + q * 4 + e;
-                  float w = 0.f;
-                  if (col < p.coutp && ci < CP) w = p.w[(size_t)(rowbase + tap * CP + ci) * p.coutp + col];
-                  const float hi = tf32_rna(w);
-                  out.push_back(part == 0 ? hi : tf32_rna(w - hi));
-                }
+          for (int part = 0; part < 2; ++part) {
+            const size_t base = out.size();
+            out.resize(base + (size_t)n_tile * 32, 0.f);
+            for (int n = 0; n < n_tile; ++n)
+              for (int cc = 0; cc < 32; ++cc) {
+                const int col = nt * n_tile + n, ci = c0 + cc;
+                float w = 0.f;
+                if (col < p.coutp && ci < CP) w = p.w[(size_t)(rowbase + tap * CP + ci) * p.coutp + col];
+                const float hi = tf32_rna(w);
+                const int chunk = (cc >> 2) ^ (n & 7);
+                out[base + (size_t)n * 32 + chunk * 4 + (cc & 3)] = part == 0 ? hi : tf32_rna(w - hi);
+              }
+          }
   }
   return out;
 }
