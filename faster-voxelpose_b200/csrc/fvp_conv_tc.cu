@@ -19,6 +19,8 @@
 // Warp roles: warps 0-3 stage operands (A ring of 2, B ring of 3, mbarrier full/empty pairs; MMA completion
 // frees a slot through tcgen05.commit) and run the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4
 // allocates TMEM and one elected lane issues every tcgen05.mma.
+#include <cstdlib>
+
 #include "fvp_kernels.h"
 
 namespace {
@@ -119,6 +121,7 @@ struct TcArgs {
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, acc_stride;
   int a_stages, b_stages;
   int resident;          // 1: the whole weight image is loaded once per CTA (b_stage_bytes = its size)
+  int bo_mode;           // descriptor base_offset for shifted taps: 0 = none, 1 = dx (A/B test of the swizzle phase rule)
   uint32_t blk_bytes;    // bytes of one (K-block, tap, N-tile) weight block = n_tile*128*2
   int tiles_x, tiles_per_img, total_items;   // work item = (image, tile, N tile)
 };
@@ -297,18 +300,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
             tc_fence_after();
             const int dy = tap / K, dx = tap - dy * K;
             const uint32_t a_tap = a_base + (uint32_t)(dy * HWP + dx) * 128;
-            // three passes: lo*hi, hi*lo, hi*hi (small terms first); one instruction = K 8 = 32 B of every row
-#pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t ao = pass == 0 ? a_lo_off : 0u, bo = pass == 1 ? b_lo_off : 0u;
+            // Descriptors are built once per tap; the 12 instructions below only add immediates to the low word
+            // (a lone issuing thread runs ~1 dependent instruction per 5 cycles: descriptor math per MMA would
+            // cost more than the MMA itself).  Passes: lo*hi, hi*lo, hi*hi (small terms first); K = 8 per MMA.
+            const uint64_t ad_hi = umma_desc(a_tap, (uint32_t)HWP * 128, t.bo_mode ? (uint32_t)dx : 0u);
+            const uint64_t ad_lo = umma_desc(a_tap + a_lo_off, (uint32_t)HWP * 128, t.bo_mode ? (uint32_t)dx : 0u);
+            const uint64_t bd_hi = umma_desc(b_base, 1024, 0);
+            const uint64_t bd_lo = umma_desc(b_base + b_lo_off, 1024, 0);
+            umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
+            umma_tf32(d_tmem, ad_lo + 2, bd_hi + 2, idesc, 1);
+            umma_tf32(d_tmem, ad_lo + 4, bd_hi + 4, idesc, 1);
+            umma_tf32(d_tmem, ad_lo + 6, bd_hi + 6, idesc, 1);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ad = umma_desc(a_tap + ao + ks * 32, (uint32_t)HWP * 128, (uint32_t)dx);
-                const uint64_t bd = umma_desc(b_base + bo + ks * 32, 1024, 0);
-                umma_tf32(d_tmem, ad, bd, idesc, accumulate);
-                accumulate = 1;
-              }
-            }
+            for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_lo + 2 * ks, idesc, 1);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_hi + 2 * ks, idesc, 1);
+            accumulate = 1;
             if (!t.resident) {
               umma_commit(b_empty + bs);                           // B slot reusable when these MMAs retire
               ++b_it;
@@ -451,6 +458,11 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float
     t.resident = 0; t.a_stages = 1; t.b_stage_bytes = t.blk_bytes;
     const int bs = (int)((budget - t.a_stage_bytes) / t.blk_bytes);
     t.b_stages = bs > TC_MAX_B ? TC_MAX_B : bs;
+  }
+  {
+    static int bo = -1;
+    if (bo < 0) { const char* e = getenv("FVP_TC_BO"); bo = e ? atoi(e) : 0; }
+    t.bo_mode = bo;
   }
   t.acc_stride = (uint32_t)fvp_round_up(t.n_tile, 32);          // two accumulators side by side in TMEM
   t.tmem_cols = 32;
