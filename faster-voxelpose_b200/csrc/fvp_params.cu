@@ -369,3 +369,35 @@ int fvp_pack_params(fvp_ctx* ctx) {
   ctx->params_ready = true;
   return FVP_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// test hook: one standalone convolution (raw [Cout][Cin][k][k] weights, no BN) through either conv engine
+// ------------------------------------------------------------------------------------------------
+int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin, const float* h_w, const float* h_b,
+                        int cout, int k, int relu, int mode, float* d_out, cudaStream_t st) {
+  Packed p;
+  const int taps = k * k, cinP = fvp_round_up(cin, 16), coutP = fvp_round_up(cout, 4);
+  p.cin = cin; p.cin2 = 0; p.coutp = coutP; p.k = k;
+  p.w.assign((size_t)taps * cinP * coutP, 0.f);
+  p.b.assign(coutP, 0.f);
+  for (int co = 0; co < cout; ++co) {
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tp = 0; tp < taps; ++tp) p.w[(size_t)(tp * cinP + ci) * coutP + co] = h_w[((size_t)co * cin + ci) * taps + tp];
+    p.b[co] = h_b[co];
+  }
+  Arena A;
+  const size_t ow = A.put(p.w), ob = A.put(p.b), ot = A.put(pack_tc(p, cin, 0));
+  float* d = nullptr;
+  FVP_CUDA_OK(cudaMalloc(&d, A.host.size() * sizeof(float)));
+  FVP_CUDA_OK(cudaMemcpy(d, A.host.data(), A.host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  FvpConvArgs a;
+  a.in = d_in; a.H = H; a.W = W; a.Cin = cin; a.in2 = nullptr; a.Cin2 = 0;
+  a.w = d + ow; a.bias = d + ob; a.out = d_out; a.CoutP = coutP; a.CoutS = coutP; a.CoutReal = cout;
+  a.res = nullptr; a.res_mode = 0; a.relu = relu; a.ksize = k; a.upsample = 0; a.nchw = 0; a.n = n; a.valid = nullptr;
+  if (mode == 1) fvp_launch_conv_tc(a, d + ot, nullptr, ctx->num_sms, st);
+  else fvp_launch_conv(a, st);
+  FVP_CUDA_OK(cudaStreamSynchronize(st));
+  FVP_CUDA_OK(cudaGetLastError());
+  cudaFree(d);
+  return FVP_OK;
+}

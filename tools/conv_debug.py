@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Single-layer TC-vs-FFMA conv comparison (per tap), plus timing of both engines on a P2PNet-sized layer."""
+import os, sys, json
+import numpy as np, torch, torch.nn.functional as F
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+from golden_util import Golden
+from fvp.engine import Engine
+g = Golden("panoptic_none_valid")
+eng = Engine(g.cfg, torch.device("cuda:0"), max_batch=1, max_sequences=1, axes=g.axes)
+rng = np.random.default_rng(0)
+def ref(x, w, b, relu):
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), torch.from_numpy(w).double().cuda(), torch.from_numpy(b).double().cuda(), padding=w.shape[2] // 2)
+    y = y.permute(0, 2, 3, 1)
+    return (y.clamp_min(0) if relu else y).float()
+def run(tag, n, H, W, cin, cout, k, wmask=None):
+    x = torch.from_numpy(rng.standard_normal((n, H, W, cin)).astype(np.float32)).cuda()
+    w = (rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32)
+    if wmask is not None:
+        w = w * wmask
+    b = rng.standard_normal(cout).astype(np.float32) * 0.1
+    r = ref(x, w, b, False)
+    e0 = float((eng.debug_conv(x, w, b, False, 0) - r).abs().max())
+    e1 = float((eng.debug_conv(x, w, b, False, 1) - r).abs().max())
+    print("%-28s ffma %.2e  tc %.2e" % (tag, e0, e1)); sys.stdout.flush()
+run("1x1 32->32 16x8", 1, 16, 8, 32, 32, 1)
+run("1x1 64->128 32x32", 2, 32, 32, 64, 128, 1)
+for dy in range(3):
+    for dx in range(3):
+        m = np.zeros((1, 1, 3, 3), np.float32); m[0, 0, dy, dx] = 1
+        run("3x3 32->32 tap(%d,%d) 16x8" % (dy, dx), 1, 16, 8, 32, 32, 3, m)
+run("3x3 32->32 full 64x64", 2, 64, 64, 32, 32, 3)
+run("3x3 64->64 32x32", 2, 32, 32, 64, 64, 3)
+run("3x3 128->128 16x16", 2, 16, 16, 128, 128, 3)
+run("3x3 16->32 64x64", 1, 64, 64, 16, 32, 3)
+run("7x7 16->16 64x64", 1, 64, 64, 16, 16, 7)
+run("3x3 32->32 80x80", 1, 80, 80, 32, 32, 3)
+run("3x3 32->64 20x20", 1, 20, 20, 32, 64, 3)
+# timing: 30 images 64x64, 32->32 3x3 (the P2PNet standard layer)
+x = torch.from_numpy(rng.standard_normal((30, 64, 64, 32)).astype(np.float32)).cuda()
+w = (rng.standard_normal((32, 32, 3, 3)) / 17).astype(np.float32); b = np.zeros(32, np.float32)
+for mode in (0, 1):
+    for _ in range(2): eng.debug_conv(x, w, b, True, mode)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): eng.debug_conv(x, w, b, True, mode)
+    e1.record(); torch.cuda.synchronize()
+    print("standard layer mode %d: %.1f us per call (incl. alloc/upload overhead)" % (mode, e0.elapsed_time(e1) / 5 * 1000))
