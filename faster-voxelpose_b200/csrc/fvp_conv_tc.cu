@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
 
   const int A_ST = t.a_stages, B_ST = t.b_stages;
   uint8_t* sA = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
-  uint8_t* sB = tc_smem + A_ST * t.a_stage_bytes;                  // [B_ST][b_stage_bytes] (hi then lo)
+  uint8_t* sB = sA + A_ST * t.a_stage_bytes;                       // [B_ST][b_stage_bytes] (hi then lo)
   uint64_t* a_full = s_bar;
   uint64_t* a_empty = s_bar + TC_MAX_A;
   uint64_t* b_full = s_bar + 2 * TC_MAX_A;

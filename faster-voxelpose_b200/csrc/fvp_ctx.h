@@ -91,4 +91,4 @@ struct fvp_ctx {
 void fvp_build_param_table(fvp_ctx* ctx);
 int fvp_pack_params(fvp_ctx* ctx);
 int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin, const float* h_w, const float* h_b,
-                        int cout, int k, int relu, int mode, float* d_out, cudaStream_t st);
+                        int cout, int k, int relu, int mode, float* d_out, int repeat, float* ms_out, cudaStream_t st);

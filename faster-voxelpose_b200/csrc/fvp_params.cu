@@ -374,7 +374,7 @@ int fvp_pack_params(fvp_ctx* ctx) {
 // test hook: one standalone convolution (raw [Cout][Cin][k][k] weights, no BN) through either conv engine
 // ------------------------------------------------------------------------------------------------
 int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin, const float* h_w, const float* h_b,
-                        int cout, int k, int relu, int mode, float* d_out, cudaStream_t st) {
+                        int cout, int k, int relu, int mode, float* d_out, int repeat, float* ms_out, cudaStream_t st) {
   Packed p;
   const int taps = k * k, cinP = fvp_round_up(cin, 16), coutP = fvp_round_up(cout, 4);
   p.cin = cin; p.cin2 = 0; p.coutp = coutP; p.k = k;
@@ -394,9 +394,17 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   a.in = d_in; a.H = H; a.W = W; a.Cin = cin; a.in2 = nullptr; a.Cin2 = 0;
   a.w = d + ow; a.bias = d + ob; a.out = d_out; a.CoutP = coutP; a.CoutS = coutP; a.CoutReal = cout;
   a.res = nullptr; a.res_mode = 0; a.relu = relu; a.ksize = k; a.upsample = 0; a.nchw = 0; a.n = n; a.valid = nullptr;
-  if (mode == 1) fvp_launch_conv_tc(a, d + ot, nullptr, ctx->num_sms, st);
-  else fvp_launch_conv(a, st);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int it = 0; it < 1 + (repeat > 0 ? repeat : 1); ++it) {     // first launch = warm-up
+    if (it == 1) cudaEventRecord(e0, st);
+    if (mode == 1) fvp_launch_conv_tc(a, d + ot, nullptr, ctx->num_sms, st);
+    else fvp_launch_conv(a, st);
+  }
+  cudaEventRecord(e1, st);
   FVP_CUDA_OK(cudaStreamSynchronize(st));
+  if (ms_out) { cudaEventElapsedTime(ms_out, e0, e1); *ms_out /= (float)(repeat > 0 ? repeat : 1); }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   FVP_CUDA_OK(cudaGetLastError());
   cudaFree(d);
   return FVP_OK;

@@ -232,16 +232,18 @@ class Engine:
     def _new(self, *shape, dtype=torch.float32):
         return torch.empty(shape, device=self.device, dtype=dtype)
 
-    def debug_conv(self, x_nhwc: torch.Tensor, weight: np.ndarray, bias: np.ndarray, relu: bool, mode: int) -> torch.Tensor:
+    def debug_conv(self, x_nhwc: torch.Tensor, weight: np.ndarray, bias: np.ndarray, relu: bool, mode: int, repeat: int = 1,
+                   want_ms: bool = False):
         x = x_nhwc.to(self.device, torch.float32).contiguous()
         n, H, W, cin = x.shape
         w = np.ascontiguousarray(weight, np.float32)
         b = np.ascontiguousarray(bias, np.float32)
         cout, k = w.shape[0], w.shape[2]
         out = torch.zeros((n, H, W, (cout + 3) // 4 * 4), device=self.device)
+        ms = C.c_float(0)
         self._ck(self.lib.fvp_debug_conv(self.ctx, x.data_ptr(), n, H, W, cin, w.ctypes.data, b.ctypes.data, cout, k,
-                                         1 if relu else 0, int(mode), out.data_ptr(), self._stream()))
-        return out[..., :cout]
+                                         1 if relu else 0, int(mode), out.data_ptr(), int(repeat), C.byref(ms), self._stream()))
+        return (out[..., :cout], float(ms.value)) if want_ms else out[..., :cout]
 
     def debug_project(self, slot: int, points: torch.Tensor):
         p = points.to(self.device, torch.float32).contiguous()

@@ -121,9 +121,10 @@ int fvp_use_cuda_graph(fvp_ctx* ctx, int enable);
  * arbitrary world points d_points [n][3] -> d_ix, d_iy [V][n]; bit-identical to oracle.project_chain_np */
 int fvp_debug_project(fvp_ctx* ctx, int slot, const float* d_points, int n, float* d_ix, float* d_iy, uintptr_t stream);
 /* test hook: one standalone NHWC convolution (d_in [n][H][W][cin], cin % 4 == 0; h_weight [cout][cin][k][k], k in {1,3,7};
- * d_out [n][H][W][round_up(cout,4)]) through conv engine `mode` (0 CUDA cores, 1 tcgen05) */
+ * d_out [n][H][W][round_up(cout,4)]) through conv engine `mode` (0 CUDA cores, 1 tcgen05); the launch is repeated `repeat`
+ * times after one warm-up and the mean CUDA-event time per launch (ms) is written to h_ms (may be NULL) */
 int fvp_debug_conv(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin, const float* h_weight, const float* h_bias,
-                   int cout, int k, int relu, int mode, float* d_out, uintptr_t stream);
+                   int cout, int k, int relu, int mode, float* d_out, int repeat, float* h_ms, uintptr_t stream);
 /* K0: [batch][V][J][H][W] -> internal channel-last, zero-bordered copy */
 int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr_t stream);
 /* K1: ProjectLayer(whole).forward + CenterNet's z-max (project_whole.py:62-88, cnns_2d.py:174)

@@ -36,14 +36,20 @@ run("3x3 16->32 64x64", 1, 64, 64, 16, 32, 3)
 run("7x7 16->16 64x64", 1, 64, 64, 16, 16, 7)
 run("3x3 32->32 80x80", 1, 80, 80, 32, 32, 3)
 run("3x3 32->64 20x20", 1, 20, 20, 32, 64, 3)
-# timing: 30 images 64x64, 32->32 3x3 (the P2PNet standard layer)
-x = torch.from_numpy(rng.standard_normal((30, 64, 64, 32)).astype(np.float32)).cuda()
-w = (rng.standard_normal((32, 32, 3, 3)) / 17).astype(np.float32); b = np.zeros(32, np.float32)
-for mode in (0, 1):
-    for _ in range(2): eng.debug_conv(x, w, b, True, mode)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5): eng.debug_conv(x, w, b, True, mode)
-    e1.record(); torch.cuda.synchronize()
-    print("standard layer mode %d: %.1f us per call (incl. alloc/upload overhead)" % (mode, e0.elapsed_time(e1) / 5 * 1000))
+# steady-state timing (CUDA events around repeated launches, weights already uploaded)
+def timing(tag, n, H, W, cin, cout, k):
+    x = torch.from_numpy(rng.standard_normal((n, H, W, cin)).astype(np.float32)).cuda()
+    w = (rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32); b = np.zeros(cout, np.float32)
+    r = []
+    for mode in (0, 1):
+        _, ms = eng.debug_conv(x, w, b, True, mode, repeat=20, want_ms=True)
+        r.append(ms * 1000)
+    gmac = n * H * W * cin * cout * k * k / 1e9
+    print("%-34s ffma %7.1f us (%5.1f TMAC/s)   tc %7.1f us (%5.1f TMAC/s)" % (tag, r[0], gmac / r[0] * 1e3, r[1], gmac / r[1] * 1e3)); sys.stdout.flush()
+timing("3x3 32->32 64x64 n=30", 30, 64, 64, 32, 32, 3)
+timing("3x3 32->32 64x64 n=120", 120, 64, 64, 32, 32, 3)
+timing("3x3 32->32 64x64 n=480", 480, 64, 64, 32, 32, 3)
+timing("3x3 64->64 32x32 n=480", 480, 32, 32, 64, 64, 3)
+timing("3x3 128->128 16x16 n=480", 480, 16, 16, 128, 128, 3)
+timing("7x7 16->16 64x64 n=120", 120, 64, 64, 16, 16, 7)
+timing("1x1 64->128 32x32 n=480", 480, 32, 32, 64, 128, 1)
