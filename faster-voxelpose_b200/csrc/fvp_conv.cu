@@ -217,7 +217,9 @@ static void conv(const FvpConvW& w, const float* in, int H, int W, const float* 
   a.out = out; a.CoutP = w.coutp; a.CoutS = couts; a.CoutReal = cout_real;
   a.res = res; a.res_mode = res_mode; a.relu = relu; a.ksize = w.k; a.upsample = upsample;
   a.nchw = nchw; a.n = n; a.valid = valid;
-  if (g_tc && w.wtc) fvp_launch_conv_tc(a, w.wtc, w.wtc_narrow, 148, st);
+  // 7x7 front conv: 49 taps x 16 input channels would run half-empty 32-channel K-blocks on the tensor path
+  // (measured 6.6 vs 11.4 TMAC/s): it stays on the CUDA-core kernel
+  if (g_tc && w.wtc && w.k != 7) fvp_launch_conv_tc(a, w.wtc, w.wtc_narrow, 148, st);
   else fvp_launch_conv(a, st);
   if (launches) ++*launches;
 }

@@ -79,8 +79,10 @@ __device__ __forceinline__ float to_tf32(float x) {
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B (32 tf32), 16-B
 // chunks XOR-swizzled with the row index mod 8.
 //   [0,14) start>>4, [16,30) leading byte offset>>4 (unused for swizzled K-major: 1), [32,46) stride byte offset>>4
-//   (stride between 8-row groups), [46,48) version = 1, [49,52) base offset = swizzle phase of the first row
-//   ((start >> 7) & 7 when the start is not 1024-B aligned), [61,64) layout type = 2 (SWIZZLE_128B).
+//   (stride between 8-row groups), [46,48) version = 1, [49,52) base offset (left 0), [61,64) layout type = 2.
+// Measured on B200 (tools/conv_debug.py): the hardware applies the 128-B swizzle to ABSOLUTE shared-memory address
+// bits (chunk ^= (addr >> 7) & 7), so a tap-shifted operand that starts in the middle of a 1024-B atom needs no
+// base offset as long as the data was stored with the same absolute-address rule (setting base_offset = dx breaks it).
 // (Round-1 note: the un-swizzled "interleave" layout computes correctly but the tensor core then fetches one 16-B row
 //  per cycle: ~(128+N)*2 cycles per MMA, 13x below peak - measured in profiles/r01_launches_tc_noswizzle.csv.)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
@@ -121,7 +123,6 @@ struct TcArgs {
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, acc_stride;
   int a_stages, b_stages;
   int resident;          // 1: the whole weight image is loaded once per CTA (b_stage_bytes = its size)
-  int bo_mode;           // descriptor base_offset for shifted taps: 0 = none, 1 = dx (A/B test of the swizzle phase rule)
   uint32_t blk_bytes;    // bytes of one (K-block, tap, N-tile) weight block = n_tile*128*2
   int tiles_x, tiles_per_img, total_items;   // work item = (image, tile, N tile)
 };
@@ -303,8 +304,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
             // Descriptors are built once per tap; the 12 instructions below only add immediates to the low word
             // (a lone issuing thread runs ~1 dependent instruction per 5 cycles: descriptor math per MMA would
             // cost more than the MMA itself).  Passes: lo*hi, hi*lo, hi*hi (small terms first); K = 8 per MMA.
-            const uint64_t ad_hi = umma_desc(a_tap, (uint32_t)HWP * 128, t.bo_mode ? (uint32_t)dx : 0u);
-            const uint64_t ad_lo = umma_desc(a_tap + a_lo_off, (uint32_t)HWP * 128, t.bo_mode ? (uint32_t)dx : 0u);
+            const uint64_t ad_hi = umma_desc(a_tap, (uint32_t)HWP * 128, 0u);
+            const uint64_t ad_lo = umma_desc(a_tap + a_lo_off, (uint32_t)HWP * 128, 0u);
             const uint64_t bd_hi = umma_desc(b_base, 1024, 0);
             const uint64_t bd_lo = umma_desc(b_base + b_lo_off, 1024, 0);
             umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
@@ -458,11 +459,6 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float
     t.resident = 0; t.a_stages = 1; t.b_stage_bytes = t.blk_bytes;
     const int bs = (int)((budget - t.a_stage_bytes) / t.blk_bytes);
     t.b_stages = bs > TC_MAX_B ? TC_MAX_B : bs;
-  }
-  {
-    static int bo = -1;
-    if (bo < 0) { const char* e = getenv("FVP_TC_BO"); bo = e ? atoi(e) : 0; }
-    t.bo_mode = bo;
   }
   t.acc_stride = (uint32_t)fvp_round_up(t.n_tile, 32);          // two accumulators side by side in TMEM
   t.tmem_cols = 32;
