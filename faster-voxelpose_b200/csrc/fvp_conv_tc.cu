@@ -26,8 +26,9 @@
 namespace {
 
 constexpr int TC_TH = 16, TC_TW = 8;       // output tile (pixels)
-constexpr int TC_LOADERS = 128;            // warps 0..3: A staging + epilogue
-constexpr int TC_THREADS = 320;            // + warp 4 (MMA issuer, TMEM owner), warp 5 (weight TMA producer), warps 6-9 (epilogue)
+constexpr int TC_LOADERS = 256;            // warps 0..7: A staging
+constexpr int TC_LW = TC_LOADERS / 32;     // warp 8 = MMA issuer / TMEM owner, warp 9 = weight TMA producer, warps 10-13 = epilogue
+constexpr int TC_THREADS = TC_LOADERS + 64 + 128;
 constexpr int TC_EPI = 128;
 constexpr int TC_MAX_A = 2, TC_MAX_B = 8;  // ring depths are chosen per launch (a_stages, b_stages)
 
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  if (warp == 4) {                                                 // TMEM allocation (power of two >= 32 columns)
+  if (warp == TC_LW) {                                             // TMEM allocation (power of two >= 32 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(t.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
@@ -181,50 +182,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   const uint32_t tmem = s_tmem;
   const int nph = a.in2 ? 2 : 1;
 
-  if (warp < 4) {
-    // =============================== A staging (128 threads) ========================================
+  if (warp < TC_LW) {
+    // =============================== A staging (256 threads) ========================================
+    // Thread (q = tid & 7, p0 = tid >> 3) always handles channel quad q of halo pixels p0, p0+32, p0+64, ...:
+    // their halo coordinates, shared-memory destinations and global offsets do not depend on the work item, so they
+    // are computed once; per item only the image bounds tests and one base pointer remain.
+    constexpr int EPT = 10;                                        // elements per thread: ceil(22*14 / 32)
+    const int q = tid & 7, p0 = tid >> 3;
+    int e_hyx[2][EPT], e_dst[2][EPT];                              // [phase][element]: (hy<<8)|hx ; smem byte offset or -1
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      const int K = ph == 0 ? a.ksize : 1;
+      const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int pix = p0 + 32 * j, hy = pix / HW, hx = pix - hy * HW;
+        e_hyx[ph][j] = (hy << 8) | hx;
+        e_dst[ph][j] = pix < HW * HH ? (hy * HWP + hx) * 128 + ((q ^ (hx & 7)) << 4) : -1;
+      }
+    }
     int a_it = 0;
     for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
       TcItem w;
       if (!tc_decode(t, item, w)) continue;
-      for (int ph = 0; ph < nph; ++ph) {
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        if (ph >= nph) break;
         const float* src = ph == 0 ? a.in : a.in2;
         const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
         const int CinP = (Cin + 31) & ~31, pad = (K - 1) / 2;
-        const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, npix = HW * HH;
-        const int HWP = K == 1 ? 8 : 16;                         // halo row pitch (pixels): group stride = HWP*128 B
-        const int hw_magic = 65536 / HW + 1;                     // pix / HW for pix < 512 (HW in {8,10,14})
+        const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
         const uint32_t lo_off = (uint32_t)HH * HWP * 128;
         const float* img_in = src + (size_t)w.img * a.H * a.W * Cin;
         for (int c0 = 0; c0 < CinP; c0 += 32) {
           const int as = a_it % A_ST;
           if (a_it >= A_ST) mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1);
           uint8_t* hi = sA + (size_t)as * t.a_stage_bytes;
-          // 8 loads in flight per thread; pixel rows of 128 B (32 channels), chunk q stored at q ^ (hx & 7)
-          constexpr int UNR = 8;
-          const int total = 8 * npix;
-          for (int base = tid; base < total; base += TC_LOADERS * UNR) {
-            float4 v[UNR];
-            int dst[UNR];
+          const int c = c0 + q * 4;
+          const bool c_ok = c < Cin;
+          float4 v[EPT];
 #pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-              const int i = base + j * TC_LOADERS;
-              const int pix = i >> 3, q = i & 7;                   // channel quad fastest: coalesced 128-B reads
-              const int hy = (pix * hw_magic) >> 16, hx = pix - hy * HW;
-              const int gy = w.y0 + hy - pad, gx = w.x0 + hx - pad, c = c0 + q * 4;
-              v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-              dst[j] = i < total ? (hy * HWP + hx) * 128 + ((q ^ (hx & 7)) << 4) : -1;
-              if (i < total && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W && c < Cin)
-                v[j] = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
-            }
+          for (int j = 0; j < EPT; ++j) {                            // all loads of the K-block in flight together
+            const int gy = w.y0 + (e_hyx[ph][j] >> 8) - pad, gx = w.x0 + (e_hyx[ph][j] & 255) - pad;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e_dst[ph][j] >= 0 && c_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W)
+              v[j] = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
+          }
 #pragma unroll
-            for (int j = 0; j < UNR; ++j) {
-              if (dst[j] < 0) continue;
-              const float4 h = make_float4(to_tf32(v[j].x), to_tf32(v[j].y), to_tf32(v[j].z), to_tf32(v[j].w));
-              *(float4*)(hi + dst[j]) = h;
-              *(float4*)(hi + lo_off + dst[j]) = make_float4(to_tf32(v[j].x - h.x), to_tf32(v[j].y - h.y),
-                                                             to_tf32(v[j].z - h.z), to_tf32(v[j].w - h.w));
-            }
+          for (int j = 0; j < EPT; ++j) {
+            if (e_dst[ph][j] < 0) continue;
+            const float4 h = make_float4(to_tf32(v[j].x), to_tf32(v[j].y), to_tf32(v[j].z), to_tf32(v[j].w));
+            *(float4*)(hi + e_dst[ph][j]) = h;
+            *(float4*)(hi + lo_off + e_dst[ph][j]) = make_float4(to_tf32(v[j].x - h.x), to_tf32(v[j].y - h.y),
+                                                                 to_tf32(v[j].z - h.z), to_tf32(v[j].w - h.w));
           }
           fence_proxy_async();
           mbar_arrive(a_full + as);
@@ -330,8 +340,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       umma_commit(acc_full + buf);
       ++it;
     }
-  } else if (warp >= 6) {
-    // =================================== epilogue (warps 6-9) =========================================
+  } else if (warp >= TC_LW + 2) {
+    // =================================== epilogue (4 warps) ===========================================
     const int quarter = warp & 3;                                  // TMEM lanes this warp may read
     const int r = quarter * 32 + (tid & 31);                       // accumulator row = output pixel of the tile
     int it = 0;
@@ -413,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_LW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(t.tmem_cols));
   }
