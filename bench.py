@@ -137,6 +137,15 @@ def cpu_reference_fps(cfg, cams, resize, frames: np.ndarray, sd_np, warm: int, s
     return len(ts) / sum(ts), torch.get_num_threads(), float(np.median(ts)) * 1e3
 
 
+def _emit(line: dict) -> None:
+    """Exactly one JSON line on the real stdout (library chatter such as NCCL's version banner goes to stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)          # anything a library prints to fd 1 from here on lands on stderr
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,7 +183,7 @@ def main():
         frames = make_frames(cfg, cams, 4, seed0=5000)
         fps, cores, med_ms = cpu_reference_fps(cfg, cams, resize, frames, sd_np, warm, steps)
         sample = "%d forwards of one frame each (after %d warm-up), best of {8,16,32,all} = %d host threads" % (steps, warm, cores)
-        print(json.dumps({
+        _emit(({
             "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": 1e3 / fps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": conf,
@@ -323,7 +332,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_base, "kernels": extra_kernels, "valid_people_last_step": n_valid,
         "cuda_graph": not args.no_graph,
     }
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -405,7 +405,7 @@ int fvp_use_cuda_graph(fvp_ctx* ctx, int enable) {
 }
 
 int fvp_set_conv_mode(fvp_ctx* ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 1) return FVP_E_INVALID;
+  if (!ctx || mode < 0 || mode > 2) return FVP_E_INVALID;
   if (mode != ctx->conv_mode && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
   ctx->conv_mode = mode;
   return FVP_OK;

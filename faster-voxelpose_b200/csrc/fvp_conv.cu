@@ -217,9 +217,10 @@ static void conv(const FvpConvW& w, const float* in, int H, int W, const float* 
   a.out = out; a.CoutP = w.coutp; a.CoutS = couts; a.CoutReal = cout_real;
   a.res = res; a.res_mode = res_mode; a.relu = relu; a.ksize = w.k; a.upsample = upsample;
   a.nchw = nchw; a.n = n; a.valid = valid;
-  // 7x7 front conv: 49 taps x 16 input channels would run half-empty 32-channel K-blocks on the tensor path
-  // (measured 6.6 vs 11.4 TMAC/s): it stays on the CUDA-core kernel
-  if (g_tc && w.wtc && w.k != 7) fvp_launch_conv_tc(a, w.wtc, w.wtc_narrow, 148, st);
+  // engine 2: fp16-split tcgen05 kernel (all layers); engine 1: 3xTF32 tcgen05 kernel, where the 7x7 front conv (49 taps
+  // of half-empty 32-channel K-blocks, measured 6.6 vs 11.4 TMAC/s) stays on the CUDA-core kernel; engine 0: CUDA cores.
+  if (g_tc == 2 && w.wtc16) fvp_launch_conv_tc(a, w.wtc16, w.wtc16_narrow, 1, 148, st);
+  else if (g_tc == 1 && w.wtc && w.k != 7) fvp_launch_conv_tc(a, w.wtc, w.wtc_narrow, 0, 148, st);
   else fvp_launch_conv(a, st);
   if (launches) ++*launches;
 }

@@ -1,7 +1,14 @@
 // fvp_conv_tc.cu - tcgen05 / TMEM implicit-GEMM convolution for the CenterNet / P2PNet trunks
 // (cnns_2d.py:12-178), same fused epilogues and NHWC fp32 interface as fvp_conv.cu (k_conv_nhwc).
 //
-// Precision: "3xTF32" error-compensated split.  Every fp32 operand x is split on the fly into
+// Precision: two error-compensated operand splits (template parameter F16):
+//   F16 = true  (default): x = hi + lo * 2^-11 with hi = fp16(x), lo = fp16((x - hi) * 2^11); kind::f16 MMAs with K = 16,
+//                D1 += A_hi*B_hi and D2 += A_hi*B_lo + A_lo*B_hi in two fp32 TMEM accumulators, D = D1 + 2^-11 * D2.
+//                22 significant bits per operand like 3xTF32 but HALF the MMA instructions (the tensor unit spends
+//                ~48 cycles of fixed overhead per instruction with cta_group::1); operands must stay
+//                inside the fp16 range (|x| < 65504 - activations here are O(1)).
+//   F16 = false: "3xTF32" (below).
+// Precision (tf32 variant): "3xTF32" error-compensated split.  Every fp32 operand x is split on the fly into
 // hi = tf32(x) (round-to-nearest) and lo = tf32(x - hi); D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi accumulates
 // in fp32 in tensor memory.  A single kind::tf32 pass moves joints by 1.33 mm; the split keeps
 // the convolution at ~1e-6 relative of the exact-fp32 kernel (tests/test_gpu_parity.py compares both).
@@ -19,6 +26,8 @@
 // Warp roles: warps 0-3 stage operands (A ring of 2, B ring of 3, mbarrier full/empty pairs; MMA completion
 // frees a slot through tcgen05.commit) and run the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4
 // allocates TMEM and one elected lane issues every tcgen05.mma.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "fvp_kernels.h"
@@ -86,18 +95,29 @@ __device__ __forceinline__ float to_tf32(float x) {
 // base offset as long as the data was stored with the same absolute-address rule (setting base_offset = dx breaks it).
 // (Round-1 note: the un-swizzled "interleave" layout computes correctly but the tensor core then fetches one 16-B row
 //  per cycle: ~(128+N)*2 cycles per MMA, 13x below peak - measured in profiles/r01_launches_tc_noswizzle.csv.)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)(base_offset & 7) << 49) | ((uint64_t)2 << 61);
+         ((uint64_t)1 << 46) | ((uint64_t)layout_type << 61);     // layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N>>3, M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with A = B = F16 (format 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -149,7 +169,10 @@ __device__ __forceinline__ bool tc_decode(const TcArgs& t, int item, TcItem& w) 
 //   warps 6-9  epilogue    : tcgen05.ld of the finished accumulator, bias/residual/ReLU, stores
 // Two accumulator buffers in TMEM (acc_full / acc_empty) let the MMAs of tile i+1 run under the epilogue of
 // tile i, and the staging of tile i+1 under the MMAs of tile i.
+template <bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
+  constexpr int ROWB = F16 ? 64 : 128;        // bytes of one pixel row (32 channels) in shared memory
+  constexpr uint32_t LAYOUT = F16 ? 4u : 2u;  // SWIZZLE_64B / SWIZZLE_128B
   extern __shared__ __align__(128) uint8_t tc_smem[];
   __shared__ uint64_t s_bar[2 * TC_MAX_A + 2 * TC_MAX_B + 4];
   __shared__ uint32_t s_tmem;
@@ -187,8 +210,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
     // Thread (q = tid & 7, p0 = tid >> 3) always handles channel quad q of halo pixels p0, p0+32, p0+64, ...:
     // their halo coordinates, shared-memory destinations and global offsets do not depend on the work item, so they
     // are computed once; per item only the image bounds tests and one base pointer remain.
-    constexpr int EPT = 10;                                        // elements per thread: ceil(22*14 / 32)
-    const int q = tid & 7, p0 = tid >> 3;
+    constexpr int CH = F16 ? 4 : 8;                                // 16-B chunks per pixel row
+    constexpr int PPI = TC_LOADERS / CH;                           // pixels covered per pass of the 256 threads
+    constexpr int EPT = (22 * 14 + PPI - 1) / PPI;                 // elements per thread (largest halo: 7x7)
+    const int q = tid % CH, p0 = tid / CH;
     int e_hyx[2][EPT], e_dst[2][EPT];                              // [phase][element]: (hy<<8)|hx ; smem byte offset or -1
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph) {
@@ -196,9 +221,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       const int HW = TC_TW + K - 1, HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
-        const int pix = p0 + 32 * j, hy = pix / HW, hx = pix - hy * HW;
+        const int pix = p0 + PPI * j, hy = pix / HW, hx = pix - hy * HW;
         e_hyx[ph][j] = (hy << 8) | hx;
-        e_dst[ph][j] = pix < HW * HH ? (hy * HWP + hx) * 128 + ((q ^ (hx & 7)) << 4) : -1;
+        // swizzle on absolute address bits: chunk ^= (row address >> 7) & (CH-1); halo rows are 1024-B multiples apart
+        const int phase = F16 ? ((hx >> 1) & 3) : (hx & 7);
+        e_dst[ph][j] = pix < HW * HH ? (hy * HWP + hx) * ROWB + ((q ^ phase) << 4) : -1;
       }
     }
     int a_it = 0;
@@ -212,29 +239,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
         const int CinP = (Cin + 31) & ~31, pad = (K - 1) / 2;
         const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
-        const uint32_t lo_off = (uint32_t)HH * HWP * 128;
+        const uint32_t lo_off = (uint32_t)HH * HWP * ROWB;
         const float* img_in = src + (size_t)w.img * a.H * a.W * Cin;
         for (int c0 = 0; c0 < CinP; c0 += 32) {
           const int as = a_it % A_ST;
           if (a_it >= A_ST) mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1);
           uint8_t* hi = sA + (size_t)as * t.a_stage_bytes;
-          const int c = c0 + q * 4;
-          const bool c_ok = c < Cin;
-          float4 v[EPT];
+          if constexpr (F16) {
+            const int c = c0 + q * 8;                                // 8 channels -> one 16-B chunk of halves
+            float4 v[EPT][2];
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) {                            // all loads of the K-block in flight together
-            const int gy = w.y0 + (e_hyx[ph][j] >> 8) - pad, gx = w.x0 + (e_hyx[ph][j] & 255) - pad;
-            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e_dst[ph][j] >= 0 && c_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W)
-              v[j] = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
-          }
+            for (int j = 0; j < EPT; ++j) {                          // all loads of the K-block in flight together
+              const int gy = w.y0 + (e_hyx[ph][j] >> 8) - pad, gx = w.x0 + (e_hyx[ph][j] & 255) - pad;
+              v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (e_dst[ph][j] >= 0 && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+                const float* pp = img_in + ((size_t)gy * a.W + gx) * Cin + c;
+                if (c < Cin) v[j][0] = __ldg((const float4*)pp);
+                if (c + 4 < Cin) v[j][1] = __ldg((const float4*)(pp + 4));
+              }
+            }
 #pragma unroll
-          for (int j = 0; j < EPT; ++j) {
-            if (e_dst[ph][j] < 0) continue;
-            const float4 h = make_float4(to_tf32(v[j].x), to_tf32(v[j].y), to_tf32(v[j].z), to_tf32(v[j].w));
-            *(float4*)(hi + e_dst[ph][j]) = h;
-            *(float4*)(hi + lo_off + e_dst[ph][j]) = make_float4(to_tf32(v[j].x - h.x), to_tf32(v[j].y - h.y),
-                                                                 to_tf32(v[j].z - h.z), to_tf32(v[j].w - h.w));
+            for (int j = 0; j < EPT; ++j) {
+              if (e_dst[ph][j] < 0) continue;
+              const float x[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
+              uint32_t ph_[4], pl_[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half h0 = __float2half_rn(x[2 * e]), h1 = __float2half_rn(x[2 * e + 1]);
+                const __half l0 = __float2half_rn((x[2 * e] - __half2float(h0)) * 2048.0f);
+                const __half l1 = __float2half_rn((x[2 * e + 1] - __half2float(h1)) * 2048.0f);
+                ph_[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                pl_[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              }
+              *(uint4*)(hi + e_dst[ph][j]) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
+              *(uint4*)(hi + lo_off + e_dst[ph][j]) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
+            }
+          } else {
+            const int c = c0 + q * 4;
+            const bool c_ok = c < Cin;
+            float4 v[EPT];
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {                          // all loads of the K-block in flight together
+              const int gy = w.y0 + (e_hyx[ph][j] >> 8) - pad, gx = w.x0 + (e_hyx[ph][j] & 255) - pad;
+              v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (e_dst[ph][j] >= 0 && c_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W)
+                v[j] = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
+            }
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+              if (e_dst[ph][j] < 0) continue;
+              const float4 h = make_float4(to_tf32(v[j].x), to_tf32(v[j].y), to_tf32(v[j].z), to_tf32(v[j].w));
+              *(float4*)(hi + e_dst[ph][j]) = h;
+              *(float4*)(hi + lo_off + e_dst[ph][j]) = make_float4(to_tf32(v[j].x - h.x), to_tf32(v[j].y - h.y),
+                                                                   to_tf32(v[j].z - h.z), to_tf32(v[j].w - h.w));
+            }
           }
           fence_proxy_async();
           mbar_arrive(a_full + as);
@@ -275,7 +333,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
     }
   } else if (tid == TC_LOADERS) {
     // =============================== MMA issue (one thread) =========================================
-    const uint32_t idesc = umma_idesc_tf32(128, t.n_tile);
+    const uint32_t idesc = F16 ? umma_idesc_f16(128, t.n_tile) : umma_idesc_tf32(128, t.n_tile);
     int a_it = 0, b_it = 0, it = 0;
     bool b_ready = false;
     for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
@@ -284,14 +342,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       const int buf = it & 1;
       if (it >= 2) mbar_wait(acc_empty + buf, ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem + (uint32_t)buf * t.acc_stride;
+      const uint32_t d_tmem = tmem + (uint32_t)buf * (F16 ? 2u : 1u) * t.acc_stride;   // F16: D1 | D2 side by side
       uint32_t accumulate = 0;
       uint32_t blk = 0;                                            // running weight block index (resident image)
       for (int ph = 0; ph < nph; ++ph) {
         const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
         const int CinP = (Cin + 31) & ~31;
         const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
-        const uint32_t a_lo_off = (uint32_t)HH * HWP * 128, b_lo_off = (uint32_t)t.n_tile * 128;
+        const uint32_t a_lo_off = (uint32_t)HH * HWP * ROWB, b_lo_off = (uint32_t)t.n_tile * ROWB;
         for (int c0 = 0; c0 < CinP; c0 += 32) {
           const int as = a_it % A_ST;
           mbar_wait(a_full + as, (a_it / A_ST) & 1);
@@ -310,22 +368,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
             }
             tc_fence_after();
             const int dy = tap / K, dx = tap - dy * K;
-            const uint32_t a_tap = a_base + (uint32_t)(dy * HWP + dx) * 128;
-            // Descriptors are built once per tap; the 12 instructions below only add immediates to the low word
-            // (a lone issuing thread runs ~1 dependent instruction per 5 cycles: descriptor math per MMA would
-            // cost more than the MMA itself).  Passes: lo*hi, hi*lo, hi*hi (small terms first); K = 8 per MMA.
-            const uint64_t ad_hi = umma_desc(a_tap, (uint32_t)HWP * 128, 0u);
-            const uint64_t ad_lo = umma_desc(a_tap + a_lo_off, (uint32_t)HWP * 128, 0u);
-            const uint64_t bd_hi = umma_desc(b_base, 1024, 0);
-            const uint64_t bd_lo = umma_desc(b_base + b_lo_off, 1024, 0);
-            umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
-            umma_tf32(d_tmem, ad_lo + 2, bd_hi + 2, idesc, 1);
-            umma_tf32(d_tmem, ad_lo + 4, bd_hi + 4, idesc, 1);
-            umma_tf32(d_tmem, ad_lo + 6, bd_hi + 6, idesc, 1);
+            const uint32_t a_tap = a_base + (uint32_t)(dy * HWP + dx) * ROWB;
+            // Descriptors are built once per tap; the MMAs below only add immediates to the low word (K advance of
+            // 32 B = +2).  A lone issuing thread runs ~1 dependent instruction per 5 cycles, so descriptor math per
+            // MMA would cost more than the MMA itself.
+            const uint64_t ad_hi = umma_desc(a_tap, (uint32_t)HWP * ROWB, LAYOUT);
+            const uint64_t ad_lo = umma_desc(a_tap + a_lo_off, (uint32_t)HWP * ROWB, LAYOUT);
+            const uint64_t bd_hi = umma_desc(b_base, 8 * ROWB, LAYOUT);
+            const uint64_t bd_lo = umma_desc(b_base + b_lo_off, 8 * ROWB, LAYOUT);
+            if constexpr (F16) {                                   // K = 16 per instruction: 2 steps per 32 channels
+              const uint32_t d2 = d_tmem + t.acc_stride;
+              umma_f16(d_tmem, ad_hi, bd_hi, idesc, accumulate);
+              umma_f16(d_tmem, ad_hi + 2, bd_hi + 2, idesc, 1);
+              umma_f16(d2, ad_hi, bd_lo, idesc, accumulate);
+              umma_f16(d2, ad_hi + 2, bd_lo + 2, idesc, 1);
+              umma_f16(d2, ad_lo, bd_hi, idesc, 1);
+              umma_f16(d2, ad_lo + 2, bd_hi + 2, idesc, 1);
+            } else {                                               // 3xTF32, K = 8: lo*hi, hi*lo, hi*hi
+              umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
+              umma_tf32(d_tmem, ad_lo + 2, bd_hi + 2, idesc, 1);
+              umma_tf32(d_tmem, ad_lo + 4, bd_hi + 4, idesc, 1);
+              umma_tf32(d_tmem, ad_lo + 6, bd_hi + 6, idesc, 1);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_lo + 2 * ks, idesc, 1);
+              for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_lo + 2 * ks, idesc, 1);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_hi + 2 * ks, idesc, 1);
+              for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_hi + 2 * ks, idesc, 1);
+            }
             accumulate = 1;
             if (!t.resident) {
               umma_commit(b_empty + bs);                           // B slot reusable when these MMAs retire
@@ -354,7 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       const int oy = w.y0 + (r >> 3), ox = w.x0 + (r & 7);
       const bool px_ok = oy < a.H && ox < a.W;
       const int co_base = w.nt * t.n_tile;
-      const uint32_t t_row = tmem + (uint32_t)buf * t.acc_stride + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t t_row = tmem + (uint32_t)buf * (F16 ? 2u : 1u) * t.acc_stride + ((uint32_t)(quarter * 32) << 16);
       // output location of a 4-channel group (NHWC, pixel-shuffled for ConvTranspose k2s2)
       auto locate = [&](int co, size_t& opix, int& ch, int& Y, int& X, int& Ho, int& Wo) {
         Y = oy; X = ox; Ho = a.H; Wo = a.W; ch = co;
@@ -389,6 +457,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         fetch_res(cb + 16, rnext);                                 // next chunk's residuals fly under this chunk
         float v[16];
         tmem_ld16(t_row + (uint32_t)cb, v);
+        if constexpr (F16) {                                       // D = D1 + 2^-11 * D2
+          float v2[16];
+          tmem_ld16(t_row + t.acc_stride + (uint32_t)cb, v2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(v2[i], 1.0f / 2048.0f, v[i]);
+        }
         if (cb + 16 >= t.n_tile) {                                 // last chunk read: hand the accumulator back
           tc_fence_before();
           mbar_arrive(acc_empty + buf);
@@ -440,9 +514,11 @@ void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
   *n_tiles = fvp_cdiv(npad, *n_tile);
 }
 
-void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int num_sms, cudaStream_t st) {
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int f16, int num_sms,
+                        cudaStream_t st) {
   TcArgs t;
   t.c = a;
+  const uint32_t rowb = f16 ? 64 : 128;
   const int tiles = fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW) * a.n;
   int n_tile, n_tiles;
   fvp_tc_geometry(a.CoutP, 0, &n_tile, &n_tiles);
@@ -450,10 +526,10 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float
   fvp_tc_geometry(a.CoutP, narrow, &t.n_tile, &t.n_tiles);
   t.wtc = narrow ? wtc_narrow : wtc_wide;
   const int k = a.ksize;
-  const uint32_t a0 = (uint32_t)(TC_TH + k - 1) * (k == 1 ? 8 : 16) * 128 * 2;
-  const uint32_t a1 = a.in2 ? (uint32_t)TC_TH * 8 * 128 * 2 : 0;
+  const uint32_t a0 = (uint32_t)(TC_TH + k - 1) * (k == 1 ? 8 : 16) * rowb * 2;
+  const uint32_t a1 = a.in2 ? (uint32_t)TC_TH * 8 * rowb * 2 : 0;
   t.a_stage_bytes = a0 > a1 ? a0 : a1;                            // multiples of 1024
-  t.blk_bytes = (uint32_t)t.n_tile * 128 * 2;
+  t.blk_bytes = (uint32_t)t.n_tile * rowb * 2;
   const int nblocks = k * k * (fvp_round_up(a.Cin, 32) / 32) + (a.in2 ? fvp_round_up(a.Cin2, 32) / 32 : 0);
   const uint32_t image_bytes = (uint32_t)nblocks * t.n_tiles * t.blk_bytes;
   const uint32_t budget = 224 * 1024 - 1024;                       // dynamic smem we may use (1 KB alignment slack)
@@ -470,18 +546,20 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float
     const int bs = (int)((budget - t.a_stage_bytes) / t.blk_bytes);
     t.b_stages = bs > TC_MAX_B ? TC_MAX_B : bs;
   }
-  t.acc_stride = (uint32_t)fvp_round_up(t.n_tile, 32);          // two accumulators side by side in TMEM
+  t.acc_stride = (uint32_t)fvp_round_up(t.n_tile, 32);          // accumulators side by side in TMEM: 2 buffers x (D1[,D2])
   t.tmem_cols = 32;
-  while (t.tmem_cols < 2 * t.acc_stride) t.tmem_cols <<= 1;
+  while (t.tmem_cols < (f16 ? 4u : 2u) * t.acc_stride) t.tmem_cols <<= 1;
   t.tiles_x = fvp_cdiv(a.W, TC_TW);
   t.tiles_per_img = t.tiles_x * fvp_cdiv(a.H, TC_TH);
   t.total_items = t.tiles_per_img * a.n * t.n_tiles;
   const size_t smem = 1024 + (size_t)t.a_stages * t.a_stage_bytes + (size_t)t.b_stages * t.b_stage_bytes;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr = true;
   }
   const int grid = t.total_items < num_sms ? t.total_items : num_sms;   // persistent: one CTA per SM
-  k_conv_tc<<<grid, TC_THREADS, smem, st>>>(t);
+  if (f16) k_conv_tc<true><<<grid, TC_THREADS, smem, st>>>(t);
+  else k_conv_tc<false><<<grid, TC_THREADS, smem, st>>>(t);
 }

@@ -20,9 +20,8 @@ def run(tag, n, H, W, cin, cout, k, wmask=None):
         w = w * wmask
     b = rng.standard_normal(cout).astype(np.float32) * 0.1
     r = ref(x, w, b, False)
-    e0 = float((eng.debug_conv(x, w, b, False, 0) - r).abs().max())
-    e1 = float((eng.debug_conv(x, w, b, False, 1) - r).abs().max())
-    print("%-28s ffma %.2e  tc %.2e" % (tag, e0, e1)); sys.stdout.flush()
+    e = [float((eng.debug_conv(x, w, b, False, m) - r).abs().max()) for m in (0, 1, 2)]
+    print("%-28s ffma %.2e  tf32x3 %.2e  fp16x3 %.2e" % (tag, e[0], e[1], e[2])); sys.stdout.flush()
 run("1x1 32->32 16x8", 1, 16, 8, 32, 32, 1)
 run("1x1 64->128 32x32", 2, 32, 32, 64, 128, 1)
 for dy in range(3):
@@ -41,11 +40,12 @@ def timing(tag, n, H, W, cin, cout, k):
     x = torch.from_numpy(rng.standard_normal((n, H, W, cin)).astype(np.float32)).cuda()
     w = (rng.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)).astype(np.float32); b = np.zeros(cout, np.float32)
     r = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         _, ms = eng.debug_conv(x, w, b, True, mode, repeat=20, want_ms=True)
         r.append(ms * 1000)
     gmac = n * H * W * cin * cout * k * k / 1e9
-    print("%-34s ffma %7.1f us (%5.1f TMAC/s)   tc %7.1f us (%5.1f TMAC/s)" % (tag, r[0], gmac / r[0] * 1e3, r[1], gmac / r[1] * 1e3)); sys.stdout.flush()
+    print("%-30s ffma %7.1f us (%5.1f)  tf32x3 %7.1f us (%5.1f)  fp16x3 %7.1f us (%5.1f TMAC/s)" % (
+        tag, r[0], gmac / r[0] * 1e3, r[1], gmac / r[1] * 1e3, r[2], gmac / r[2] * 1e3)); sys.stdout.flush()
 timing("3x3 32->32 64x64 n=30", 30, 64, 64, 32, 32, 3)
 timing("3x3 32->32 64x64 n=120", 120, 64, 64, 32, 32, 3)
 timing("3x3 32->32 64x64 n=480", 480, 64, 64, 32, 32, 3)
