@@ -71,7 +71,7 @@ struct fvp_ctx {
   int* h_frame_seq = nullptr;         // pinned
   int frame_seq_uploaded = 0;         // how many leading entries of d_frame_seq mirror h_frame_seq
   int num_sms = 148;
-  int conv_mode = 1;                  // 0 = fp32 CUDA cores, 1 = tcgen05 3xTF32 (7x7 on CUDA cores), 2 = tcgen05 fp16 split
+  int conv_mode = 2;                  // 0 = fp32 CUDA cores, 1 = tcgen05 3xTF32 (7x7 on CUDA cores), 2 = tcgen05 fp16 split
 
   // cuda graph
   bool use_graph = false;

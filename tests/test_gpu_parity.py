@@ -160,21 +160,22 @@ def test_p2p_net(case):
 
 
 def test_tcgen05_convs_match_fp32_cuda_core_convs(case):
-    """The tcgen05 3xTF32 engine (default) against the exact-fp32 CUDA-core engine on the same inputs:
-    CenterNet <= 3e-6, P2PNet <= 2e-6 (a single-pass TF32 conv would be ~1e-3 off)."""
+    """Both tcgen05 engines (2 = fp16 hi/scaled-lo split, the default; 1 = 3xTF32) against the exact-fp32 CUDA-core
+    engine on the same inputs: CenterNet <= 3e-6, P2PNet <= 2e-6 (a single-pass TF32 conv would be ~1e-3 off)."""
     g, eng, slots = case
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         eng.set_conv_mode(mode)
         hm, size = eng.center_net(torch.from_numpy(g["hdn_plane"]), g.B)
         feat = None
         if g.has("b0_planes_keep"):
             feat = eng.p2p_net(torch.from_numpy(g["b0_planes_keep"].reshape(-1, g.J, 64, 64))).cpu().numpy()
         out[mode] = (hm.cpu().numpy(), size.cpu().numpy(), feat)
-    eng.set_conv_mode(1)
-    assert _maxerr(out[1][0], out[0][0]) <= 3e-6 and _maxerr(out[1][1], out[0][1]) <= 3e-6
-    if out[0][2] is not None:
-        assert _maxerr(out[1][2], out[0][2]) <= 2e-6
+    eng.set_conv_mode(2)
+    for m in (1, 2):
+        assert _maxerr(out[m][0], out[0][0]) <= 3e-6 and _maxerr(out[m][1], out[0][1]) <= 3e-6
+        if out[0][2] is not None:
+            assert _maxerr(out[m][2], out[0][2]) <= 2e-6
 
 
 def test_single_conv_layers_both_engines(built_library, golden):
@@ -194,6 +195,7 @@ def test_single_conv_layers_both_engines(built_library, golden):
                        padding=k // 2).permute(0, 2, 3, 1).float()
         assert float((eng.debug_conv(x, w, b, False, 0) - ref).abs().max()) <= 2e-5      # fp32 FFMA
         assert float((eng.debug_conv(x, w, b, False, 1) - ref).abs().max()) <= 1e-4      # 3xTF32 on O(1) outputs
+        assert float((eng.debug_conv(x, w, b, False, 2) - ref).abs().max()) <= 3e-5      # fp16 split (measured <= 7e-6)
 
     check(1, 16, 8, 32, 32, 1)
     check(2, 32, 32, 64, 128, 1)
