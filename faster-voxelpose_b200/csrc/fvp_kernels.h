@@ -91,6 +91,7 @@ void fvp_launch_nms_topk(const float* d_hm, size_t img_stride, int X, int Y, int
 struct FvpC2CW {            // packed 1-D trunk, weights [tap][ci][co] per conv
   const float* w[24];
   const float* b[24];
+  const float* w2[24];      // same, ci-major ([ci][tap][co], then the fused-skip rows) for the split-K kernel
 };
 struct FvpPropArgs {
   FvpGeom g;

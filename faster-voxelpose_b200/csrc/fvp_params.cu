@@ -361,6 +361,19 @@ int fvp_pack_params(fvp_ctx* ctx) {
   // ---- C2CNet --------------------------------------------------------------------------------
   pack_trunk(ctx, "pose_net.c2c_net", A, c2c, false);
   c2c.push_back(stash(A, pack_conv(ctx, "pose_net.c2c_net.output_hm")));
+  // ci-major copies for the split-K 1-D kernel: rows [ci][tap] (real input channels only), then the skip rows [ci]
+  std::vector<size_t> c2c_cimajor;
+  for (const PendingConv& pc : c2c) {
+    const int cinP = fvp_round_up(pc.cin, 16), taps = pc.k;      // 1-D: taps = k
+    const float* src = A.host.data() + pc.w_off;
+    std::vector<float> v((size_t)(pc.cin * taps + pc.cin2) * pc.coutp, 0.f);
+    for (int ci = 0; ci < pc.cin; ++ci)
+      for (int tp = 0; tp < taps; ++tp)
+        std::memcpy(&v[(size_t)(ci * taps + tp) * pc.coutp], src + (size_t)(tp * cinP + ci) * pc.coutp, pc.coutp * sizeof(float));
+    for (int ci = 0; ci < pc.cin2; ++ci)
+      std::memcpy(&v[(size_t)(pc.cin * taps + ci) * pc.coutp], src + (size_t)(taps * cinP + ci) * pc.coutp, pc.coutp * sizeof(float));
+    c2c_cimajor.push_back(A.put(v));
+  }
   // ---- P2PNet --------------------------------------------------------------------------------
   pack_trunk(ctx, "joint_net.conv_net", A, p2p, true);
   p2p.push_back(stash(A, pack_conv(ctx, "joint_net.conv_net.output_layer"), true));
@@ -397,6 +410,7 @@ int fvp_pack_params(fvp_ctx* ctx) {
   for (int i = 0; i < 20; ++i) {
     ctx->w_c2c.w[i] = base + c2c[i].w_off;
     ctx->w_c2c.b[i] = base + c2c[i].b_off;
+    ctx->w_c2c.w2[i] = base + c2c_cimajor[i];
   }
   ctx->w_pose.conv_w = base + o_cw;
   ctx->w_pose.conv_b = base + o_cb;

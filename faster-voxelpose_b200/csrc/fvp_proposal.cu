@@ -239,6 +239,147 @@ __device__ void c2c_forward(const C2CNet& net, const float* x0, int J, int Z, fl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Register-tiled 1-D conv with K split across the thread block (round-1 profile: the row-major c2c_conv above
+// spends ~20 instructions per weight row and predicated position; 0.35 ms per column).  Thread (co, ks) owns ALL L
+// output positions of channel co for the input channels ci = ks, ks+KS, ...: per ci it loads the L+K-1 inputs once
+// into registers (warp-broadcast) and runs K*L FMAs; the KS partial sums meet in shared memory in fixed order.
+// Weights are packed ci-major ([ci][tap][CoutG], then the fused 1x1 skip rows [ci][CoutG]) and streamed through the
+// same cp.async double buffer.
+// ------------------------------------------------------------------------------------------------
+template <int L, int K>
+__device__ void c2c_conv2(const float* __restrict__ in, int Cin, const float* __restrict__ in2, int Cin2, const float* w2,
+                          const float* bias_p, float* __restrict__ out, int CoutG, const float* __restrict__ res,
+                          int res_mode, bool relu, bool upsample, float* __restrict__ wbuf, float* __restrict__ red) {
+  constexpr int PAD = (K - 1) / 2;
+  const int tid = threadIdx.x;
+  const int KS = C2C_THREADS / CoutG;
+  const int co = tid % CoutG, ks = tid / CoutG;
+  float acc[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) acc[l] = 0.f;
+
+  for (int part = 0; part < 2; ++part) {                 // 0: main K-tap conv on `in`, 1: fused 1x1 on `in2`
+    const float* src = part == 0 ? in : in2;
+    if (src == nullptr) break;
+    const int C = part == 0 ? Cin : Cin2;
+    const int taps = part == 0 ? K : 1;
+    const float* wsrc = part == 0 ? w2 : w2 + (size_t)Cin * K * CoutG;
+    int cpc = C2C_WCHUNK / (taps * CoutG);               // input channels per weight chunk
+    if (cpc > C) cpc = C;
+    const int nchunks = (C + cpc - 1) / cpc;
+    auto issue = [&](int ch) {
+      const int c_lo = ch * cpc, nc = min(cpc, C - c_lo);
+      const float* g = wsrc + (size_t)c_lo * taps * CoutG;
+      float* d = wbuf + (ch & 1) * C2C_WCHUNK;
+      for (int i = tid * 4; i < nc * taps * CoutG; i += C2C_THREADS * 4) c2c_cp16(d + i, g + i);
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
+    issue(0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+      if (ch + 1 < nchunks) {
+        issue(ch + 1);
+        asm volatile("cp.async.wait_group 1;\n" ::);
+      } else {
+        asm volatile("cp.async.wait_group 0;\n" ::);
+      }
+      __syncthreads();
+      const int c_lo = ch * cpc, c_hi = min(C, c_lo + cpc);
+      const float* wb = wbuf + (ch & 1) * C2C_WCHUNK + co;
+      for (int ci = c_lo + ks; ci < c_hi; ci += KS) {
+        const float* xr_src = src + ci * L;
+        const float* wr = wb + (size_t)(ci - c_lo) * taps * CoutG;
+        if (part == 0) {
+          float xr[L + 2 * PAD];
+#pragma unroll
+          for (int i = 0; i < L + 2 * PAD; ++i) xr[i] = (i >= PAD && i < L + PAD) ? xr_src[i - PAD] : 0.f;
+#pragma unroll
+          for (int tp = 0; tp < K; ++tp) {
+            const float wv = wr[tp * CoutG];
+#pragma unroll
+            for (int l = 0; l < L; ++l) acc[l] = fmaf(wv, xr[l + tp], acc[l]);
+          }
+        } else {
+          const float wv = wr[0];
+#pragma unroll
+          for (int l = 0; l < L; ++l) acc[l] = fmaf(wv, xr_src[l], acc[l]);
+        }
+      }
+      __syncthreads();                                   // buffer (ch&1) may be refilled by chunk ch+2
+    }
+  }
+  // ---- fixed-order reduction over the K split, then the epilogue ----
+#pragma unroll
+  for (int l = 0; l < L; ++l) red[(ks * CoutG + co) * L + l] = acc[l];
+  __syncthreads();
+  for (int e = tid; e < CoutG * L; e += C2C_THREADS) {
+    const int c = e / L, l = e - c * L;
+    float v = 0.f;
+    for (int k2 = 0; k2 < KS; ++k2) v += red[(k2 * CoutG + c) * L + l];
+    v += __ldg(bias_p + c);
+    int oc = c, ol = l, Lo = L;
+    if (upsample) {
+      const int Co = CoutG >> 1;
+      const int d = c / Co;
+      oc = c - d * Co;
+      ol = 2 * l + d;
+      Lo = 2 * L;
+    }
+    if (res_mode == 1) v += res[oc * Lo + ol];
+    if (relu) v = fmaxf(v, 0.f);
+    if (res_mode == 2) v += res[oc * Lo + ol];
+    out[oc * Lo + ol] = v;
+  }
+  __syncthreads();
+}
+
+template <int L>
+__device__ void c2c_pool2(const float* __restrict__ in, int C, float* __restrict__ out) {
+  constexpr int Lo = L / 2;
+  for (int i = threadIdx.x; i < C * Lo; i += C2C_THREADS) {
+    const int c = i / Lo, l = i - c * Lo;
+    out[i] = fmaxf(in[c * L + 2 * l], in[c * L + 2 * l + 1]);
+  }
+  __syncthreads();
+}
+
+struct C2CNet2 {          // ci-major weights (w2) + bias per layer
+  const float* w[20];
+  const float* b[20];
+};
+
+template <int Z>
+__device__ void c2c_forward2(const C2CNet2& n, const float* x0, int J, float* buf, float* out, float* wbuf, float* red) {
+  float *B0 = buf, *B1 = buf + C2C_BUF, *B2 = buf + 2 * C2C_BUF, *B3 = buf + 3 * C2C_BUF, *B4 = buf + 4 * C2C_BUF,
+        *B5 = buf + 5 * C2C_BUF;
+  constexpr int L = Z, L2 = Z / 2, L4 = Z / 4;
+#define CV(Lx, Kx, i, inp, cin, inp2, cin2, outp, cg, resp, rm, up) \
+  c2c_conv2<Lx, Kx>(inp, cin, inp2, cin2, n.w[i], n.b[i], outp, cg, resp, rm, true, up, wbuf, red)
+  CV(L, 7, 0, x0, J, nullptr, 0, B0, 16, nullptr, 0, false);
+  CV(L, 3, 1, B0, 16, nullptr, 0, B1, 32, nullptr, 0, false);
+  CV(L, 3, 2, B1, 32, B0, 16, B2, 32, nullptr, 0, false);
+  CV(L, 3, 3, B2, 32, nullptr, 0, B0, 32, nullptr, 0, false);
+  CV(L, 3, 4, B0, 32, nullptr, 0, B3, 32, B2, 1, false);           // skip1
+  c2c_pool2<L>(B2, 32, B0);
+  CV(L2, 3, 5, B0, 32, nullptr, 0, B1, 64, nullptr, 0, false);
+  CV(L2, 3, 6, B1, 64, B0, 32, B4, 64, nullptr, 0, false);         // e1
+  CV(L2, 3, 7, B4, 64, nullptr, 0, B0, 64, nullptr, 0, false);
+  CV(L2, 3, 8, B0, 64, nullptr, 0, B5, 64, B4, 1, false);          // skip2
+  c2c_pool2<L2>(B4, 64, B0);
+  CV(L4, 3, 9, B0, 64, nullptr, 0, B1, 128, nullptr, 0, false);
+  CV(L4, 3, 10, B1, 128, B0, 64, B2, 128, nullptr, 0, false);      // e2
+  CV(L4, 3, 11, B2, 128, nullptr, 0, B0, 128, nullptr, 0, false);
+  CV(L4, 3, 12, B0, 128, nullptr, 0, B1, 128, B2, 1, false);       // m
+  CV(L4, 3, 13, B1, 128, nullptr, 0, B0, 128, nullptr, 0, false);
+  CV(L4, 3, 14, B0, 128, nullptr, 0, B2, 128, B1, 1, false);       // d2
+  CV(L4, 1, 15, B2, 128, nullptr, 0, B0, 128, B5, 2, true);        // u2 = relu(convT)+skip2
+  CV(L2, 3, 16, B0, 64, nullptr, 0, B1, 64, nullptr, 0, false);
+  CV(L2, 3, 17, B1, 64, nullptr, 0, B2, 64, B0, 1, false);         // d1
+  CV(L2, 1, 18, B2, 64, nullptr, 0, B0, 64, B3, 2, true);          // u1 = relu(convT)+skip1
+#undef CV
+  c2c_conv2<L, 1>(B0, 32, nullptr, 0, n.w[19], n.b[19], out, 4, nullptr, 0, false, false, wbuf, red);   // head (row 0 of 4)
+}
+
+// ------------------------------------------------------------------------------------------------
 // crop parameters of one proposal (project_individual.py:110-121), exact fp32 op order
 // ------------------------------------------------------------------------------------------------
 __device__ void fvp_make_person(const FvpPropArgs& a, const float* c7, int seq, FvpPerson& pd) {
@@ -270,12 +411,13 @@ __device__ void fvp_make_person(const FvpPropArgs& a, const float* c7, int seq, 
 }
 
 // one CTA per proposal slot
-__global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet net) {
+__global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet net, C2CNet2 net2) {
   extern __shared__ __align__(16) float c2c_smem[];
   float* s_wbuf = c2c_smem;                       // 2 x C2C_WCHUNK weight staging
   float* s_buf = s_wbuf + 2 * C2C_WCHUNK;         // 6 activation buffers
   float* s_x0 = s_buf + 6 * C2C_BUF;              // [JP][Z] input columns
   float* s_out = s_x0 + 24 * C2C_MAXZ;            // [4][Z] head output
+  float* s_red = s_out + 4 * C2C_MAXZ;            // [KS][CoutG][L] split-K partial sums (512 * L floats)
   __shared__ FvpSeq s_seq;
   const FvpGeom& g = a.g;
   const int slot = blockIdx.x, b = slot / g.P;
@@ -323,7 +465,9 @@ __global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet
     for (int i = tid; i < J * Z; i += C2C_THREADS) a.cols_out[(size_t)slot * J * Z + i] = s_x0[i];
   (void)JP;
 
-  c2c_forward(net, s_x0, J, Z, s_buf, s_out, s_wbuf);    // s_out[0..Z) = 1-D heat map
+  if (Z == 20) c2c_forward2<20>(net2, s_x0, J, s_buf, s_out, s_wbuf, s_red);        // s_out[0..Z) = 1-D heat map
+  else if (Z == 40) c2c_forward2<40>(net2, s_x0, J, s_buf, s_out, s_wbuf, s_red);
+  else c2c_forward(net, s_x0, J, Z, s_buf, s_out, s_wbuf);
 
   if (a.hm1d_out)
     for (int i = tid; i < Z; i += C2C_THREADS) a.hm1d_out[(size_t)slot * Z + i] = s_out[i];
@@ -376,13 +520,18 @@ void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, cudaStr
     net.l[i].w = w.w[i];
     net.l[i].b = w.b[i];
   }
-  const size_t smem = (size_t)(2 * C2C_WCHUNK + 6 * C2C_BUF + 24 * C2C_MAXZ + 4 * C2C_MAXZ) * sizeof(float);
+  const size_t smem = (size_t)(2 * C2C_WCHUNK + 6 * C2C_BUF + 24 * C2C_MAXZ + 4 * C2C_MAXZ + C2C_THREADS * C2C_MAXZ) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_proposals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = true;
   }
-  k_proposals<<<n, C2C_THREADS, smem, st>>>(a, net);
+  C2CNet2 net2;
+  for (int i = 0; i < 20; ++i) {
+    net2.w[i] = w.w2[i];
+    net2.b[i] = w.b[i];
+  }
+  k_proposals<<<n, C2C_THREADS, smem, st>>>(a, net, net2);
 }
 
 void fvp_launch_people_from_centers(const FvpPropArgs& a, const float* d_centers, int n, cudaStream_t st) {
