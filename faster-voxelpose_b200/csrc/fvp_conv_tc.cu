@@ -169,10 +169,15 @@ __device__ __forceinline__ bool tc_decode(const TcArgs& t, int item, TcItem& w) 
 //   warps 6-9  epilogue    : tcgen05.ld of the finished accumulator, bias/residual/ReLU, stores
 // Two accumulator buffers in TMEM (acc_full / acc_empty) let the MMAs of tile i+1 run under the epilogue of
 // tile i, and the staging of tile i+1 under the MMAs of tile i.
-template <bool F16>
+// MODE 0: 3xTF32, 32-channel K-blocks (128-B rows, SWIZZLE_128B); MODE 1: fp16 split, 32-channel K-blocks (64-B rows,
+// SWIZZLE_64B); MODE 2: fp16 split, 16-channel K-blocks (32-B rows, SWIZZLE_32B) for layers with <= 16 input channels.
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
-  constexpr int ROWB = F16 ? 64 : 128;        // bytes of one pixel row (32 channels) in shared memory
-  constexpr uint32_t LAYOUT = F16 ? 4u : 2u;  // SWIZZLE_64B / SWIZZLE_128B
+  constexpr bool F16 = MODE != 0;
+  constexpr int ROWB = MODE == 0 ? 128 : (MODE == 1 ? 64 : 32);   // bytes of one pixel row of a K-block in shared memory
+  constexpr int CB = MODE == 2 ? 16 : 32;                          // channels per K-block
+  constexpr uint32_t LAYOUT = MODE == 0 ? 2u : (MODE == 1 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
+  constexpr int PH_SHIFT = MODE == 0 ? 0 : (MODE == 1 ? 1 : 2);    // swizzle phase = (row index >> PH_SHIFT) & (chunks - 1)
   extern __shared__ __align__(128) uint8_t tc_smem[];
   __shared__ uint64_t s_bar[2 * TC_MAX_A + 2 * TC_MAX_B + 4];
   __shared__ uint32_t s_tmem;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
     // Thread (q = tid & 7, p0 = tid >> 3) always handles channel quad q of halo pixels p0, p0+32, p0+64, ...:
     // their halo coordinates, shared-memory destinations and global offsets do not depend on the work item, so they
     // are computed once; per item only the image bounds tests and one base pointer remain.
-    constexpr int CH = F16 ? 4 : 8;                                // 16-B chunks per pixel row
+    constexpr int CH = ROWB / 16;                                  // 16-B chunks per pixel row
     constexpr int PPI = TC_LOADERS / CH;                           // pixels covered per pass of the 256 threads
     constexpr int EPT = (22 * 14 + PPI - 1) / PPI;                 // elements per thread (largest halo: 7x7)
     const int q = tid % CH, p0 = tid / CH;
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         const int pix = p0 + PPI * j, hy = pix / HW, hx = pix - hy * HW;
         e_hyx[ph][j] = (hy << 8) | hx;
         // swizzle on absolute address bits: chunk ^= (row address >> 7) & (CH-1); halo rows are 1024-B multiples apart
-        const int phase = F16 ? ((hx >> 1) & 3) : (hx & 7);
+        const int phase = (hx >> PH_SHIFT) & (CH - 1);
         e_dst[ph][j] = pix < HW * HH ? (hy * HWP + hx) * ROWB + ((q ^ phase) << 4) : -1;
       }
     }
@@ -237,11 +242,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         if (ph >= nph) break;
         const float* src = ph == 0 ? a.in : a.in2;
         const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
-        const int CinP = (Cin + 31) & ~31, pad = (K - 1) / 2;
+        const int CinP = (Cin + CB - 1) / CB * CB, pad = (K - 1) / 2;
         const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
         const uint32_t lo_off = (uint32_t)HH * HWP * ROWB;
         const float* img_in = src + (size_t)w.img * a.H * a.W * Cin;
-        for (int c0 = 0; c0 < CinP; c0 += 32) {
+        for (int c0 = 0; c0 < CinP; c0 += CB) {
           const int as = a_it % A_ST;
           if (a_it >= A_ST) mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1);
           uint8_t* hi = sA + (size_t)as * t.a_stage_bytes;
@@ -316,8 +321,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         const uint8_t* wsrc = (const uint8_t*)t.wtc;
         for (int ph = 0; ph < nph; ++ph) {
           const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
-          const int CinP = (Cin + 31) & ~31;
-          for (int c0 = 0; c0 < CinP; c0 += 32) {
+          const int CinP = (Cin + CB - 1) / CB * CB;
+          for (int c0 = 0; c0 < CinP; c0 += CB) {
             for (int tap = 0; tap < K * K; ++tap) {
               const int bs = b_it % B_ST;
               if (b_it >= B_ST) mbar_wait(b_empty + bs, ((b_it / B_ST) - 1) & 1);
@@ -347,10 +352,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       uint32_t blk = 0;                                            // running weight block index (resident image)
       for (int ph = 0; ph < nph; ++ph) {
         const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
-        const int CinP = (Cin + 31) & ~31;
+        const int CinP = (Cin + CB - 1) / CB * CB;
         const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
         const uint32_t a_lo_off = (uint32_t)HH * HWP * ROWB, b_lo_off = (uint32_t)t.n_tile * ROWB;
-        for (int c0 = 0; c0 < CinP; c0 += 32) {
+        for (int c0 = 0; c0 < CinP; c0 += CB) {
           const int as = a_it % A_ST;
           mbar_wait(a_full + as, (a_it / A_ST) & 1);
           tc_fence_after();
@@ -379,11 +384,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
             if constexpr (F16) {                                   // K = 16 per instruction: 2 steps per 32 channels
               const uint32_t d2 = d_tmem + t.acc_stride;
               umma_f16(d_tmem, ad_hi, bd_hi, idesc, accumulate);
-              umma_f16(d_tmem, ad_hi + 2, bd_hi + 2, idesc, 1);
+              if constexpr (CB == 32) umma_f16(d_tmem, ad_hi + 2, bd_hi + 2, idesc, 1);
               umma_f16(d2, ad_hi, bd_lo, idesc, accumulate);
-              umma_f16(d2, ad_hi + 2, bd_lo + 2, idesc, 1);
+              if constexpr (CB == 32) umma_f16(d2, ad_hi + 2, bd_lo + 2, idesc, 1);
               umma_f16(d2, ad_lo, bd_hi, idesc, 1);
-              umma_f16(d2, ad_lo + 2, bd_hi + 2, idesc, 1);
+              if constexpr (CB == 32) umma_f16(d2, ad_lo + 2, bd_hi + 2, idesc, 1);
             } else {                                               // 3xTF32, K = 8: lo*hi, hi*lo, hi*hi
               umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
               umma_tf32(d_tmem, ad_lo + 2, bd_hi + 2, idesc, 1);
@@ -514,11 +519,13 @@ void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
   *n_tiles = fvp_cdiv(npad, *n_tile);
 }
 
-void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int f16, int num_sms,
+// mode: 0 = 3xTF32, 1 = fp16 split with 32-channel K-blocks, 2 = fp16 split with 16-channel K-blocks
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int mode, int num_sms,
                         cudaStream_t st) {
   TcArgs t;
   t.c = a;
-  const uint32_t rowb = f16 ? 64 : 128;
+  const uint32_t rowb = mode == 0 ? 128 : (mode == 1 ? 64 : 32);
+  const int cb = mode == 2 ? 16 : 32, f16 = mode != 0;
   const int tiles = fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW) * a.n;
   int n_tile, n_tiles;
   fvp_tc_geometry(a.CoutP, 0, &n_tile, &n_tiles);
@@ -530,7 +537,7 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float
   const uint32_t a1 = a.in2 ? (uint32_t)TC_TH * 8 * rowb * 2 : 0;
   t.a_stage_bytes = a0 > a1 ? a0 : a1;                            // multiples of 1024
   t.blk_bytes = (uint32_t)t.n_tile * rowb * 2;
-  const int nblocks = k * k * (fvp_round_up(a.Cin, 32) / 32) + (a.in2 ? fvp_round_up(a.Cin2, 32) / 32 : 0);
+  const int nblocks = k * k * (fvp_round_up(a.Cin, cb) / cb) + (a.in2 ? fvp_round_up(a.Cin2, cb) / cb : 0);
   const uint32_t image_bytes = (uint32_t)nblocks * t.n_tiles * t.blk_bytes;
   const uint32_t budget = 224 * 1024 - 1024;                       // dynamic smem we may use (1 KB alignment slack)
   const int stream2 = (2 * t.a_stage_bytes + 4 * t.blk_bytes <= budget) ? (int)((budget - 2 * t.a_stage_bytes) / t.blk_bytes) : 0;
@@ -555,11 +562,13 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float
   const size_t smem = 1024 + (size_t)t.a_stages * t.a_stage_bytes + (size_t)t.b_stages * t.b_stage_bytes;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_conv_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    cudaFuncSetAttribute(k_conv_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     attr = true;
   }
   const int grid = t.total_items < num_sms ? t.total_items : num_sms;   // persistent: one CTA per SM
-  if (f16) k_conv_tc<true><<<grid, TC_THREADS, smem, st>>>(t);
-  else k_conv_tc<false><<<grid, TC_THREADS, smem, st>>>(t);
+  if (mode == 2) k_conv_tc<2><<<grid, TC_THREADS, smem, st>>>(t);
+  else if (mode == 1) k_conv_tc<1><<<grid, TC_THREADS, smem, st>>>(t);
+  else k_conv_tc<0><<<grid, TC_THREADS, smem, st>>>(t);
 }

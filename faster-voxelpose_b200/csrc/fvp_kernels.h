@@ -69,9 +69,10 @@ struct FvpConvW {         // one packed conv
   const float* wtc_narrow;  // same with 32-column N tiles (small launches), NULL when CoutP <= 32
   const float* wtc16;       // fp16 hi / scaled-lo split image (kind::f16 kernel), wide and narrow
   const float* wtc16_narrow;
+  const float* wtc16_c16;   // fp16 split with 16-channel K-blocks (layers with <= 16 input channels), NULL otherwise
 };
 // tcgen05 / TMEM implicit-GEMM conv (fvp_conv_tc.cu); same arguments as fvp_launch_conv plus the tiled weights
-void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int f16, int num_sms,
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int mode, int num_sms,
                         cudaStream_t st);
 void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles);
 struct FvpTrunkW {

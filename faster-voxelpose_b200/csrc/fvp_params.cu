@@ -182,7 +182,7 @@ struct Arena {
 };
 
 struct PendingConv {
-  size_t w_off, b_off, tc_off, tcn_off, t16_off, t16n_off;
+  size_t w_off, b_off, tc_off, tcn_off, t16_off, t16n_off, t16c_off;
   int cin, cin2, coutp, k;
 };
 
@@ -231,30 +231,31 @@ std::vector<float> pack_tc(const Packed& p, int cin_act, int narrow) {
 
 // fp16 variant of pack_tc: rows of 64 B (32 halves), chunks XOR-swizzled by (row >> 1) & 3 (SWIZZLE_64B on absolute
 // addresses, blocks are 512-B aligned); hi = fp16(w), lo = fp16((w - hi) * 2^11).  Returned as raw bytes in floats.
-std::vector<float> pack_tc16(const Packed& p, int narrow) {
+std::vector<float> pack_tc16(const Packed& p, int narrow, int cb = 32) {
   int n_tile, n_tiles;
   fvp_tc_geometry(p.coutp, narrow, &n_tile, &n_tiles);
+  const int chunks = cb / 8, ph_shift = cb == 32 ? 1 : 2;        // rows of cb halves: SWIZZLE_64B / SWIZZLE_32B
   const int taps = p.k * p.k, cinP = fvp_round_up(p.cin, 16), cin2P = p.cin2 ? fvp_round_up(p.cin2, 16) : 0;
   std::vector<uint16_t> out;
   for (int ph = 0; ph < (p.cin2 ? 2 : 1); ++ph) {
     const int K2 = ph == 0 ? taps : 1, CP = ph == 0 ? cinP : cin2P;
     const int rowbase = ph == 0 ? 0 : taps * cinP;
-    const int CP32 = fvp_round_up(CP, 32);
-    for (int c0 = 0; c0 < CP32; c0 += 32)
+    const int CPB = fvp_round_up(CP, cb);
+    for (int c0 = 0; c0 < CPB; c0 += cb)
       for (int tap = 0; tap < K2; ++tap)
         for (int nt = 0; nt < n_tiles; ++nt)
           for (int part = 0; part < 2; ++part) {
             const size_t base = out.size();
-            out.resize(base + (size_t)n_tile * 32, 0);
+            out.resize(base + (size_t)n_tile * cb, 0);
             for (int n = 0; n < n_tile; ++n)
-              for (int cc = 0; cc < 32; ++cc) {
+              for (int cc = 0; cc < cb; ++cc) {
                 const int col = nt * n_tile + n, ci = c0 + cc;
                 float w = 0.f;
                 if (col < p.coutp && ci < CP) w = p.w[(size_t)(rowbase + tap * CP + ci) * p.coutp + col];
                 const __half hi = __float2half_rn(w);
                 const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.0f);
-                const int chunk = (cc >> 3) ^ ((n >> 1) & 3);
-                out[base + (size_t)n * 32 + chunk * 8 + (cc & 7)] = __half_as_ushort(part == 0 ? hi : lo);
+                const int chunk = (cc >> 3) ^ ((n >> ph_shift) & (chunks - 1));
+                out[base + (size_t)n * cb + chunk * 8 + (cc & 7)] = __half_as_ushort(part == 0 ? hi : lo);
               }
           }
   }
@@ -271,6 +272,9 @@ PendingConv stash(Arena& A, const Packed& p, bool tc = false, int cin_act = 0) {
   pc.tcn_off = (tc && fvp_round_up(p.coutp, 16) > 32) ? A.put(pack_tc(p, cin_act ? cin_act : p.cin, 1)) : (size_t)-1;
   pc.t16_off = tc ? A.put(pack_tc16(p, 0)) : (size_t)-1;
   pc.t16n_off = (tc && fvp_round_up(p.coutp, 16) > 32) ? A.put(pack_tc16(p, 1)) : (size_t)-1;
+  // layers whose (activation) input has <= 16 channels also get a 16-channel K-block image (32-B rows)
+  const bool c16 = tc && (cin_act ? cin_act : p.cin) <= 16 && p.cin2 <= 16;
+  pc.t16c_off = c16 ? A.put(pack_tc16(p, 0, 16)) : (size_t)-1;
   pc.cin = p.cin; pc.cin2 = p.cin2; pc.coutp = p.coutp; pc.k = p.k;
   return pc;
 }
@@ -309,6 +313,7 @@ FvpConvW bind(const float* base, const PendingConv& pc) {
   w.wtc_narrow = pc.tcn_off == (size_t)-1 ? nullptr : base + pc.tcn_off;
   w.wtc16 = pc.t16_off == (size_t)-1 ? nullptr : base + pc.t16_off;
   w.wtc16_narrow = pc.t16n_off == (size_t)-1 ? nullptr : base + pc.t16n_off;
+  w.wtc16_c16 = pc.t16c_off == (size_t)-1 ? nullptr : base + pc.t16c_off;
   return w;
 }
 
@@ -405,7 +410,7 @@ int fvp_pack_params(fvp_ctx* ctx) {
   ctx->w_center.head_a = bind(base, cn[19]);
   ctx->w_center.head_b = bind(base, cn[20]);
   bind_trunk(base, p2p, ctx->w_p2p);
-  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr};
+  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
   ctx->w_p2p.head_b = bind(base, p2p[19]);
   for (int i = 0; i < 20; ++i) {
     ctx->w_c2c.w[i] = base + c2c[i].w_off;
@@ -440,7 +445,7 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
     p.b[co] = h_b[co];
   }
   Arena A;
-  const size_t ow = A.put(p.w), ob = A.put(p.b), ot = A.put(pack_tc(p, cin, 0)), ot16 = A.put(pack_tc16(p, 0));
+  const size_t ow = A.put(p.w), ob = A.put(p.b), ot = A.put(pack_tc(p, cin, 0)), ot16 = A.put(pack_tc16(p, 0)), ot16c = cin <= 16 ? A.put(pack_tc16(p, 0, 16)) : 0;
   float* d = nullptr;
   FVP_CUDA_OK(cudaMalloc(&d, A.host.size() * sizeof(float)));
   FVP_CUDA_OK(cudaMemcpy(d, A.host.data(), A.host.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -452,7 +457,8 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 1 + (repeat > 0 ? repeat : 1); ++it) {     // first launch = warm-up
     if (it == 1) cudaEventRecord(e0, st);
-    if (mode == 2) fvp_launch_conv_tc(a, d + ot16, nullptr, 1, ctx->num_sms, st);
+    if (mode == 2 && cin <= 16) fvp_launch_conv_tc(a, d + ot16c, nullptr, 2, ctx->num_sms, st);
+    else if (mode == 2 || mode == 3) fvp_launch_conv_tc(a, d + ot16, nullptr, 1, ctx->num_sms, st);
     else if (mode == 1) fvp_launch_conv_tc(a, d + ot, nullptr, 0, ctx->num_sms, st);
     else fvp_launch_conv(a, st);
   }

@@ -22,6 +22,8 @@ def run(tag, n, H, W, cin, cout, k, wmask=None):
     r = ref(x, w, b, False)
     e = [float((eng.debug_conv(x, w, b, False, m) - r).abs().max()) for m in (0, 1, 2)]
     print("%-28s ffma %.2e  tf32x3 %.2e  fp16x3 %.2e" % (tag, e[0], e[1], e[2])); sys.stdout.flush()
+run("7x7 16->16 16x8", 1, 16, 8, 16, 16, 7)
+run("3x3 16->32 16x8", 1, 16, 8, 16, 32, 3)
 run("1x1 32->32 16x8", 1, 16, 8, 32, 32, 1)
 run("1x1 64->128 32x32", 2, 32, 32, 64, 128, 1)
 for dy in range(3):
@@ -53,3 +55,4 @@ timing("3x3 64->64 32x32 n=480", 480, 32, 32, 64, 64, 3)
 timing("3x3 128->128 16x16 n=480", 480, 16, 16, 128, 128, 3)
 timing("7x7 16->16 64x64 n=120", 120, 64, 64, 16, 16, 7)
 timing("1x1 64->128 32x32 n=480", 480, 32, 32, 64, 128, 1)
+timing("3x3 16->32 64x64 n=120", 120, 64, 64, 16, 32, 3)
