@@ -194,6 +194,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   uint64_t* acc_empty = acc_full + 2;                              // [2]
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue as soon as SMs are free,
+  // and run OUR prologue (barriers, TMEM allocation, resident weight fetch) under the tail of the previous kernel.
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (tid == 0) {
     for (int i = 0; i < A_ST; ++i) { mbar_init(a_full + i, TC_LOADERS); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < B_ST; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
@@ -209,6 +212,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   tc_fence_after();
   const uint32_t tmem = s_tmem;
   const int nph = a.in2 ? 2 : 1;
+  const bool is_producer = tid == TC_LOADERS + 32;
+  if (is_producer && t.resident) {                                // weights do not depend on the previous kernel
+    mbar_arrive_expect_tx(b_full, t.b_stage_bytes);
+    for (uint32_t off = 0; off < t.b_stage_bytes; off += 32768) {
+      const uint32_t n = t.b_stage_bytes - off < 32768 ? t.b_stage_bytes - off : 32768;
+      tma_bulk_g2s(sB + off, (const uint8_t*)t.wtc + off, n, b_full);
+    }
+  }
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");           // activations of the previous kernel are now visible
 
   if (warp < TC_LW) {
     // =============================== A staging (256 threads) ========================================
@@ -307,13 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
     }
   } else if (tid == TC_LOADERS + 32) {
     // =============================== B producer (TMA bulk copies) =====================================
-    if (t.resident) {                                             // whole weight image once per CTA
-      mbar_arrive_expect_tx(b_full, t.b_stage_bytes);
-      for (uint32_t off = 0; off < t.b_stage_bytes; off += 32768) {
-        const uint32_t n = t.b_stage_bytes - off < 32768 ? t.b_stage_bytes - off : 32768;
-        tma_bulk_g2s(sB + off, (const uint8_t*)t.wtc + off, n, b_full);
-      }
-    } else {
+    if (!t.resident) {                                            // (resident image: already requested above)
       int b_it = 0;
       for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
         TcItem w;
@@ -360,49 +366,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
           mbar_wait(a_full + as, (a_it / A_ST) & 1);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + (size_t)as * t.a_stage_bytes);
-          for (int tap = 0; tap < K * K; ++tap) {
-            uint32_t b_base;
-            int bs = 0;
-            if (t.resident) {
-              if (!b_ready) { mbar_wait(b_full, 0); b_ready = true; }
-              b_base = smem_u32(sB) + (blk + (uint32_t)tap * t.n_tiles + w.nt) * t.blk_bytes;
-            } else {
-              bs = b_it % B_ST;
-              mbar_wait(b_full + bs, (b_it / B_ST) & 1);
-              b_base = smem_u32(sB + (size_t)bs * t.b_stage_bytes);
-            }
-            tc_fence_after();
-            const int dy = tap / K, dx = tap - dy * K;
-            const uint32_t a_tap = a_base + (uint32_t)(dy * HWP + dx) * ROWB;
-            // Descriptors are built once per tap; the MMAs below only add immediates to the low word (K advance of
-            // 32 B = +2).  A lone issuing thread runs ~1 dependent instruction per 5 cycles, so descriptor math per
-            // MMA would cost more than the MMA itself.
-            const uint64_t ad_hi = umma_desc(a_tap, (uint32_t)HWP * ROWB, LAYOUT);
-            const uint64_t ad_lo = umma_desc(a_tap + a_lo_off, (uint32_t)HWP * ROWB, LAYOUT);
-            const uint64_t bd_hi = umma_desc(b_base, 8 * ROWB, LAYOUT);
-            const uint64_t bd_lo = umma_desc(b_base + b_lo_off, 8 * ROWB, LAYOUT);
-            if constexpr (F16) {                                   // K = 16 per instruction: 2 steps per 32 channels
-              const uint32_t d2 = d_tmem + t.acc_stride;
-              umma_f16(d_tmem, ad_hi, bd_hi, idesc, accumulate);
-              if constexpr (CB == 32) umma_f16(d_tmem, ad_hi + 2, bd_hi + 2, idesc, 1);
-              umma_f16(d2, ad_hi, bd_lo, idesc, accumulate);
-              if constexpr (CB == 32) umma_f16(d2, ad_hi + 2, bd_lo + 2, idesc, 1);
-              umma_f16(d2, ad_lo, bd_hi, idesc, 1);
-              if constexpr (CB == 32) umma_f16(d2, ad_lo + 2, bd_hi + 2, idesc, 1);
-            } else {                                               // 3xTF32, K = 8: lo*hi, hi*lo, hi*hi
-              umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
-              umma_tf32(d_tmem, ad_lo + 2, bd_hi + 2, idesc, 1);
-              umma_tf32(d_tmem, ad_lo + 4, bd_hi + 4, idesc, 1);
-              umma_tf32(d_tmem, ad_lo + 6, bd_hi + 6, idesc, 1);
+          // One descriptor per operand per K-block; per tap only 16-B-unit offsets are added to the low word
+          // (the issuing thread is alone on its scheduler: every dependent instruction costs ~5 cycles).
+          const uint64_t ad0 = umma_desc(a_base, (uint32_t)HWP * ROWB, LAYOUT);
+          const uint64_t bd_res0 = umma_desc(smem_u32(sB), 8 * ROWB, LAYOUT);
+          const uint32_t a_lo16 = a_lo_off >> 4, b_lo16 = b_lo_off >> 4, blk16 = t.blk_bytes >> 4;
+          uint32_t bidx = (blk + (uint32_t)w.nt) * blk16;            // resident image: block of (K-block, tap 0, N tile)
+          for (int dy = 0; dy < K; ++dy) {
+            for (int dx = 0; dx < K; ++dx) {
+              uint64_t bd_hi;
+              int bs = 0;
+              if (t.resident) {
+                if (!b_ready) { mbar_wait(b_full, 0); b_ready = true; }
+                bd_hi = bd_res0 + bidx;
+                bidx += (uint32_t)t.n_tiles * blk16;
+              } else {
+                bs = b_it % B_ST;
+                mbar_wait(b_full + bs, (b_it / B_ST) & 1);
+                bd_hi = bd_res0 + (uint32_t)bs * (t.b_stage_bytes >> 4);
+              }
+              tc_fence_after();
+              const uint64_t ad_hi = ad0 + (uint32_t)((dy * HWP + dx) * (ROWB >> 4));
+              const uint64_t ad_lo = ad_hi + a_lo16, bd_lo = bd_hi + b_lo16;
+              if constexpr (F16) {                                   // K = 16 per instruction
+                const uint32_t d2 = d_tmem + t.acc_stride;
+                umma_f16(d_tmem, ad_hi, bd_hi, idesc, accumulate);
+                if constexpr (CB == 32) umma_f16(d_tmem, ad_hi + 2, bd_hi + 2, idesc, 1);
+                umma_f16(d2, ad_hi, bd_lo, idesc, accumulate);
+                if constexpr (CB == 32) umma_f16(d2, ad_hi + 2, bd_lo + 2, idesc, 1);
+                umma_f16(d2, ad_lo, bd_hi, idesc, 1);
+                if constexpr (CB == 32) umma_f16(d2, ad_lo + 2, bd_hi + 2, idesc, 1);
+              } else {                                               // 3xTF32, K = 8: lo*hi, hi*lo, hi*hi
+                umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
+                umma_tf32(d_tmem, ad_lo + 2, bd_hi + 2, idesc, 1);
+                umma_tf32(d_tmem, ad_lo + 4, bd_hi + 4, idesc, 1);
+                umma_tf32(d_tmem, ad_lo + 6, bd_hi + 6, idesc, 1);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_lo + 2 * ks, idesc, 1);
+                for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_lo + 2 * ks, idesc, 1);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_hi + 2 * ks, idesc, 1);
-            }
-            accumulate = 1;
-            if (!t.resident) {
-              umma_commit(b_empty + bs);                           // B slot reusable when these MMAs retire
-              ++b_it;
+                for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_hi + 2 * ks, idesc, 1);
+              }
+              accumulate = 1;
+              if (!t.resident) {
+                umma_commit(b_empty + bs);                           // B slot reusable when these MMAs retire
+                ++b_it;
+              }
             }
           }
           blk += (uint32_t)K * K * t.n_tiles;
@@ -568,7 +576,17 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float
     attr = true;
   }
   const int grid = t.total_items < num_sms ? t.total_items : num_sms;   // persistent: one CTA per SM
-  if (mode == 2) k_conv_tc<2><<<grid, TC_THREADS, smem, st>>>(t);
-  else if (mode == 1) k_conv_tc<1><<<grid, TC_THREADS, smem, st>>>(t);
-  else k_conv_tc<0><<<grid, TC_THREADS, smem, st>>>(t);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2>, t);
+  else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1>, t);
+  else cudaLaunchKernelEx(&cfg, k_conv_tc<0>, t);
 }
