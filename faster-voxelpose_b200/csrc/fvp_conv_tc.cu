@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   } else if (tid == TC_LOADERS) {
     // =============================== MMA issue (one thread) =========================================
     const uint32_t idesc = F16 ? umma_idesc_f16(128, t.n_tile) : umma_idesc_tf32(128, t.n_tile);
+    const uint32_t idesc2 = umma_idesc_f16(128, 2 * t.n_tile);   // fp16 engine: A_hi x [B_hi ; B_lo]
     int a_it = 0, b_it = 0, it = 0;
     bool b_ready = false;
     for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
@@ -389,11 +390,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
               const uint64_t ad_hi = ad0 + (uint32_t)((dy * HWP + dx) * (ROWB >> 4));
               const uint64_t ad_lo = ad_hi + a_lo16, bd_lo = bd_hi + b_lo16;
               if constexpr (F16) {                                   // K = 16 per instruction
-                const uint32_t d2 = d_tmem + t.acc_stride;
-                umma_f16(d_tmem, ad_hi, bd_hi, idesc, accumulate);
-                if constexpr (CB == 32) umma_f16(d_tmem, ad_hi + 2, bd_hi + 2, idesc, 1);
-                umma_f16(d2, ad_hi, bd_lo, idesc, accumulate);
-                if constexpr (CB == 32) umma_f16(d2, ad_hi + 2, bd_lo + 2, idesc, 1);
+                // A weight block is [B_hi rows ; B_lo rows] contiguously, so A_hi x [B_hi;B_lo] is ONE MMA of width
+                // 2n writing D1 | D2 side by side; only A_lo x B_hi remains as a second (width n) MMA into D2:
+                // two instructions per K step instead of three (the ~48-cycle per-instruction overhead dominates).
+                const uint32_t d2 = d_tmem + (uint32_t)t.n_tile;
+                (void)bd_lo;
+                umma_f16(d_tmem, ad_hi, bd_hi, idesc2, accumulate);
+                if constexpr (CB == 32) umma_f16(d_tmem, ad_hi + 2, bd_hi + 2, idesc2, 1);
                 umma_f16(d2, ad_lo, bd_hi, idesc, 1);
                 if constexpr (CB == 32) umma_f16(d2, ad_lo + 2, bd_hi + 2, idesc, 1);
               } else {                                               // 3xTF32, K = 8: lo*hi, hi*lo, hi*hi
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         tmem_ld16(t_row + (uint32_t)cb, v);
         if constexpr (F16) {                                       // D = D1 + 2^-11 * D2
           float v2[16];
-          tmem_ld16(t_row + t.acc_stride + (uint32_t)cb, v2);
+          tmem_ld16(t_row + (uint32_t)t.n_tile + (uint32_t)cb, v2);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaf(v2[i], 1.0f / 2048.0f, v[i]);
         }

@@ -12,7 +12,8 @@ batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 cfg, cams, resize = bench.workload("panoptic_256x192")
 eng = Engine(cfg, torch.device("cuda:0"), max_batch=batch, max_sequences=1)
 eng.load_state_dict(synth.make_weights(15, seed=2024))
-eng.set_conv_mode(int(os.environ.get('FVP_CONV_MODE', '0')))
+if 'FVP_CONV_MODE' in os.environ:
+    eng.set_conv_mode(int(os.environ['FVP_CONV_MODE']))
 slot = eng.sequence_slot(cams, resize)
 frames = bench.make_frames(cfg, cams, batch, seed0=1000)
 hm = torch.from_numpy(frames).cuda()
