@@ -248,21 +248,40 @@ def main():
     n_valid = int((out[..., 0, 3] >= 0).sum().item())
 
     # ---- e2e through the host-buffer entry point -----------------------------------------------------
-    host_out = (torch.empty((B, P, J, 5)).pin_memory(), torch.empty((3, B, P, J, 2)).pin_memory(), torch.empty((B, P, 7)).pin_memory())
+    # (a) blocking call (fvp_forward_host): per-call latency; (b) the two-deep pipeline (fvp_submit_host / fvp_wait):
+    # every step still copies its own inputs H2D from pinned memory and reads its own results back D2H, the copy of
+    # step i+1 overlapping the kernels of step i.  (b) is the throughput figure reported as e2e.value.
+    host_out = eng.new_host_outputs(B)
+    host_outs = [host_out, eng.new_host_outputs(B)]
+    e2e_steps = max(10, args.steps // 2)
     for i in range(3):
         eng.forward_host(pool_host[i % POOL], slots, host_out)
     sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(10, args.steps // 2)
     t0 = time.perf_counter()
-    e0.record()
     for i in range(e2e_steps):
         eng.forward_host(pool_host[i % POOL], slots, host_out)
-        if world > 1:
-            dist.all_gather(gather_buf, host_out[0].to(dev, non_blocking=True))
-    e1.record()
     sync_all()
-    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    sync_call_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    def pipelined(nsteps):
+        prev = None
+        for i in range(nsteps):
+            t = eng.submit_host(pool_host[i % POOL], slots, host_outs[i & 1])
+            if prev is not None:
+                eng.wait(prev)
+                if world > 1:
+                    dist.all_gather(gather_buf, host_outs[(i - 1) & 1][0].to(dev, non_blocking=True))
+            prev = t
+        eng.wait(prev)
+        if world > 1:
+            dist.all_gather(gather_buf, host_outs[(nsteps - 1) & 1][0].to(dev, non_blocking=True))
+
+    pipelined(4)
+    sync_all()
+    t0 = time.perf_counter()
+    pipelined(e2e_steps)
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3            # wall clock: the host side is part of the figure
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -328,7 +347,8 @@ def main():
         "data": "synthetic", "config": conf, "clocks": clocks, "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": launches_per_step,
         "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                "api": "fvp_submit_host/fvp_wait (2-deep pipeline)", "blocking_call_ms": sync_call_ms},
         "roofline": roofline, "cpu_baseline": cpu_base, "kernels": extra_kernels, "valid_people_last_step": n_valid,
         "cuda_graph": not args.no_graph,
     }

@@ -163,6 +163,11 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
     return fvp_fail(nullptr, FVP_E_INVALID, "NUM_CHANNEL_JOINT_FEAT must be 32, hidden 1..128");
   if (c.max_batch < 1 || c.max_sequences < 1) return fvp_fail(nullptr, FVP_E_INVALID, "max_batch / max_sequences must be >= 1");
   if (c.hm_w < 8 || c.hm_h < 8) return fvp_fail(nullptr, FVP_E_INVALID, "heat map too small");
+  {  // the projection kernels index the staged heat maps with 32-bit byte offsets
+    const double per_view = (c.hm_w * 1.1 + 6.0) * (c.hm_h * 1.1 + 6.0) * ((c.num_joints + 3) / 4);
+    if (per_view * c.num_views * c.max_batch > 2.6e8)       // x 16 B < 4 GiB
+      return fvp_fail(nullptr, FVP_E_INVALID, "max_batch x views x heat-map size exceeds the 32-bit tap index range");
+  }
 
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return fvp_fail(nullptr, FVP_E_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
@@ -255,6 +260,13 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   A(cudaMallocHost((void**)&ctx->h_frame_seq, MB * sizeof(int)));
   for (int i = 0; i < 10; ++i) A(cudaEventCreate(&ctx->ev[i]));
   A(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  A(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  A(dalloc(&ctx->d_hm_in_b, (size_t)MB * g.V * g.J * P.H * P.W));
+  for (int i = 0; i < 2; ++i) {
+    A(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&ctx->ev_k0[i], cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+  }
   if (ok) {
     A(cudaMemset(ctx->d_hm_cl, 0, (size_t)MB * g.V * g.view_stride4 * 16));   // zero borders (never written again)
     A(cudaMemset(ctx->d_seqs, 0, (size_t)c.max_sequences * sizeof(FvpSeq)));
@@ -290,7 +302,7 @@ void fvp_destroy(fvp_ctx* ctx) {
   void* ptrs[] = {ctx->d_weights, ctx->d_axes, ctx->d_seqs, ctx->d_hm_in, ctx->d_hm_cl, ctx->d_plane_cl, ctx->d_hmsize,
                   ctx->d_conf2d, ctx->d_flat, ctx->d_centers, ctx->d_people, ctx->d_img_valid, ctx->d_planes_cl,
                   ctx->d_yz_scratch, ctx->d_xy_scratch, ctx->d_feat, ctx->d_pose, ctx->d_maxw, ctx->d_wts, ctx->d_fused, ctx->d_conf,
-                  ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq};
+                  ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq, ctx->d_hm_in_b};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 6; ++i) {
@@ -299,6 +311,12 @@ void fvp_destroy(fvp_ctx* ctx) {
   }
   if (ctx->h_frame_seq) cudaFreeHost(ctx->h_frame_seq);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+    if (ctx->ev_k0[i]) cudaEventDestroy(ctx->ev_k0[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+  }
   for (int i = 0; i < 10; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   delete ctx;
@@ -441,6 +459,8 @@ static int forward_device(fvp_ctx* ctx, const float* d_heatmaps, int batch, cons
   if (rc != FVP_OK) return rc;
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");
   if (!d_heatmaps) return fvp_fail(ctx, FVP_E_INVALID, "null heat maps");
+  if (ctx->tickets != ctx->waited && !ctx->k0_done)
+    return fvp_fail(ctx, FVP_E_STATE, "fvp_submit_host tickets are outstanding: call fvp_wait before other entry points");
   cudaSetDevice(ctx->device);
   rc = upload_frame_seq(ctx, batch, h_seq_slots, st);
   if (rc != FVP_OK) return rc;
@@ -450,6 +470,7 @@ static int forward_device(fvp_ctx* ctx, const float* d_heatmaps, int batch, cons
   StageTimer T{ctx, st};
   T.mark(0);
   fvp_launch_stage_heatmaps(g, d_heatmaps, ctx->d_hm_cl, batch, st); ++launches;
+  if (ctx->k0_done) FVP_CUDA_OK(cudaEventRecord(ctx->k0_done, st));   // the input buffer is free again
 
   // Stream capture is illegal on the legacy default stream: in graph mode run on the context's own
   // stream, ordered after / before the caller's stream with events.
@@ -526,6 +547,50 @@ int fvp_forward_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int
   if (h_plane) FVP_CUDA_OK(cudaMemcpyAsync(h_plane, ctx->d_out_plane, (size_t)3 * n * g.J * 2 * 4, cudaMemcpyDeviceToHost, st));
   if (h_centers) FVP_CUDA_OK(cudaMemcpyAsync(h_centers, ctx->d_out_centers, (size_t)n * 7 * 4, cudaMemcpyDeviceToHost, st));
   FVP_CUDA_OK(cudaStreamSynchronize(st));
+  return FVP_OK;
+}
+
+// Pipelined host entry: fvp_submit_host enqueues H2D (copy stream) -> forward (context stream) -> D2H and returns a
+// ticket without waiting; the copy of step i+1 overlaps the kernels of step i (two device input buffers).  Results
+// land in the caller's host buffers once fvp_wait(ticket) returns.  At most two tickets may be outstanding and they
+// must be waited for in order; buffers of an outstanding ticket must not be reused.  Pinned host memory is needed
+// for the copies to be asynchronous (pageable memory still works, without the overlap).
+int fvp_submit_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int32_t* h_seq_slots, float* h_fused,
+                    float* h_plane, float* h_centers, long long* ticket) {
+  if (!ctx) return FVP_E_INVALID;
+  int rc = check_stage_ready(ctx, batch);
+  if (rc != FVP_OK) return rc;
+  if (!h_heatmaps || !ticket) return fvp_fail(ctx, FVP_E_INVALID, "null heat maps / ticket");
+  if (ctx->tickets - ctx->waited >= 2) return fvp_fail(ctx, FVP_E_STATE, "two tickets outstanding: call fvp_wait first");
+  cudaSetDevice(ctx->device);
+  const FvpGeom& g = ctx->geom;
+  const int n = batch * g.P, p = (int)(ctx->tickets & 1);
+  float* d_in = p ? ctx->d_hm_in_b : ctx->d_hm_in;
+  const size_t in_bytes = (size_t)batch * g.V * g.J * g.proj.H * g.proj.W * sizeof(float);
+  if (ctx->tickets >= 2) FVP_CUDA_OK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_k0[p], 0));   // last reader of d_in
+  FVP_CUDA_OK(cudaMemcpyAsync(d_in, h_heatmaps, in_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  FVP_CUDA_OK(cudaEventRecord(ctx->ev_h2d[p], ctx->copy_stream));
+  cudaStream_t st = ctx->own_stream;
+  FVP_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_h2d[p], 0));
+  ctx->k0_done = ctx->ev_k0[p];
+  rc = forward_device(ctx, d_in, batch, h_seq_slots, ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, st);
+  ctx->k0_done = nullptr;
+  if (rc != FVP_OK) return rc;
+  if (h_fused) FVP_CUDA_OK(cudaMemcpyAsync(h_fused, ctx->d_out_fused, (size_t)n * g.J * 5 * 4, cudaMemcpyDeviceToHost, st));
+  if (h_plane) FVP_CUDA_OK(cudaMemcpyAsync(h_plane, ctx->d_out_plane, (size_t)3 * n * g.J * 2 * 4, cudaMemcpyDeviceToHost, st));
+  if (h_centers) FVP_CUDA_OK(cudaMemcpyAsync(h_centers, ctx->d_out_centers, (size_t)n * 7 * 4, cudaMemcpyDeviceToHost, st));
+  FVP_CUDA_OK(cudaEventRecord(ctx->ev_done[p], st));
+  *ticket = ctx->tickets++;
+  return FVP_OK;
+}
+
+int fvp_wait(fvp_ctx* ctx, long long ticket) {
+  if (!ctx) return FVP_E_INVALID;
+  if (ticket < ctx->waited) return FVP_OK;                               // already complete
+  if (ticket >= ctx->tickets) return fvp_fail(ctx, FVP_E_INVALID, "unknown ticket %lld", ticket);
+  cudaSetDevice(ctx->device);
+  for (long long t = ctx->waited; t <= ticket; ++t) FVP_CUDA_OK(cudaEventSynchronize(ctx->ev_done[t & 1]));
+  ctx->waited = ticket + 1;
   return FVP_OK;
 }
 

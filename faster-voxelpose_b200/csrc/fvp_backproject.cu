@@ -14,6 +14,7 @@
 // record and a warp-wide LDG.128 touches 32/CG records -> fully used sectors.  The CG lanes of a column
 // split the (z, view) projection work between them and exchange tap descriptors by shuffle.
 #include "fvp_kernels.h"
+#include <cstdlib>
 #include "fvp_project.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -81,7 +82,6 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
   const int V = g.V, ZW = g.Z >> 2, z0 = warp * ZW, npairs = ZW * V;
   const float fV = (float)V, rV = 1.0f / fV;
   const int row4 = P.WP * g.JG, px4 = g.JG;
-  const float4* hm_b = hm_cl + (size_t)b * V * g.view_stride4 + (s < g.JG ? s : 0);
   const bool ch_ok = s < g.JG;
 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), zmax = acc;
@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
       float ix, iy;
       fvp_project(s_seq.cam[v], s_seq.A, P, wx, wy, smem_f[z0 + z], ix, iy);
       t = fvp_taps(P, ix, iy);
+      t.off += (b * V + v) * (int)g.view_stride4;
     }
 #pragma unroll
     for (int k = 0; k < CG; ++k) {
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
       const float w10 = __shfl_sync(0xffffffffu, t.w10, group_base + k);
       const float w11 = __shfl_sync(0xffffffffu, t.w11, group_base + k);
       const int zk = ik / V, vk = ik - zk * V;
-      if (ch_ok) fvp_tap_accumulate(acc, hm_b + (size_t)vk * g.view_stride4, off, row4, px4, w00, w01, w10, w11);
+      if (ch_ok) fvp_tap_accumulate(acc, hm_cl, off + s, row4, px4, w00, w01, w10, w11);
       if (vk == V - 1) {                         // last view of this z: mean, clamp, running z-max
         zmax = fvp_max4(zmax, fvp_mean_clamp4(acc, fV, rV));
         acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -173,8 +174,8 @@ void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int
 //                        >= 0, so their bit patterns order like unsigned ints), then a shared-memory
 //                        max over the warps (double-buffered: one barrier per a).
 
-template <int CG, int TA, int K3_CCH>
-__global__ void __launch_bounds__(64 * CG, (CG == 4) ? 3 : 1)
+template <int CG, int TA, int K3_CCH, int MINB, int PX16>      // PX16: pixel stride in bytes when JG == CG, else 0
+__global__ void __launch_bounds__(64 * CG, MINB)
 k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __restrict__ people,
                float4* __restrict__ planes_cl, float4* __restrict__ yz_scratch, float4* __restrict__ xy_scratch,
                int n_people, int nslab, int ncpart) {
@@ -247,7 +248,7 @@ k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __r
   const int V = g.V;
   const float fV = (float)V, rV = 1.0f / fV;
   const int row4 = P.WP * JG, px4 = JG;
-  const float4* hm_b = hm_cl + (size_t)(person / g.P) * V * g.view_stride4 + (ch_ok ? s : 0);
+  const int vs4 = (int)g.view_stride4, frame_off = (person / g.P) * V * vs4;
   const bool sample_ok = ch_ok && b_ok;
   unsigned rmask = 0;                            // lanes of this warp that hold my channel group
 #pragma unroll
@@ -268,22 +269,23 @@ k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __r
       if (row_live) {
         const float wx = s_fx[a];
         for (int v = 0; v < V; ++v) {
-          const float4* hm_v = hm_b + (size_t)v * g.view_stride4;
+          const int view_off = frame_off + v * vs4;
 #pragma unroll
           for (int r = 0; r < ROUNDS; ++r) {
             float ix, iy;
             fvp_project(s_seq.cam[v], s_seq.A, P, wx, wy, s_fz[cc + r * CG + s], ix, iy);
             const FvpTaps t = fvp_taps(P, ix, iy);
+            const int my_off = t.off + view_off;
 #pragma unroll
             for (int k = 0; k < CG; ++k) {
               const int c = r * CG + k;          // compile-time depth index within the chunk
-              const int off = __shfl_sync(0xffffffffu, t.off, group_base + k);
+              const int off = __shfl_sync(0xffffffffu, my_off, group_base + k);
               const float w00 = __shfl_sync(0xffffffffu, t.w00, group_base + k);
               const float w01 = __shfl_sync(0xffffffffu, t.w01, group_base + k);
               const float w10 = __shfl_sync(0xffffffffu, t.w10, group_base + k);
               const float w11 = __shfl_sync(0xffffffffu, t.w11, group_base + k);
               const bool c_ok = (cc + c) >= pd.lo[2] && (cc + c) < pd.hi[2];     // uniform
-              if (sample_ok && c_ok) fvp_tap_accumulate(acc[c], hm_v, off, row4, px4, w00, w01, w10, w11);
+              if (sample_ok && c_ok) fvp_tap_accumulate<PX16>(acc[c], hm_cl, off + s, row4, px4, w00, w01, w10, w11);
             }
           }
         }
@@ -356,12 +358,20 @@ void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPer
   if (g.JG <= 4) {
     nslab = 16;                                  // TA = 4 rows per slab
     dim3 grid(nslab * ncpart, n_people);
-    k3_jln_project<4, 4, 4><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                               (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
+    static const int occ4 = getenv("FVP_K3_OCC4") ? atoi(getenv("FVP_K3_OCC4")) : 1;   // 64 regs, 4 CTAs / SM
+    if (g.JG != 4)
+      k3_jln_project<4, 4, 4, 3, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                       (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
+    else if (occ4)
+      k3_jln_project<4, 4, 4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                    (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
+    else
+      k3_jln_project<4, 4, 4, 3, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                    (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
   } else {
     nslab = 32;                                  // TA = 2
     dim3 grid(nslab * ncpart, n_people);
-    k3_jln_project<8, 2, 8><<<grid, 512, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+    k3_jln_project<8, 2, 8, 1, 0><<<grid, 512, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
                                                (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
   }
   dim3 grid2(fvp_cdiv(img4, 256), n_people);

@@ -219,9 +219,10 @@ static void conv(const FvpConvW& w, const float* in, int H, int W, const float* 
   a.nchw = nchw; a.n = n; a.valid = valid;
   // engine 2: fp16-split tcgen05 kernel (all layers); engine 1: 3xTF32 tcgen05 kernel, where the 7x7 front conv (49 taps
   // of half-empty 32-channel K-blocks, measured 6.6 vs 11.4 TMAC/s) stays on the CUDA-core kernel; engine 0: CUDA cores.
-  if (g_tc == 2 && w.wtc16_c16) fvp_launch_conv_tc(a, w.wtc16_c16, nullptr, 2, 148, st);     // <= 16 input channels
-  else if (g_tc == 2 && w.wtc16) fvp_launch_conv_tc(a, w.wtc16, w.wtc16_narrow, 1, 148, st);
-  else if (g_tc == 1 && w.wtc && w.k != 7) fvp_launch_conv_tc(a, w.wtc, w.wtc_narrow, 0, 148, st);
+  const float* const c16[3] = {w.wtc16_c16, nullptr, nullptr};
+  if (g_tc == 2 && w.wtc16_c16) fvp_launch_conv_tc(a, c16, 2, 148, st);                       // <= 16 input channels
+  else if (g_tc == 2 && w.wtc16[0]) fvp_launch_conv_tc(a, w.wtc16, 1, 148, st);
+  else if (g_tc == 1 && w.wtc[0] && w.k != 7) fvp_launch_conv_tc(a, w.wtc, 0, 148, st);
   else fvp_launch_conv(a, st);
   if (launches) ++*launches;
 }

@@ -525,24 +525,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
 // (more CTAs for small launches), otherwise up to 128 columns per CTA.  K-blocks are always 32 channels.
 void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
   const int npad = fvp_round_up(coutp, 16);
-  const int cap = narrow ? 32 : 128;
+  const int cap = narrow == 1 ? 32 : (narrow == 2 ? 64 : 128);     // 0: up to 128 columns, 1: 32, 2: 64
   *n_tile = npad <= cap ? npad : cap;
   *n_tiles = fvp_cdiv(npad, *n_tile);
 }
 
 // mode: 0 = 3xTF32, 1 = fp16 split with 32-channel K-blocks, 2 = fp16 split with 16-channel K-blocks
-void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int mode, int num_sms,
-                        cudaStream_t st) {
+// wtc[3]: weight images tiled for N tiles of up to 128 / 32 / 64 columns (NULL where not packed)
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st) {
   TcArgs t;
   t.c = a;
   const uint32_t rowb = mode == 0 ? 128 : (mode == 1 ? 64 : 32);
   const int cb = mode == 2 ? 16 : 32, f16 = mode != 0;
   const int tiles = fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW) * a.n;
-  int n_tile, n_tiles;
-  fvp_tc_geometry(a.CoutP, 0, &n_tile, &n_tiles);
-  const int narrow = (wtc_narrow != nullptr && n_tile > 32 && tiles * n_tiles < 2 * num_sms) ? 1 : 0;
-  fvp_tc_geometry(a.CoutP, narrow, &t.n_tile, &t.n_tiles);
-  t.wtc = narrow ? wtc_narrow : wtc_wide;
+  // N-tile width: the persistent grid runs ceil(items / SMs) rounds of items; per K step an item costs roughly
+  // (48 + fetch + math) cycles per MMA.  Pick the width that minimises rounds x per-item cost.
+  int best = 0;
+  double best_cost = 1e30;
+  for (int v = 0; v < 3; ++v) {
+    if (!wtc[v]) continue;
+    int nt, nts;
+    fvp_tc_geometry(a.CoutP, v, &nt, &nts);
+    const double per_item = f16 ? (48 + (128 + 2 * nt) / 4.0 + nt) + (48 + (128 + nt) / 4.0 + nt / 2.0)
+                                : 3.0 * (48 + (128 + nt) / 4.0 + nt / 2.0);
+    const double cost = (double)fvp_cdiv(tiles * nts, num_sms) * per_item + 1.0 * nts;    // ties go to the wider tile
+    if (cost < best_cost) { best_cost = cost; best = v; }
+  }
+  fvp_tc_geometry(a.CoutP, best, &t.n_tile, &t.n_tiles);
+  t.wtc = wtc[best];
   const int k = a.ksize;
   const uint32_t a0 = (uint32_t)(TC_TH + k - 1) * (k == 1 ? 8 : 16) * rowb * 2;
   const uint32_t a1 = a.in2 ? (uint32_t)TC_TH * 8 * rowb * 2 : 0;

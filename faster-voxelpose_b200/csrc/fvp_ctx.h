@@ -85,6 +85,13 @@ struct fvp_ctx {
   int last_launches = 0;
   bool profiling = false;
   cudaEvent_t ev[10] = {nullptr};
+  // pipelined host entry (fvp_submit_host / fvp_wait): two input buffers, a copy stream and per-slot events
+  float* d_hm_in_b = nullptr;         // second [MB][V][J][H][W] input buffer
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k0[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t k0_done = nullptr;      // when set, forward_device records it right after the staging kernel
+  long long tickets = 0;              // submitted so far
+  long long waited = 0;               // tickets already waited for
   float stage_ms[9] = {0};
 };
 

@@ -65,15 +65,13 @@ struct FvpConvW {         // one packed conv
   const float* w;         // [(taps*CinP + Cin2P)][CoutP] fp32 (CUDA-core kernel)
   const float* b;
   int cin, cin2, coutp, k;
-  const float* wtc;       // tf32 hi/lo split, tiled per (K-block, tap, N-tile<=128) (tcgen05 kernel)
-  const float* wtc_narrow;  // same with 32-column N tiles (small launches), NULL when CoutP <= 32
-  const float* wtc16;       // fp16 hi / scaled-lo split image (kind::f16 kernel), wide and narrow
-  const float* wtc16_narrow;
+  // weight images for the tcgen05 kernel, tiled per (K-block, tap, N-tile); index = N-tile cap: [0] <=128, [1] 32, [2] 64
+  const float* wtc[3];      // tf32 hi/lo split (engine 1)
+  const float* wtc16[3];    // fp16 hi / scaled-lo split (engine 2)
   const float* wtc16_c16;   // fp16 split with 16-channel K-blocks (layers with <= 16 input channels), NULL otherwise
 };
 // tcgen05 / TMEM implicit-GEMM conv (fvp_conv_tc.cu); same arguments as fvp_launch_conv plus the tiled weights
-void fvp_launch_conv_tc(const FvpConvArgs& a, const float* wtc_wide, const float* wtc_narrow, int mode, int num_sms,
-                        cudaStream_t st);
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st);
 void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles);
 struct FvpTrunkW {
   FvpConvW front, r1a, r1b, s1a, s1b, e1a, e1b, s2a, s2b, e2a, e2b, ma, mb, d2a, d2b, up2, d1a, d1b, up1;

@@ -182,7 +182,7 @@ struct Arena {
 };
 
 struct PendingConv {
-  size_t w_off, b_off, tc_off, tcn_off, t16_off, t16n_off, t16c_off;
+  size_t w_off, b_off, tc_off[3], t16_off[3], t16c_off;
   int cin, cin2, coutp, k;
 };
 
@@ -268,10 +268,12 @@ PendingConv stash(Arena& A, const Packed& p, bool tc = false, int cin_act = 0) {
   PendingConv pc;
   pc.w_off = A.put(p.w);
   pc.b_off = A.put(p.b);
-  pc.tc_off = tc ? A.put(pack_tc(p, cin_act ? cin_act : p.cin, 0)) : (size_t)-1;
-  pc.tcn_off = (tc && fvp_round_up(p.coutp, 16) > 32) ? A.put(pack_tc(p, cin_act ? cin_act : p.cin, 1)) : (size_t)-1;
-  pc.t16_off = tc ? A.put(pack_tc16(p, 0)) : (size_t)-1;
-  pc.t16n_off = (tc && fvp_round_up(p.coutp, 16) > 32) ? A.put(pack_tc16(p, 1)) : (size_t)-1;
+  const int npad = fvp_round_up(p.coutp, 16);
+  for (int v = 0; v < 3; ++v) {                      // N-tile caps 128 / 32 / 64 (only where they differ from the wide image)
+    const bool need = tc && (v == 0 || (v == 1 && npad > 32) || (v == 2 && npad > 64));
+    pc.tc_off[v] = need ? A.put(pack_tc(p, cin_act ? cin_act : p.cin, v)) : (size_t)-1;
+    pc.t16_off[v] = need ? A.put(pack_tc16(p, v)) : (size_t)-1;
+  }
   // layers whose (activation) input has <= 16 channels also get a 16-channel K-block image (32-B rows)
   const bool c16 = tc && (cin_act ? cin_act : p.cin) <= 16 && p.cin2 <= 16;
   pc.t16c_off = c16 ? A.put(pack_tc16(p, 0, 16)) : (size_t)-1;
@@ -309,10 +311,10 @@ FvpConvW bind(const float* base, const PendingConv& pc) {
   w.w = base + pc.w_off;
   w.b = base + pc.b_off;
   w.cin = pc.cin; w.cin2 = pc.cin2; w.coutp = pc.coutp; w.k = pc.k;
-  w.wtc = pc.tc_off == (size_t)-1 ? nullptr : base + pc.tc_off;
-  w.wtc_narrow = pc.tcn_off == (size_t)-1 ? nullptr : base + pc.tcn_off;
-  w.wtc16 = pc.t16_off == (size_t)-1 ? nullptr : base + pc.t16_off;
-  w.wtc16_narrow = pc.t16n_off == (size_t)-1 ? nullptr : base + pc.t16n_off;
+  for (int v = 0; v < 3; ++v) {
+    w.wtc[v] = pc.tc_off[v] == (size_t)-1 ? nullptr : base + pc.tc_off[v];
+    w.wtc16[v] = pc.t16_off[v] == (size_t)-1 ? nullptr : base + pc.t16_off[v];
+  }
   w.wtc16_c16 = pc.t16c_off == (size_t)-1 ? nullptr : base + pc.t16c_off;
   return w;
 }
@@ -410,7 +412,7 @@ int fvp_pack_params(fvp_ctx* ctx) {
   ctx->w_center.head_a = bind(base, cn[19]);
   ctx->w_center.head_b = bind(base, cn[20]);
   bind_trunk(base, p2p, ctx->w_p2p);
-  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+  ctx->w_p2p.head_a = FvpConvW{nullptr, nullptr, 0, 0, 0, 0, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, nullptr};
   ctx->w_p2p.head_b = bind(base, p2p[19]);
   for (int i = 0; i < 20; ++i) {
     ctx->w_c2c.w[i] = base + c2c[i].w_off;
@@ -457,9 +459,12 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 1 + (repeat > 0 ? repeat : 1); ++it) {     // first launch = warm-up
     if (it == 1) cudaEventRecord(e0, st);
-    if (mode == 2 && cin <= 16) fvp_launch_conv_tc(a, d + ot16c, nullptr, 2, ctx->num_sms, st);
-    else if (mode == 2 || mode == 3) fvp_launch_conv_tc(a, d + ot16, nullptr, 1, ctx->num_sms, st);
-    else if (mode == 1) fvp_launch_conv_tc(a, d + ot, nullptr, 0, ctx->num_sms, st);
+    const float* const i16c[3] = {d + ot16c, nullptr, nullptr};
+    const float* const i16[3] = {d + ot16, nullptr, nullptr};
+    const float* const i32[3] = {d + ot, nullptr, nullptr};
+    if (mode == 2 && cin <= 16) fvp_launch_conv_tc(a, i16c, 2, ctx->num_sms, st);
+    else if (mode == 2 || mode == 3) fvp_launch_conv_tc(a, i16, 1, ctx->num_sms, st);
+    else if (mode == 1) fvp_launch_conv_tc(a, i32, 0, ctx->num_sms, st);
     else fvp_launch_conv(a, st);
   }
   cudaEventRecord(e1, st);

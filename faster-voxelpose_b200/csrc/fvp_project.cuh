@@ -80,9 +80,9 @@ __device__ __forceinline__ FvpTaps fvp_taps(const FvpProj& P, float ix, float iy
   const float x0f = floorf(ix), y0f = floorf(iy);
   const float fx = __fsub_rn(ix, x0f), fy = __fsub_rn(iy, y0f);
   const float ex = __fsub_rn(1.0f, fx), ey = __fsub_rn(1.0f, fy);
-  int x0 = (int)x0f, y0 = (int)y0f;
-  x0 = min(max(x0, -P.PADX), P.W + P.PADX - 2);            // only bites for NaN/garbage coordinates
-  y0 = min(max(y0, -P.PADY), P.H + P.PADY - 2);
+  // No index clamp: fvp_project's last clamp uses fminf/fmaxf, which return the non-NaN operand, so g is always
+  // inside [-1.1, 1.1] (NaN and Inf included) and floor(ix) inside [-(PAD-1), size-1+PAD-2].
+  const int x0 = (int)x0f, y0 = (int)y0f;
   t.off = ((y0 + P.PADY) * P.WP + (x0 + P.PADX)) * (P.JP >> 2);
   t.w00 = __fmul_rn(ey, ex);
   t.w01 = __fmul_rn(ey, fx);
@@ -91,14 +91,27 @@ __device__ __forceinline__ FvpTaps fvp_taps(const FvpProj& P, float ix, float iy
   return t;
 }
 
-__device__ __forceinline__ void fvp_tap_accumulate(float4& acc, const float4* __restrict__ view_base, int off,
+// base = staged heat-map buffer (kernel-uniform); off = 32-bit float4 index of the NW tap including the (frame, view)
+// image offset and the thread's channel group.  Byte offsets stay unsigned 32-bit so that every tap address is
+// uniform base + zero-extended register (fvp_create bounds the buffer below 4 GiB).
+__device__ __forceinline__ float4 fvp_ldg_at(const float4* __restrict__ base, unsigned byte_off) {
+  return __ldg((const float4*)((const char*)base + byte_off));
+}
+// PX16 > 0: compile-time pixel stride in bytes (lets the east taps share the west taps' address register).
+template <int PX16 = 0>
+__device__ __forceinline__ void fvp_tap_accumulate(float4& acc, const float4* __restrict__ base, int off,
                                                    int row_stride4, int px_stride4, float w00, float w01,
                                                    float w10, float w11) {
-  const float4* p = view_base + off;
-  const float4 a = __ldg(p);
-  const float4 b = __ldg(p + px_stride4);
-  const float4 c = __ldg(p + row_stride4);
-  const float4 d = __ldg(p + row_stride4 + px_stride4);
+  const unsigned o0 = (unsigned)off << 4, o2 = o0 + ((unsigned)row_stride4 << 4);
+  float4 a, b, c, d;
+  if (PX16 > 0) {
+    const float4* pn = (const float4*)((const char*)base + o0);
+    const float4* ps = (const float4*)((const char*)base + o2);
+    a = __ldg(pn); b = __ldg(pn + PX16 / 16); c = __ldg(ps); d = __ldg(ps + PX16 / 16);
+  } else {
+    const unsigned px = (unsigned)px_stride4 << 4;
+    a = fvp_ldg_at(base, o0); b = fvp_ldg_at(base, o0 + px); c = fvp_ldg_at(base, o2); d = fvp_ldg_at(base, o2 + px);
+  }
   acc.x = fmaf(d.x, w11, fmaf(c.x, w10, fmaf(b.x, w01, fmaf(a.x, w00, acc.x))));
   acc.y = fmaf(d.y, w11, fmaf(c.y, w10, fmaf(b.y, w01, fmaf(a.y, w00, acc.y))));
   acc.z = fmaf(d.z, w11, fmaf(c.z, w10, fmaf(b.z, w01, fmaf(a.z, w00, acc.z))));

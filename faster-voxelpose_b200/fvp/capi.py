@@ -59,6 +59,8 @@ SYMBOLS = {
     "fvp_set_sequence": (C.c_int, [_CTX, C.c_int, _P, C.c_int, _P]),
     "fvp_forward": (C.c_int, [_CTX, _P, C.c_int, _P, _P, _P, _P, C.c_size_t]),
     "fvp_forward_host": (C.c_int, [_CTX, _P, C.c_int, _P, _P, _P, _P, C.c_size_t]),
+    "fvp_submit_host": (C.c_int, [_CTX, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_longlong)]),
+    "fvp_wait": (C.c_int, [_CTX, C.c_longlong]),
     "fvp_use_cuda_graph": (C.c_int, [_CTX, C.c_int]),
     "fvp_debug_conv": (C.c_int, [_CTX, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_float), C.c_size_t]),
     "fvp_debug_project": (C.c_int, [_CTX, C.c_int, _P, C.c_int, _P, _P, C.c_size_t]),

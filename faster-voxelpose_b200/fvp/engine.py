@@ -205,11 +205,50 @@ class Engine:
                                                out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), self._stream()))
         return out
 
+    def new_host_outputs(self, B: int) -> Tuple[torch.Tensor, ...]:
+        """Pinned (fused_poses, plane_poses, proposal_centers) host tensors for the host entry points."""
+        return (torch.empty((B, self.P, self.J, 5)).pin_memory(), torch.empty((3, B, self.P, self.J, 2)).pin_memory(),
+                torch.empty((B, self.P, 7)).pin_memory())
+
+    def submit_host(self, heatmaps: torch.Tensor, slots: Sequence[int], out: Tuple[torch.Tensor, ...]) -> int:
+        """Pipelined host entry (fvp_submit_host): enqueue H2D -> forward -> D2H and return a ticket without waiting.
+        At most two tickets may be outstanding; `out` must not be reused until wait(ticket) returned."""
+        B = self._check_hm(heatmaps)
+        assert heatmaps.device.type == "cpu" and heatmaps.dtype == torch.float32 and heatmaps.is_contiguous()
+        assert all(t.device.type == "cpu" and t.is_contiguous() for t in out)
+        ticket = C.c_longlong(-1)
+        self._ck(self.lib.fvp_submit_host(self.ctx, heatmaps.data_ptr(), B, self._slots_arr(slots), out[0].data_ptr(),
+                                          out[1].data_ptr(), out[2].data_ptr(), C.byref(ticket)))
+        return int(ticket.value)
+
+    def wait(self, ticket: int) -> None:
+        self._ck(self.lib.fvp_wait(self.ctx, int(ticket)))
+
+    def stream_host(self, frames, slots_of=None):
+        """Run an iterable of host heat-map batches through the two-deep pipeline; yields (index, outputs) in order.
+        Mirrors the reference's validation loop (lib/core/function.py: one model call per loader batch) with the
+        copy of batch i+1 overlapping the kernels of batch i.  The yielded tensors are reused two batches later."""
+        bufs, pending = {}, []
+        for i, hm in enumerate(frames):
+            B = hm.shape[0]
+            slots = slots_of(i) if slots_of else [0] * B
+            key = (B, i & 1)
+            if key not in bufs:
+                bufs[key] = self.new_host_outputs(B)
+            pending.append((i, self.submit_host(hm, slots, bufs[key]), bufs[key]))
+            if len(pending) == 2:
+                j, t, o = pending.pop(0)
+                self.wait(t)
+                yield j, o
+        for j, t, o in pending:
+            self.wait(t)
+            yield j, o
+
     def use_cuda_graph(self, on: bool = True) -> None:
         self._ck(self.lib.fvp_use_cuda_graph(self.ctx, 1 if on else 0))
 
     def set_conv_mode(self, mode: int) -> None:
-        """0 = fp32 CUDA-core convolutions, 1 = tcgen05 3xTF32 convolutions."""
+        """0 = fp32 CUDA-core convolutions, 1 = tcgen05 3xTF32, 2 = tcgen05 fp16 hi/lo split (default)."""
         self._ck(self.lib.fvp_set_conv_mode(self.ctx, int(mode)))
 
     def set_profiling(self, on: bool) -> None:

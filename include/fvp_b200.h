@@ -112,6 +112,16 @@ int fvp_forward(fvp_ctx* ctx, const float* d_heatmaps, int batch, const int32_t*
 int fvp_forward_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int32_t* h_seq_slots,
                      float* h_fused_poses, float* h_plane_poses, float* h_proposal_centers, uintptr_t stream);
 
+/* Pipelined form of fvp_forward_host for a stream of frames (the reference's validate loop, lib/core/function.py:
+ * one model(...) call per data-loader batch): fvp_submit_host enqueues H2D -> forward -> D2H on the context's own
+ * streams and returns a ticket at once; the H2D of the next step overlaps the kernels of the current one (two device
+ * input buffers).  Results are in the host buffers once fvp_wait(ticket) returns.  At most two tickets may be
+ * outstanding (FVP_E_STATE otherwise); tickets complete in order; host buffers of an outstanding ticket must not be
+ * reused.  Pinned host memory is required for real overlap, pageable memory still works. */
+int fvp_submit_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int32_t* h_seq_slots,
+                    float* h_fused_poses, float* h_plane_poses, float* h_proposal_centers, long long* ticket);
+int fvp_wait(fvp_ctx* ctx, long long ticket);
+
 /* Capture the forward for (batch, seq slots) into a CUDA graph bound to fixed internal I/O buffers
  * and replay it on later fvp_forward* calls with the same signature (1 = on, 0 = off). */
 int fvp_use_cuda_graph(fvp_ctx* ctx, int enable);

@@ -334,6 +334,43 @@ def test_host_entry_matches_device_entry(bench_setup):
     assert all(torch.equal(d.cpu(), h) for d, h in zip(dev, host))
 
 
+def test_pipelined_host_entry(bench_setup):
+    """fvp_submit_host / fvp_wait: a stream of different batches through the two-deep pipeline gives, for every batch,
+    exactly what the blocking call gives; ticket misuse is refused loudly."""
+    from fvp.capi import FvpError
+    g, eng, slots = bench_setup
+    rng = np.random.default_rng(11)
+    base = torch.from_numpy(g.heatmaps)
+    frames = [base.pin_memory()]
+    for _ in range(5):
+        noise = torch.from_numpy((rng.random(g.heatmaps.shape, dtype=np.float32) < 0.02).astype(np.float32) * 0.25)
+        frames.append(torch.clamp(base + noise, 0, 1).pin_memory())
+    want = [tuple(t.clone() for t in eng.forward_host(f, slots)) for f in frames]
+    eng.use_cuda_graph(True)
+    got = {}
+    for i, out in eng.stream_host(frames, lambda i: slots):
+        got[i] = tuple(t.clone() for t in out)
+    assert sorted(got) == list(range(len(frames)))
+    for i in range(len(frames)):
+        assert all(torch.equal(a, b) for a, b in zip(want[i], got[i])), i
+    # ticket rules
+    o = [eng.new_host_outputs(base.shape[0]) for _ in range(3)]
+    t0 = eng.submit_host(frames[0], slots, o[0])
+    t1 = eng.submit_host(frames[1], slots, o[1])
+    with pytest.raises(FvpError):
+        eng.submit_host(frames[2], slots, o[2])             # two outstanding
+    with pytest.raises(FvpError):
+        eng.forward(base.cuda(), slots)                     # other entry points refuse while tickets are open
+    eng.wait(t1)                                            # waits for t0 as well (in-order completion)
+    eng.wait(t0)
+    assert all(torch.equal(a, b) for a, b in zip(want[1], o[1])) and all(torch.equal(a, b) for a, b in zip(want[0], o[0]))
+    with pytest.raises(FvpError):
+        eng.wait(t1 + 5)
+    eng.use_cuda_graph(False)
+    again = eng.forward_host(frames[0], slots)
+    assert all(torch.equal(a, b) for a, b in zip(want[0], again))
+
+
 def test_live_oracle_parity_on_fresh_inputs(built_library):
     """Oracle run live on this host vs the CUDA path on inputs no golden contains (Shelf geometry, ring cameras)."""
     from fvp import config as fcfg, synth
