@@ -608,7 +608,7 @@ int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr
 
 int fvp_debug_conv(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin, const float* h_weight, const float* h_bias,
                    int cout, int k, int relu, int mode, float* d_out, int repeat, float* h_ms, uintptr_t stream) {
-  if (!ctx || !d_in || !h_weight || !h_bias || !d_out || (k != 1 && k != 3 && k != 7) || cin % 4 || mode < 0 || mode > 3) return FVP_E_INVALID;
+  if (!ctx || !d_in || !h_weight || !h_bias || !d_out || (k != 1 && k != 3 && k != 7) || cin % 4 || mode < 0 || (mode & 0xff) > 3) return FVP_E_INVALID;
   cudaSetDevice(ctx->device);
   return fvp_debug_conv_impl(ctx, d_in, n, H, W, cin, h_weight, h_bias, cout, k, relu, mode, d_out, repeat, h_ms, (cudaStream_t)stream);
 }

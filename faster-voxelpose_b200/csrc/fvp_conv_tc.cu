@@ -76,6 +76,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// One lane of a CONVERGED warp (the MMA warp enters its role through a warp-uniform branch, see below): ptxas then
+// emits ELECT + a predicated UTCHMMA instead of the per-instruction "for every active lane" loop it generates around
+// uniform-datapath instructions in divergent code (6 extra instructions and ~40 cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -121,20 +129,61 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One tap of the fp16 engine as a single instruction group: A_hi x [B_hi;B_lo] -> D1|D2 (width 2n), A_lo x B_hi -> D2
+// (width n), for one (KSTEPS = 1) or two (KSTEPS = 2) K = 16 steps.  Descriptors advance by 2 (32 B) per K step.
+template <int KSTEPS>
+__device__ __forceinline__ void umma_tap_f16(uint32_t d1, uint32_t d2, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint32_t idesc2,
+                                             uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KSTEPS == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 a2, al2, b2;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "add.u64 a2, %2, 2;\n\tadd.u64 al2, %3, 2;\n\tadd.u64 b2, %4, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %4, %5, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %5, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, pt;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], al2, b2, %6, pt;\n\t}\n" ::"r"(d1),
+        "r"(d2), "l"(a_hi), "l"(a_lo), "l"(b_hi), "r"(idesc2), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %4, %5, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, pt;\n\t}\n" ::"r"(d1),
+        "r"(d2), "l"(a_hi), "l"(a_lo), "l"(b_hi), "r"(idesc2), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// All taps of one K-block of the fp16 engine with resident weights, fully unrolled: the tap offsets into the halo are
+// compile-time immediates on one base descriptor, the weight descriptor advances by a constant stride - no per-tap
+// scalar work is left on the issuing lane (measured: ~130 cycles of per-tap overhead in the generic loop below).
+template <int ROWB, int K, int KSTEPS>
+__device__ __forceinline__ void umma_kblock_f16(uint32_t d1, uint32_t d2, uint64_t ad0, uint32_t a_lo16, uint64_t bd, uint32_t b_stride16,
+                                                uint32_t idesc2, uint32_t idesc, uint32_t accumulate) {
+  constexpr int HWP = K == 1 ? 8 : 16;
+#pragma unroll
+  for (int dy = 0; dy < K; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < K; ++dx) {
+      const uint64_t ah = ad0 + (uint32_t)((dy * HWP + dx) * (ROWB >> 4));
+      umma_tap_f16<KSTEPS>(d1, d2, ah, ah + a_lo16, bd, idesc2, idesc, (dy | dx) ? 1u : accumulate);
+      bd += b_stride16;
+    }
+  }
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// issue only: the destination registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 struct TcArgs {
   FvpConvArgs c;
@@ -146,7 +195,20 @@ struct TcArgs {
   int resident;          // 1: the whole weight image is loaded once per CTA (b_stage_bytes = its size)
   uint32_t blk_bytes;    // bytes of one (K-block, tap, N-tile) weight block = n_tile*128*2
   int tiles_x, tiles_per_img, total_items;   // work item = (image, tile, N tile)
+  unsigned long long* prof;                  // debug: per-role wait / busy cycle counters (NULL in production)
 };
+
+// debug instrumentation: add the cycles spent in `stmt` to counter `slot` when profiling is on
+#define TC_TIMED(slot, stmt)                                   \
+  do {                                                         \
+    if (t.prof) {                                              \
+      const long long c0_ = clock64();                         \
+      stmt;                                                    \
+      pc[slot] += clock64() - c0_;                             \
+    } else {                                                   \
+      stmt;                                                    \
+    }                                                          \
+  } while (0)
 
 struct TcItem {
   int img, y0, x0, nt;
@@ -181,6 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   __shared__ uint64_t s_bar[2 * TC_MAX_A + 2 * TC_MAX_B + 4];
   __shared__ uint32_t s_tmem;
+  __shared__ __align__(16) float s_bias[512];                      // bias of every output channel (CoutP <= 512)
   const FvpConvArgs& a = t.c;
 
   const int A_ST = t.a_stages, B_ST = t.b_stages;
@@ -193,7 +256,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
   uint64_t* acc_full = b_empty + TC_MAX_B;                         // [2]
   uint64_t* acc_empty = acc_full + 2;                              // [2]
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform role index
   // Programmatic dependent launch: let the next kernel of the stream start its own prologue as soon as SMs are free,
   // and run OUR prologue (barriers, TMEM allocation, resident weight fetch) under the tail of the previous kernel.
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
@@ -203,6 +267,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  for (int i = tid; i < a.CoutP; i += TC_THREADS) s_bias[i] = a.bias[i];   // weights: independent of the previous kernel
   if (warp == TC_LW) {                                             // TMEM allocation (power of two >= 32 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(t.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -246,6 +311,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
       }
     }
     int a_it = 0;
+    long long pc[2] = {0, 0};
+    const long long lt0 = clock64();
     for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
       TcItem w;
       if (!tc_decode(t, item, w)) continue;
@@ -260,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         const float* img_in = src + (size_t)w.img * a.H * a.W * Cin;
         for (int c0 = 0; c0 < CinP; c0 += CB) {
           const int as = a_it % A_ST;
-          if (a_it >= A_ST) mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1);
+          if (a_it >= A_ST) TC_TIMED(0, mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1));
           uint8_t* hi = sA + (size_t)as * t.a_stage_bytes;
           if constexpr (F16) {
             const int c = c0 + q * 8;                                // 8 channels -> one 16-B chunk of halves
@@ -281,12 +348,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
               const float x[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
               uint32_t ph_[4], pl_[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __half h0 = __float2half_rn(x[2 * e]), h1 = __float2half_rn(x[2 * e + 1]);
-                const __half l0 = __float2half_rn((x[2 * e] - __half2float(h0)) * 2048.0f);
-                const __half l1 = __float2half_rn((x[2 * e + 1] - __half2float(h1)) * 2048.0f);
-                ph_[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                pl_[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+              for (int e = 0; e < 4; ++e) {                        // packed converts (F2FP on the ALU pipe, not the
+                const __half2 h2 = __floats2half2_rn(x[2 * e], x[2 * e + 1]);   // quarter-rate scalar F2F)
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn((x[2 * e] - hf.x) * 2048.0f, (x[2 * e + 1] - hf.y) * 2048.0f);
+                ph_[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                pl_[e] = *reinterpret_cast<const uint32_t*>(&l2);
               }
               *(uint4*)(hi + e_dst[ph][j]) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
               *(uint4*)(hi + lo_off + e_dst[ph][j]) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
@@ -317,6 +384,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         }
       }
     }
+    if (t.prof && tid == 0) {
+      atomicAdd(t.prof + 0, (unsigned long long)pc[0]);
+      atomicAdd(t.prof + 1, (unsigned long long)(clock64() - lt0));
+    }
   } else if (tid == TC_LOADERS + 32) {
     // =============================== B producer (TMA bulk copies) =====================================
     if (!t.resident) {                                            // (resident image: already requested above)
@@ -342,17 +413,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         }
       }
     }
-  } else if (tid == TC_LOADERS) {
-    // =============================== MMA issue (one thread) =========================================
+  } else if (warp == TC_LW) {
+    // ======================= MMA issue (whole warp converged, one elected lane issues) ===============
     const uint32_t idesc = F16 ? umma_idesc_f16(128, t.n_tile) : umma_idesc_tf32(128, t.n_tile);
     const uint32_t idesc2 = umma_idesc_f16(128, 2 * t.n_tile);   // fp16 engine: A_hi x [B_hi ; B_lo]
     int a_it = 0, b_it = 0, it = 0;
     bool b_ready = false;
+    long long pc[4] = {0, 0, 0, 0};
+    const long long mt0 = clock64();
     for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
       TcItem w;
       if (!tc_decode(t, item, w)) continue;
       const int buf = it & 1;
-      if (it >= 2) mbar_wait(acc_empty + buf, ((it >> 1) - 1) & 1);   // epilogue drained this accumulator
+      if (it >= 2) TC_TIMED(1, mbar_wait(acc_empty + buf, ((it >> 1) - 1) & 1));   // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem + (uint32_t)buf * (F16 ? 2u : 1u) * t.acc_stride;   // F16: D1 | D2 side by side
       uint32_t accumulate = 0;
@@ -364,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         const uint32_t a_lo_off = (uint32_t)HH * HWP * ROWB, b_lo_off = (uint32_t)t.n_tile * ROWB;
         for (int c0 = 0; c0 < CinP; c0 += CB) {
           const int as = a_it % A_ST;
-          mbar_wait(a_full + as, (a_it / A_ST) & 1);
+          TC_TIMED(0, mbar_wait(a_full + as, (a_it / A_ST) & 1));
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + (size_t)as * t.a_stage_bytes);
           // One descriptor per operand per K-block; per tap only 16-B-unit offsets are added to the low word
@@ -373,17 +446,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
           const uint64_t bd_res0 = umma_desc(smem_u32(sB), 8 * ROWB, LAYOUT);
           const uint32_t a_lo16 = a_lo_off >> 4, b_lo16 = b_lo_off >> 4, blk16 = t.blk_bytes >> 4;
           uint32_t bidx = (blk + (uint32_t)w.nt) * blk16;            // resident image: block of (K-block, tap 0, N tile)
+          if (F16 && t.resident) {                                   // fast path: whole K-block from one elected region
+            if (!b_ready) { TC_TIMED(2, mbar_wait(b_full, 0)); b_ready = true; tc_fence_after(); }
+            const uint32_t d2 = d_tmem + (uint32_t)t.n_tile, bstride = (uint32_t)t.n_tiles * blk16;
+            constexpr int KS = CB == 32 ? 2 : 1;
+            if (elect_one()) {
+              if (K == 3) umma_kblock_f16<ROWB, 3, KS>(d_tmem, d2, ad0, a_lo16, bd_res0 + bidx, bstride, idesc2, idesc, accumulate);
+              else if (K == 7) umma_kblock_f16<ROWB, 7, KS>(d_tmem, d2, ad0, a_lo16, bd_res0 + bidx, bstride, idesc2, idesc, accumulate);
+              else umma_kblock_f16<ROWB, 1, KS>(d_tmem, d2, ad0, a_lo16, bd_res0 + bidx, bstride, idesc2, idesc, accumulate);
+            }
+            accumulate = 1;
+          } else
           for (int dy = 0; dy < K; ++dy) {
             for (int dx = 0; dx < K; ++dx) {
               uint64_t bd_hi;
               int bs = 0;
               if (t.resident) {
-                if (!b_ready) { mbar_wait(b_full, 0); b_ready = true; }
+                if (!b_ready) { TC_TIMED(2, mbar_wait(b_full, 0)); b_ready = true; }
                 bd_hi = bd_res0 + bidx;
                 bidx += (uint32_t)t.n_tiles * blk16;
               } else {
                 bs = b_it % B_ST;
-                mbar_wait(b_full + bs, (b_it / B_ST) & 1);
+                TC_TIMED(2, mbar_wait(b_full + bs, (b_it / B_ST) & 1));
                 bd_hi = bd_res0 + (uint32_t)bs * (t.b_stage_bytes >> 4);
               }
               tc_fence_after();
@@ -395,73 +479,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
                 // two instructions per K step instead of three (the ~48-cycle per-instruction overhead dominates).
                 const uint32_t d2 = d_tmem + (uint32_t)t.n_tile;
                 (void)bd_lo;
-                umma_f16(d_tmem, ad_hi, bd_hi, idesc2, accumulate);
-                if constexpr (CB == 32) umma_f16(d_tmem, ad_hi + 2, bd_hi + 2, idesc2, 1);
-                umma_f16(d2, ad_lo, bd_hi, idesc, 1);
-                if constexpr (CB == 32) umma_f16(d2, ad_lo + 2, bd_hi + 2, idesc, 1);
+                if (elect_one()) umma_tap_f16<CB == 32 ? 2 : 1>(d_tmem, d2, ad_hi, ad_lo, bd_hi, idesc2, idesc, accumulate);
               } else {                                               // 3xTF32, K = 8: lo*hi, hi*lo, hi*hi
-                umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
-                umma_tf32(d_tmem, ad_lo + 2, bd_hi + 2, idesc, 1);
-                umma_tf32(d_tmem, ad_lo + 4, bd_hi + 4, idesc, 1);
-                umma_tf32(d_tmem, ad_lo + 6, bd_hi + 6, idesc, 1);
+                if (elect_one()) {
+                  umma_tf32(d_tmem, ad_lo, bd_hi, idesc, accumulate);
+                  umma_tf32(d_tmem, ad_lo + 2, bd_hi + 2, idesc, 1);
+                  umma_tf32(d_tmem, ad_lo + 4, bd_hi + 4, idesc, 1);
+                  umma_tf32(d_tmem, ad_lo + 6, bd_hi + 6, idesc, 1);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_lo + 2 * ks, idesc, 1);
+                  for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_lo + 2 * ks, idesc, 1);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_hi + 2 * ks, idesc, 1);
+                  for (int ks = 0; ks < 4; ++ks) umma_tf32(d_tmem, ad_hi + 2 * ks, bd_hi + 2 * ks, idesc, 1);
+                }
               }
               accumulate = 1;
               if (!t.resident) {
-                umma_commit(b_empty + bs);                           // B slot reusable when these MMAs retire
+                if (elect_one()) umma_commit(b_empty + bs);          // B slot reusable when these MMAs retire
                 ++b_it;
               }
             }
           }
           blk += (uint32_t)K * K * t.n_tiles;
-          umma_commit(a_empty + as);
+          if (elect_one()) umma_commit(a_empty + as);
           ++a_it;
         }
       }
-      umma_commit(acc_full + buf);
+      if (elect_one()) umma_commit(acc_full + buf);
       ++it;
+    }
+    if (t.prof && (tid & 31) == 0) {
+      atomicAdd(t.prof + 2, (unsigned long long)pc[0]);
+      atomicAdd(t.prof + 3, (unsigned long long)pc[1]);
+      atomicAdd(t.prof + 4, (unsigned long long)pc[2]);
+      atomicAdd(t.prof + 5, (unsigned long long)(clock64() - mt0));
+      atomicAdd(t.prof + 8, (unsigned long long)it);
     }
   } else if (warp >= TC_LW + 2) {
     // =================================== epilogue (4 warps) ===========================================
     const int quarter = warp & 3;                                  // TMEM lanes this warp may read
     const int r = quarter * 32 + (tid & 31);                       // accumulator row = output pixel of the tile
     int it = 0;
+    long long pc[4] = {0, 0, 0, 0};
+    const long long et0 = clock64();
     for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
       TcItem w;
       if (!tc_decode(t, item, w)) continue;
       const int buf = it & 1;
-      mbar_wait(acc_full + buf, (it >> 1) & 1);
+      TC_TIMED(0, mbar_wait(acc_full + buf, (it >> 1) & 1));
       tc_fence_after();
       const int oy = w.y0 + (r >> 3), ox = w.x0 + (r & 7);
       const bool px_ok = oy < a.H && ox < a.W;
       const int co_base = w.nt * t.n_tile;
       const uint32_t t_row = tmem + (uint32_t)buf * (F16 ? 2u : 1u) * t.acc_stride + ((uint32_t)(quarter * 32) << 16);
-      // output location of a 4-channel group (NHWC, pixel-shuffled for ConvTranspose k2s2)
-      auto locate = [&](int co, size_t& opix, int& ch, int& Y, int& X, int& Ho, int& Wo) {
-        Y = oy; X = ox; Ho = a.H; Wo = a.W; ch = co;
-        if (a.upsample) {                                          // co' = q*Co + c, q = dy*2+dx
-          const int Co = a.CoutP >> 2, q = co / Co;
-          ch = co - q * Co;
-          Y = 2 * oy + (q >> 1);
-          X = 2 * ox + (q & 1);
-          Ho = 2 * a.H;
-          Wo = 2 * a.W;
-        }
-        opix = ((size_t)w.img * Ho + Y) * Wo + X;
+      // Output addressing, hoisted per item.  plain: NHWC pixel (oy, ox); upsample (ConvTranspose k2s2 as 1x1 to 4*Co +
+      // pixel shuffle): column co = q*Co + c goes to pixel (2*oy + q/2, 2*ox + q%2), channel c - a 16-column chunk never
+      // straddles q because Co is a multiple of 16; nchw: planar store of the real channels.
+      const int Co = a.upsample ? (a.CoutP >> 2) : a.CoutP;
+      const int Ho = a.upsample ? 2 * a.H : a.H, Wo = a.upsample ? 2 * a.W : a.W;
+      const size_t img_px = (size_t)w.img * Ho * Wo;
+      const size_t px_plain = img_px + (size_t)(a.upsample ? 2 * oy : oy) * Wo + (a.upsample ? 2 * ox : ox);
+      auto chunk_offset = [&](int co, int& ch) -> size_t {        // float offset of column co's pixel (NHWC) ; ch = channel
+        if (!a.upsample) { ch = co; return px_plain * a.CoutS; }
+        const int q = co / Co;
+        ch = co - q * Co;
+        return (px_plain + (size_t)(q >> 1) * Wo + (q & 1)) * a.CoutS;
       };
       auto fetch_res = [&](int cb, float4* rr) {                   // residuals of one 16-column chunk, issued early
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-          const int co = co_base + cb + g4 * 4;
-          rr[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.res_mode && px_ok && co < a.CoutP && cb < t.n_tile) {
-            size_t opix; int ch, Y, X, Ho, Wo;
-            locate(co, opix, ch, Y, X, Ho, Wo);
-            rr[g4] = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
-          }
+        for (int g4 = 0; g4 < 4; ++g4) rr[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.res_mode && px_ok && cb < t.n_tile) {
+          int ch;
+          const size_t off = chunk_offset(co_base + cb, ch);
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4)
+            if (co_base + cb + g4 * 4 < a.CoutP) rr[g4] = __ldg((const float4*)(a.res + off + ch + g4 * 4));
         }
       };
       float4 rnext[4];
@@ -470,37 +561,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         float4 rcur[4];
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) rcur[g4] = rnext[g4];
+        uint32_t u1[16], u2[16];
+        const long long tl0 = t.prof ? clock64() : 0;
+        tmem_ld16_issue(t_row + (uint32_t)cb, u1);                 // both accumulators in flight, one wait
+        if constexpr (F16) tmem_ld16_issue(t_row + (uint32_t)t.n_tile + (uint32_t)cb, u2);
         fetch_res(cb + 16, rnext);                                 // next chunk's residuals fly under this chunk
+        tmem_ld_wait();
+        if (t.prof) pc[1] += clock64() - tl0;
         float v[16];
-        tmem_ld16(t_row + (uint32_t)cb, v);
-        if constexpr (F16) {                                       // D = D1 + 2^-11 * D2
-          float v2[16];
-          tmem_ld16(t_row + (uint32_t)t.n_tile + (uint32_t)cb, v2);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaf(v2[i], 1.0f / 2048.0f, v[i]);
+        for (int i = 0; i < 16; ++i) {
+          v[i] = __uint_as_float(u1[i]);
+          if constexpr (F16) v[i] = fmaf(__uint_as_float(u2[i]), 1.0f / 2048.0f, v[i]);   // D = D1 + 2^-11 * D2
         }
         if (cb + 16 >= t.n_tile) {                                 // last chunk read: hand the accumulator back
           tc_fence_before();
           mbar_arrive(acc_empty + buf);
         }
         if (!px_ok) continue;
+        int ch0;
+        const size_t off = chunk_offset(co_base + cb, ch0);
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) {
           const int co = co_base + cb + g4 * 4;
           if (co >= a.CoutP) break;
-          const float4 bias = __ldg((const float4*)(a.bias + co));
+          const float4 bias = *(const float4*)(s_bias + co);
           float4 o = make_float4(v[g4 * 4] + bias.x, v[g4 * 4 + 1] + bias.y, v[g4 * 4 + 2] + bias.z, v[g4 * 4 + 3] + bias.w);
-          size_t opix; int ch, Y, X, Ho, Wo;
-          locate(co, opix, ch, Y, X, Ho, Wo);
           const float4 rr = rcur[g4];
           if (a.res_mode == 1) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
           if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           if (a.res_mode == 2) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+          const int ch = ch0 + g4 * 4;
           if (!a.nchw) {
-            *(float4*)(a.out + opix * a.CoutS + ch) = o;
-          } else {
+            *(float4*)(a.out + off + ch) = o;
+          } else {                                                 // planar [n][CoutReal][Ho][Wo] (final layers, no upsample)
             const size_t plane = (size_t)Ho * Wo;
-            float* op = a.out + (size_t)w.img * a.CoutReal * plane + (size_t)Y * Wo + X;
+            float* op = a.out + (size_t)w.img * a.CoutReal * plane + (size_t)oy * Wo + ox;
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -509,6 +605,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         }
       }
       ++it;
+    }
+    if (t.prof && tid == TC_LOADERS + 64) {
+      atomicAdd(t.prof + 6, (unsigned long long)pc[0]);
+      atomicAdd(t.prof + 7, (unsigned long long)(clock64() - et0));
+      atomicAdd(t.prof + 9, (unsigned long long)pc[1]);
     }
   }
   tc_fence_before();
@@ -530,11 +631,15 @@ void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
   *n_tiles = fvp_cdiv(npad, *n_tile);
 }
 
+static unsigned long long* g_tc_prof = nullptr;
+void fvp_tc_set_prof(unsigned long long* d_counters) { g_tc_prof = d_counters; }   // debug hook (fvp_debug_conv)
+
 // mode: 0 = 3xTF32, 1 = fp16 split with 32-channel K-blocks, 2 = fp16 split with 16-channel K-blocks
 // wtc[3]: weight images tiled for N tiles of up to 128 / 32 / 64 columns (NULL where not packed)
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st) {
   TcArgs t;
   t.c = a;
+  t.prof = g_tc_prof;
   const uint32_t rowb = mode == 0 ? 128 : (mode == 1 ? 64 : 32);
   const int cb = mode == 2 ? 16 : 32, f16 = mode != 0;
   const int tiles = fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW) * a.n;

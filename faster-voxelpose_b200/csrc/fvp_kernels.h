@@ -72,6 +72,7 @@ struct FvpConvW {         // one packed conv
 };
 // tcgen05 / TMEM implicit-GEMM conv (fvp_conv_tc.cu); same arguments as fvp_launch_conv plus the tiled weights
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st);
+void fvp_tc_set_prof(unsigned long long* d_counters);   // debug: 9 role counters (see fvp_debug_conv)
 void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles);
 struct FvpTrunkW {
   FvpConvW front, r1a, r1b, s1a, s1b, e1a, e1b, s2a, s2b, e2a, e2b, ma, mb, d2a, d2b, up2, d1a, d1b, up1;

@@ -457,8 +457,15 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   a.res = nullptr; a.res_mode = 0; a.relu = relu; a.ksize = k; a.upsample = 0; a.nchw = 0; a.n = n; a.valid = nullptr;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const bool prof = (mode & 0x100) != 0;                            // role counters: ms_out must hold 1 + 12 floats
+  mode &= 0xff;
+  unsigned long long* d_prof = nullptr;
+  if (prof) { FVP_CUDA_OK(cudaMalloc(&d_prof, 12 * sizeof(unsigned long long))); }
   for (int it = 0; it < 1 + (repeat > 0 ? repeat : 1); ++it) {     // first launch = warm-up
-    if (it == 1) cudaEventRecord(e0, st);
+    if (it == 1) {
+      cudaEventRecord(e0, st);
+      if (prof) { cudaMemsetAsync(d_prof, 0, 12 * sizeof(unsigned long long), st); fvp_tc_set_prof(d_prof); }
+    }
     const float* const i16c[3] = {d + ot16c, nullptr, nullptr};
     const float* const i16[3] = {d + ot16, nullptr, nullptr};
     const float* const i32[3] = {d + ot, nullptr, nullptr};
@@ -469,7 +476,14 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   }
   cudaEventRecord(e1, st);
   FVP_CUDA_OK(cudaStreamSynchronize(st));
+  fvp_tc_set_prof(nullptr);
   if (ms_out) { cudaEventElapsedTime(ms_out, e0, e1); *ms_out /= (float)(repeat > 0 ? repeat : 1); }
+  if (prof && ms_out) {                                             // kilo-cycles per launch, summed over CTAs
+    unsigned long long h[12];
+    cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < 12; ++i) ms_out[1 + i] = (float)((double)h[i] / 1000.0 / (repeat > 0 ? repeat : 1));
+  }
+  if (d_prof) cudaFree(d_prof);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   FVP_CUDA_OK(cudaGetLastError());
   cudaFree(d);

@@ -279,10 +279,13 @@ class Engine:
         b = np.ascontiguousarray(bias, np.float32)
         cout, k = w.shape[0], w.shape[2]
         out = torch.zeros((n, H, W, (cout + 3) // 4 * 4), device=self.device)
-        ms = C.c_float(0)
+        ms = (C.c_float * 13)()                  # [0] = ms per launch; [1..12] = role counters when mode has bit 0x100
         self._ck(self.lib.fvp_debug_conv(self.ctx, x.data_ptr(), n, H, W, cin, w.ctypes.data, b.ctypes.data, cout, k,
-                                         1 if relu else 0, int(mode), out.data_ptr(), int(repeat), C.byref(ms), self._stream()))
-        return (out[..., :cout], float(ms.value)) if want_ms else out[..., :cout]
+                                         1 if relu else 0, int(mode), out.data_ptr(), int(repeat),
+                                         C.cast(ms, C.POINTER(C.c_float)), self._stream()))
+        if int(mode) & 0x100:
+            return out[..., :cout], float(ms[0]), [float(v) for v in ms[1:]]
+        return (out[..., :cout], float(ms[0])) if want_ms else out[..., :cout]
 
     def debug_project(self, slot: int, points: torch.Tensor):
         p = points.to(self.device, torch.float32).contiguous()
