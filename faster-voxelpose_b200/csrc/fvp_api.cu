@@ -55,6 +55,11 @@ int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaSt
       return fvp_fail(ctx, FVP_E_CALIB, "missing camera parameters for the current sequence (slot %d of frame %d)", s, b);
     if (ctx->h_frame_seq[b] != s || b >= ctx->frame_seq_uploaded) same = false;
     want[b] = s;
+    if (!ctx->grid_ready[s]) {                     // sample-grid cache of this calibration (two small kernels, once)
+      fvp_launch_build_sample_grids(ctx->geom, s, st);
+      FVP_CUDA_OK(cudaGetLastError());
+      ctx->grid_ready[s] = 1;
+    }
   }
   if (same) return FVP_OK;                       // device copy already holds these slots
   FVP_CUDA_OK(cudaStreamSynchronize(st));        // the pinned staging buffer may still be in flight
@@ -227,6 +232,8 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   bool ok = true;
   auto A = [&](cudaError_t r) { if (r != cudaSuccess && ok) { ok = false; e = r; } };
   A(dalloc(&ctx->d_axes, n_axes));
+  A(dalloc(&ctx->d_coarse_grid, (size_t)c.max_sequences * g.V * g.X * g.Y * g.Z));
+  A(dalloc(&ctx->d_fine_grid, (size_t)c.max_sequences * g.V * g.fine[0] * g.fine[1] * g.fine[2]));
   A(dalloc(&ctx->d_seqs, (size_t)c.max_sequences));
   A(dalloc(&ctx->d_hm_in, (size_t)MB * g.V * g.J * P.H * P.W));
   A(dalloc(&ctx->d_hm_cl, (size_t)MB * g.V * g.view_stride4 * 4));
@@ -280,9 +287,12 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
     return FVP_E_CUDA;
   }
   ctx->seq_set.assign(c.max_sequences, 0);
+  ctx->grid_ready.assign(c.max_sequences, 0);
   g.coarse_axes = ctx->d_axes;
   g.fine_axes = ctx->d_axes + g.X + g.Y + g.Z;
   g.ind_axes = g.fine_axes + g.fine[0] + g.fine[1] + g.fine[2];
+  g.coarse_grid = ctx->d_coarse_grid;
+  g.fine_grid = ctx->d_fine_grid;
   g.seqs = ctx->d_seqs;
   ctx->num_sms = prop.multiProcessorCount;
   int rc = fvp_set_axes(ctx, nullptr, nullptr, nullptr);
@@ -302,7 +312,7 @@ void fvp_destroy(fvp_ctx* ctx) {
   void* ptrs[] = {ctx->d_weights, ctx->d_axes, ctx->d_seqs, ctx->d_hm_in, ctx->d_hm_cl, ctx->d_plane_cl, ctx->d_hmsize,
                   ctx->d_conf2d, ctx->d_flat, ctx->d_centers, ctx->d_people, ctx->d_img_valid, ctx->d_planes_cl,
                   ctx->d_yz_scratch, ctx->d_xy_scratch, ctx->d_feat, ctx->d_pose, ctx->d_maxw, ctx->d_wts, ctx->d_fused, ctx->d_conf,
-                  ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq, ctx->d_hm_in_b};
+                  ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq, ctx->d_hm_in_b, ctx->d_coarse_grid, ctx->d_fine_grid};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 6; ++i) {
@@ -389,6 +399,7 @@ int fvp_set_axes(fvp_ctx* ctx, const float* h_coarse, const float* h_fine, const
       linspace_plus(-c.ind_space_size[d] / 2, c.ind_space_size[d] / 2, 64, c.space_center[d], q + 64 * d);
   cudaDeviceSynchronize();
   FVP_CUDA_OK(cudaMemcpy(ctx->d_axes, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->grid_ready.assign(ctx->cfg.max_sequences, 0);      // sample grids depend on the axes
   return FVP_OK;
 }
 
@@ -412,6 +423,7 @@ int fvp_set_sequence(fvp_ctx* ctx, int slot, const float* h_cameras, int num_vie
   cudaDeviceSynchronize();
   FVP_CUDA_OK(cudaMemcpy(ctx->d_seqs + slot, &s, sizeof(s), cudaMemcpyHostToDevice));
   ctx->seq_set[slot] = 1;
+  ctx->grid_ready[slot] = 0;                               // rebuilt on first use (upload_frame_seq)
   return FVP_OK;
 }
 

@@ -47,6 +47,32 @@ void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_
 }
 
 // ------------------------------------------------------------------------------------------------
+// sample-grid cache: (ix, iy) of every coarse / fine grid voxel in every view of one calibration slot
+// ------------------------------------------------------------------------------------------------
+// fine != 0: out[v][x][y][z] over the fine grid; fine == 0: out[x][y][z][v] over the coarse grid (K1 walks (z, view)
+// pairs of a column, which are contiguous in that order).  Same fvp_project(), same axis values as the kernels used
+// to evaluate in place, so the cached positions are bit-identical to the on-the-fly ones.
+__global__ void __launch_bounds__(256) k_build_sample_grid(FvpGeom g, int slot, int fine, float2* __restrict__ out) {
+  const int n0 = fine ? g.fine[0] : g.X, n1 = fine ? g.fine[1] : g.Y, n2 = fine ? g.fine[2] : g.Z;
+  const float* ax = fine ? g.fine_axes : g.coarse_axes;
+  const int nvox = n0 * n1 * n2;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= nvox * g.V) return;
+  int v, vox;
+  if (fine) { v = i / nvox; vox = i - v * nvox; } else { vox = i / g.V; v = i - vox * g.V; }
+  const int z = vox % n2, xy = vox / n2, y = xy % n1, x = xy / n1;
+  const FvpSeq& sq = g.seqs[slot];
+  float ix, iy;
+  fvp_project(sq.cam[v], sq.A, g.proj, ax[x], ax[n0 + y], ax[n0 + n1 + z], ix, iy);
+  out[i] = make_float2(ix, iy);
+}
+void fvp_launch_build_sample_grids(const FvpGeom& g, int slot, cudaStream_t st) {
+  const size_t nc = (size_t)g.X * g.Y * g.Z * g.V, nf = (size_t)g.fine[0] * g.fine[1] * g.fine[2] * g.V;
+  k_build_sample_grid<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(g, slot, 0, const_cast<float2*>(g.coarse_grid) + slot * nc);
+  k_build_sample_grid<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(g, slot, 1, const_cast<float2*>(g.fine_grid) + slot * nf);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
 // CTA = 4 warps that all own the same 32/CG voxel columns; warp w takes the z range [w*Z/4, (w+1)*Z/4) so a
@@ -55,18 +81,9 @@ template <int CG>
 __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const float4* __restrict__ hm_cl,
                                                             const int* __restrict__ frame_seq,
                                                             float4* __restrict__ plane_cl) {
-  extern __shared__ float smem_f[];
-  __shared__ FvpSeq s_seq;
   __shared__ float4 s_part[4][32];
   const int b = blockIdx.y;
   const FvpProj& P = g.proj;
-  {
-    const int* src = (const int*)(g.seqs + frame_seq[b]);
-    int* dst = (int*)&s_seq;
-    for (int i = threadIdx.x; i < (int)(sizeof(FvpSeq) / 4); i += blockDim.x) dst[i] = src[i];
-    for (int i = threadIdx.x; i < g.Z; i += blockDim.x) smem_f[i] = g.coarse_axes[g.X + g.Y + i];
-  }
-  __syncthreads();
 
   constexpr int COLS_PER_WARP = 32 / CG;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,8 +93,8 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
   int col = blockIdx.x * COLS_PER_WARP + lane / CG;
   const bool col_ok = col < ncols;
   if (!col_ok) col = ncols - 1;                  // keep the warp convergent for the shuffles
-  const int cx = col / g.Y, cy = col - cx * g.Y;
-  const float wx = g.coarse_axes[cx], wy = g.coarse_axes[g.X + cy];
+  // cached sample positions of this column: [z][view] pairs, contiguous
+  const float2* grid_col = g.coarse_grid + ((size_t)frame_seq[b] * g.X * g.Y + col) * g.Z * g.V;
 
   const int V = g.V, ZW = g.Z >> 2, z0 = warp * ZW, npairs = ZW * V;
   const float fV = (float)V, rV = 1.0f / fV;
@@ -91,9 +108,8 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
     t.off = 0; t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
     if (idx < npairs) {
       const int z = idx / V, v = idx - z * V;
-      float ix, iy;
-      fvp_project(s_seq.cam[v], s_seq.A, P, wx, wy, smem_f[z0 + z], ix, iy);
-      t = fvp_taps(P, ix, iy);
+      const float2 q = __ldg(grid_col + z0 * V + idx);
+      t = fvp_taps(P, q.x, q.y);
       t.off += (b * V + v) * (int)g.view_stride4;
     }
 #pragma unroll
@@ -124,7 +140,7 @@ __global__ void __launch_bounds__(128) k1_hdn_project_zmax(FvpGeom g, const floa
 void fvp_launch_hdn_project(const FvpGeom& g, const float* d_hm_cl, const int* d_frame_seq, float* d_plane_cl,
                             int batch, cudaStream_t st) {
   const int ncols = g.X * g.Y;
-  const size_t smem = g.Z * sizeof(float);
+  const size_t smem = 0;
   if (g.JG <= 4) {
     dim3 grid(fvp_cdiv(ncols, 8), batch);
     k1_hdn_project_zmax<4><<<grid, 128, smem, st>>>(g, (const float4*)d_hm_cl, d_frame_seq, (float4*)d_plane_cl);
@@ -184,9 +200,6 @@ k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __r
   constexpr int BPW = 32 / CG;                   // columns b per warp
   constexpr int ROUNDS = K3_CCH / CG;            // projection rounds per (a, view)
   static_assert(K3_CCH % CG == 0, "chunk must be a multiple of the lane group");
-  __shared__ FvpSeq s_seq;
-  __shared__ float s_fz[64];
-  __shared__ float s_fx[TA];
   constexpr int NBUF = (CG == 4) ? 2 : 1;        // double buffer when it fits the 48 KB static limit
   __shared__ float4 s_xz[NBUF][K3_CCH][NW][CG];  // per-warp partial maxima
   __shared__ float4 s_xy[TA][NT];                // per-thread running max over c for every a of the slab
@@ -225,26 +238,15 @@ k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __r
     return;
   }
 
-  {
-    const int* src = (const int*)(g.seqs + pd.seq);
-    int* dst = (int*)&s_seq;
-    for (int i = tid; i < (int)(sizeof(FvpSeq) / 4); i += NT) dst[i] = src[i];
-    if (tid < 64) {
-      const int gz = pd.tl[2] + tid;
-      s_fz[tid] = (gz >= 0 && gz < g.fine[2]) ? g.fine_axes[g.fine[0] + g.fine[1] + gz] : 0.f;
-    }
-    if (tid < TA) {
-      const int gx = pd.tl[0] + a0 + tid;
-      s_fx[tid] = (gx >= 0 && gx < g.fine[0]) ? g.fine_axes[gx] : 0.f;
-    }
 #pragma unroll
-    for (int a = 0; a < TA; ++a) s_xy[a][tid] = zero4;
-  }
-  __syncthreads();
+  for (int a = 0; a < TA; ++a) s_xy[a][tid] = zero4;      // own slot only: no barrier needed
 
+  // Sample positions come from the per-calibration cache (fine_grid[slot][view][x][y][z]); the crop of this person is
+  // the window tl + (a, b, c), and [lo, hi) is its part inside the grid, so every index used below is in range.
   const bool b_ok = b >= pd.lo[1] && b < pd.hi[1];
-  const int gy = pd.tl[1] + b;
-  const float wy = (gy >= 0 && gy < g.fine[1]) ? g.fine_axes[g.fine[0] + gy] : 0.f;
+  const int F1 = g.fine[1], F2 = g.fine[2], nfine = g.fine[0] * F1 * F2;
+  const float2* grid_s = g.fine_grid + (size_t)pd.seq * nfine * g.V;
+  const int col_y = (pd.tl[1] + b) * F2 + pd.tl[2];          // + gx * F1 * F2 + view * nfine + c
   const int V = g.V;
   const float fV = (float)V, rV = 1.0f / fV;
   const int row4 = P.WP * JG, px4 = JG;
@@ -267,14 +269,17 @@ k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __r
       for (int c = 0; c < K3_CCH; ++c) acc[c] = zero4;
       const bool row_live = chunk_live && (a0 + a) >= alo && (a0 + a) < ahi;     // uniform
       if (row_live) {
-        const float wx = s_fx[a];
+        const int col = (pd.tl[0] + a0 + a) * F1 * F2 + col_y;
         for (int v = 0; v < V; ++v) {
           const int view_off = frame_off + v * vs4;
+          FvpTapCache tcache;
+          tcache.off = -1;
 #pragma unroll
           for (int r = 0; r < ROUNDS; ++r) {
-            float ix, iy;
-            fvp_project(s_seq.cam[v], s_seq.A, P, wx, wy, s_fz[cc + r * CG + s], ix, iy);
-            const FvpTaps t = fvp_taps(P, ix, iy);
+            const int cz = cc + r * CG + s;                         // the depth this lane looks up for its column
+            float2 q = make_float2(0.f, 0.f);
+            if (b_ok && cz >= pd.lo[2] && cz < pd.hi[2]) q = __ldg(grid_s + v * nfine + col + cz);
+            const FvpTaps t = fvp_taps(P, q.x, q.y);
             const int my_off = t.off + view_off;
 #pragma unroll
             for (int k = 0; k < CG; ++k) {
@@ -285,7 +290,7 @@ k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __r
               const float w10 = __shfl_sync(0xffffffffu, t.w10, group_base + k);
               const float w11 = __shfl_sync(0xffffffffu, t.w11, group_base + k);
               const bool c_ok = (cc + c) >= pd.lo[2] && (cc + c) < pd.hi[2];     // uniform
-              if (sample_ok && c_ok) fvp_tap_accumulate<PX16>(acc[c], hm_cl, off + s, row4, px4, w00, w01, w10, w11);
+              if (sample_ok && c_ok) fvp_tap_accumulate_cached<PX16>(acc[c], tcache, hm_cl, off + s, row4, px4, w00, w01, w10, w11);
             }
           }
         }

@@ -86,6 +86,9 @@ struct fvp_ctx {
   bool profiling = false;
   cudaEvent_t ev[10] = {nullptr};
   // pipelined host entry (fvp_submit_host / fvp_wait): two input buffers, a copy stream and per-slot events
+  float2* d_coarse_grid = nullptr;    // sample-grid cache, see FvpGeom
+  float2* d_fine_grid = nullptr;
+  std::vector<char> grid_ready;       // per slot: grids match the current cameras and axes
   float* d_hm_in_b = nullptr;         // second [MB][V][J][H][W] input buffer
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k0[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};

@@ -14,10 +14,18 @@ struct FvpGeom {
   const float* ind_axes;     // [64*3] individual-space axes incl. space centre (center_grid)
   const FvpSeq* seqs;        // [max_sequences]
   size_t view_stride4;       // float4 per view of the channel-last heat map (HP*WP*JG)
+  // Sample-grid cache per calibration slot (the reference caches the same thing: project_whole.py:66-76,
+  // project_individual.py sample_grid[seq]): unnormalised heat-map positions (ix, iy) of every grid voxel in every
+  // view, computed ONCE per slot by fvp_project (k_build_sample_grid) and only looked up by K1 / K3.
+  const float2* coarse_grid; // [max_sequences][X][Y][Z][V]
+  const float2* fine_grid;   // [max_sequences][V][fine0][fine1][fine2]
 };
 
 // K0: [B][V][J][H][W] -> channel-last, zero-bordered [B][V][HP][WP][JP]
 void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_cl, int batch, cudaStream_t st);
+
+// (re)build both sample grids of calibration slot `slot`
+void fvp_launch_build_sample_grids(const FvpGeom& g, int slot, cudaStream_t st);
 
 // K1: fused back-projection + view mean + clamp + z-max -> plane_cl [B][X][Y][JP]
 void fvp_launch_hdn_project(const FvpGeom& g, const float* d_hm_cl, const int* d_frame_seq, float* d_plane_cl,
