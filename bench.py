@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--conv-mode", type=int, default=-1, help="-1 library default, 0 fp32 CUDA cores, 1 tcgen05 3xTF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="frames in flight on one GPU (independent contexts on their own "
+                    "streams, fvp.engine.EngineLanes); 1 = strictly serial forwards")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -197,46 +199,60 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     import torch.distributed as dist
     from fvp import dist as fdist
-    from fvp.engine import Engine
+    from fvp.engine import EngineLanes
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         fdist.init_from_env("nccl")
     B = args.batch
-    eng = Engine(cfg, dev, max_batch=B, max_sequences=1)
-    eng.load_state_dict(sd_np)
+    L = max(1, args.lanes)
+    lanes = EngineLanes(cfg, dev, lanes=L, max_batch=B, max_sequences=1)
+    lanes.load_state_dict(sd_np)
     if args.conv_mode >= 0:
-        eng.set_conv_mode(args.conv_mode)
-    slot = eng.sequence_slot(cams, resize)
+        lanes.set_conv_mode(args.conv_mode)
+    slot = lanes.sequence_slot(cams, resize)
     slots = [slot] * B
+    eng = lanes.engines[0]                       # lane 0 alone: serial latency and per-stage times
+    conf["frames_in_flight"] = L
+    conf["pipelining"] = ("%d independent batch-%d forwards in flight on %d streams (one context each); per-frame latency "
+                          "is reported as serial_ms_per_step" % (L, B, L)) if L > 1 else "none (serial forwards)"
     frames = make_frames(cfg, cams, POOL, seed0=1000 + 100 * rank)           # distinct frames per rank
     pool_dev = [torch.from_numpy(np.stack([frames[(i + b) % POOL] for b in range(B)])).to(dev) for i in range(POOL)]
     pool_host = [torch.from_numpy(np.stack([frames[(i + b) % POOL] for b in range(B)])).pin_memory() for i in range(POOL)]
     if not args.no_graph:
-        eng.use_cuda_graph(True)
+        lanes.use_cuda_graph(True)
     gather_buf = [torch.empty((B, P, J, 5), device=dev) for _ in range(world)] if world > 1 else None
 
-    def step(i):
-        fused, plane, centers = eng.forward(pool_dev[i % POOL], slots)
+    def finish_one():
+        fused, plane, centers = lanes.collect()      # the current stream now waits for that frame
         if world > 1:
             dist.all_gather(gather_buf, fused)       # the single collective of the path (run/validate.py:114)
         return fused
+
+    def run_steps(i0, nsteps):
+        """nsteps forwards, L in flight; returns the last frame's fused poses (all work ordered on the current stream)."""
+        out = None
+        for i in range(i0, i0 + nsteps):
+            lanes.submit(pool_dev[i % POOL], slots)
+            if lanes.outstanding() == L:
+                out = finish_one()
+        while lanes.outstanding():
+            out = finish_one()
+        return out
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
-        step(i)
+    run_steps(0, max(args.warmup, 2 * L))
     sync_all()
     launches_per_step = eng.last_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     ev0.record()
-    for i in range(args.steps):
-        out = step(i)
+    out = run_steps(0, args.steps)
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1)
@@ -247,12 +263,25 @@ def main():
     clocks = sampler.stop() if sampler else None
     n_valid = int((out[..., 0, 3] >= 0).sum().item())
 
+    # ---- serial forwards on one lane (one frame in flight): the per-frame latency ------------------------------
+    ser_steps = max(10, args.steps // 4)
+    for i in range(3):
+        eng.forward(pool_dev[i % POOL], slots)
+    sync_all()
+    ev0.record()
+    for i in range(ser_steps):
+        eng.forward(pool_dev[i % POOL], slots)
+    ev1.record()
+    sync_all()
+    serial_ms = ev0.elapsed_time(ev1) / ser_steps
+
     # ---- e2e through the host-buffer entry point -----------------------------------------------------
     # (a) blocking call (fvp_forward_host): per-call latency; (b) the two-deep pipeline (fvp_submit_host / fvp_wait):
     # every step still copies its own inputs H2D from pinned memory and reads its own results back D2H, the copy of
     # step i+1 overlapping the kernels of step i.  (b) is the throughput figure reported as e2e.value.
     host_out = eng.new_host_outputs(B)
-    host_outs = [host_out, eng.new_host_outputs(B)]
+    depth = L + 1 if L > 1 else 2                # frames in flight through the host entry (<= 2 tickets per lane)
+    host_outs = [host_out] + [eng.new_host_outputs(B) for _ in range(depth)]
     e2e_steps = max(10, args.steps // 2)
     for i in range(3):
         eng.forward_host(pool_host[i % POOL], slots, host_out)
@@ -264,19 +293,23 @@ def main():
     sync_call_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
 
     def pipelined(nsteps):
-        prev = None
-        for i in range(nsteps):
-            t = eng.submit_host(pool_host[i % POOL], slots, host_outs[i & 1])
-            if prev is not None:
-                eng.wait(prev)
-                if world > 1:
-                    dist.all_gather(gather_buf, host_outs[(i - 1) & 1][0].to(dev, non_blocking=True))
-            prev = t
-        eng.wait(prev)
-        if world > 1:
-            dist.all_gather(gather_buf, host_outs[(nsteps - 1) & 1][0].to(dev, non_blocking=True))
+        nb, done = len(host_outs), 0
 
-    pipelined(4)
+        def finish():
+            nonlocal done
+            lanes.wait_oldest()                  # results of step `done` are now in its pinned host buffers
+            if world > 1:
+                dist.all_gather(gather_buf, host_outs[done % nb][0].to(dev, non_blocking=True))
+            done += 1
+
+        for i in range(nsteps):
+            lanes.submit_host(pool_host[i % POOL], slots, host_outs[i % nb])
+            if lanes.host_outstanding() == depth:
+                finish()
+        while lanes.host_outstanding():
+            finish()
+
+    pipelined(2 * depth)
     sync_all()
     t0 = time.perf_counter()
     pipelined(e2e_steps)
@@ -348,9 +381,10 @@ def main():
         "launches_per_step": launches_per_step,
         "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "fvp_submit_host/fvp_wait (2-deep pipeline)", "blocking_call_ms": sync_call_ms},
+                "api": "fvp_submit_host/fvp_wait, %d frames in flight over %d lanes" % (depth, L),
+                "blocking_call_ms": sync_call_ms},
         "roofline": roofline, "cpu_baseline": cpu_base, "kernels": extra_kernels, "valid_people_last_step": n_valid,
-        "cuda_graph": not args.no_graph,
+        "cuda_graph": not args.no_graph, "serial_ms_per_step": serial_ms, "serial_fps": world * B / (serial_ms * 1e-3),
     }
     _emit(line)
     if world > 1:

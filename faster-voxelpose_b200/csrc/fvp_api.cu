@@ -71,8 +71,13 @@ int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaSt
 
 // depth parts per person for K3: enough CTAs for ~3 waves of (3 CTAs/SM) at small batch
 int fvp_k3_parts(const fvp_ctx* ctx, int batch) {
-  const int base = 16 * batch * ctx->geom.P;                 // slabs x persons
   int parts = 1;
+  if (fvp_k3_version() == 2) {                               // patch kernel: 64 (JG <= 4) or 128 patches per person
+    const int base = (ctx->geom.JG <= 4 ? 64 : 128) * batch * ctx->geom.P;
+    while (parts < 8 && base * parts < 12 * ctx->num_sms) parts *= 2;   // >= 3 waves of 4 CTAs / SM
+    return parts;
+  }
+  const int base = 16 * batch * ctx->geom.P;                 // slabs x persons
   while (parts < 8 && base * parts < 9 * ctx->num_sms) parts *= 2;
   return parts;
 }

@@ -335,6 +335,158 @@ k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3 v2 ("patch"): same arithmetic per sample as k3_jln_project (bit-identical planes), different decomposition.
+// One CTA = one person x one compact patch of 8 cube rows a (one per warp) x BPW = 32/CG cube columns b x one depth
+// part.  A pass of the patch over one view and one chunk of CG depths touches a compact ~(8*1.5)^2-pixel window of the
+// heat map instead of the 64-column sheet of v1, so the 2x2 footprints of neighbouring voxels share L1 lines whatever
+// the direction the camera looks along.  No shared state survives a chunk:
+//   xy[a][b] = max_c : the thread owns (a, b) - a register, stored once (partial over the depth parts)
+//   xz[a][c] = max_b : REDUX.MAX over the warp's lanes of one channel group; partial over the 64/BPW b-blocks
+//   yz[b][c] = max_a : the 8 warps (8 rows) meet in shared memory; partial over the 8 a-blocks
+// k3b_reduce folds the partial images.
+template <int CG, int MINB, int PX16>
+__global__ void __launch_bounds__(256, MINB)
+k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __restrict__ people,
+             float4* __restrict__ planes_cl, float4* __restrict__ xy_scratch, float4* __restrict__ xz_scratch,
+             float4* __restrict__ yz_scratch, int n_people, int ncpart) {
+  constexpr int BPW = 32 / CG;                   // cube columns b per warp = patch extent in b
+  constexpr int NBB = 64 / BPW;                  // b-blocks per cube
+  constexpr int NAB = 8;                         // a-blocks per cube (8 rows each, one row per warp)
+  constexpr int CCH = CG;                        // depths per chunk: one projection round of the lane group
+  constexpr int NBUF = (CG == 4) ? 2 : 1;        // double buffer when it fits the 48 KB static limit
+  __shared__ float4 s_yz[NBUF][CCH][8][32];      // [depth][warp = row][lane = (b, channel group)]
+
+  const int person = blockIdx.y;
+  const int patch = blockIdx.x % (NAB * NBB), cpart = blockIdx.x / (NAB * NBB);
+  const int ablk = patch / NBB, bblk = patch - ablk * NBB;
+  const int c_begin = cpart * (64 / ncpart), c_end = c_begin + 64 / ncpart;
+  const FvpPerson pd = people[person];
+  const FvpProj& P = g.proj;
+  const int JG = g.JG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = lane % CG, group_base = lane - s;
+  const int a = ablk * 8 + warp;                 // cube row    (world x index within the cube), warp-uniform
+  const int b = bblk * BPW + lane / CG;          // cube column (world y index within the cube)
+  const bool ch_ok = s < JG;
+  const size_t img4 = (size_t)64 * 64 * JG;      // float4 per plane image
+  float4* xy_img = ncpart == 1 ? planes_cl + ((size_t)0 * n_people + person) * img4
+                               : xy_scratch + ((size_t)person * ncpart + cpart) * img4;
+  float4* xz_part = xz_scratch + ((size_t)person * NBB + bblk) * img4;
+  float4* yz_part = yz_scratch + ((size_t)person * NAB + ablk) * img4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const bool live = pd.valid && !pd.empty;
+  const bool any = live && max(ablk * 8, pd.lo[0]) < min(ablk * 8 + 8, pd.hi[0]) &&
+                   max(bblk * BPW, pd.lo[1]) < min(bblk * BPW + BPW, pd.hi[1]) &&
+                   max(c_begin, pd.lo[2]) < min(c_end, pd.hi[2]);
+  if (!any) {                                    // nothing to sample in this patch: its outputs are zero
+    if (ch_ok) {
+      xy_img[((size_t)a * 64 + b) * JG + s] = zero4;
+      for (int c = c_begin; c < c_end; ++c) {
+        if (lane < CG) xz_part[((size_t)a * 64 + c) * JG + s] = zero4;
+        if (warp == 0) yz_part[((size_t)b * 64 + c) * JG + s] = zero4;
+      }
+    }
+    return;
+  }
+
+  const bool a_ok = a >= pd.lo[0] && a < pd.hi[0];           // warp-uniform
+  const bool b_ok = b >= pd.lo[1] && b < pd.hi[1];
+  const int F1 = g.fine[1], F2 = g.fine[2], nfine = g.fine[0] * F1 * F2;
+  const float2* grid_s = g.fine_grid + (size_t)pd.seq * nfine * g.V;
+  const int col = ((pd.tl[0] + a) * F1 + pd.tl[1] + b) * F2 + pd.tl[2];     // + view * nfine + c
+  const int V = g.V;
+  const float fV = (float)V, rV = 1.0f / fV;
+  const int row4 = P.WP * JG, px4 = JG;
+  const int vs4 = (int)g.view_stride4, frame_off = (person / g.P) * V * vs4;
+  const bool sample_ok = ch_ok && b_ok;
+  unsigned rmask = 0;                            // lanes of this warp that hold my channel group
+#pragma unroll
+  for (int i = 0; i < BPW; ++i) rmask |= 1u << (i * CG + s);
+
+  float4 xy_m = zero4;
+  int it = 0;
+  for (int cc = c_begin; cc < c_end; cc += CCH, ++it) {
+    float4 acc[CCH];
+#pragma unroll
+    for (int c = 0; c < CCH; ++c) acc[c] = zero4;
+    const bool row_live = a_ok && max(cc, pd.lo[2]) < min(cc + CCH, pd.hi[2]);   // warp-uniform
+    if (row_live) {
+      const int cz = cc + s;                     // the depth this lane looks up for its column
+      const bool q_ok = b_ok && cz >= pd.lo[2] && cz < pd.hi[2];
+      for (int v = 0; v < V; ++v) {
+        FvpTapCache tcache;
+        tcache.off = -1;
+        float2 q = make_float2(0.f, 0.f);
+        if (q_ok) q = __ldg(grid_s + (size_t)v * nfine + col + cz);
+        const FvpTaps t = fvp_taps(P, q.x, q.y);
+        const int my_off = t.off + frame_off + v * vs4;
+#pragma unroll
+        for (int k = 0; k < CG; ++k) {           // compile-time depth index within the chunk
+          const int off = __shfl_sync(0xffffffffu, my_off, group_base + k);
+          const float w00 = __shfl_sync(0xffffffffu, t.w00, group_base + k);
+          const float w01 = __shfl_sync(0xffffffffu, t.w01, group_base + k);
+          const float w10 = __shfl_sync(0xffffffffu, t.w10, group_base + k);
+          const float w11 = __shfl_sync(0xffffffffu, t.w11, group_base + k);
+          const bool c_ok = (cc + k) >= pd.lo[2] && (cc + k) < pd.hi[2];         // uniform
+          if (sample_ok && c_ok) fvp_tap_accumulate_cached<PX16>(acc[k], tcache, hm_cl, off + s, row4, px4, w00, w01, w10, w11);
+        }
+      }
+    }
+    // mean + clamp + the three maxima of this chunk
+    float4(*yzb)[8][32] = s_yz[NBUF == 2 ? (it & 1) : 0];
+#pragma unroll
+    for (int c = 0; c < CCH; ++c) {
+      const float4 val = row_live ? fvp_mean_clamp4(acc[c], fV, rV) : zero4;     // untouched acc -> 0
+      xy_m = fvp_max4(xy_m, val);
+      yzb[c][warp][lane] = val;
+      float4 m;
+      m.x = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.x)));
+      m.y = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.y)));
+      m.z = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.z)));
+      m.w = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.w)));
+      if (lane < CG && ch_ok) xz_part[((size_t)a * 64 + cc + c) * JG + s] = m;
+    }
+    __syncthreads();
+    if (tid < CCH * 32) {                        // yz[b][cc + c]: max over the 8 rows of the patch
+      const int c = tid >> 5, l = tid & 31, ss = l % CG;
+      if (ss < JG) {
+        float4 m = yzb[c][0][l];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fvp_max4(m, yzb[c][w][l]);
+        yz_part[((size_t)(bblk * BPW + l / CG) * 64 + cc + c) * JG + ss] = m;
+      }
+    }
+    if (NBUF == 1) __syncthreads();
+  }
+  if (ch_ok) xy_img[((size_t)a * 64 + b) * JG + s] = xy_m;
+}
+
+// K3b for the patch kernel: xz = max over the b-block partials, yz = max over the a-block partials, xy = max over the
+// depth parts (when there are several)
+__global__ void __launch_bounds__(256) k3b_reduce(const float4* __restrict__ xy_scratch, const float4* __restrict__ xz_scratch,
+                                                  const float4* __restrict__ yz_scratch, float4* __restrict__ planes_cl,
+                                                  int n_people, int nbb, int nab, int ncpart, int img4) {
+  const int person = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= img4) return;
+  const float4* sz = xz_scratch + (size_t)person * nbb * img4 + i;
+  float4 m = sz[0];
+  for (int k = 1; k < nbb; ++k) m = fvp_max4(m, sz[(size_t)k * img4]);
+  planes_cl[((size_t)1 * n_people + person) * img4 + i] = m;
+  const float4* sy = yz_scratch + (size_t)person * nab * img4 + i;
+  m = sy[0];
+  for (int k = 1; k < nab; ++k) m = fvp_max4(m, sy[(size_t)k * img4]);
+  planes_cl[((size_t)2 * n_people + person) * img4 + i] = m;
+  if (ncpart > 1) {
+    const float4* sx = xy_scratch + (size_t)person * ncpart * img4 + i;
+    m = sx[0];
+    for (int k = 1; k < ncpart; ++k) m = fvp_max4(m, sx[(size_t)k * img4]);
+    planes_cl[((size_t)0 * n_people + person) * img4 + i] = m;
+  }
+}
+
 // K3b: yz plane = max over the slab partials
 __global__ void __launch_bounds__(256) k3b_yz_reduce(const float4* __restrict__ yz_scratch,
                                                       const float4* __restrict__ xy_scratch,
@@ -355,10 +507,40 @@ __global__ void __launch_bounds__(256) k3b_yz_reduce(const float4* __restrict__ 
   }
 }
 
+// 2 = patch kernel (default), 1 = slab kernel; FVP_K3_VERSION overrides (A/B measurements)
+int fvp_k3_version() {
+  static const int v = getenv("FVP_K3_VERSION") ? atoi(getenv("FVP_K3_VERSION")) : 2;
+  return v;
+}
+
 void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
                             float* d_yz_scratch, float* d_xy_scratch, int batch, int ncpart, cudaStream_t st) {
   const int n_people = batch * g.P;
   const int img4 = 64 * 64 * g.JG;
+  if (fvp_k3_version() == 2) {
+    // patch kernel: the 32 scratch images per person hold the xz partials (<= 16 b-blocks) then the 8 yz partials
+    float4* xz_s = (float4*)d_yz_scratch;
+    float4* yz_s = xz_s + (size_t)n_people * 16 * img4;
+    const int nbb = g.JG <= 4 ? 8 : 16;
+    dim3 grid(8 * nbb * ncpart, n_people);
+    static const int occ = getenv("FVP_K3_OCC") ? atoi(getenv("FVP_K3_OCC")) : 4;   // CTAs / SM the registers are capped for
+    if (g.JG == 4 && occ == 3)
+      k3_jln_patch<4, 3, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                   (float4*)d_xy_scratch, xz_s, yz_s, n_people, ncpart);
+    else if (g.JG == 4)
+      k3_jln_patch<4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                   (float4*)d_xy_scratch, xz_s, yz_s, n_people, ncpart);
+    else if (g.JG < 4)
+      k3_jln_patch<4, 4, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                  (float4*)d_xy_scratch, xz_s, yz_s, n_people, ncpart);
+    else
+      k3_jln_patch<8, 2, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
+                                                  (float4*)d_xy_scratch, xz_s, yz_s, n_people, ncpart);
+    dim3 grid2(fvp_cdiv(img4, 256), n_people);
+    k3b_reduce<<<grid2, 256, 0, st>>>((const float4*)d_xy_scratch, xz_s, yz_s, (float4*)d_planes_cl, n_people, nbb, 8,
+                                      ncpart, img4);
+    return;
+  }
   int nslab;
   if (g.JG <= 4) {
     nslab = 16;                                  // TA = 4 rows per slab

@@ -41,6 +41,7 @@ void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int
 // K3: per-person back-projection + three-plane max.
 //   planes_cl [3][B*P][64][64][JP]; yz partial scratch [B*P][nslab][64][64][JP]
 //   xy partial scratch [B*P][ncpart][64][64][JP] (used when the depth range is split, ncpart in {1,2,4,8})
+int fvp_k3_version();
 void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
                             float* d_yz_scratch, float* d_xy_scratch, int batch, int ncpart, cudaStream_t st);
 

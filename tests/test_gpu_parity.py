@@ -442,3 +442,42 @@ def test_empty_and_border_crops_match_oracle(built_library, golden):
     assert np.abs(planes[:, 1]).max() == 0.0 and np.abs(planes[:, 3:]).max() == 0.0
     assert np.array_equal(off.cpu().numpy()[:3], crop["offset"].numpy())
     eng.close()
+
+
+def test_engine_lanes_match_single_context(bench_setup):
+    """EngineLanes (several contexts / streams / graphs on one GPU, frames dispatched round-robin): every frame's
+    result is bit-identical to the single-context forward, in submission order, on the device and the host entry."""
+    from fvp.engine import EngineLanes
+    g, eng, slots = bench_setup
+    rng = np.random.default_rng(23)
+    base = torch.from_numpy(g.heatmaps)
+    frames = [base]
+    for _ in range(6):
+        noise = torch.from_numpy((rng.random(g.heatmaps.shape, dtype=np.float32) < 0.02).astype(np.float32) * 0.25)
+        frames.append(torch.clamp(base + noise, 0, 1))
+    want = [tuple(t.cpu() for t in eng.forward(f.cuda(), slots)) for f in frames]
+    lanes = EngineLanes(g.cfg, torch.device("cuda:0"), lanes=3, max_batch=g.B, max_sequences=2, axes=g.axes)
+    lanes.load_state_dict(g.weights)
+    ls = [lanes.sequence_slot(g.cams, g.resize)] * g.B
+    for graph in (False, True):
+        lanes.use_cuda_graph(graph)
+        for rep in range(2):                                  # second pass replays the captured graphs
+            got = []
+            for f in frames:
+                lanes.submit(f.cuda(), ls)
+                if lanes.outstanding() == len(lanes):
+                    got.append(lanes.collect())
+            while lanes.outstanding():
+                got.append(lanes.collect())
+            torch.cuda.current_stream().synchronize()
+            assert len(got) == len(frames)
+            for i, (w, o) in enumerate(zip(want, got)):
+                assert all(torch.equal(a, b.cpu()) for a, b in zip(w, o)), (graph, rep, i)
+    pinned = [f.pin_memory() for f in frames]
+    seen = {}
+    for i, out in lanes.stream_host(pinned, lambda i: ls):
+        seen[i] = tuple(t.clone() for t in out)
+    assert sorted(seen) == list(range(len(frames)))
+    for i in range(len(frames)):
+        assert all(torch.equal(a, b) for a, b in zip(want[i], seen[i])), i
+    lanes.close()
