@@ -6,7 +6,7 @@ OUT="${1:-$HERE/..}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off
        -Xptxas -v)
-SRCS=(fvp_api.cu fvp_params.cu fvp_backproject.cu fvp_conv.cu fvp_conv_tc.cu fvp_proposal.cu fvp_pose.cu)
+SRCS=(fvp_api.cu fvp_params.cu fvp_backproject.cu fvp_conv.cu fvp_conv_tc.cu fvp_proposal.cu fvp_pose.cu fvp_render.cu)
 mkdir -p "$HERE/build"
 pids=()
 for s in "${SRCS[@]}"; do

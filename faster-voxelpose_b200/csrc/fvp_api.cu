@@ -317,7 +317,8 @@ void fvp_destroy(fvp_ctx* ctx) {
   void* ptrs[] = {ctx->d_weights, ctx->d_axes, ctx->d_seqs, ctx->d_hm_in, ctx->d_hm_cl, ctx->d_plane_cl, ctx->d_hmsize,
                   ctx->d_conf2d, ctx->d_flat, ctx->d_centers, ctx->d_people, ctx->d_img_valid, ctx->d_planes_cl,
                   ctx->d_yz_scratch, ctx->d_xy_scratch, ctx->d_feat, ctx->d_pose, ctx->d_maxw, ctx->d_wts, ctx->d_fused, ctx->d_conf,
-                  ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq, ctx->d_hm_in_b, ctx->d_coarse_grid, ctx->d_fine_grid};
+                  ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq, ctx->d_hm_in_b, ctx->d_coarse_grid, ctx->d_fine_grid,
+                  ctx->d_rj, ctx->d_rn, ctx->d_rv, ctx->d_rp};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (int i = 0; i < 6; ++i) {
@@ -790,6 +791,42 @@ int fvp_pose_head(fvp_ctx* ctx, const float* d_feat, const float* d_offset, int 
     g1.P = 1;
     fvp_launch_finalize(g1, ctx->d_people, ctx->d_maxw, pose, fused, ctx->d_centers, n, d_conf, nullptr, nullptr, nullptr, st);
   }
+  FVP_CUDA_OK(cudaGetLastError());
+  return FVP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// N1: heat-map renderer (the step before the hot path for TEST_HEATMAP_SRC 'pred' / 'gt')
+// ------------------------------------------------------------------------------------------------
+int fvp_render_heatmaps(fvp_ctx* ctx, const double* h_joints, const int32_t* h_num_people, const uint8_t* h_vis, int batch,
+                        int max_people, double sigma, float* d_heatmaps, uintptr_t stream) {
+  int rc = check_stage_ready(ctx, batch);
+  if (rc != FVP_OK) return rc;
+  if (!h_joints || !h_num_people || !d_heatmaps) return fvp_fail(ctx, FVP_E_INVALID, "null joints / counts / output");
+  if (max_people < 1 || max_people > FVP_MAX_PEOPLE)
+    return fvp_fail(ctx, FVP_E_INVALID, "max_people %d outside [1, %d]", max_people, FVP_MAX_PEOPLE);
+  if (!(sigma > 0.0)) return fvp_fail(ctx, FVP_E_INVALID, "sigma must be positive");
+  const FvpGeom& g = ctx->geom;
+  const int views = batch * g.V;
+  for (int i = 0; i < views; ++i)
+    if (h_num_people[i] < 0 || h_num_people[i] > max_people)
+      return fvp_fail(ctx, FVP_E_INVALID, "num_people[%d] = %d outside [0, %d]", i, h_num_people[i], max_people);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!ctx->d_rj) {                              // staging sized once for (max_batch, FVP_MAX_PEOPLE)
+    const size_t cap = (size_t)ctx->cfg.max_batch * g.V * FVP_MAX_PEOPLE;
+    FVP_CUDA_OK(cudaMalloc((void**)&ctx->d_rj, cap * g.J * 2 * sizeof(double)));
+    FVP_CUDA_OK(cudaMalloc((void**)&ctx->d_rn, (size_t)ctx->cfg.max_batch * g.V * sizeof(int)));
+    FVP_CUDA_OK(cudaMalloc((void**)&ctx->d_rv, cap * g.J));
+    FVP_CUDA_OK(cudaMalloc(&ctx->d_rp, fvp_render_patch_bytes(ctx->cfg.max_batch * g.V, FVP_MAX_PEOPLE, g.J)));
+  }
+  const size_t n = (size_t)views * max_people;
+  FVP_CUDA_OK(cudaMemcpyAsync(ctx->d_rj, h_joints, n * g.J * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  FVP_CUDA_OK(cudaMemcpyAsync(ctx->d_rn, h_num_people, views * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (h_vis) FVP_CUDA_OK(cudaMemcpyAsync(ctx->d_rv, h_vis, n * g.J, cudaMemcpyHostToDevice, st));
+  const double sx = (double)ctx->cfg.image_w / (double)g.proj.W, sy = (double)ctx->cfg.image_h / (double)g.proj.H;
+  fvp_launch_render_heatmaps(ctx->d_rj, ctx->d_rn, h_vis ? ctx->d_rv : nullptr, views, max_people, g.J, g.proj.W, g.proj.H,
+                             sx, sy, sigma, ctx->d_rp, d_heatmaps, st);
   FVP_CUDA_OK(cudaGetLastError());
   return FVP_OK;
 }

@@ -400,10 +400,8 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
   const float fV = (float)V, rV = 1.0f / fV;
   const int row4 = P.WP * JG, px4 = JG;
   const int vs4 = (int)g.view_stride4, frame_off = (person / g.P) * V * vs4;
-  const bool sample_ok = ch_ok && b_ok;
-  unsigned rmask = 0;                            // lanes of this warp that hold my channel group
-#pragma unroll
-  for (int i = 0; i < BPW; ++i) rmask |= 1u << (i * CG + s);
+  const bool sample_ok = ch_ok && b_ok && a_ok;
+  const int s_me = ch_ok ? s : JG - 1;           // idle channel-group lanes re-read the last group (same sectors)
 
   float4 xy_m = zero4;
   int it = 0;
@@ -411,13 +409,16 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
     float4 acc[CCH];
 #pragma unroll
     for (int c = 0; c < CCH; ++c) acc[c] = zero4;
-    const bool row_live = a_ok && max(cc, pd.lo[2]) < min(cc + CCH, pd.hi[2]);   // warp-uniform
+    // Every branch of the sampling loop is a vote, i.e. provably warp-uniform: lanes outside the crop (b, channel group)
+    // sample pixel (0,0) of the view like everybody else and are zeroed afterwards - no divergent regions.
+    const bool row_live = __any_sync(0xffffffffu, a_ok && max(cc, pd.lo[2]) < min(cc + CCH, pd.hi[2]));
     if (row_live) {
       const int cz = cc + s;                     // the depth this lane looks up for its column
       const bool q_ok = b_ok && cz >= pd.lo[2] && cz < pd.hi[2];
       for (int v = 0; v < V; ++v) {
-        FvpTapCache tcache;
-        tcache.off = -1;
+        FvpTapRegs tr;
+        tr.off = -1;
+        tr.a = tr.b = tr.c = tr.d = zero4;
         float2 q = make_float2(0.f, 0.f);
         if (q_ok) q = __ldg(grid_s + (size_t)v * nfine + col + cz);
         const FvpTaps t = fvp_taps(P, q.x, q.y);
@@ -429,33 +430,42 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
           const float w01 = __shfl_sync(0xffffffffu, t.w01, group_base + k);
           const float w10 = __shfl_sync(0xffffffffu, t.w10, group_base + k);
           const float w11 = __shfl_sync(0xffffffffu, t.w11, group_base + k);
-          const bool c_ok = (cc + k) >= pd.lo[2] && (cc + k) < pd.hi[2];         // uniform
-          if (sample_ok && c_ok) fvp_tap_accumulate_cached<PX16>(acc[k], tcache, hm_cl, off + s, row4, px4, w00, w01, w10, w11);
+          if (__any_sync(0xffffffffu, (cc + k) >= pd.lo[2] && (cc + k) < pd.hi[2]))
+            fvp_tap_accumulate_vote<PX16>(acc[k], tr, hm_cl, off + s_me, row4, px4, w00, w01, w10, w11);
         }
       }
     }
-    // mean + clamp + the three maxima of this chunk
+    // mean + clamp + the three maxima of this chunk.  Both cross-thread maxima go through ONE shared-memory image of
+    // the chunk ([depth][row][lane]): a partial-mask REDUX per channel group costs a serialised collective per mask
+    // (CREDUX + ENDCOLLECTIVE + BSSY/BSYNC were ~20 % of the instructions and ~35 % of the stall samples in ncu).
     float4(*yzb)[8][32] = s_yz[NBUF == 2 ? (it & 1) : 0];
 #pragma unroll
     for (int c = 0; c < CCH; ++c) {
-      const float4 val = row_live ? fvp_mean_clamp4(acc[c], fV, rV) : zero4;     // untouched acc -> 0
+      const bool c_in = (cc + c) >= pd.lo[2] && (cc + c) < pd.hi[2];
+      const float4 val = (sample_ok && c_in) ? fvp_mean_clamp4(acc[c], fV, rV) : zero4;   // outside the crop: 0
       xy_m = fvp_max4(xy_m, val);
       yzb[c][warp][lane] = val;
-      float4 m;
-      m.x = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.x)));
-      m.y = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.y)));
-      m.z = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.z)));
-      m.w = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.w)));
-      if (lane < CG && ch_ok) xz_part[((size_t)a * 64 + cc + c) * JG + s] = m;
     }
     __syncthreads();
-    if (tid < CCH * 32) {                        // yz[b][cc + c]: max over the 8 rows of the patch
-      const int c = tid >> 5, l = tid & 31, ss = l % CG;
-      if (ss < JG) {
-        float4 m = yzb[c][0][l];
+    constexpr int N_YZ = CCH * 32;               // yz outputs of the chunk: (depth, b, channel group)
+    constexpr int N_XZ = 8 * CCH * CG;           // xz outputs of the chunk: (row, depth, channel group)
+    for (int o = tid; o < N_YZ + N_XZ; o += 256) {
+      if (o < N_YZ) {                            // yz[b][cc + c] = max over the 8 rows of the patch
+        const int c = o >> 5, l = o & 31, ss = l % CG;
+        if (ss < JG) {
+          float4 m = yzb[c][0][l];
 #pragma unroll
-        for (int w = 1; w < 8; ++w) m = fvp_max4(m, yzb[c][w][l]);
-        yz_part[((size_t)(bblk * BPW + l / CG) * 64 + cc + c) * JG + ss] = m;
+          for (int w = 1; w < 8; ++w) m = fvp_max4(m, yzb[c][w][l]);
+          yz_part[((size_t)(bblk * BPW + l / CG) * 64 + cc + c) * JG + ss] = m;
+        }
+      } else {                                   // xz[a][cc + c] = max over the BPW columns of the patch
+        const int x = o - N_YZ, ss = x % CG, c = (x / CG) % CCH, w = x / (CG * CCH);
+        if (ss < JG) {
+          float4 m = yzb[c][w][ss];
+#pragma unroll
+          for (int i = 1; i < BPW; ++i) m = fvp_max4(m, yzb[c][w][i * CG + ss]);
+          xz_part[((size_t)(ablk * 8 + w) * 64 + cc + c) * JG + ss] = m;
+        }
       }
     }
     if (NBUF == 1) __syncthreads();

@@ -96,6 +96,11 @@ struct fvp_ctx {
   long long tickets = 0;              // submitted so far
   long long waited = 0;               // tickets already waited for
   float stage_ms[9] = {0};
+  // heat-map renderer (fvp_render_heatmaps): device copies of the poses / counts / visibility and the patch table
+  double* d_rj = nullptr;
+  int* d_rn = nullptr;
+  unsigned char* d_rv = nullptr;
+  void* d_rp = nullptr;
 };
 
 void fvp_build_param_table(fvp_ctx* ctx);

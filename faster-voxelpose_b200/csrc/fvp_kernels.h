@@ -45,6 +45,13 @@ int fvp_k3_version();
 void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
                             float* d_yz_scratch, float* d_xy_scratch, int batch, int ncpart, cudaStream_t st);
 
+// N1 heat-map renderer (JointsDataset.generate_input_heatmap): joints [views][max_people][J][2] float64 in IMAGE_SIZE pixels,
+// num [views], vis [views][max_people][J] or NULL -> out [views][J][H][W]; d_patches = fvp_render_patch_bytes(...) bytes
+size_t fvp_render_patch_bytes(int total_views, int max_people, int J);
+void fvp_launch_render_heatmaps(const double* d_joints, const int* d_num, const unsigned char* d_vis, int total_views,
+                                int max_people, int J, int W, int H, double stride_x, double stride_y, double sigma,
+                                void* d_patches, float* d_out, cudaStream_t st);
+
 // ---- convolutions (fp32 CUDA-core implicit GEMM, NHWC) ----------------------------------------
 struct FvpConvArgs {
   const float* in;    // [n][H][W][Cin]

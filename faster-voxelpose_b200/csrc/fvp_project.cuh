@@ -148,6 +148,36 @@ __device__ __forceinline__ void fvp_tap_accumulate_cached(float4& acc, FvpTapCac
   acc.w = fmaf(d.w, w11, fmaf(c.w, w10, fmaf(b.w, w01, fmaf(a.w, w00, acc.w))));
 }
 
+// Warp-uniform form of the footprint cache (K3 patch kernel): the four taps are reloaded by ALL lanes as soon as ANY lane
+// left its 2x2 cell, so the test is a vote + uniform branch instead of a divergent region (BSSY/BSYNC, serialised
+// paths); lanes that would have hit re-read the same bytes, values are identical.  Must be called by converged warps.
+struct FvpTapRegs {
+  int off;
+  float4 a, b, c, d;
+};
+template <int PX16 = 0>
+__device__ __forceinline__ void fvp_tap_accumulate_vote(float4& acc, FvpTapRegs& tr, const float4* __restrict__ base, int off,
+                                                        int row_stride4, int px_stride4, float w00, float w01, float w10,
+                                                        float w11) {
+  if (__any_sync(0xffffffffu, off != tr.off)) {
+    const unsigned o0 = (unsigned)off << 4, o2 = o0 + ((unsigned)row_stride4 << 4);
+    if (PX16 > 0) {
+      const float4* pn = (const float4*)((const char*)base + o0);
+      const float4* ps = (const float4*)((const char*)base + o2);
+      tr.a = __ldg(pn); tr.b = __ldg(pn + PX16 / 16); tr.c = __ldg(ps); tr.d = __ldg(ps + PX16 / 16);
+    } else {
+      const unsigned px = (unsigned)px_stride4 << 4;
+      tr.a = fvp_ldg_at(base, o0); tr.b = fvp_ldg_at(base, o0 + px); tr.c = fvp_ldg_at(base, o2); tr.d = fvp_ldg_at(base, o2 + px);
+    }
+  }
+  tr.off = off;
+  const float4 a = tr.a, b = tr.b, c = tr.c, d = tr.d;
+  acc.x = fmaf(d.x, w11, fmaf(c.x, w10, fmaf(b.x, w01, fmaf(a.x, w00, acc.x))));
+  acc.y = fmaf(d.y, w11, fmaf(c.y, w10, fmaf(b.y, w01, fmaf(a.y, w00, acc.y))));
+  acc.z = fmaf(d.z, w11, fmaf(c.z, w10, fmaf(b.z, w01, fmaf(a.z, w00, acc.z))));
+  acc.w = fmaf(d.w, w11, fmaf(c.w, w10, fmaf(b.w, w01, fmaf(a.w, w00, acc.w))));
+}
+
 // mean over V views followed by clamp(0,1): correctly rounded acc / V through one Newton correction
 // (q = acc*r; q += fma(-q,V,acc)*r), then min/max.
 __device__ __forceinline__ float fvp_mean_clamp(float acc, float fV, float rV) {

@@ -73,6 +73,7 @@ SYMBOLS = {
     "fvp_p2p_net": (C.c_int, [_CTX, _P, C.c_int, _P, _P, C.c_size_t]),
     "fvp_pose_head": (C.c_int, [_CTX, _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t]),
     "fvp_c2c_net": (C.c_int, [_CTX, _P, C.c_int, _P, C.c_size_t]),
+    "fvp_render_heatmaps": (C.c_int, [_CTX, _P, _P, _P, C.c_int, C.c_int, C.c_double, _P, C.c_size_t]),
     "fvp_set_conv_mode": (C.c_int, [_CTX, C.c_int]),
     "fvp_last_launch_count": (C.c_int, [_CTX]),
     "fvp_set_profiling": (C.c_int, [_CTX, C.c_int]),

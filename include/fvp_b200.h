@@ -166,6 +166,20 @@ int fvp_pose_head(fvp_ctx* ctx, const float* d_feat, const float* d_offset, int 
 /* C2CNet alone (cnns_1d.py:128-132): [n][J][Z] -> [n][Z] */
 int fvp_c2c_net(fvp_ctx* ctx, const float* d_cols, int n, float* d_hm1d, uintptr_t stream);
 
+/* ---- N1: heat-map renderer, the step before the hot path when TEST_HEATMAP_SRC is 'pred' or 'gt' --------
+ * replaces JointsDataset.generate_input_heatmap + compute_human_scale (lib/dataset/JointsDataset.py:271-337,197-203,
+ * evaluation branch) called from __getitem__ (:144-190), once per view.
+ * h_joints     [batch][V][max_people][J][2] float64, joint positions in IMAGE_SIZE pixels (i.e. after the resize affine of
+ *              JointsDataset.py:150 / :178, which stays on the host)
+ * h_num_people [batch][V] people present in every view (0..max_people); a view without people gives a zero map
+ * h_vis        [batch][V][max_people][J] 0/1 visibility (the 'gt' source) or NULL = all drawn (the 'pred' source)
+ * sigma        NETWORK.SIGMA
+ * d_heatmaps   [batch][V][J][H][W] fp32 - the input_heatmaps layout fvp_forward consumes.
+ * Arithmetic: person scale, patch bounds and the Gaussian in IEEE float64 as NumPy 2 evaluates the reference, rounded once
+ * to float32 (see oracle/heatmap_oracle.py). */
+int fvp_render_heatmaps(fvp_ctx* ctx, const double* h_joints, const int32_t* h_num_people, const uint8_t* h_vis, int batch,
+                        int max_people, double sigma, float* d_heatmaps, uintptr_t stream);
+
 /* convolution engine of CenterNet / P2PNet: 0 = exact-fp32 CUDA-core implicit GEMM, 1 = tcgen05/TMEM implicit GEMM with
  * the error-compensated 3xTF32 split (default set at build time) */
 int fvp_set_conv_mode(fvp_ctx* ctx, int mode);

@@ -52,3 +52,29 @@ class Golden:
 
     def has(self, k):
         return k in self.z.files
+
+
+HEATMAP_CASES = ["heatmaps_panoptic_256x192_crowd", "heatmaps_panoptic_border", "heatmaps_campus_tiny",
+                 "heatmaps_shelf_huge", "heatmaps_shelf_crowd"]
+
+
+class HeatmapGolden:
+    """tests/golden/heatmaps_*.npz (oracle/gen_golden_heatmaps.py: the reference's JointsDataset.__getitem__ on synthetic
+    'pred' / 'gt' records).  The rendered maps are stored sparsely (non-zero values)."""
+
+    def __init__(self, name: str):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.z = z
+        self.cfg = fcfg.preset(str(z["preset"]))
+        self.shape = tuple(int(v) for v in z["shape"])                  # [V,J,H,W]
+        self.resize = z["resize"]
+        self.num_people = z["num_people"]
+        self.preds = [[z["preds"][v, n] for n in range(int(self.num_people[v]))] for v in range(self.shape[0])]
+        self.joints_3d = [a for a in z["joints_3d"]]
+        self.joints_3d_vis = [a for a in z["joints_3d_vis"]]
+        self.cams = synth.cameras_from_array(z["cameras"])
+
+    def dense(self, which: str) -> np.ndarray:
+        out = np.zeros(int(np.prod(self.shape)), np.float32)
+        out[self.z[which + "_nz_index"]] = self.z[which + "_nz_value"]
+        return out.reshape(self.shape)

@@ -481,3 +481,32 @@ def test_engine_lanes_match_single_context(bench_setup):
     for i in range(len(frames)):
         assert all(torch.equal(a, b) for a, b in zip(want[i], seen[i])), i
     lanes.close()
+
+
+@pytest.mark.parametrize("views,voxels", [(8, (160, 160, 40)), (4, (120, 120, 30))])
+def test_k1_config5_ring_sweep_points_match_oracle(built_library, views, voxels):
+    """BASELINE configs[4]: synthetic ring calibration, high-resolution coarse grid (up to 8 views, 160x160x40 =
+    1.024 M voxels, 122.9 M samples per frame).  K0+K1 against the oracle's grid_sample + z-max on the same inputs
+    (<= 1e-6 abs on values in [0,1]); a second frame of uniform noise checks the batch stride at this size."""
+    from fvp import config as fcfg, synth
+    from fvp.engine import Engine
+    from oracle import fvp_oracle as O
+    cfg = fcfg.preset("ring8_160")
+    cfg.DATASET.CAMERA_NUM = views
+    cfg.CAPTURE_SPEC.VOXELS_PER_AXIS = list(voxels)
+    cams = synth.ring_cameras(views, cfg.CAPTURE_SPEC.SPACE_CENTER)
+    resize = synth.resize_transform(cfg.DATASET.ORI_IMAGE_SIZE, cfg.DATASET.IMAGE_SIZE)
+    blobs = synth.render_heatmaps(cfg, cams, synth.make_skeletons(cfg, 6, seed=11), sigma=3.0)
+    noise = np.random.default_rng(5).random(blobs.shape, dtype=np.float32)
+    hm = torch.from_numpy(np.stack([blobs, noise]))
+    eng = Engine(cfg, torch.device("cuda:0"), max_batch=2, max_sequences=1)
+    slot = eng.sequence_slot(cams, resize)
+    eng.stage_heatmaps(hm)
+    plane = eng.hdn_project(2, [slot, slot]).cpu()
+    eng.close()
+    with torch.no_grad():
+        grids = O.hdn_sample_grids(cfg, cams, torch.as_tensor(resize, dtype=torch.float))
+        ref = O.hdn_cubes(cfg, hm, [grids, grids]).max(dim=4)[0]
+    assert plane.shape == ref.shape == (2, int(cfg.DATASET.NUM_JOINTS), voxels[0], voxels[1])
+    assert float((plane - ref).abs().max()) <= 1e-6
+    assert float(ref[0].max()) > 0.5                     # the blobs are visible: the comparison is not zeros vs zeros

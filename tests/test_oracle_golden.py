@@ -88,3 +88,33 @@ def test_crop_params_edge_cases(golden):
     assert (crop["start"][0] >= 0).all() and (crop["start"][0] == 0).any()
     assert (crop["start"][1] >= crop["end"][1]).any()
     assert (crop["end"] <= K.fine).all()
+
+
+# ---- N1: heat-map renderer oracle vs the reference's JointsDataset output ----------------------------------------
+from golden_util import HEATMAP_CASES, HeatmapGolden  # noqa: E402
+from oracle import heatmap_oracle as HO               # noqa: E402
+
+
+@pytest.mark.parametrize("name", HEATMAP_CASES)
+def test_heatmap_oracle_is_bit_identical_to_reference_golden(name):
+    """generate_input_heatmap restated (oracle/heatmap_oracle.py) vs the maps the unmodified reference rendered:
+    bit-exact for the 'pred' and the 'gt' source (float64 arithmetic, one rounding to float32)."""
+    g = HeatmapGolden(name)
+    ds = g.cfg.DATASET
+    pred = HO.pred_heatmaps(g.preds, g.resize, ds.HEATMAP_SIZE, ds.IMAGE_SIZE, g.cfg.NETWORK.SIGMA)
+    assert np.array_equal(pred.view(np.int32), g.dense("pred").view(np.int32))
+    gt = HO.gt_heatmaps(g.joints_3d, g.joints_3d_vis, g.cams, g.resize, ds.ORI_IMAGE_SIZE, ds.IMAGE_SIZE, ds.HEATMAP_SIZE,
+                        g.cfg.NETWORK.SIGMA)
+    assert np.array_equal(gt.view(np.int32), g.dense("gt").view(np.int32))
+
+
+def test_heatmap_oracle_edge_cases():
+    """int() truncation toward zero at negative coordinates, the 'completely outside' skip, a masked joint."""
+    W, H = 40, 30
+    pose = np.array([[-9.0, 12.0], [170.0, 60.0], [80.0, 500.0]])         # image px, stride 4: mu = (-2,3), (42,15), (20,125)
+    hm = HO.render_input_heatmap([pose], None, (W, H), (160, 120), 3)
+    assert hm.shape == (3, H, W) and hm[0].max() > 0 and hm[2].max() == 0   # joint 2 lies below the map: skipped
+    # person extent 122 px -> sigma 5.39 -> half width 16.2: joint 1 (mu_x = 42) starts at column int(42 - 16.2) = 25
+    assert hm[1, :, 25:].max() > 0 and hm[1, :, :25].max() == 0             # patch cut by the right border
+    masked = HO.render_input_heatmap([pose], [np.array([0, 1, 1])], (W, H), (160, 120), 3)
+    assert masked[0].max() == 0 and np.array_equal(masked[1], hm[1])
