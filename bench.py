@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--conv-mode", type=int, default=-1, help="-1 library default, 0 fp32 CUDA cores, 1 tcgen05 3xTF32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, help="frames in flight on one GPU (independent contexts on their own "
+    ap.add_argument("--lanes", type=int, default=6, help="frames in flight on one GPU (independent contexts on their own "
                     "streams, fvp.engine.EngineLanes); 1 = strictly serial forwards")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -128,13 +128,13 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
   }
   T.mark(5);
   fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, ctx->d_yz_scratch, ctx->d_xy_scratch, batch, fvp_k3_parts(ctx, batch), st);
-  *launches += 2;
+  *launches += fvp_k3_version() == 2 ? 1 : 2;    // patch kernel (+ a memset node) | slab kernel + partial reduce
   T.mark(6);
   fvp_run_trunk2d(ctx->w_p2p, ctx->d_planes_cl, g.proj.JP, 3 * n, 64, 64, ctx->p2p_buf, ctx->d_img_valid, false,
                   ctx->d_feat, g.J, launches, st, ctx->conv_mode);
   T.mark(7);
   fvp_launch_pose_head(g, ctx->w_pose, ctx->d_feat, ctx->d_people, nullptr, n, ctx->cfg.beta, ctx->d_pose,
-                       ctx->d_maxw, ctx->d_wts, ctx->d_fused, st); ++*launches;
+                       ctx->d_maxw, ctx->d_wts, ctx->d_fused, st); *launches += 2;   // k_pose_head + k_fuse
   fvp_launch_finalize(g, ctx->d_people, ctx->d_maxw, ctx->d_pose, ctx->d_fused, ctx->d_centers, batch, ctx->d_conf,
                       d_fused_poses, d_plane_poses, d_centers_out, st); ++*launches;
   T.mark(8);

@@ -335,21 +335,33 @@ k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __r
   }
 }
 
+// max-fold a float4 of values >= +0 into a zero-initialised plane: one RED.MAX.U32 per non-zero component
+// (x > 0 is false for +0, -0 and NaN, none of which may enter an unsigned comparison)
+__device__ __forceinline__ void fvp_red_max4(float4* dst, float4 m) {
+  unsigned* p = reinterpret_cast<unsigned*>(dst);
+  if (m.x > 0.0f) atomicMax(p + 0, __float_as_uint(m.x));
+  if (m.y > 0.0f) atomicMax(p + 1, __float_as_uint(m.y));
+  if (m.z > 0.0f) atomicMax(p + 2, __float_as_uint(m.z));
+  if (m.w > 0.0f) atomicMax(p + 3, __float_as_uint(m.w));
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3 v2 ("patch"): same arithmetic per sample as k3_jln_project (bit-identical planes), different decomposition.
 // One CTA = one person x one compact patch of 8 cube rows a (one per warp) x BPW = 32/CG cube columns b x one depth
 // part.  A pass of the patch over one view and one chunk of CG depths touches a compact ~(8*1.5)^2-pixel window of the
 // heat map instead of the 64-column sheet of v1, so the 2x2 footprints of neighbouring voxels share L1 lines whatever
 // the direction the camera looks along.  No shared state survives a chunk:
-//   xy[a][b] = max_c : the thread owns (a, b) - a register, stored once (partial over the depth parts)
-//   xz[a][c] = max_b : REDUX.MAX over the warp's lanes of one channel group; partial over the 64/BPW b-blocks
-//   yz[b][c] = max_a : the 8 warps (8 rows) meet in shared memory; partial over the 8 a-blocks
-// k3b_reduce folds the partial images.
+//   xy[a][b] = max_c : the thread owns (a, b) - a register, stored once (complete when there is one depth part)
+//   xz[a][c] = max_b : the BPW columns of a row meet in shared memory; partial over the 64/BPW b-blocks
+//   yz[b][c] = max_a : the 8 warps (8 rows) meet in the same shared-memory image; partial over the 8 a-blocks
+// Partial maxima are folded straight into the zero-initialised output planes with RED.MAX on the float bit patterns
+// (values are >= +0, so they order like unsigned ints; max is exact and order-independent, the result is deterministic).
+// Only non-zero values are sent - heat maps are sparse, >90 % of the partial maxima are 0 - so there are no scratch
+// images and no second reduce kernel: DRAM traffic stays near the algorithmic bytes.
 template <int CG, int MINB, int PX16>
 __global__ void __launch_bounds__(256, MINB)
 k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __restrict__ people,
-             float4* __restrict__ planes_cl, float4* __restrict__ xy_scratch, float4* __restrict__ xz_scratch,
-             float4* __restrict__ yz_scratch, int n_people, int ncpart) {
+             float4* __restrict__ planes_cl, int n_people, int ncpart) {
   constexpr int BPW = 32 / CG;                   // cube columns b per warp = patch extent in b
   constexpr int NBB = 64 / BPW;                  // b-blocks per cube
   constexpr int NAB = 8;                         // a-blocks per cube (8 rows each, one row per warp)
@@ -370,26 +382,16 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
   const int b = bblk * BPW + lane / CG;          // cube column (world y index within the cube)
   const bool ch_ok = s < JG;
   const size_t img4 = (size_t)64 * 64 * JG;      // float4 per plane image
-  float4* xy_img = ncpart == 1 ? planes_cl + ((size_t)0 * n_people + person) * img4
-                               : xy_scratch + ((size_t)person * ncpart + cpart) * img4;
-  float4* xz_part = xz_scratch + ((size_t)person * NBB + bblk) * img4;
-  float4* yz_part = yz_scratch + ((size_t)person * NAB + ablk) * img4;
+  float4* xy_img = planes_cl + ((size_t)0 * n_people + person) * img4;
+  float4* xz_img = planes_cl + ((size_t)1 * n_people + person) * img4;
+  float4* yz_img = planes_cl + ((size_t)2 * n_people + person) * img4;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const bool live = pd.valid && !pd.empty;
   const bool any = live && max(ablk * 8, pd.lo[0]) < min(ablk * 8 + 8, pd.hi[0]) &&
                    max(bblk * BPW, pd.lo[1]) < min(bblk * BPW + BPW, pd.hi[1]) &&
                    max(c_begin, pd.lo[2]) < min(c_end, pd.hi[2]);
-  if (!any) {                                    // nothing to sample in this patch: its outputs are zero
-    if (ch_ok) {
-      xy_img[((size_t)a * 64 + b) * JG + s] = zero4;
-      for (int c = c_begin; c < c_end; ++c) {
-        if (lane < CG) xz_part[((size_t)a * 64 + c) * JG + s] = zero4;
-        if (warp == 0) yz_part[((size_t)b * 64 + c) * JG + s] = zero4;
-      }
-    }
-    return;
-  }
+  if (!any) return;                              // nothing to sample in this patch: the planes are already zero
 
   const bool a_ok = a >= pd.lo[0] && a < pd.hi[0];           // warp-uniform
   const bool b_ok = b >= pd.lo[1] && b < pd.hi[1];
@@ -456,7 +458,7 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
           float4 m = yzb[c][0][l];
 #pragma unroll
           for (int w = 1; w < 8; ++w) m = fvp_max4(m, yzb[c][w][l]);
-          yz_part[((size_t)(bblk * BPW + l / CG) * 64 + cc + c) * JG + ss] = m;
+          fvp_red_max4(yz_img + ((size_t)(bblk * BPW + l / CG) * 64 + cc + c) * JG + ss, m);
         }
       } else {                                   // xz[a][cc + c] = max over the BPW columns of the patch
         const int x = o - N_YZ, ss = x % CG, c = (x / CG) % CCH, w = x / (CG * CCH);
@@ -464,36 +466,15 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
           float4 m = yzb[c][w][ss];
 #pragma unroll
           for (int i = 1; i < BPW; ++i) m = fvp_max4(m, yzb[c][w][i * CG + ss]);
-          xz_part[((size_t)(ablk * 8 + w) * 64 + cc + c) * JG + ss] = m;
+          fvp_red_max4(xz_img + ((size_t)(ablk * 8 + w) * 64 + cc + c) * JG + ss, m);
         }
       }
     }
     if (NBUF == 1) __syncthreads();
   }
-  if (ch_ok) xy_img[((size_t)a * 64 + b) * JG + s] = xy_m;
-}
-
-// K3b for the patch kernel: xz = max over the b-block partials, yz = max over the a-block partials, xy = max over the
-// depth parts (when there are several)
-__global__ void __launch_bounds__(256) k3b_reduce(const float4* __restrict__ xy_scratch, const float4* __restrict__ xz_scratch,
-                                                  const float4* __restrict__ yz_scratch, float4* __restrict__ planes_cl,
-                                                  int n_people, int nbb, int nab, int ncpart, int img4) {
-  const int person = blockIdx.y;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= img4) return;
-  const float4* sz = xz_scratch + (size_t)person * nbb * img4 + i;
-  float4 m = sz[0];
-  for (int k = 1; k < nbb; ++k) m = fvp_max4(m, sz[(size_t)k * img4]);
-  planes_cl[((size_t)1 * n_people + person) * img4 + i] = m;
-  const float4* sy = yz_scratch + (size_t)person * nab * img4 + i;
-  m = sy[0];
-  for (int k = 1; k < nab; ++k) m = fvp_max4(m, sy[(size_t)k * img4]);
-  planes_cl[((size_t)2 * n_people + person) * img4 + i] = m;
-  if (ncpart > 1) {
-    const float4* sx = xy_scratch + (size_t)person * ncpart * img4 + i;
-    m = sx[0];
-    for (int k = 1; k < ncpart; ++k) m = fvp_max4(m, sx[(size_t)k * img4]);
-    planes_cl[((size_t)0 * n_people + person) * img4 + i] = m;
+  if (ch_ok) {
+    if (ncpart == 1) xy_img[((size_t)a * 64 + b) * JG + s] = xy_m;           // complete: plain store
+    else fvp_red_max4(xy_img + ((size_t)a * 64 + b) * JG + s, xy_m);          // partial over the depth parts
   }
 }
 
@@ -528,27 +509,19 @@ void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPer
   const int n_people = batch * g.P;
   const int img4 = 64 * 64 * g.JG;
   if (fvp_k3_version() == 2) {
-    // patch kernel: the 32 scratch images per person hold the xz partials (<= 16 b-blocks) then the 8 yz partials
-    float4* xz_s = (float4*)d_yz_scratch;
-    float4* yz_s = xz_s + (size_t)n_people * 16 * img4;
+    // patch kernel: partial maxima are RED-folded into the planes, which therefore start from zero
+    cudaMemsetAsync(d_planes_cl, 0, (size_t)3 * n_people * img4 * sizeof(float4), st);
     const int nbb = g.JG <= 4 ? 8 : 16;
     dim3 grid(8 * nbb * ncpart, n_people);
     static const int occ = getenv("FVP_K3_OCC") ? atoi(getenv("FVP_K3_OCC")) : 4;   // CTAs / SM the registers are capped for
     if (g.JG == 4 && occ == 3)
-      k3_jln_patch<4, 3, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                   (float4*)d_xy_scratch, xz_s, yz_s, n_people, ncpart);
+      k3_jln_patch<4, 3, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
     else if (g.JG == 4)
-      k3_jln_patch<4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                   (float4*)d_xy_scratch, xz_s, yz_s, n_people, ncpart);
+      k3_jln_patch<4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
     else if (g.JG < 4)
-      k3_jln_patch<4, 4, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                  (float4*)d_xy_scratch, xz_s, yz_s, n_people, ncpart);
+      k3_jln_patch<4, 4, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
     else
-      k3_jln_patch<8, 2, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                  (float4*)d_xy_scratch, xz_s, yz_s, n_people, ncpart);
-    dim3 grid2(fvp_cdiv(img4, 256), n_people);
-    k3b_reduce<<<grid2, 256, 0, st>>>((const float4*)d_xy_scratch, xz_s, yz_s, (float4*)d_planes_cl, n_people, nbb, 8,
-                                      ncpart, img4);
+      k3_jln_patch<8, 2, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
     return;
   }
   int nslab;

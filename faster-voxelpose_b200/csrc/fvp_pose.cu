@@ -3,8 +3,8 @@
 //   WeightNet (weight_net.py:48-80: conv3x3(1->F)+BN, MaxPool2, ReLU, global average, MLP, sigmoid),
 //   fuse_pose_preds, offset add, confidence mean and the final [B,P,J,5] packing
 //   (faster_voxelpose.py:102-103).
-// One CTA per (joint, person); the 64x64 map of each plane is staged once in shared memory and used
-// by both the soft-argmax and the WeightNet.  Expectations are accumulated in fp64 (joint
+// One CTA per (joint, person, plane) - 3*J*n CTAs, three per SM at batch 1 instead of one; the 64x64 map is staged once
+// in shared memory and used by both the soft-argmax and the WeightNet; k_fuse blends the three planes per joint.  Expectations are accumulated in fp64 (joint
 // coordinates are ~1e3 mm where one fp32 ulp is 1.2e-4 mm; see DESIGN.md "numerics").
 #include "fvp_kernels.h"
 
@@ -37,20 +37,19 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 template <int F>
-__global__ void __launch_bounds__(PT) k_pose_head(FvpGeom g, FvpPoseW w, const float* __restrict__ feat,
+__global__ void __launch_bounds__(PT, 3) k_pose_head(FvpGeom g, FvpPoseW w, const float* __restrict__ feat,
                                                   const FvpPerson* __restrict__ people,
                                                   const float* __restrict__ offsets, int n, float beta,
                                                   float* __restrict__ pose, float* __restrict__ maxw,
-                                                  float* __restrict__ weights, float* __restrict__ fused) {
+                                                  float* __restrict__ weights) {
   __shared__ float s_map[66 * MS];
   __shared__ float s_cw[F * 9], s_cb[F];
   __shared__ float s_red[PT / 32];
   __shared__ double s_dred[PT / 32];
   __shared__ float s_gap[PT / 32][F];
   __shared__ float s_feat[F], s_hid[128];
-  __shared__ float s_pos[3][2], s_wt[3];
 
-  const int j = blockIdx.x, person = blockIdx.y, tid = threadIdx.x;
+  const int j = blockIdx.x, person = blockIdx.y, q = blockIdx.z, tid = threadIdx.x;
   const int J = g.J;
   float off[3];
   if (people) {
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(PT) k_pose_head(FvpGeom g, FvpPoseW w, const f
   for (int i = tid; i < 66 * MS; i += PT) s_map[i] = 0.f;
   __syncthreads();
 
-  for (int q = 0; q < 3; ++q) {
+  {
     const float* m = feat + (((size_t)q * n + person) * J + j) * 4096;
     // ---- stage the map; soft-argmax statistics -------------------------------------------------
     float t[16];
@@ -152,28 +151,35 @@ __global__ void __launch_bounds__(PT) k_pose_head(FvpGeom g, FvpPoseW w, const f
       float a = w.fc2_b[0];
       for (int c = 0; c < w.hidden; ++c) a = fmaf(w.fc2_w[c], s_hid[c], a);
       const float sg = 1.0f / (1.0f + expf(-a));
-      s_wt[q] = sg;
       const float p0 = (float)(s0 / se), p1 = (float)(s1 / se);
       const int o0 = q == 2 ? 1 : 0, o1 = q == 0 ? 1 : 2;   // offsets: (x,y) (x,z) (y,z)
-      s_pos[q][0] = __fadd_rn(p0, off[o0]);
-      s_pos[q][1] = __fadd_rn(p1, off[o1]);
       const size_t o = ((size_t)q * n + person) * J + j;
       maxw[o] = (float)(1.0 / se);
       weights[o] = sg;
-      pose[o * 2] = s_pos[q][0];
-      pose[o * 2 + 1] = s_pos[q][1];
+      pose[o * 2] = __fadd_rn(p0, off[o0]);
+      pose[o * 2 + 1] = __fadd_rn(p1, off[o1]);
     }
-    __syncthreads();
   }
-  if (tid == 0) {   // fuse_pose_preds: normalise the pair of weights, then blend (joint_localization_net.py:50-59)
-    const float wxy = s_wt[0], wxz = s_wt[1], wyz = s_wt[2];
-    const float sx = __fadd_rn(wxy, wxz), sy = __fadd_rn(wxy, wyz), sz = __fadd_rn(wxz, wyz);
-    const float x = __fadd_rn(__fmul_rn(__fdiv_rn(wxy, sx), s_pos[0][0]), __fmul_rn(__fdiv_rn(wxz, sx), s_pos[1][0]));
-    const float y = __fadd_rn(__fmul_rn(__fdiv_rn(wxy, sy), s_pos[0][1]), __fmul_rn(__fdiv_rn(wyz, sy), s_pos[2][0]));
-    const float z = __fadd_rn(__fmul_rn(__fdiv_rn(wxz, sz), s_pos[1][1]), __fmul_rn(__fdiv_rn(wyz, sz), s_pos[2][1]));
-    float* f = fused + ((size_t)person * J + j) * 3;
-    f[0] = x; f[1] = y; f[2] = z;
-  }
+}
+
+// fuse_pose_preds (joint_localization_net.py:50-59): one thread per (person, joint) normalises the pair of plane
+// weights of every axis and blends the two plane coordinates
+__global__ void k_fuse(const FvpPerson* __restrict__ people, int n, int J, const float* __restrict__ pose,
+                       const float* __restrict__ weights, float* __restrict__ fused) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // person * J + joint
+  if (i >= n * J) return;
+  if (people && !people[i / J].valid) return;
+  const size_t nj = (size_t)n * J;
+  const float wxy = weights[i], wxz = weights[nj + i], wyz = weights[2 * nj + i];
+  const float* pxy = pose + (size_t)i * 2;
+  const float* pxz = pose + (nj + i) * 2;
+  const float* pyz = pose + (2 * nj + i) * 2;
+  const float sx = __fadd_rn(wxy, wxz), sy = __fadd_rn(wxy, wyz), sz = __fadd_rn(wxz, wyz);
+  const float x = __fadd_rn(__fmul_rn(__fdiv_rn(wxy, sx), pxy[0]), __fmul_rn(__fdiv_rn(wxz, sx), pxz[0]));
+  const float y = __fadd_rn(__fmul_rn(__fdiv_rn(wxy, sy), pxy[1]), __fmul_rn(__fdiv_rn(wyz, sy), pyz[0]));
+  const float z = __fadd_rn(__fmul_rn(__fdiv_rn(wxz, sz), pxz[1]), __fmul_rn(__fdiv_rn(wyz, sz), pyz[1]));
+  float* f = fused + (size_t)i * 3;
+  f[0] = x; f[1] = y; f[2] = z;
 }
 
 // one thread per (slot, joint): confidence + final packing
@@ -223,8 +229,9 @@ __global__ void k_finalize(FvpGeom g, const FvpPerson* __restrict__ people, cons
 void fvp_launch_pose_head(const FvpGeom& g, const FvpPoseW& w, const float* d_feat, const FvpPerson* d_people,
                           const float* d_offset, int n, float beta, float* d_pose, float* d_maxw, float* d_weights,
                           float* d_fused, cudaStream_t st) {
-  dim3 grid(g.J, n);
-  k_pose_head<32><<<grid, PT, 0, st>>>(g, w, d_feat, d_people, d_offset, n, beta, d_pose, d_maxw, d_weights, d_fused);
+  dim3 grid(g.J, n, 3);
+  k_pose_head<32><<<grid, PT, 0, st>>>(g, w, d_feat, d_people, d_offset, n, beta, d_pose, d_maxw, d_weights);
+  k_fuse<<<fvp_cdiv(n * g.J, 128), 128, 0, st>>>(d_people, n, g.J, d_pose, d_weights, d_fused);
 }
 
 void fvp_launch_finalize(const FvpGeom& g, const FvpPerson* d_people, const float* d_maxw, const float* d_pose,

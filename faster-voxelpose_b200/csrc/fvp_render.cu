@@ -7,8 +7,9 @@
 //   k_hm_prepare : one thread per (frame, view, person): person scale -> sigma -> per-joint patch descriptor
 //                  (integer patch origin with the reference's int() truncation toward zero, clipped window, centre index,
 //                  denominator), all in IEEE float64 exactly as NumPy evaluates them;
-//   k_hm_render  : one thread per output pixel of a (frame, view, joint) plane, a CTA = 256 consecutive pixels; the CTA
-//                  first keeps the descriptors whose window meets its rows, then every pixel takes the maximum over them
+//   k_hm_render  : four consecutive pixels of a (frame, view, joint) plane per thread (one 16-byte store), a CTA = 1024
+//                  pixels; one warp first keeps the descriptors whose window meets the CTA's rows (ballot compaction),
+//                  then every pixel takes the maximum over them
 //                  of float(exp(-((gx-c0)^2 + (gy-c0)^2) / den)) - float64 argument and exp, rounded once to float32,
 //                  which is what the reference's float32 assignment does.  The map is written exactly once (zeros
 //                  included): the kernel is bound by the 4*V*J*H*W bytes it stores.
@@ -77,37 +78,56 @@ __global__ void k_hm_prepare(const double* __restrict__ joints, const int* __res
 }
 
 constexpr int HM_MAXP = FVP_MAX_PEOPLE;
+static_assert(HM_MAXP <= 32, "the descriptor filter is one warp wide");
 
+// VEC pixels per thread (4 when W % 4 == 0: one 16-byte store).  A CTA covers 256*VEC consecutive pixels of one plane.
+template <int VEC>
 __global__ void __launch_bounds__(256) k_hm_render(const HmPatch* __restrict__ patches, int max_people, int J, int W, int H,
                                                     float* __restrict__ out) {
   __shared__ HmPatch s_p[HM_MAXP];
   __shared__ int s_n;
-  const int plane = blockIdx.y;                               // (frame*V + view) * J + joint
-  const int i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
-  const int row_lo = i0 / W, row_hi = min(H - 1, (i0 + 255) / W);
-  if (threadIdx.x == 0) {
-    int k = 0;
-    const HmPatch* src = patches + (size_t)plane * max_people;
-    for (int n = 0; n < max_people; ++n) {
-      const HmPatch d = src[n];
-      if (d.x0 < d.x1 && d.y0 <= row_hi && d.y1 > row_lo) s_p[k++] = d;
+  const int plane = blockIdx.x;                               // (frame*V + view) * J + joint
+  const int i0 = blockIdx.y * 256 * VEC, i = i0 + threadIdx.x * VEC;
+  if (threadIdx.x < 32) {                                     // keep the patches whose window meets this CTA's rows
+    const int row_lo = i0 / W, row_hi = min(H - 1, (i0 + 256 * VEC - 1) / W);
+    HmPatch d;
+    bool keep = false;
+    if ((int)threadIdx.x < max_people) {
+      d = patches[(size_t)plane * max_people + threadIdx.x];
+      keep = d.x0 < d.x1 && d.y0 <= row_hi && d.y1 > row_lo;
     }
-    s_n = k;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) s_p[__popc(m & ((1u << threadIdx.x) - 1u))] = d;
+    if (threadIdx.x == 0) s_n = __popc(m);
   }
   __syncthreads();
   if (i >= W * H) return;
-  const int py = i / W, px = i - py * W;
-  float v = 0.0f;
+  const int py = i / W, px0 = i - py * W;                     // VEC > 1: W % VEC == 0, so the pixels share the row
+  float v[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) v[e] = 0.0f;
   const int np_ = s_n;
   for (int k = 0; k < np_; ++k) {
     const HmPatch d = s_p[k];
-    if (px >= d.x0 && px < d.x1 && py >= d.y0 && py < d.y1) {
-      const double dx = (double)(px - d.ulx) - d.c0, dy = (double)(py - d.uly) - d.c0;
-      const double g = exp(-(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) / d.den);
-      v = fmaxf(v, (float)g);                                  // np.maximum into the float32 map
+    if (py < d.y0 || py >= d.y1 || px0 + VEC <= d.x0 || px0 >= d.x1) continue;
+    const double dy = (double)(py - d.uly) - d.c0, dy2 = __dmul_rn(dy, dy);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int px = px0 + e;
+      if (px >= d.x0 && px < d.x1) {
+        const double dx = (double)(px - d.ulx) - d.c0;
+        const double g = exp(-(__dadd_rn(__dmul_rn(dx, dx), dy2)) / d.den);
+        v[e] = fmaxf(v[e], (float)g);                          // np.maximum into the float32 map
+      }
     }
   }
-  out[(size_t)plane * W * H + i] = fminf(fmaxf(v, 0.0f), 1.0f);   // np.clip(target, 0, 1)
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) v[e] = fminf(fmaxf(v[e], 0.0f), 1.0f);   // np.clip(target, 0, 1)
+  float* dst = out + (size_t)plane * W * H + i;
+  if (VEC == 4) *(float4*)dst = make_float4(v[0], v[1], v[2], v[3]);
+  else
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) dst[e] = v[e];
 }
 
 }  // namespace
@@ -122,6 +142,11 @@ void fvp_launch_render_heatmaps(const double* d_joints, const int* d_num, const 
   const int n = total_views * max_people;
   k_hm_prepare<<<fvp_cdiv(n, 64), 64, 0, st>>>(d_joints, d_num, d_vis, total_views, max_people, J, W, H, stride_x, stride_y,
                                                sigma, (HmPatch*)d_patches);
-  dim3 grid(fvp_cdiv(W * H, 256), total_views * J);
-  k_hm_render<<<grid, 256, 0, st>>>((const HmPatch*)d_patches, max_people, J, W, H, d_out);
+  if (W % 4 == 0 && ((size_t)d_out & 15) == 0) {
+    dim3 grid(total_views * J, fvp_cdiv(W * H, 1024));
+    k_hm_render<4><<<grid, 256, 0, st>>>((const HmPatch*)d_patches, max_people, J, W, H, d_out);
+  } else {
+    dim3 grid(total_views * J, fvp_cdiv(W * H, 256));
+    k_hm_render<1><<<grid, 256, 0, st>>>((const HmPatch*)d_patches, max_people, J, W, H, d_out);
+  }
 }

@@ -483,11 +483,13 @@ def test_engine_lanes_match_single_context(bench_setup):
     lanes.close()
 
 
-@pytest.mark.parametrize("views,voxels", [(8, (160, 160, 40)), (4, (120, 120, 30))])
+@pytest.mark.parametrize("views,voxels", [(8, (160, 160, 40)), (4, (120, 120, 32))])
 def test_k1_config5_ring_sweep_points_match_oracle(built_library, views, voxels):
     """BASELINE configs[4]: synthetic ring calibration, high-resolution coarse grid (up to 8 views, 160x160x40 =
     1.024 M voxels, 122.9 M samples per frame).  K0+K1 against the oracle's grid_sample + z-max on the same inputs
-    (<= 1e-6 abs on values in [0,1]); a second frame of uniform noise checks the batch stride at this size."""
+    (<= 1e-6 abs on values in [0,1]); a second frame of uniform noise checks the batch stride at this size.
+    (Z must be a multiple of 4 - C2CNet pools the z-columns twice, cnns_1d.py:84-109 - so the middle sweep point of
+    SURVEY.md 8(d) is 120x120x32 here, not 120x120x30.)"""
     from fvp import config as fcfg, synth
     from fvp.engine import Engine
     from oracle import fvp_oracle as O

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """BASELINE configs[4]: back-projection bandwidth sweep of K0 + K1 (stage heat maps, HDN back-projection + z-max) on the
-synthetic ring calibration: grid in {80x80x20, 120x120x30, 160x160x40} x views in {4, 5, 8}, 256x192 heat maps, uniform
+synthetic ring calibration: grid in {80x80x20, 120x120x32, 160x160x40} x views in {4, 5, 8}, 256x192 heat maps, uniform
 random inputs (timing is value-independent).  Prints achieved GB/s on the algorithmic bytes of SURVEY.md 8(d)
 (Hm + 4*J*X*Y + 84*V per frame) and bilinear samples/s; CUDA events, inputs rotated through a pool larger than L2."""
 import json
@@ -25,7 +25,7 @@ except Exception:
     pass
 print("# K0+K1 sweep, batch %d, HBM peak %.0f GB/s (measured copy)" % (B, peak))
 print("%-12s %2s | %9s %9s | %9s %8s | %12s" % ("grid", "V", "k0 us/fr", "k1 us/fr", "GB/s(alg)", "frac", "samples/s"))
-for vox in ((80, 80, 20), (120, 120, 30), (160, 160, 40)):
+for vox in ((80, 80, 20), (120, 120, 32), (160, 160, 40)):   # Z % 4 == 0 (C2CNet pools z twice)
     for V in (4, 5, 8):
         cfg = fcfg.preset("ring8_160")
         cfg.DATASET.CAMERA_NUM = V
