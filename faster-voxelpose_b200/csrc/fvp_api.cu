@@ -71,14 +71,9 @@ int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaSt
 
 // depth parts per person for K3: enough CTAs for ~3 waves of (3 CTAs/SM) at small batch
 int fvp_k3_parts(const fvp_ctx* ctx, int batch) {
+  const int base = fvp_k3_patches(ctx->geom.JG) * batch * ctx->geom.P;
   int parts = 1;
-  if (fvp_k3_version() == 2) {                               // patch kernel: 64 (JG <= 4) or 128 patches per person
-    const int base = (ctx->geom.JG <= 4 ? 64 : 128) * batch * ctx->geom.P;
-    while (parts < 8 && base * parts < 12 * ctx->num_sms) parts *= 2;   // >= 3 waves of 4 CTAs / SM
-    return parts;
-  }
-  const int base = 16 * batch * ctx->geom.P;                 // slabs x persons
-  while (parts < 8 && base * parts < 9 * ctx->num_sms) parts *= 2;
+  while (parts < 8 && base * parts < 12 * ctx->num_sms) parts *= 2;   // >= 3 waves of 4 CTAs / SM
   return parts;
 }
 
@@ -127,8 +122,8 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
     fvp_launch_proposals(a, ctx->w_c2c, n, st); ++*launches;
   }
   T.mark(5);
-  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, ctx->d_yz_scratch, ctx->d_xy_scratch, batch, fvp_k3_parts(ctx, batch), st);
-  *launches += fvp_k3_version() == 2 ? 1 : 2;    // patch kernel (+ a memset node) | slab kernel + partial reduce
+  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, batch, fvp_k3_parts(ctx, batch), st);
+  ++*launches;                                   // (+ one memset node)
   T.mark(6);
   fvp_run_trunk2d(ctx->w_p2p, ctx->d_planes_cl, g.proj.JP, 3 * n, 64, 64, ctx->p2p_buf, ctx->d_img_valid, false,
                   ctx->d_feat, g.J, launches, st, ctx->conv_mode);
@@ -250,8 +245,6 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   A(dalloc(&ctx->d_people, (size_t)n));
   A(dalloc(&ctx->d_img_valid, (size_t)3 * n));
   A(dalloc(&ctx->d_planes_cl, (size_t)3 * n * 4096 * JP));
-  A(dalloc(&ctx->d_yz_scratch, (size_t)n * 32 * 4096 * JP));
-  A(dalloc(&ctx->d_xy_scratch, (size_t)n * 8 * 4096 * JP));
   A(dalloc(&ctx->d_feat, (size_t)3 * n * g.J * 4096));
   A(dalloc(&ctx->d_pose, (size_t)3 * n * g.J * 2));
   A(dalloc(&ctx->d_maxw, (size_t)3 * n * g.J));
@@ -316,7 +309,7 @@ void fvp_destroy(fvp_ctx* ctx) {
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   void* ptrs[] = {ctx->d_weights, ctx->d_axes, ctx->d_seqs, ctx->d_hm_in, ctx->d_hm_cl, ctx->d_plane_cl, ctx->d_hmsize,
                   ctx->d_conf2d, ctx->d_flat, ctx->d_centers, ctx->d_people, ctx->d_img_valid, ctx->d_planes_cl,
-                  ctx->d_yz_scratch, ctx->d_xy_scratch, ctx->d_feat, ctx->d_pose, ctx->d_maxw, ctx->d_wts, ctx->d_fused, ctx->d_conf,
+                  ctx->d_feat, ctx->d_pose, ctx->d_maxw, ctx->d_wts, ctx->d_fused, ctx->d_conf,
                   ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq, ctx->d_hm_in_b, ctx->d_coarse_grid, ctx->d_fine_grid,
                   ctx->d_rj, ctx->d_rn, ctx->d_rv, ctx->d_rp};
   for (void* p : ptrs)
@@ -737,7 +730,7 @@ int fvp_jln_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const f
   FvpPropArgs a = prop_args(ctx);
   a.people = ctx->d_people; a.img_valid = ctx->d_img_valid; a.n_slots = n;
   fvp_launch_people_from_centers(a, d_centers, n, st);
-  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, ctx->d_yz_scratch, ctx->d_xy_scratch, batch, fvp_k3_parts(ctx, batch), st);
+  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, batch, fvp_k3_parts(ctx, batch), st);
   if (d_planes) fvp_launch_nhwc_to_nchw(ctx->d_planes_cl, d_planes, 3 * n, 4096, g.proj.JP, g.J, st);
   if (d_offset) {
     FVP_CUDA_OK(cudaMemcpy2DAsync(d_offset, 3 * sizeof(float), (const char*)ctx->d_people + offsetof(FvpPerson, offset),

@@ -179,162 +179,6 @@ void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int
 // ------------------------------------------------------------------------------------------------
 // K3
 // ------------------------------------------------------------------------------------------------
-// One CTA = one person x one slab of TA consecutive cube rows (index a, world x).  Threads = 64 cube
-// columns b (world y) x CG lanes.  Loop: 8 chunks of 8 cube depths c (world z); inside a chunk, for
-// every a of the slab and every view, the CG lanes of a column project the chunk's 8 depths (one or two
-// each), exchange tap descriptors by shuffle and accumulate into 8 statically indexed registers; after
-// the last view: mean, clamp and
-//   xy[a][b] = max_c   : max of the 8 values, folded into a per-thread shared-memory slot per a
-//   yz[b][c] = max_a   : register running max over the slab; slab partials are combined by k3b
-//   xz[a][c] = max_b   : REDUX.MAX over the lanes of the warp that share a channel group (values are
-//                        >= 0, so their bit patterns order like unsigned ints), then a shared-memory
-//                        max over the warps (double-buffered: one barrier per a).
-
-template <int CG, int TA, int K3_CCH, int MINB, int PX16>      // PX16: pixel stride in bytes when JG == CG, else 0
-__global__ void __launch_bounds__(64 * CG, MINB)
-k3_jln_project(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __restrict__ people,
-               float4* __restrict__ planes_cl, float4* __restrict__ yz_scratch, float4* __restrict__ xy_scratch,
-               int n_people, int nslab, int ncpart) {
-  constexpr int NT = 64 * CG;                    // threads
-  constexpr int NW = NT / 32;                    // warps
-  constexpr int BPW = 32 / CG;                   // columns b per warp
-  constexpr int ROUNDS = K3_CCH / CG;            // projection rounds per (a, view)
-  static_assert(K3_CCH % CG == 0, "chunk must be a multiple of the lane group");
-  constexpr int NBUF = (CG == 4) ? 2 : 1;        // double buffer when it fits the 48 KB static limit
-  __shared__ float4 s_xz[NBUF][K3_CCH][NW][CG];  // per-warp partial maxima
-  __shared__ float4 s_xy[TA][NT];                // per-thread running max over c for every a of the slab
-
-  // blockIdx.x = slab + nslab * cpart : the cube's depth range is split into ncpart parts handled by different
-  // CTAs (more CTAs at small batch); xz columns of a part are complete, xy becomes a partial over the parts.
-  const int person = blockIdx.y, slab = blockIdx.x % nslab, cpart = blockIdx.x / nslab;
-  const int c_begin = cpart * (64 / ncpart), c_end = c_begin + 64 / ncpart;
-  const FvpPerson pd = people[person];
-  const FvpProj& P = g.proj;
-  const int JG = g.JG;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = lane % CG, group_base = lane - s;
-  const int b = warp * BPW + lane / CG;          // cube column (world y index within the cube)
-  const bool ch_ok = s < JG;
-  const size_t img4 = (size_t)64 * 64 * JG;      // float4 per plane image
-  float4* xy_img = ncpart == 1 ? planes_cl + ((size_t)0 * n_people + person) * img4
-                               : xy_scratch + ((size_t)person * ncpart + cpart) * img4;
-  float4* xz_img = planes_cl + ((size_t)1 * n_people + person) * img4;
-  float4* yz_part = yz_scratch + ((size_t)person * nslab + slab) * img4;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int a0 = slab * TA;
-
-  const bool live = pd.valid && !pd.empty;
-  const int alo = max(a0, pd.lo[0]), ahi = min(a0 + TA, pd.hi[0]);   // active rows of this slab
-  const bool any = live && alo < ahi && pd.lo[1] < pd.hi[1] && max(c_begin, pd.lo[2]) < min(c_end, pd.hi[2]);
-
-  if (!any) {                                    // nothing to sample: this CTA's outputs are zero
-    if (ch_ok) {
-      for (int a = 0; a < TA; ++a) xy_img[((size_t)(a0 + a) * 64 + b) * JG + s] = zero4;
-      for (int c = c_begin; c < c_end; ++c) yz_part[((size_t)b * 64 + c) * JG + s] = zero4;
-    }
-    const int ncol = (c_end - c_begin) * JG;
-    for (int i = tid; i < TA * ncol; i += NT)
-      xz_img[((size_t)(a0 + i / ncol) * 64 + c_begin) * JG + i % ncol] = zero4;
-    return;
-  }
-
-#pragma unroll
-  for (int a = 0; a < TA; ++a) s_xy[a][tid] = zero4;      // own slot only: no barrier needed
-
-  // Sample positions come from the per-calibration cache (fine_grid[slot][view][x][y][z]); the crop of this person is
-  // the window tl + (a, b, c), and [lo, hi) is its part inside the grid, so every index used below is in range.
-  const bool b_ok = b >= pd.lo[1] && b < pd.hi[1];
-  const int F1 = g.fine[1], F2 = g.fine[2], nfine = g.fine[0] * F1 * F2;
-  const float2* grid_s = g.fine_grid + (size_t)pd.seq * nfine * g.V;
-  const int col_y = (pd.tl[1] + b) * F2 + pd.tl[2];          // + gx * F1 * F2 + view * nfine + c
-  const int V = g.V;
-  const float fV = (float)V, rV = 1.0f / fV;
-  const int row4 = P.WP * JG, px4 = JG;
-  const int vs4 = (int)g.view_stride4, frame_off = (person / g.P) * V * vs4;
-  const bool sample_ok = ch_ok && b_ok;
-  unsigned rmask = 0;                            // lanes of this warp that hold my channel group
-#pragma unroll
-  for (int i = 0; i < BPW; ++i) rmask |= 1u << (i * CG + s);
-
-  int it = 0;                                    // (chunk, a) iteration counter -> xz buffer parity
-  for (int cc = c_begin; cc < c_end; cc += K3_CCH) {
-    float4 yz_acc[K3_CCH];
-#pragma unroll
-    for (int c = 0; c < K3_CCH; ++c) yz_acc[c] = zero4;
-    const bool chunk_live = max(cc, pd.lo[2]) < min(cc + K3_CCH, pd.hi[2]);
-
-    for (int a = 0; a < TA; ++a, ++it) {
-      float4 acc[K3_CCH];
-#pragma unroll
-      for (int c = 0; c < K3_CCH; ++c) acc[c] = zero4;
-      const bool row_live = chunk_live && (a0 + a) >= alo && (a0 + a) < ahi;     // uniform
-      if (row_live) {
-        const int col = (pd.tl[0] + a0 + a) * F1 * F2 + col_y;
-        for (int v = 0; v < V; ++v) {
-          const int view_off = frame_off + v * vs4;
-          FvpTapCache tcache;
-          tcache.off = -1;
-#pragma unroll
-          for (int r = 0; r < ROUNDS; ++r) {
-            const int cz = cc + r * CG + s;                         // the depth this lane looks up for its column
-            float2 q = make_float2(0.f, 0.f);
-            if (b_ok && cz >= pd.lo[2] && cz < pd.hi[2]) q = __ldg(grid_s + v * nfine + col + cz);
-            const FvpTaps t = fvp_taps(P, q.x, q.y);
-            const int my_off = t.off + view_off;
-#pragma unroll
-            for (int k = 0; k < CG; ++k) {
-              const int c = r * CG + k;          // compile-time depth index within the chunk
-              const int off = __shfl_sync(0xffffffffu, my_off, group_base + k);
-              const float w00 = __shfl_sync(0xffffffffu, t.w00, group_base + k);
-              const float w01 = __shfl_sync(0xffffffffu, t.w01, group_base + k);
-              const float w10 = __shfl_sync(0xffffffffu, t.w10, group_base + k);
-              const float w11 = __shfl_sync(0xffffffffu, t.w11, group_base + k);
-              const bool c_ok = (cc + c) >= pd.lo[2] && (cc + c) < pd.hi[2];     // uniform
-              if (sample_ok && c_ok) fvp_tap_accumulate_cached<PX16>(acc[c], tcache, hm_cl, off + s, row4, px4, w00, w01, w10, w11);
-            }
-          }
-        }
-      }
-      // mean + clamp + the three running maxima
-      float4 xy_m = zero4;
-      float4(*xzb)[NW][CG] = s_xz[NBUF == 2 ? (it & 1) : 0];
-#pragma unroll
-      for (int c = 0; c < K3_CCH; ++c) {
-        const float4 val = row_live ? fvp_mean_clamp4(acc[c], fV, rV) : zero4;   // untouched acc -> 0
-        xy_m = fvp_max4(xy_m, val);
-        yz_acc[c] = fvp_max4(yz_acc[c], val);
-        float4 m;
-        m.x = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.x)));
-        m.y = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.y)));
-        m.z = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.z)));
-        m.w = __uint_as_float(__reduce_max_sync(rmask, __float_as_uint(val.w)));
-        if (lane < CG) xzb[c][warp][s] = m;
-      }
-      s_xy[a][tid] = fvp_max4(s_xy[a][tid], xy_m);
-      __syncthreads();
-      // xz[a][cc..cc+7]: max over warps, one float4 per (c, channel group)
-      if (tid < K3_CCH * CG) {
-        const int ss = tid % CG, c = tid / CG;
-        if (ss < JG) {
-          float4 m = xzb[c][0][ss];
-#pragma unroll
-          for (int w = 1; w < NW; ++w) m = fvp_max4(m, xzb[c][w][ss]);
-          xz_img[((size_t)(a0 + a) * 64 + (cc + c)) * JG + ss] = m;
-        }
-      }
-      if (NBUF == 1) __syncthreads();
-    }
-    if (ch_ok) {                                 // yz partial of this slab for the chunk's depths
-#pragma unroll
-      for (int c = 0; c < K3_CCH; ++c) yz_part[((size_t)b * 64 + cc + c) * JG + s] = yz_acc[c];
-    }
-  }
-  if (ch_ok) {
-#pragma unroll
-    for (int a = 0; a < TA; ++a) xy_img[((size_t)(a0 + a) * 64 + b) * JG + s] = s_xy[a][tid];
-  }
-}
-
 // max-fold a float4 of values >= +0 into a zero-initialised plane: one RED.MAX.U32 per non-zero component
 // (x > 0 is false for +0, -0 and NaN, none of which may enter an unsigned comparison)
 __device__ __forceinline__ void fvp_red_max4(float4* dst, float4 m) {
@@ -346,10 +190,9 @@ __device__ __forceinline__ void fvp_red_max4(float4* dst, float4 m) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3 v2 ("patch"): same arithmetic per sample as k3_jln_project (bit-identical planes), different decomposition.
 // One CTA = one person x one compact patch of 8 cube rows a (one per warp) x BPW = 32/CG cube columns b x one depth
 // part.  A pass of the patch over one view and one chunk of CG depths touches a compact ~(8*1.5)^2-pixel window of the
-// heat map instead of the 64-column sheet of v1, so the 2x2 footprints of neighbouring voxels share L1 lines whatever
+// heat map (a 64-column sheet of one row, the first design, touched ~4x more pixels per pass), so the 2x2 footprints of neighbouring voxels share L1 lines whatever
 // the direction the camera looks along.  No shared state survives a chunk:
 //   xy[a][b] = max_c : the thread owns (a, b) - a register, stored once (complete when there is one depth part)
 //   xz[a][c] = max_b : the BPW columns of a row meet in shared memory; partial over the 64/BPW b-blocks
@@ -478,75 +321,19 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
   }
 }
 
-// K3b: yz plane = max over the slab partials
-__global__ void __launch_bounds__(256) k3b_yz_reduce(const float4* __restrict__ yz_scratch,
-                                                      const float4* __restrict__ xy_scratch,
-                                                      float4* __restrict__ planes_cl, int n_people, int nslab,
-                                                      int ncpart, int img4) {
-  const int person = blockIdx.y;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= img4) return;
-  const float4* src = yz_scratch + (size_t)person * nslab * img4 + i;
-  float4 m = src[0];
-  for (int sl = 1; sl < nslab; ++sl) m = fvp_max4(m, src[(size_t)sl * img4]);
-  planes_cl[((size_t)2 * n_people + person) * img4 + i] = m;
-  if (ncpart > 1) {                              // xy plane = max over the depth parts
-    const float4* sx = xy_scratch + (size_t)person * ncpart * img4 + i;
-    float4 mx = sx[0];
-    for (int cp = 1; cp < ncpart; ++cp) mx = fvp_max4(mx, sx[(size_t)cp * img4]);
-    planes_cl[((size_t)0 * n_people + person) * img4 + i] = mx;
-  }
-}
-
-// 2 = patch kernel (default), 1 = slab kernel; FVP_K3_VERSION overrides (A/B measurements)
-int fvp_k3_version() {
-  static const int v = getenv("FVP_K3_VERSION") ? atoi(getenv("FVP_K3_VERSION")) : 2;
-  return v;
-}
-
 void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
-                            float* d_yz_scratch, float* d_xy_scratch, int batch, int ncpart, cudaStream_t st) {
+                            int batch, int ncpart, cudaStream_t st) {
   const int n_people = batch * g.P;
   const int img4 = 64 * 64 * g.JG;
-  if (fvp_k3_version() == 2) {
-    // patch kernel: partial maxima are RED-folded into the planes, which therefore start from zero
-    cudaMemsetAsync(d_planes_cl, 0, (size_t)3 * n_people * img4 * sizeof(float4), st);
-    const int nbb = g.JG <= 4 ? 8 : 16;
-    dim3 grid(8 * nbb * ncpart, n_people);
-    static const int occ = getenv("FVP_K3_OCC") ? atoi(getenv("FVP_K3_OCC")) : 4;   // CTAs / SM the registers are capped for
-    if (g.JG == 4 && occ == 3)
-      k3_jln_patch<4, 3, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
-    else if (g.JG == 4)
-      k3_jln_patch<4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
-    else if (g.JG < 4)
-      k3_jln_patch<4, 4, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
-    else
-      k3_jln_patch<8, 2, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
-    return;
-  }
-  int nslab;
-  if (g.JG <= 4) {
-    nslab = 16;                                  // TA = 4 rows per slab
-    dim3 grid(nslab * ncpart, n_people);
-    static const int occ4 = getenv("FVP_K3_OCC4") ? atoi(getenv("FVP_K3_OCC4")) : 1;   // 64 regs, 4 CTAs / SM
-    if (g.JG != 4)
-      k3_jln_project<4, 4, 4, 3, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                       (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
-    else if (occ4)
-      k3_jln_project<4, 4, 4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                    (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
-    else
-      k3_jln_project<4, 4, 4, 3, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                                    (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
-  } else {
-    nslab = 32;                                  // TA = 2
-    dim3 grid(nslab * ncpart, n_people);
-    k3_jln_project<8, 2, 8, 1, 0><<<grid, 512, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl,
-                                               (float4*)d_yz_scratch, (float4*)d_xy_scratch, n_people, nslab, ncpart);
-  }
-  dim3 grid2(fvp_cdiv(img4, 256), n_people);
-  k3b_yz_reduce<<<grid2, 256, 0, st>>>((const float4*)d_yz_scratch, (const float4*)d_xy_scratch, (float4*)d_planes_cl,
-                                       n_people, nslab, ncpart, img4);
+  // partial maxima are RED-folded into the planes, which therefore start from zero
+  cudaMemsetAsync(d_planes_cl, 0, (size_t)3 * n_people * img4 * sizeof(float4), st);
+  dim3 grid(fvp_k3_patches(g.JG) * ncpart, n_people);
+  if (g.JG == 4)
+    k3_jln_patch<4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
+  else if (g.JG < 4)
+    k3_jln_patch<4, 4, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
+  else
+    k3_jln_patch<8, 2, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -52,8 +52,6 @@ struct fvp_ctx {
   FvpPerson* d_people = nullptr;      // [MB*P]
   int* d_img_valid = nullptr;         // [3*MB*P]
   float* d_planes_cl = nullptr;       // [3][MB*P][64][64][JP]
-  float* d_yz_scratch = nullptr;
-  float* d_xy_scratch = nullptr;
   float* d_feat = nullptr;            // [3][MB*P][J][64][64]
   float* d_pose = nullptr;            // [3][MB*P][J][2]
   float* d_maxw = nullptr;            // [3][MB*P][J]

@@ -38,12 +38,11 @@ void fvp_launch_debug_project(const FvpGeom& g, int seq, const float* d_pts, int
 void fvp_launch_nhwc_to_nchw(const float* d_in, float* d_out, int n, int hw, int cp, int c, cudaStream_t st);
 void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int cp, int c, cudaStream_t st);
 
-// K3: per-person back-projection + three-plane max.
-//   planes_cl [3][B*P][64][64][JP]; yz partial scratch [B*P][nslab][64][64][JP]
-//   xy partial scratch [B*P][ncpart][64][64][JP] (used when the depth range is split, ncpart in {1,2,4,8})
-int fvp_k3_version();
+// K3: per-person back-projection + three-plane max -> planes_cl [3][B*P][64][64][JP] (zeroed, then RED.MAX-folded).
+// A person is 64 (JG <= 4) or 128 column patches, times ncpart depth parts (1, 2, 4 or 8) - one CTA each.
+static inline int fvp_k3_patches(int JG) { return JG <= 4 ? 64 : 128; }
 void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
-                            float* d_yz_scratch, float* d_xy_scratch, int batch, int ncpart, cudaStream_t st);
+                            int batch, int ncpart, cudaStream_t st);
 
 // N1 heat-map renderer (JointsDataset.generate_input_heatmap): joints [views][max_people][J][2] float64 in IMAGE_SIZE pixels,
 // num [views], vis [views][max_people][J] or NULL -> out [views][J][H][W]; d_patches = fvp_render_patch_bytes(...) bytes

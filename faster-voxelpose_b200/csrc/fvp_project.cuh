@@ -118,39 +118,10 @@ __device__ __forceinline__ void fvp_tap_accumulate(float4& acc, const float4* __
   acc.w = fmaf(d.w, w11, fmaf(c.w, w10, fmaf(b.w, w01, fmaf(a.w, w00, acc.w))));
 }
 
-// Same with a one-entry footprint cache: consecutive depths of a column usually fall into the same 2x2 pixel cell of a
-// view (a 32 mm voxel is a fraction of a heat-map pixel), so the four float4 taps are reloaded only when the cell
-// changes.  K3 is bound by L1 wavefronts (one 64-B pixel per wavefront), not by arithmetic; values are identical.
-struct FvpTapCache {
-  int off;
-  float4 a, b, c, d;
-};
-template <int PX16 = 0>
-__device__ __forceinline__ void fvp_tap_accumulate_cached(float4& acc, FvpTapCache& tc, const float4* __restrict__ base, int off,
-                                                          int row_stride4, int px_stride4, float w00, float w01, float w10,
-                                                          float w11) {
-  if (off != tc.off) {
-    tc.off = off;
-    const unsigned o0 = (unsigned)off << 4, o2 = o0 + ((unsigned)row_stride4 << 4);
-    if (PX16 > 0) {
-      const float4* pn = (const float4*)((const char*)base + o0);
-      const float4* ps = (const float4*)((const char*)base + o2);
-      tc.a = __ldg(pn); tc.b = __ldg(pn + PX16 / 16); tc.c = __ldg(ps); tc.d = __ldg(ps + PX16 / 16);
-    } else {
-      const unsigned px = (unsigned)px_stride4 << 4;
-      tc.a = fvp_ldg_at(base, o0); tc.b = fvp_ldg_at(base, o0 + px); tc.c = fvp_ldg_at(base, o2); tc.d = fvp_ldg_at(base, o2 + px);
-    }
-  }
-  const float4 a = tc.a, b = tc.b, c = tc.c, d = tc.d;
-  acc.x = fmaf(d.x, w11, fmaf(c.x, w10, fmaf(b.x, w01, fmaf(a.x, w00, acc.x))));
-  acc.y = fmaf(d.y, w11, fmaf(c.y, w10, fmaf(b.y, w01, fmaf(a.y, w00, acc.y))));
-  acc.z = fmaf(d.z, w11, fmaf(c.z, w10, fmaf(b.z, w01, fmaf(a.z, w00, acc.z))));
-  acc.w = fmaf(d.w, w11, fmaf(c.w, w10, fmaf(b.w, w01, fmaf(a.w, w00, acc.w))));
-}
-
-// Warp-uniform form of the footprint cache (K3 patch kernel): the four taps are reloaded by ALL lanes as soon as ANY lane
-// left its 2x2 cell, so the test is a vote + uniform branch instead of a divergent region (BSSY/BSYNC, serialised
-// paths); lanes that would have hit re-read the same bytes, values are identical.  Must be called by converged warps.
+// Footprint cache of K3: consecutive depths of a column often fall into the same 2x2 pixel cell of a view, so the four
+// float4 taps are kept in registers and reloaded by ALL lanes as soon as ANY lane left its cell - a vote + uniform branch
+// instead of a divergent region (BSSY/BSYNC, serialised paths); lanes that would have hit re-read the same bytes, values
+// are identical.  Must be called by converged warps.
 struct FvpTapRegs {
   int off;
   float4 a, b, c, d;
