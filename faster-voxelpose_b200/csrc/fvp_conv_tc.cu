@@ -183,6 +183,16 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+template <int CW>
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t* r) {
+  if constexpr (CW == 16) tmem_ld16_issue(taddr, r);
+  else tmem_ld8_issue(taddr, r);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
 struct TcArgs {
@@ -195,6 +205,7 @@ struct TcArgs {
   int resident;          // 1: the whole weight image is loaded once per CTA (b_stage_bytes = its size)
   uint32_t blk_bytes;    // bytes of one (K-block, tap, N-tile) weight block = n_tile*128*2
   int tiles_x, tiles_per_img, total_items;   // work item = (image, tile, N tile)
+  uint32_t m_ntiles, m_tpi, m_tx;            // ceil(2^32 / d) of the three divisors of tc_decode (0: use the division)
   unsigned long long* prof;                  // debug: per-role wait / busy cycle counters (NULL in production)
 };
 
@@ -213,12 +224,14 @@ struct TcArgs {
 struct TcItem {
   int img, y0, x0, nt;
 };
+// n / d through one multiply-high with m = ceil(2^32 / d): exact while n * d < 2^32 (checked on the host, m = 0 otherwise)
+__device__ __forceinline__ int tc_div(int n, int d, uint32_t m) { return m ? (int)__umulhi((uint32_t)n, m) : n / d; }
 __device__ __forceinline__ bool tc_decode(const TcArgs& t, int item, TcItem& w) {
-  const int nt = item % t.n_tiles, r = item / t.n_tiles;
-  w.nt = nt;
-  w.img = r / t.tiles_per_img;
+  const int r = t.n_tiles == 1 ? item : tc_div(item, t.n_tiles, t.m_ntiles);
+  w.nt = item - r * t.n_tiles;
+  w.img = tc_div(r, t.tiles_per_img, t.m_tpi);
   const int tile = r - w.img * t.tiles_per_img;
-  const int ty = tile / t.tiles_x;
+  const int ty = tc_div(tile, t.tiles_x, t.m_tx);
   w.y0 = ty * TC_TH;
   w.x0 = (tile - ty * t.tiles_x) * TC_TW;
   return !(t.c.valid && !t.c.valid[w.img]);
@@ -233,8 +246,11 @@ __device__ __forceinline__ bool tc_decode(const TcArgs& t, int item, TcItem& w) 
 // tile i, and the staging of tile i+1 under the MMAs of tile i.
 // MODE 0: 3xTF32, 32-channel K-blocks (128-B rows, SWIZZLE_128B); MODE 1: fp16 split, 32-channel K-blocks (64-B rows,
 // SWIZZLE_64B); MODE 2: fp16 split, 16-channel K-blocks (32-B rows, SWIZZLE_32B) for layers with <= 16 input channels.
-template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
+// OCC = CTAs per SM the kernel is compiled for: 2 caps the registers at 72 so that two persistent CTAs (each with its own
+// loaders / MMA issuer / epilogue) share an SM when the launch needs <= ~110 KB of shared memory and <= 256 TMEM columns -
+// every role of this kernel is latency-bound per item, a second CTA fills the idle issue slots and tensor-pipe gaps.
+template <int MODE, int OCC>
+__global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
   constexpr bool F16 = MODE != 0;
   constexpr int ROWB = MODE == 0 ? 128 : (MODE == 1 ? 64 : 32);   // bytes of one pixel row of a K-block in shared memory
   constexpr int CB = MODE == 2 ? 16 : 32;                          // channels per K-block
@@ -294,7 +310,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
     // are computed once; per item only the image bounds tests and one base pointer remain.
     constexpr int CH = ROWB / 16;                                  // 16-B chunks per pixel row
     constexpr int PPI = TC_LOADERS / CH;                           // pixels covered per pass of the 256 threads
-    constexpr int EPT = (22 * 14 + PPI - 1) / PPI;                 // elements per thread (largest halo: 7x7)
+    constexpr int MAXHALO = MODE == 2 ? 22 * 14 : 18 * 10;         // 7x7 layers always run in MODE 2 (launcher)
+    constexpr int EPT = (MAXHALO + PPI - 1) / PPI;                 // elements per thread
+    constexpr int NV = F16 ? 2 : 1;                                // float4 loads per element
     const int q = tid % CH, p0 = tid / CH;
     int e_hyx[2][EPT], e_dst[2][EPT];                              // [phase][element]: (hy<<8)|hx ; smem byte offset or -1
 #pragma unroll
@@ -310,78 +328,107 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         e_dst[ph][j] = pix < HW * HH ? (hy * HWP + hx) * ROWB + ((q ^ phase) << 4) : -1;
       }
     }
+    // The K-blocks of this CTA form one flat sequence (item, phase, 32-channel block).  The global loads of block i+1
+    // are issued BEFORE block i is converted and stored, so their L2 latency (the loaders' largest stall, ncu: 38 % of
+    // the samples on the first dependent convert) runs under the conversion and the wait for a free stage.
+    struct KBlock { const float* img; int y0, x0, c0, ph; };
+    int it_item = blockIdx.x, it_ph = 0, it_c0 = 0;
+    bool it_open = false;
+    TcItem it_w;
+    auto advance = [&](KBlock& kb) -> bool {
+      while (it_item < t.total_items) {
+        if (!it_open) {
+          if (!tc_decode(t, it_item, it_w)) { it_item += gridDim.x; continue; }
+          it_open = true; it_ph = 0; it_c0 = 0;
+        }
+        const int Cin = it_ph == 0 ? a.Cin : a.Cin2;
+        if (it_c0 >= Cin) {                                         // K-blocks of this phase are done (CinP = round-up)
+          it_c0 = 0;
+          if (++it_ph >= nph) { it_open = false; it_item += gridDim.x; }
+          continue;
+        }
+        kb.img = (it_ph == 0 ? a.in : a.in2) + (size_t)it_w.img * a.H * a.W * Cin;
+        kb.y0 = it_w.y0; kb.x0 = it_w.x0; kb.c0 = it_c0; kb.ph = it_ph;
+        it_c0 += CB;
+        return true;
+      }
+      return false;
+    };
+    auto issue = [&](const KBlock& kb, float4 (&v)[EPT][NV]) {
+      const int K = kb.ph == 0 ? a.ksize : 1, Cin = kb.ph == 0 ? a.Cin : a.Cin2, pad = (K - 1) / 2;
+      const int c = kb.c0 + q * (F16 ? 8 : 4);
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int hyx = kb.ph == 0 ? e_hyx[0][j] : e_hyx[1][j], dst = kb.ph == 0 ? e_dst[0][j] : e_dst[1][j];
+        const int gy = kb.y0 + (hyx >> 8) - pad, gx = kb.x0 + (hyx & 255) - pad;
+#pragma unroll
+        for (int h = 0; h < NV; ++h) v[j][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dst >= 0 && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+          const float* pp = kb.img + ((size_t)gy * a.W + gx) * Cin + c;
+#pragma unroll
+          for (int h = 0; h < NV; ++h)
+            if (c + 4 * h < Cin) v[j][h] = __ldg((const float4*)(pp + 4 * h));
+        }
+      }
+    };
     int a_it = 0;
     long long pc[2] = {0, 0};
     const long long lt0 = clock64();
-    for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
-      TcItem w;
-      if (!tc_decode(t, item, w)) continue;
+    auto stage = [&](const KBlock& kb, const float4 (&v)[EPT][NV]) {
+      const int K = kb.ph == 0 ? a.ksize : 1;
+      const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
+      const uint32_t lo_off = (uint32_t)HH * HWP * ROWB;
+      const int as = a_it % A_ST;
+      if (a_it >= A_ST) TC_TIMED(0, mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1));
+      uint8_t* hi = sA + (size_t)as * t.a_stage_bytes;
 #pragma unroll
-      for (int ph = 0; ph < 2; ++ph) {
-        if (ph >= nph) break;
-        const float* src = ph == 0 ? a.in : a.in2;
-        const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
-        const int CinP = (Cin + CB - 1) / CB * CB, pad = (K - 1) / 2;
-        const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16;
-        const uint32_t lo_off = (uint32_t)HH * HWP * ROWB;
-        const float* img_in = src + (size_t)w.img * a.H * a.W * Cin;
-        for (int c0 = 0; c0 < CinP; c0 += CB) {
-          const int as = a_it % A_ST;
-          if (a_it >= A_ST) TC_TIMED(0, mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1));
-          uint8_t* hi = sA + (size_t)as * t.a_stage_bytes;
-          if constexpr (F16) {
-            const int c = c0 + q * 8;                                // 8 channels -> one 16-B chunk of halves
-            float4 v[EPT][2];
+      for (int j = 0; j < EPT; ++j) {
+        const int dst = kb.ph == 0 ? e_dst[0][j] : e_dst[1][j];
+        if (dst < 0) continue;
+        if constexpr (F16) {
+          const float x[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][NV - 1].x, v[j][NV - 1].y, v[j][NV - 1].z, v[j][NV - 1].w};
+          uint32_t ph_[4], pl_[4];
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {                          // all loads of the K-block in flight together
-              const int gy = w.y0 + (e_hyx[ph][j] >> 8) - pad, gx = w.x0 + (e_hyx[ph][j] & 255) - pad;
-              v[j][0] = v[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (e_dst[ph][j] >= 0 && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-                const float* pp = img_in + ((size_t)gy * a.W + gx) * Cin + c;
-                if (c < Cin) v[j][0] = __ldg((const float4*)pp);
-                if (c + 4 < Cin) v[j][1] = __ldg((const float4*)(pp + 4));
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-              if (e_dst[ph][j] < 0) continue;
-              const float x[8] = {v[j][0].x, v[j][0].y, v[j][0].z, v[j][0].w, v[j][1].x, v[j][1].y, v[j][1].z, v[j][1].w};
-              uint32_t ph_[4], pl_[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {                        // packed converts (F2FP on the ALU pipe, not the
-                const __half2 h2 = __floats2half2_rn(x[2 * e], x[2 * e + 1]);   // quarter-rate scalar F2F)
-                const float2 hf = __half22float2(h2);
-                const __half2 l2 = __floats2half2_rn((x[2 * e] - hf.x) * 2048.0f, (x[2 * e + 1] - hf.y) * 2048.0f);
-                ph_[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                pl_[e] = *reinterpret_cast<const uint32_t*>(&l2);
-              }
-              *(uint4*)(hi + e_dst[ph][j]) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
-              *(uint4*)(hi + lo_off + e_dst[ph][j]) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
-            }
-          } else {
-            const int c = c0 + q * 4;
-            const bool c_ok = c < Cin;
-            float4 v[EPT];
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {                          // all loads of the K-block in flight together
-              const int gy = w.y0 + (e_hyx[ph][j] >> 8) - pad, gx = w.x0 + (e_hyx[ph][j] & 255) - pad;
-              v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (e_dst[ph][j] >= 0 && c_ok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W)
-                v[j] = __ldg((const float4*)(img_in + ((size_t)gy * a.W + gx) * Cin + c));
-            }
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-              if (e_dst[ph][j] < 0) continue;
-              const float4 h = make_float4(to_tf32(v[j].x), to_tf32(v[j].y), to_tf32(v[j].z), to_tf32(v[j].w));
-              *(float4*)(hi + e_dst[ph][j]) = h;
-              *(float4*)(hi + lo_off + e_dst[ph][j]) = make_float4(to_tf32(v[j].x - h.x), to_tf32(v[j].y - h.y),
-                                                                   to_tf32(v[j].z - h.z), to_tf32(v[j].w - h.w));
-            }
+          for (int e = 0; e < 4; ++e) {                            // packed converts (F2FP on the ALU pipe, not the
+            const __half2 h2 = __floats2half2_rn(x[2 * e], x[2 * e + 1]);   // quarter-rate scalar F2F)
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn((x[2 * e] - hf.x) * 2048.0f, (x[2 * e + 1] - hf.y) * 2048.0f);
+            ph_[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            pl_[e] = *reinterpret_cast<const uint32_t*>(&l2);
           }
-          fence_proxy_async();
-          mbar_arrive(a_full + as);
-          ++a_it;
+          *(uint4*)(hi + dst) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
+          *(uint4*)(hi + lo_off + dst) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
+        } else {
+          const float4 x = v[j][0];
+          const float4 h = make_float4(to_tf32(x.x), to_tf32(x.y), to_tf32(x.z), to_tf32(x.w));
+          *(float4*)(hi + dst) = h;
+          *(float4*)(hi + lo_off + dst) = make_float4(to_tf32(x.x - h.x), to_tf32(x.y - h.y), to_tf32(x.z - h.z), to_tf32(x.w - h.w));
         }
+      }
+      fence_proxy_async();
+      mbar_arrive(a_full + as);
+      ++a_it;
+    };
+    if constexpr (OCC == 1) {
+      float4 va[EPT][NV], vb[EPT][NV];
+      KBlock ka, kb;
+      bool more = advance(ka);
+      if (more) issue(ka, va);
+      while (more) {
+        const bool more_b = advance(kb);
+        if (more_b) issue(kb, vb);
+        stage(ka, va);
+        if (!more_b) break;
+        more = advance(ka);
+        if (more) issue(ka, va);
+        stage(kb, vb);
+      }
+    } else {                                                       // 72-register variant: the sibling CTA hides the latency
+      float4 va[EPT][NV];
+      KBlock ka;
+      while (advance(ka)) {
+        issue(ka, va);
+        stage(ka, va);
       }
     }
     if (t.prof && tid == 0) {
@@ -544,37 +591,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         ch = co - q * Co;
         return (px_plain + (size_t)(q >> 1) * Wo + (q & 1)) * a.CoutS;
       };
-      auto fetch_res = [&](int cb, float4* rr) {                   // residuals of one 16-column chunk, issued early
+      constexpr int CW = OCC == 2 ? 8 : 16, G4 = CW / 4;         // columns per chunk (8 keeps the 2-CTA variant in 72 registers)
+      auto fetch_res = [&](int cb, float4* rr) {                   // residuals of one chunk, issued early
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) rr[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g4 = 0; g4 < G4; ++g4) rr[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.res_mode && px_ok && cb < t.n_tile) {
           int ch;
           const size_t off = chunk_offset(co_base + cb, ch);
 #pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4)
+          for (int g4 = 0; g4 < G4; ++g4)
             if (co_base + cb + g4 * 4 < a.CoutP) rr[g4] = __ldg((const float4*)(a.res + off + ch + g4 * 4));
         }
       };
-      float4 rnext[4];
+      float4 rnext[G4];
       fetch_res(0, rnext);
-      for (int cb = 0; cb < t.n_tile; cb += 16) {
-        float4 rcur[4];
+      for (int cb = 0; cb < t.n_tile; cb += CW) {
+        float4 rcur[G4];
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) rcur[g4] = rnext[g4];
-        uint32_t u1[16], u2[16];
+        for (int g4 = 0; g4 < G4; ++g4) rcur[g4] = rnext[g4];
+        uint32_t u1[CW], u2[CW];
         const long long tl0 = t.prof ? clock64() : 0;
-        tmem_ld16_issue(t_row + (uint32_t)cb, u1);                 // both accumulators in flight, one wait
-        if constexpr (F16) tmem_ld16_issue(t_row + (uint32_t)t.n_tile + (uint32_t)cb, u2);
-        fetch_res(cb + 16, rnext);                                 // next chunk's residuals fly under this chunk
+        tmem_ld_issue<CW>(t_row + (uint32_t)cb, u1);               // both accumulators in flight, one wait
+        if constexpr (F16) tmem_ld_issue<CW>(t_row + (uint32_t)t.n_tile + (uint32_t)cb, u2);
+        fetch_res(cb + CW, rnext);                                 // next chunk's residuals fly under this chunk
         tmem_ld_wait();
         if (t.prof) pc[1] += clock64() - tl0;
-        float v[16];
+        float v[CW];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < CW; ++i) {
           v[i] = __uint_as_float(u1[i]);
           if constexpr (F16) v[i] = fmaf(__uint_as_float(u2[i]), 1.0f / 2048.0f, v[i]);   // D = D1 + 2^-11 * D2
         }
-        if (cb + 16 >= t.n_tile) {                                 // last chunk read: hand the accumulator back
+        if (cb + CW >= t.n_tile) {                                 // last chunk read: hand the accumulator back
           tc_fence_before();
           mbar_arrive(acc_empty + buf);
         }
@@ -582,7 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_conv_tc(TcArgs t) {
         int ch0;
         const size_t off = chunk_offset(co_base + cb, ch0);
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
+        for (int g4 = 0; g4 < G4; ++g4) {
           const int co = co_base + cb + g4 * 4;
           if (co >= a.CoutP) break;
           const float4 bias = *(const float4*)(s_bias + co);
@@ -632,11 +680,16 @@ void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
 }
 
 static unsigned long long* g_tc_prof = nullptr;
+static int g_tc_occ = [] { const char* e = std::getenv("FVP_TC_OCC"); return e ? std::atoi(e) : 2; }();   // 1: never co-schedule two CTAs per SM (A/B switch)
 void fvp_tc_set_prof(unsigned long long* d_counters) { g_tc_prof = d_counters; }   // debug hook (fvp_debug_conv)
 
 // mode: 0 = 3xTF32, 1 = fp16 split with 32-channel K-blocks, 2 = fp16 split with 16-channel K-blocks
 // wtc[3]: weight images tiled for N tiles of up to 128 / 32 / 64 columns (NULL where not packed)
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st) {
+  if (mode != 2 && a.ksize > 3) {     // the loaders of the 32-channel K-block variants hold a 3x3 halo at most (EPT); 7x7 layers
+    fvp_launch_conv(a, st);           // of this network have <= 16 input channels and run in mode 2
+    return;
+  }
   TcArgs t;
   t.c = a;
   t.prof = g_tc_prof;
@@ -685,15 +738,26 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   t.tiles_x = fvp_cdiv(a.W, TC_TW);
   t.tiles_per_img = t.tiles_x * fvp_cdiv(a.H, TC_TH);
   t.total_items = t.tiles_per_img * a.n * t.n_tiles;
+  auto magic = [&](int d) -> uint32_t {            // d == 1 would need 2^32: the plain division handles it
+    return (d > 1 && (unsigned long long)t.total_items * d < (1ull << 32)) ? (uint32_t)(((1ull << 32) + d - 1) / d) : 0u;
+  };
+  t.m_ntiles = magic(t.n_tiles); t.m_tpi = magic(t.tiles_per_img); t.m_tx = magic(t.tiles_x);
   const size_t smem = 1024 + (size_t)t.a_stages * t.a_stage_bytes + (size_t)t.b_stages * t.b_stage_bytes;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    const void* fns[6] = {(const void*)k_conv_tc<0, 1>, (const void*)k_conv_tc<1, 1>, (const void*)k_conv_tc<2, 1>,
+                          (const void*)k_conv_tc<0, 2>, (const void*)k_conv_tc<1, 2>, (const void*)k_conv_tc<2, 2>};
+    for (int i = 0; i < 6; ++i) {
+      cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+      if (i >= 3) cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     attr = true;
   }
-  const int grid = t.total_items < num_sms ? t.total_items : num_sms;   // persistent: one CTA per SM
+  // Two CTAs per SM when both fit: 228 KB of shared memory per SM, 1 KB reserved per CTA, 2304 B static; 512 TMEM columns.
+  // (A CTA that needs more than 256 columns must never share an SM with a sibling: its tcgen05.alloc would block.)
+  const bool occ2 = g_tc_occ != 1 && 2 * (smem + 2304 + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
+  const int slots = num_sms * (occ2 ? 2 : 1);
+  const int grid = t.total_items < slots ? t.total_items : slots;        // persistent: one or two CTAs per SM
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);
@@ -704,7 +768,13 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2>, t);
-  else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1>, t);
-  else cudaLaunchKernelEx(&cfg, k_conv_tc<0>, t);
+  if (occ2) {
+    if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2, 2>, t);
+    else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1, 2>, t);
+    else cudaLaunchKernelEx(&cfg, k_conv_tc<0, 2>, t);
+  } else {
+    if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2, 1>, t);
+    else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1, 1>, t);
+    else cudaLaunchKernelEx(&cfg, k_conv_tc<0, 1>, t);
+  }
 }
