@@ -755,7 +755,11 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   }
   // Two CTAs per SM when both fit: 228 KB of shared memory per SM, 1 KB reserved per CTA, 2304 B static; 512 TMEM columns.
   // (A CTA that needs more than 256 columns must never share an SM with a sibling: its tcgen05.alloc would block.)
-  const bool occ2 = g_tc_occ != 1 && 2 * (smem + 2304 + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
+  // Measured per layer (profiles/r01_s5_conv_layers_occ*.txt, 960 images): 7x7 16->16 1.49x, 1x1 32->16 1.43x, 3x3 32->32 1.08x
+  // faster with two CTAs per SM; the 3x3 16->32 layer (16-channel K-blocks, loader-bound) is 9 % slower and keeps one.
+  // (Also tried and dropped: one LDG.128 per lane over whole 128-B lines with 8-byte shared stores - fewer L1 sector
+  //  lookups but twice the store instructions: 3 % slower over the trunk's layer mix.)
+  const bool occ2 = g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + 2304 + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
   const int slots = num_sms * (occ2 ? 2 : 1);
   const int grid = t.total_items < slots ? t.total_items : slots;        // persistent: one or two CTAs per SM
   cudaLaunchConfig_t cfg = {};
