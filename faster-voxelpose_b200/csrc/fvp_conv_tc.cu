@@ -28,6 +28,7 @@
 // allocates TMEM and one elected lane issues every tcgen05.mma.
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "fvp_kernels.h"
@@ -40,6 +41,9 @@ constexpr int TC_LW = TC_LOADERS / 32;     // warp 8 = MMA issuer / TMEM owner, 
 constexpr int TC_THREADS = TC_LOADERS + 64 + 128;
 constexpr int TC_EPI = 128;
 constexpr int TC_MAX_A = 2, TC_MAX_B = 8;  // ring depths are chosen per launch (a_stages, b_stages)
+constexpr int TC_MAX_COUT = 256;           // bias staged in static shared memory (largest layer: ConvTranspose 128->4x64)
+constexpr int TC_STATIC_SMEM = 1280;       // s_bar + s_tmem + s_bias, as reported by ptxas (checked in fvp_launch_conv_tc)
+constexpr int TC_DYN_SMEM_MAX = 227 * 1024 - TC_STATIC_SMEM;   // opt-in limit per CTA minus the static part
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,6 +199,9 @@ __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+// NOTE: ptxas's register allocation of the 72-register (two CTAs per SM) variants is sensitive to this struct: adding one int
+// field raised the spills of k_conv_tc<1,2> from 16 B to 116 B and made the 3x3 32->32 layer 45 % slower (local memory thrashes
+// the 28 KB of L1 left beside 2 x 111 KB of shared memory).  tests/test_host_logic.py pins the spill sizes from the build log.
 struct TcArgs {
   FvpConvArgs c;
   const float* wtc;      // tiled hi/lo weights (see pack_tc in fvp_params.cu)
@@ -202,7 +209,8 @@ struct TcArgs {
   int n_tiles;           // CoutPad / n_tile
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, acc_stride;
   int a_stages, b_stages;
-  int resident;          // 1: the whole weight image is loaded once per CTA (b_stage_bytes = its size)
+  int resident;          // 1: the whole weight image is loaded once per CTA (b_stage_bytes = its size); 2: only the blocks of
+                         // ONE N tile (b_stage_bytes / blk_bytes of them) - the grid is a multiple of n_tiles, so CTA b only ever sees N tile b % n_tiles
   uint32_t blk_bytes;    // bytes of one (K-block, tap, N-tile) weight block = n_tile*128*2
   int tiles_x, tiles_per_img, total_items;   // work item = (image, tile, N tile)
   uint32_t m_ntiles, m_tpi, m_tx;            // ceil(2^32 / d) of the three divisors of tc_decode (0: use the division)
@@ -259,8 +267,11 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   __shared__ uint64_t s_bar[2 * TC_MAX_A + 2 * TC_MAX_B + 4];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(16) float s_bias[512];                      // bias of every output channel (CoutP <= 512)
+  __shared__ __align__(16) float s_bias[TC_MAX_COUT];              // bias of every output channel
   const FvpConvArgs& a = t.c;
+  // per-N-tile weight residency needs > 113 KB of shared memory, i.e. it only exists in the one-CTA-per-SM variant (keeping it
+  // out of the 72-register variant avoids spills there: local memory thrashes the 28 KB of L1 left beside 2 x 111 KB of smem)
+  const bool per_nt = OCC == 1 && t.resident == 2;
 
   const int A_ST = t.a_stages, B_ST = t.b_stages;
   uint8_t* sA = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);   // swizzle atoms need 1024-B alignment
@@ -296,9 +307,16 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
   const bool is_producer = tid == TC_LOADERS + 32;
   if (is_producer && t.resident) {                                // weights do not depend on the previous kernel
     mbar_arrive_expect_tx(b_full, t.b_stage_bytes);
-    for (uint32_t off = 0; off < t.b_stage_bytes; off += 32768) {
-      const uint32_t n = t.b_stage_bytes - off < 32768 ? t.b_stage_bytes - off : 32768;
-      tma_bulk_g2s(sB + off, (const uint8_t*)t.wtc + off, n, b_full);
+    if (per_nt) {                                         // my N tile's blocks, compacted: block b -> sB + b * blk_bytes
+      const uint32_t nt = blockIdx.x % (uint32_t)t.n_tiles;
+      const int nblk = (int)(t.b_stage_bytes / t.blk_bytes);     // (K-block, tap) blocks of one N tile
+      for (int b = 0; b < nblk; ++b)
+        tma_bulk_g2s(sB + (size_t)b * t.blk_bytes, (const uint8_t*)t.wtc + ((size_t)b * t.n_tiles + nt) * t.blk_bytes, t.blk_bytes, b_full);
+    } else {
+      for (uint32_t off = 0; off < t.b_stage_bytes; off += 32768) {
+        const uint32_t n = t.b_stage_bytes - off < 32768 ? t.b_stage_bytes - off : 32768;
+        tma_bulk_g2s(sB + off, (const uint8_t*)t.wtc + off, n, b_full);
+      }
     }
   }
   asm volatile("griddepcontrol.wait;\n" ::: "memory");           // activations of the previous kernel are now visible
@@ -477,6 +495,8 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
       const uint32_t d_tmem = tmem + (uint32_t)buf * (F16 ? 2u : 1u) * t.acc_stride;   // F16: D1 | D2 side by side
       uint32_t accumulate = 0;
       uint32_t blk = 0;                                            // running weight block index (resident image)
+      const uint32_t nts_img = per_nt ? 1u : (uint32_t)t.n_tiles;   // N tiles interleaved in the shared-memory image
+      const uint32_t nt_img = per_nt ? 0u : (uint32_t)w.nt;
       for (int ph = 0; ph < nph; ++ph) {
         const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
         const int CinP = (Cin + CB - 1) / CB * CB;
@@ -492,10 +512,10 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
           const uint64_t ad0 = umma_desc(a_base, (uint32_t)HWP * ROWB, LAYOUT);
           const uint64_t bd_res0 = umma_desc(smem_u32(sB), 8 * ROWB, LAYOUT);
           const uint32_t a_lo16 = a_lo_off >> 4, b_lo16 = b_lo_off >> 4, blk16 = t.blk_bytes >> 4;
-          uint32_t bidx = (blk + (uint32_t)w.nt) * blk16;            // resident image: block of (K-block, tap 0, N tile)
+          uint32_t bidx = (blk + nt_img) * blk16;            // resident image: block of (K-block, tap 0, N tile)
           if (F16 && t.resident) {                                   // fast path: whole K-block from one elected region
             if (!b_ready) { TC_TIMED(2, mbar_wait(b_full, 0)); b_ready = true; tc_fence_after(); }
-            const uint32_t d2 = d_tmem + (uint32_t)t.n_tile, bstride = (uint32_t)t.n_tiles * blk16;
+            const uint32_t d2 = d_tmem + (uint32_t)t.n_tile, bstride = nts_img * blk16;
             constexpr int KS = CB == 32 ? 2 : 1;
             if (elect_one()) {
               if (K == 3) umma_kblock_f16<ROWB, 3, KS>(d_tmem, d2, ad0, a_lo16, bd_res0 + bidx, bstride, idesc2, idesc, accumulate);
@@ -511,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
               if (t.resident) {
                 if (!b_ready) { TC_TIMED(2, mbar_wait(b_full, 0)); b_ready = true; }
                 bd_hi = bd_res0 + bidx;
-                bidx += (uint32_t)t.n_tiles * blk16;
+                bidx += nts_img * blk16;
               } else {
                 bs = b_it % B_ST;
                 TC_TIMED(2, mbar_wait(b_full + bs, (b_it / B_ST) & 1));
@@ -546,7 +566,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
               }
             }
           }
-          blk += (uint32_t)K * K * t.n_tiles;
+          blk += (uint32_t)K * K * nts_img;
           if (elect_one()) umma_commit(a_empty + as);
           ++a_it;
         }
@@ -686,7 +706,7 @@ void fvp_tc_set_prof(unsigned long long* d_counters) { g_tc_prof = d_counters; }
 // mode: 0 = 3xTF32, 1 = fp16 split with 32-channel K-blocks, 2 = fp16 split with 16-channel K-blocks
 // wtc[3]: weight images tiled for N tiles of up to 128 / 32 / 64 columns (NULL where not packed)
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st) {
-  if (mode != 2 && a.ksize > 3) {     // the loaders of the 32-channel K-block variants hold a 3x3 halo at most (EPT); 7x7 layers
+  if ((mode != 2 && a.ksize > 3) || a.CoutP > TC_MAX_COUT) {     // the loaders of the 32-channel K-block variants hold a 3x3 halo at most (EPT); 7x7 layers
     fvp_launch_conv(a, st);           // of this network have <= 16 input channels and run in mode 2
     return;
   }
@@ -698,6 +718,23 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   const int tiles = fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW) * a.n;
   // N-tile width: the persistent grid runs ceil(items / SMs) rounds of items; per K step an item costs roughly
   // (48 + fetch + math) cycles per MMA.  Pick the width that minimises rounds x per-item cost.
+  const int k = a.ksize;
+  const uint32_t a0 = (uint32_t)(TC_TH + k - 1) * (k == 1 ? 8 : 16) * rowb * 2;
+  const uint32_t a1 = a.in2 ? (uint32_t)TC_TH * 8 * rowb * 2 : 0;
+  t.a_stage_bytes = a0 > a1 ? a0 : a1;                            // multiples of 1024
+  const int nblocks = k * k * (fvp_round_up(a.Cin, cb) / cb) + (a.in2 ? fvp_round_up(a.Cin2, cb) / cb : 0);
+  const uint32_t budget = TC_DYN_SMEM_MAX - 1024;                  // dynamic smem we may use (1 KB alignment slack)
+  // Weight residency of a variant: 1 = the whole image fits beside a double-buffered halo; 2 = only one N tile's blocks fit
+  // (small launches: every CTA then serves a single N tile); 0 = streamed per tap (measured ~1.8x the per-MMA cost of the
+  // unrolled resident issue path: per-tap barrier waits and commits on the issuing lane).
+  auto residency = [&](int nt, int nts) -> int {
+    const uint32_t blk = (uint32_t)nt * rowb * 2;
+    if ((uint64_t)nblocks * nts * blk + 2 * t.a_stage_bytes <= budget) return 1;
+    if (f16 && nts > 1 && num_sms >= nts && (uint64_t)nblocks * blk + 2 * t.a_stage_bytes <= budget &&
+        fvp_cdiv(tiles * nts, num_sms - num_sms % nts) <= 2)
+      return 2;
+    return 0;
+  };
   int best = 0;
   double best_cost = 1e30;
   for (int v = 0; v < 3; ++v) {
@@ -706,22 +743,19 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
     fvp_tc_geometry(a.CoutP, v, &nt, &nts);
     const double per_item = f16 ? (48 + (128 + 2 * nt) / 4.0 + nt) + (48 + (128 + nt) / 4.0 + nt / 2.0)
                                 : 3.0 * (48 + (128 + nt) / 4.0 + nt / 2.0);
-    const double cost = (double)fvp_cdiv(tiles * nts, num_sms) * per_item + 1.0 * nts;    // ties go to the wider tile
+    const double cost = (double)fvp_cdiv(tiles * nts, num_sms) * per_item * (residency(nt, nts) ? 1.0 : 1.8) + 1.0 * nts;   // ties: wider tile
     if (cost < best_cost) { best_cost = cost; best = v; }
   }
   fvp_tc_geometry(a.CoutP, best, &t.n_tile, &t.n_tiles);
   t.wtc = wtc[best];
-  const int k = a.ksize;
-  const uint32_t a0 = (uint32_t)(TC_TH + k - 1) * (k == 1 ? 8 : 16) * rowb * 2;
-  const uint32_t a1 = a.in2 ? (uint32_t)TC_TH * 8 * rowb * 2 : 0;
-  t.a_stage_bytes = a0 > a1 ? a0 : a1;                            // multiples of 1024
   t.blk_bytes = (uint32_t)t.n_tile * rowb * 2;
-  const int nblocks = k * k * (fvp_round_up(a.Cin, cb) / cb) + (a.in2 ? fvp_round_up(a.Cin2, cb) / cb : 0);
   const uint32_t image_bytes = (uint32_t)nblocks * t.n_tiles * t.blk_bytes;
-  const uint32_t budget = 224 * 1024 - 1024;                       // dynamic smem we may use (1 KB alignment slack)
+  const int res = residency(t.n_tile, t.n_tiles);
   const int stream2 = (2 * t.a_stage_bytes + 4 * t.blk_bytes <= budget) ? (int)((budget - 2 * t.a_stage_bytes) / t.blk_bytes) : 0;
-  if (image_bytes + 2 * t.a_stage_bytes <= budget) {              // weights resident, double-buffered halo
+  if (res == 1) {                                                  // weights resident, double-buffered halo
     t.resident = 1; t.a_stages = 2; t.b_stages = 1; t.b_stage_bytes = image_bytes;
+  } else if (res == 2) {                                           // one N tile's weights resident per CTA
+    t.resident = 2; t.a_stages = 2; t.b_stages = 1; t.b_stage_bytes = (uint32_t)nblocks * t.blk_bytes;
   } else if (stream2 >= 4) {                                       // streamed weights, double-buffered halo
     t.resident = 0; t.a_stages = 2; t.b_stage_bytes = t.blk_bytes;
     t.b_stages = stream2 > TC_MAX_B ? TC_MAX_B : stream2;
@@ -748,7 +782,12 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
     const void* fns[6] = {(const void*)k_conv_tc<0, 1>, (const void*)k_conv_tc<1, 1>, (const void*)k_conv_tc<2, 1>,
                           (const void*)k_conv_tc<0, 2>, (const void*)k_conv_tc<1, 2>, (const void*)k_conv_tc<2, 2>};
     for (int i = 0; i < 6; ++i) {
-      cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, fns[i]) != cudaSuccess || fa.sharedSizeBytes > (size_t)TC_STATIC_SMEM) {
+        fprintf(stderr, "fvp_launch_conv_tc: static shared memory %zu B exceeds TC_STATIC_SMEM\n", fa.sharedSizeBytes);
+        abort();
+      }
+      cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_DYN_SMEM_MAX);
       if (i >= 3) cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     attr = true;
@@ -759,9 +798,10 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   // faster with two CTAs per SM; the 3x3 16->32 layer (16-channel K-blocks, loader-bound) is 9 % slower and keeps one.
   // (Also tried and dropped: one LDG.128 per lane over whole 128-B lines with 8-byte shared stores - fewer L1 sector
   //  lookups but twice the store instructions: 3 % slower over the trunk's layer mix.)
-  const bool occ2 = g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + 2304 + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
+  const bool occ2 = g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
   const int slots = num_sms * (occ2 ? 2 : 1);
-  const int grid = t.total_items < slots ? t.total_items : slots;        // persistent: one or two CTAs per SM
+  int grid = t.total_items < slots ? t.total_items : slots;              // persistent: one or two CTAs per SM
+  if (t.resident == 2) grid -= grid % t.n_tiles;                         // CTA b serves N tile b % n_tiles only
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);

@@ -87,6 +87,19 @@ def test_library_is_sm100a_with_lineinfo(built_library):
     assert "sm_100a" in out
 
 
+def test_two_cta_conv_variants_do_not_spill_more_than_measured(built_library):
+    """The 72-register variants of k_conv_tc (two CTAs per SM) run beside 2 x 111 KB of shared memory, i.e. with 28 KB of L1:
+    ptxas spills beyond the sizes measured fast on B200 (profiles/r01_s5_conv_layers_final.txt) cost up to 45 % on the
+    full-resolution layers.  The build log is the evidence (csrc/build.sh keeps -Xptxas -v output per source file)."""
+    import re
+    log = open(os.path.join(os.path.dirname(built_library), "csrc", "build", "fvp_conv_tc.log")).read()
+    spills = {}
+    for m in re.finditer(r"k_conv_tcILi(\d)ELi(\d)EE.*?\n.*?(\d+) bytes spill stores", log):
+        spills[(int(m.group(1)), int(m.group(2)))] = int(m.group(3))
+    assert set(spills) == {(m, o) for m in (0, 1, 2) for o in (1, 2)}, spills
+    assert spills[(1, 2)] <= 32 and spills[(2, 2)] <= 128 and spills[(1, 1)] <= 32, spills
+
+
 # ---- reference-facing module -----------------------------------------------------------------------
 def test_model_has_reference_state_dict_and_no_cpu_path(built_library, golden):
     import models
