@@ -15,17 +15,18 @@
 //
 // GEMM view per CTA: M = 128 output pixels (tile 16 rows x 8 cols), N = N_TILE <= 128 output channels,
 // K = taps x Cin (+ Cin2 of the fused 1x1 skip conv).
-//   * A (activations): the (16+k-1)x(8+k-1) input halo of a 32-channel K-block is staged ONCE in shared memory
-//     as [channel-quad][halo pixel][4 floats] (the canonical K-major / no-swizzle UMMA layout: core matrix =
-//     8 pixels x 16 B contiguous).  Because the tile is 8 pixels wide, the operand of tap (dy,dx) is the same
-//     buffer with start address + (dy*HW+dx)*16 B and stride-byte-offset HW*16 B: nine taps = nine descriptors.
+//   * A (activations): the (16+k-1)x(8+k-1) input halo of one K-block (32 or 16 channels) is staged ONCE in shared memory
+//     as pixel rows in the canonical K-major swizzled UMMA layout, hi plane then lo plane, with the halo row pitch padded
+//     to 16 pixels.  Because the tile is 8 pixels wide, the operand of tap (dy,dx) is the same buffer with its start
+//     address advanced by (dy*16+dx) rows: nine taps = nine descriptors, no im2col copies.
 //   * B (weights): pre-split hi/lo and pre-tiled on the host into the exact shared-memory image of each
-//     (K-block, tap, N-tile): a stage is one contiguous copy.
-//   * D: 128 lanes x N_TILE fp32 columns of TMEM; epilogue = tcgen05.ld 32x32b, bias/residual/ReLU, NHWC store
-//     (or pixel-shuffle for ConvTranspose k2s2, or planar store for the final layers).
-// Warp roles: warps 0-3 stage operands (A ring of 2, B ring of 3, mbarrier full/empty pairs; MMA completion
-// frees a slot through tcgen05.commit) and run the epilogue (warp w owns TMEM lanes 32w..32w+31); warp 4
-// allocates TMEM and one elected lane issues every tcgen05.mma.
+//     (K-block, tap, N-tile): whole image resident, one N tile resident, or streamed per tap by TMA bulk copies.
+//   * D: 128 lanes x N_TILE fp32 columns of TMEM (two buffers, D1|D2 side by side in the fp16 modes); epilogue =
+//     tcgen05.ld 32x32b, D1 + 2^-11 D2, bias/residual/ReLU, NHWC store (or pixel-shuffle for ConvTranspose k2s2, or planar
+//     store for the final layers).
+// Warp roles (14 warps, see the kernel): 8 loader warps | MMA issuer + TMEM owner | weight TMA producer | 4 epilogue warps,
+// connected by mbarrier full/empty rings; MMA completion frees a slot through tcgen05.commit.
+// DESIGN.md 4.1 has the measured hardware facts this layout rests on and what bounds the kernel.
 #include <cuda_fp16.h>
 
 #include <cstdio>
@@ -245,11 +246,11 @@ __device__ __forceinline__ bool tc_decode(const TcArgs& t, int item, TcItem& w) 
   return !(t.c.valid && !t.c.valid[w.img]);
 }
 
-// Persistent CTA (one per SM), 10 warps:
-//   warps 0-3  A staging   : halo of the next K-block -> tf32 hi/lo planes            (a_full / a_empty ring)
-//   warp  4    MMA issue   : one lane issues every tcgen05.mma; owns the TMEM allocation
-//   warp  5    B producer  : one lane issues one TMA bulk copy per (K-block, tap)       (b_full / b_empty ring)
-//   warps 6-9  epilogue    : tcgen05.ld of the finished accumulator, bias/residual/ReLU, stores
+// Persistent CTA (one or two per SM), 14 warps:
+//   warps 0-7    A staging   : halo of the next K-block -> hi/lo planes                   (a_full / a_empty ring)
+//   warp  8      MMA issue   : one elected lane issues every tcgen05.mma; owns the TMEM allocation
+//   warp  9      B producer  : one lane issues the weight TMA bulk copies                 (b_full / b_empty ring)
+//   warps 10-13  epilogue    : tcgen05.ld of the finished accumulator, bias/residual/ReLU, stores
 // Two accumulator buffers in TMEM (acc_full / acc_empty) let the MMAs of tile i+1 run under the epilogue of
 // tile i, and the staging of tile i+1 under the MMAs of tile i.
 // MODE 0: 3xTF32, 32-channel K-blocks (128-B rows, SWIZZLE_128B); MODE 1: fp16 split, 32-channel K-blocks (64-B rows,
