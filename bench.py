@@ -268,12 +268,15 @@ def main():
     for i in range(3):
         eng.forward(pool_dev[i % POOL], slots)
     sync_all()
-    ev0.record()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(ser_steps + 1)]
+    marks[0].record()
     for i in range(ser_steps):
         eng.forward(pool_dev[i % POOL], slots)
-    ev1.record()
+        marks[i + 1].record()
     sync_all()
-    serial_ms = ev0.elapsed_time(ev1) / ser_steps
+    serial_ms = marks[0].elapsed_time(marks[-1]) / ser_steps
+    per_step = np.array([marks[i].elapsed_time(marks[i + 1]) for i in range(ser_steps)])     # per-frame latency distribution
+    serial_p50, serial_p95 = float(np.percentile(per_step, 50)), float(np.percentile(per_step, 95))
 
     # ---- e2e through the host-buffer entry point -----------------------------------------------------
     # (a) blocking call (fvp_forward_host): per-call latency; (b) the two-deep pipeline (fvp_submit_host / fvp_wait):
@@ -396,6 +399,7 @@ def main():
                 "blocking_call_ms": sync_call_ms},
         "roofline": roofline, "cpu_baseline": cpu_base, "kernels": extra_kernels, "valid_people_last_step": n_valid,
         "cuda_graph": not args.no_graph, "serial_ms_per_step": serial_ms, "serial_fps": world * B / (serial_ms * 1e-3),
+        "serial_ms_p50": serial_p50, "serial_ms_p95": serial_p95,
     }
     _emit(line)
     if world > 1:

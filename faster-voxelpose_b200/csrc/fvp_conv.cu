@@ -207,6 +207,14 @@ void fvp_launch_maxpool2(const float* in, float* out, int n, int H, int W, int C
 // trunk program: front_layers + EncoderDecorder (+ heads), cnns_2d.py:94-135,173-178
 // ------------------------------------------------------------------------------------------------
 static int g_tc = 0;   // set by fvp_run_trunk2d for the duration of one (single-threaded) trunk enqueue
+static int num_sms() {                       // SM count of the current device (148 on B200), queried once
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    return v;
+  }();
+  return n;
+}
 static void conv(const FvpConvW& w, const float* in, int H, int W, const float* in2, float* out, int couts,
                  const float* res, int res_mode, int relu, int upsample, int n, const int* valid, int* launches,
                  cudaStream_t st, int nchw = 0, int cout_real = 0) {
@@ -220,9 +228,9 @@ static void conv(const FvpConvW& w, const float* in, int H, int W, const float* 
   // engine 2: fp16-split tcgen05 kernel (all layers); engine 1: 3xTF32 tcgen05 kernel, where the 7x7 front conv (49 taps
   // of half-empty 32-channel K-blocks, measured 6.6 vs 11.4 TMAC/s) stays on the CUDA-core kernel; engine 0: CUDA cores.
   const float* const c16[3] = {w.wtc16_c16, nullptr, nullptr};
-  if (g_tc == 2 && w.wtc16_c16) fvp_launch_conv_tc(a, c16, 2, 148, st);                       // <= 16 input channels
-  else if (g_tc == 2 && w.wtc16[0]) fvp_launch_conv_tc(a, w.wtc16, 1, 148, st);
-  else if (g_tc == 1 && w.wtc[0] && w.k != 7) fvp_launch_conv_tc(a, w.wtc, 0, 148, st);
+  if (g_tc == 2 && w.wtc16_c16) fvp_launch_conv_tc(a, c16, 2, num_sms(), st);                       // <= 16 input channels
+  else if (g_tc == 2 && w.wtc16[0]) fvp_launch_conv_tc(a, w.wtc16, 1, num_sms(), st);
+  else if (g_tc == 1 && w.wtc[0] && w.k != 7) fvp_launch_conv_tc(a, w.wtc, 0, num_sms(), st);
   else fvp_launch_conv(a, st);
   if (launches) ++*launches;
 }
