@@ -91,6 +91,11 @@ class FasterVoxelPoseNet(nn.Module):
             input_heatmaps = torch.stack([backbone(views[:, c]) for c in range(num_views)], dim=1)
         eng = self.engine()
         B = input_heatmaps.shape[0]
+        if len(set(meta["seq"][:B])) > eng.max_sequences:
+            # every calibration of a batch needs its own device slot (camera block + sample-grid caches); recycling one
+            # while the batch is assembled would silently project some frames with another sequence's cameras
+            raise ValueError("batch mixes %d sequences but the model was built for max_sequences=%d"
+                             % (len(set(meta["seq"][:B])), eng.max_sequences))
         slots = []
         for i in range(B):
             seq = meta["seq"][i]
