@@ -137,6 +137,23 @@ def cpu_reference_fps(cfg, cams, resize, frames: np.ndarray, sd_np, warm: int, s
     return len(ts) / sum(ts), torch.get_num_threads(), float(np.median(ts)) * 1e3
 
 
+def conv_tensor_rooflines(stage_ms: dict, batch: int, people_per_frame: int, J: int, grid_xy, peak_tflops: float) -> dict:
+    """Tensor-pipe figures of the two conv trunks from their CUDA-event stage times.  useful = 2 x MACs of the reference
+    layers (fvp.netspec); executed = 3 x useful: the fp16 hi/lo split issues A_hi*B_hi, A_hi*B_lo and
+    A_lo*B_hi (csrc/fvp_conv_tc.cu).  peak = dense bf16/fp16 TFLOP/s measured on this pool (MEASURED_PEAKS.json)."""
+    from fvp import netspec
+    out = {}
+    work = {"p2p_net": netspec.macs_per_image(netspec.p2p_net(J), (64, 64)) * 3 * people_per_frame * batch,
+            "center_net": netspec.macs_per_image(netspec.center_net(J), tuple(grid_xy)) * batch}
+    for name, macs in work.items():
+        ms = float(stage_ms[name])
+        useful = 2.0 * macs / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        out[name] = {"bound": "tensor", "ms": ms, "gmac": macs / 1e9, "useful_tflops": useful, "executed_tflops": 3.0 * useful,
+                     "peak": peak_tflops, "unit": "TFLOP/s", "frac_useful": useful / peak_tflops,
+                     "frac_executed": 3.0 * useful / peak_tflops}
+    return out
+
+
 def _emit(line: dict) -> None:
     """Exactly one JSON line on the real stdout (library chatter such as NCCL's version banner goes to stderr)."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -376,6 +393,13 @@ def main():
         "stage_ms": {n: float(v) for n, v in zip(["k0_stage", "k1_hdn_project", "center_net", "nms_topk", "proposals_c2c",
                                                   "k3_jln_project", "p2p_net", "pose_head", "total"], stage)},
     }
+
+    try:        # secondary rooflines (tensor pipe) of the conv trunks; never allowed to take the bench line down
+        extra_kernels["conv_tensor_pipe"] = conv_tensor_rooflines(
+            extra_kernels["stage_ms"], B, max(1, n_valid // B), J, [int(v) for v in cfg.CAPTURE_SPEC.VOXELS_PER_AXIS[:2]],
+            float(peaks.get("bf16_tflops", 2250.0)))
+    except Exception as e:      # pragma: no cover
+        extra_kernels["conv_tensor_pipe"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:

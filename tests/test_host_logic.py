@@ -87,6 +87,18 @@ def test_library_is_sm100a_with_lineinfo(built_library):
     assert "sm_100a" in out
 
 
+def test_bench_conv_tensor_rooflines():
+    """bench.py's tensor-pipe figures: useful FLOPs = 2 x reference MACs, executed = 3 x (hi/lo split), against a given peak."""
+    import bench
+    st = {"p2p_net": 0.352, "center_net": 0.178}
+    r = bench.conv_tensor_rooflines(st, 1, 10, 15, (80, 80), 1635.6)
+    assert abs(r["p2p_net"]["gmac"] - 18.618) < 0.01 and abs(r["center_net"]["gmac"] - 1.085) < 0.002
+    assert abs(r["p2p_net"]["useful_tflops"] - 2 * 18.618 / 0.352) < 0.1           # GMAC / ms = TMAC/s
+    assert abs(r["p2p_net"]["frac_executed"] - 3 * r["p2p_net"]["useful_tflops"] / 1635.6) < 1e-12
+    r32 = bench.conv_tensor_rooflines({"p2p_net": 6.38, "center_net": 0.65}, 32, 10, 15, (80, 80), 1635.6)
+    assert abs(r32["p2p_net"]["useful_tflops"] - 2 * 32 * 18.618 / 6.38) < 0.5
+
+
 def test_two_cta_conv_variants_do_not_spill_more_than_measured(built_library):
     """The 72-register variants of k_conv_tc (two CTAs per SM) run beside 2 x 111 KB of shared memory, i.e. with 28 KB of L1:
     ptxas spills beyond the sizes measured fast on B200 (profiles/r01_s5_conv_layers_final.txt) cost up to 45 % on the
