@@ -85,6 +85,14 @@ _DEFAULTS: Dict[str, Any] = {
         "SIGMA": 3,
         "BETA": 100.0,
     },
+    "RESNET": {                       # lib/core/config.py:101-108 (pose_resnet backbone)
+        "NUM_LAYERS": 50,
+        "DECONV_WITH_BIAS": False,
+        "NUM_DECONV_LAYERS": 3,
+        "NUM_DECONV_FILTERS": [256, 256, 256],
+        "NUM_DECONV_KERNELS": [4, 4, 4],
+        "FINAL_CONV_KERNEL": 1,
+    },
     "TRAIN": {
         "BATCH_SIZE": 8,
         "SHUFFLE": True,

@@ -37,6 +37,31 @@ class Rng:
 # ----------------------------------------------------------------------------------------------
 # weights
 # ----------------------------------------------------------------------------------------------
+def make_backbone_weights(layers, seed: int = 0) -> Dict[str, np.ndarray]:
+    """state_dict (numpy) of the PoseResNet backbone described by ``fvp.backbone_spec`` layers, keyed like the reference's.
+
+    conv: U(-b, b) with b = sqrt(3 / fan_in) (unit gain, so activations neither die nor explode over 50 layers);
+    BatchNorm: gamma U(0.7,1.3) - U(0.15,0.35) on the last BN of a residual block so the residual sum stays O(1) -
+    beta / running_mean U(-0.1,0.1), running_var U(0.6,1.4); ``num_batches_tracked`` = 0."""
+    rng = Rng(seed)
+    sd: Dict[str, np.ndarray] = {}
+    for c in layers:
+        fan_in = (c.cout if c.transposed else c.cin) * c.k * c.k
+        b = math.sqrt(3.0 / fan_in)
+        shape = (c.cin, c.cout, c.k, c.k) if c.transposed else (c.cout, c.cin, c.k, c.k)
+        sd[c.key + ".weight"] = rng.uniform(shape, -b, b)
+        if c.bias:
+            sd[c.key + ".bias"] = rng.uniform((c.cout,), -0.1, 0.1)
+        if c.bn:
+            lo, hi = (0.15, 0.35) if c.role == "last" else (0.7, 1.3)
+            sd[c.bn + ".weight"] = rng.uniform((c.cout,), lo, hi)
+            sd[c.bn + ".bias"] = rng.uniform((c.cout,), -0.1, 0.1)
+            sd[c.bn + ".running_mean"] = rng.uniform((c.cout,), -0.1, 0.1)
+            sd[c.bn + ".running_var"] = rng.uniform((c.cout,), 0.6, 1.4)
+            sd[c.bn + ".num_batches_tracked"] = np.zeros((), np.int64)
+    return sd
+
+
 def make_weights(J: int, seed: int = 0, feat: int = 32, hidden: int = 64,
                  p2p_out_gain: float = 0.25, hm_head_bias: float = 0.5,
                  c2c_head_bias: float = 0.5, c2c_in_gain: float = 4.0, wn_in_gain: float = 20.0,
