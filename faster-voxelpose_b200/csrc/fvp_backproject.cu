@@ -189,6 +189,22 @@ __device__ __forceinline__ void fvp_red_max4(float4* dst, float4 m) {
   if (m.w > 0.0f) atomicMax(p + 3, __float_as_uint(m.w));
 }
 
+#ifdef FVP_K3_SPLIT_BARRIER
+__device__ __forceinline__ void fvp_k3_bar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void fvp_k3_bar_arrive(uint64_t* bar) {      // release: the chunk image written before is visible
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fvp_k3_bar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // One CTA = one person x one compact patch of 8 cube rows a (one per warp) x BPW = 32/CG cube columns b x one depth
 // part.  A pass of the patch over one view and one chunk of CG depths touches a compact ~(8*1.5)^2-pixel window of the
@@ -248,6 +264,35 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
   const bool sample_ok = ch_ok && b_ok && a_ok;
   const int s_me = ch_ok ? s : JG - 1;           // idle channel-group lanes re-read the last group (same sectors)
 
+#ifdef FVP_K3_SPLIT_BARRIER
+  // the two cross-thread maxima of one chunk image (depths cc0 .. cc0+CCH-1), folded into the planes
+  auto reduce_chunk = [&](float4(*yzb)[8][32], int cc0) {
+    constexpr int N_YZ = CCH * 32;               // yz outputs of the chunk: (depth, b, channel group)
+    constexpr int N_XZ = 8 * CCH * CG;           // xz outputs of the chunk: (row, depth, channel group)
+    for (int o = tid; o < N_YZ + N_XZ; o += 256) {
+      if (o < N_YZ) {                            // yz[b][cc0 + c] = max over the 8 rows of the patch
+        const int c = o >> 5, l = o & 31, ss = l % CG;
+        if (ss < JG) {
+          float4 m = yzb[c][0][l];
+#pragma unroll
+          for (int w = 1; w < 8; ++w) m = fvp_max4(m, yzb[c][w][l]);
+          fvp_red_max4(yz_img + ((size_t)(bblk * BPW + l / CG) * 64 + cc0 + c) * JG + ss, m);
+        }
+      } else {                                   // xz[a][cc0 + c] = max over the BPW columns of the patch
+        const int x = o - N_YZ, ss = x % CG, c = (x / CG) % CCH, w = x / (CG * CCH);
+        if (ss < JG) {
+          float4 m = yzb[c][w][ss];
+#pragma unroll
+          for (int i = 1; i < BPW; ++i) m = fvp_max4(m, yzb[c][w][i * CG + ss]);
+          fvp_red_max4(xz_img + ((size_t)(ablk * 8 + w) * 64 + cc0 + c) * JG + ss, m);
+        }
+      }
+    }
+  };
+  __shared__ uint64_t s_bar[2];
+  if (tid == 0) { fvp_k3_bar_init(&s_bar[0], 256); fvp_k3_bar_init(&s_bar[1], 256); }
+  __syncthreads();
+#endif
   float4 xy_m = zero4;
   int it = 0;
   for (int cc = c_begin; cc < c_end; cc += CCH, ++it) {
@@ -294,6 +339,44 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
     // mean + clamp + the three maxima of this chunk.  Both cross-thread maxima go through ONE shared-memory image of
     // the chunk ([depth][row][lane]): a partial-mask REDUX per channel group costs a serialised collective per mask
     // (CREDUX + ENDCOLLECTIVE + BSSY/BSYNC were ~20 % of the instructions and ~35 % of the stall samples in ncu).
+#ifdef FVP_K3_SPLIT_BARRIER
+    // Experimental (off by default, not yet measured on a B200): split-phase barrier.  The values of chunk i stay in
+    // registers while the thread waits for and reduces chunk i-1 (whose writers arrived a whole sampling pass ago), then
+    // they are written and the thread arrives for chunk i: nobody waits for the slowest warp of the CURRENT chunk
+    // (ncu: 14 % of K3's stall samples sit on the per-chunk __syncthreads).  Two buffers suffice: a thread overwrites
+    // buffer b only after its wait for the other buffer's phase, which completes after every thread has left reduce(b).
+    // (the 8-lane-group instantiation has a single buffer and keeps the classic barrier)
+    float4 vals[CCH];
+#pragma unroll
+    for (int c = 0; c < CCH; ++c) {
+      const bool c_in = (cc + c) >= pd.lo[2] && (cc + c) < pd.hi[2];
+      vals[c] = (sample_ok && c_in) ? fvp_mean_clamp4(acc[c], fV, rV) : zero4;
+      xy_m = fvp_max4(xy_m, vals[c]);
+    }
+    if constexpr (NBUF == 2) {
+      if (it > 0) {
+        fvp_k3_bar_wait(&s_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        reduce_chunk(s_yz[(it - 1) & 1], cc - CCH);
+      }
+      float4(*yzw)[8][32] = s_yz[it & 1];
+#pragma unroll
+      for (int c = 0; c < CCH; ++c) yzw[c][warp][lane] = vals[c];
+      fvp_k3_bar_arrive(&s_bar[it & 1]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CCH; ++c) s_yz[0][c][warp][lane] = vals[c];
+      __syncthreads();
+      reduce_chunk(s_yz[0], cc);
+      __syncthreads();
+    }
+  }
+  if constexpr (NBUF == 2) {
+    if (it > 0) {                                // the last chunk
+      fvp_k3_bar_wait(&s_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      reduce_chunk(s_yz[(it - 1) & 1], c_end - CCH);
+    }
+  }
+#else
     float4(*yzb)[8][32] = s_yz[NBUF == 2 ? (it & 1) : 0];
 #pragma unroll
     for (int c = 0; c < CCH; ++c) {
@@ -326,6 +409,7 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
     }
     if (NBUF == 1) __syncthreads();
   }
+#endif
   if (ch_ok) {
     if (ncpart == 1) xy_img[((size_t)a * 64 + b) * JG + s] = xy_m;           // complete: plain store
     else fvp_red_max4(xy_img + ((size_t)a * 64 + b) * JG + s, xy_m);          // partial over the depth parts
