@@ -37,7 +37,10 @@
 namespace {
 
 constexpr int TC_TH = 16, TC_TW = 8;       // output tile (pixels)
-constexpr int TC_LOADERS = 256;            // warps 0..7: A staging
+#ifndef FVP_TC_LOADERS
+#define FVP_TC_LOADERS 256                 // experiment switch: -DFVP_TC_LOADERS=512 = 16 loader warps (one CTA per SM only)
+#endif
+constexpr int TC_LOADERS = FVP_TC_LOADERS; // warps 0..7: A staging
 constexpr int TC_LW = TC_LOADERS / 32;     // warp 8 = MMA issuer / TMEM owner, warp 9 = weight TMA producer, warps 10-13 = epilogue
 constexpr int TC_THREADS = TC_LOADERS + 64 + 128;
 constexpr int TC_EPI = 128;
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
       mbar_arrive(a_full + as);
       ++a_it;
     };
-    if constexpr (OCC == 1) {
+    if constexpr (OCC == 1 && TC_LOADERS == 256) {
       float4 va[EPT][NV], vb[EPT][NV];
       KBlock ka, kb;
       bool more = advance(ka);
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
         ch = co - q * Co;
         return (px_plain + (size_t)(q >> 1) * Wo + (q & 1)) * a.CoutS;
       };
-      constexpr int CW = OCC == 2 ? 8 : 16, G4 = CW / 4;         // columns per chunk (8 keeps the 2-CTA variant in 72 registers)
+      constexpr int CW = (OCC == 2 || TC_LOADERS != 256) ? 8 : 16, G4 = CW / 4;         // columns per chunk (8 keeps the 2-CTA variant in 72 registers)
       auto fetch_res = [&](int cb, float4* rr) {                   // residuals of one chunk, issued early
 #pragma unroll
         for (int g4 = 0; g4 < G4; ++g4) rr[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -799,7 +802,7 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   // faster with two CTAs per SM; the 3x3 16->32 layer (16-channel K-blocks, loader-bound) is 9 % slower and keeps one.
   // (Also tried and dropped: one LDG.128 per lane over whole 128-B lines with 8-byte shared stores - fewer L1 sector
   //  lookups but twice the store instructions: 3 % slower over the trunk's layer mix.)
-  const bool occ2 = g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
+  const bool occ2 = TC_LOADERS == 256 && g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
   const int slots = num_sms * (occ2 ? 2 : 1);
   int grid = t.total_items < slots ? t.total_items : slots;              // persistent: one or two CTAs per SM
   if (t.resident == 2) grid -= grid % t.n_tiles;                         // CTA b serves N tile b % n_tiles only
