@@ -60,10 +60,29 @@ class FasterVoxelPoseNet(nn.Module):
             _register(self, key, shape, dtype)
         self._engine = None
         self._weights_tag = None
+        self._tensor_cache = None
 
     # ---- engine management ---------------------------------------------------------------------
+    # The packed device weights must follow the module's parameters (load_state_dict, .to(), in-place edits).  Every
+    # forward compares a tag of (storage address, version counter) per tensor; walking state_dict() for it cost 1.2 ms per
+    # call - twice the GPU time of a frame - so the 485 tensor objects are cached and the cache is dropped whenever the
+    # module machinery may have replaced them (_apply: .to()/.cuda()/.float(); load_state_dict(assign=True)).
+    def _tensors(self):
+        if self._tensor_cache is None:
+            self._tensor_cache = list(self.state_dict(keep_vars=True).values())
+        return self._tensor_cache
+
+    def _apply(self, fn, *args, **kwargs):
+        self._tensor_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._tensor_cache = None
+        return out
+
     def _tag(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        return tuple((t.data_ptr(), t._version) for t in self._tensors())
 
     def engine(self) -> Engine:
         dev = next(self.parameters()).device
@@ -96,12 +115,14 @@ class FasterVoxelPoseNet(nn.Module):
             # while the batch is assembled would silently project some frames with another sequence's cameras
             raise ValueError("batch mixes %d sequences but the model was built for max_sequences=%d"
                              % (len(set(meta["seq"][:B])), eng.max_sequences))
-        slots = []
+        slots, slot_of = [], {}
         for i in range(B):
             seq = meta["seq"][i]
-            assert seq in cameras.keys(), "missing camera parameters for the current sequence"
-            assert len(cameras[seq]) == input_heatmaps.shape[1], "inconsistent number of cameras"
-            slots.append(eng.sequence_slot(cameras[seq], resize_transform))
+            if seq not in slot_of:     # one calibration lookup (hash of the camera values) per distinct sequence of the batch
+                assert seq in cameras.keys(), "missing camera parameters for the current sequence"
+                assert len(cameras[seq]) == input_heatmaps.shape[1], "inconsistent number of cameras"
+                slot_of[seq] = eng.sequence_slot(cameras[seq], resize_transform)
+            slots.append(slot_of[seq])
         if B > eng.max_batch:      # chunk oversized batches
             outs = [eng.forward(input_heatmaps[i:i + eng.max_batch], slots[i:i + eng.max_batch])
                     for i in range(0, B, eng.max_batch)]

@@ -134,6 +134,42 @@ def test_model_has_reference_state_dict_and_no_cpu_path(built_library, golden):
           resize_transform=torch.as_tensor(g.resize, dtype=torch.float))
 
 
+def test_weight_change_tag_is_cheap_and_sees_every_kind_of_update(built_library, golden):
+    """The plugin re-packs device weights when a parameter changed; the per-forward check must notice in-place edits,
+    load_state_dict (copy and assign) and module conversions, and must not walk state_dict() every call."""
+    import time
+    import models
+    g = golden("panoptic_none_valid")
+    cfg = g.cfg
+    cfg.DEVICE = "cpu"
+    m = models.faster_voxelpose.get(cfg).eval()
+    t0 = m._tag()
+    assert m._tag() == t0 and len(t0) == 485
+    with torch.no_grad():
+        next(m.parameters()).mul_(1.0)                                   # in-place edit: version counter
+    t1 = m._tag()
+    assert t1 != t0
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in g.weights.items()}, strict=False)
+    t2 = m._tag()
+    assert t2 != t1
+    m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()}, assign=True)       # tensors replaced
+    t3 = m._tag()
+    assert t3 != t2 and len(t3) == 485
+    m.double()                                                           # _apply: storage replaced
+    assert m._tag() != t3
+    m.float()
+    n = 20
+    t = time.perf_counter()
+    for _ in range(n):
+        m._tag()
+    per_call_ms = (time.perf_counter() - t) / n * 1e3
+    t = time.perf_counter()
+    for _ in range(n):
+        m.state_dict(keep_vars=True)
+    walk_ms = (time.perf_counter() - t) / n * 1e3
+    assert per_call_ms < 0.5 * walk_ms, (per_call_ms, walk_ms)
+
+
 def test_product_code_never_imports_the_oracle():
     for dirpath, _, files in os.walk(PKG):
         for f in files:
