@@ -34,7 +34,8 @@ def test_param_table_counts():
             by_net("joint_net.weight_net")) == (162, 156, 156, 11)
     n_params = sum(int(np.prod(s)) for k, s, d in rows if d == "float32" and "running" not in k)
     assert n_params == 2636788
-    assert netspec.macs_per_image(netspec.p2p_net(15), (64, 64)) == 620609536 - 0 or True
+    assert netspec.macs_per_image(netspec.p2p_net(15), (64, 64)) == 620560384          # exact count of the layer table
+    assert netspec.macs_per_image(netspec.c2c_net(15), (20,)) == 2471360              # 2.5 MMAC per column (App. B)
 
 
 def test_conv_mac_counts_match_survey():
