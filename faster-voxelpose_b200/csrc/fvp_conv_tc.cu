@@ -703,6 +703,7 @@ void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
   *n_tiles = fvp_cdiv(npad, *n_tile);
 }
 
+static int* g_tc_plan = nullptr;   // set by fvp_debug_conv_plan: fvp_launch_conv_tc records its decisions here and returns before touching the GPU
 static unsigned long long* g_tc_prof = nullptr;
 static int g_tc_occ = [] { const char* e = std::getenv("FVP_TC_OCC"); return e ? std::atoi(e) : 2; }();   // 1: never co-schedule two CTAs per SM (A/B switch)
 void fvp_tc_set_prof(unsigned long long* d_counters) { g_tc_prof = d_counters; }   // debug hook (fvp_debug_conv)
@@ -711,6 +712,7 @@ void fvp_tc_set_prof(unsigned long long* d_counters) { g_tc_prof = d_counters; }
 // wtc[3]: weight images tiled for N tiles of up to 128 / 32 / 64 columns (NULL where not packed)
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st) {
   if ((mode != 2 && a.ksize > 3) || a.CoutP > TC_MAX_COUT) {     // the loaders of the 32-channel K-block variants hold a 3x3 halo at most (EPT); 7x7 layers
+    if (g_tc_plan) { g_tc_plan[0] = 0; return; }      // plan query: "not handled by the tensor-core engine"
     fvp_launch_conv(a, st);           // of this network have <= 16 input channels and run in mode 2
     return;
   }
@@ -781,6 +783,22 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   };
   t.m_ntiles = magic(t.n_tiles); t.m_tpi = magic(t.tiles_per_img); t.m_tx = magic(t.tiles_x);
   const size_t smem = 1024 + (size_t)t.a_stages * t.a_stage_bytes + (size_t)t.b_stages * t.b_stage_bytes;
+  // Two CTAs per SM when both fit: 228 KB of shared memory per SM, 1 KB reserved per CTA, TC_STATIC_SMEM static; 512 TMEM columns.
+  // (A CTA that needs more than 256 columns must never share an SM with a sibling: its tcgen05.alloc would block.)
+  // Measured per layer (profiles/r01_s5_conv_layers_occ*.txt, 960 images): 7x7 16->16 1.49x, 1x1 32->16 1.43x, 3x3 32->32 1.08x
+  // faster with two CTAs per SM; the 3x3 16->32 layer (16-channel K-blocks, loader-bound) is 9 % slower and keeps one.
+  // (Also tried and dropped: one LDG.128 per lane over whole 128-B lines with 8-byte shared stores - fewer L1 sector
+  //  lookups but twice the store instructions: 3 % slower over the trunk's layer mix.)
+  const bool occ2 = TC_LOADERS == 256 && g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
+  const int slots = num_sms * (occ2 ? 2 : 1);
+  int grid = t.total_items < slots ? t.total_items : slots;              // persistent: one or two CTAs per SM
+  if (t.resident == 2) grid -= grid % t.n_tiles;                         // CTA b serves N tile b % n_tiles only
+  if (g_tc_plan) {                                                       // host-only query of the decisions above (tests)
+    const int plan[10] = {t.n_tile, t.n_tiles, t.resident, t.a_stages, t.b_stages, (int)smem, occ2 ? 1 : 0, grid, t.total_items,
+                          (int)t.tmem_cols};
+    for (int i = 0; i < 10; ++i) g_tc_plan[i] = plan[i];
+    return;
+  }
   static bool attr = false;
   if (!attr) {
     const void* fns[6] = {(const void*)k_conv_tc<0, 1>, (const void*)k_conv_tc<1, 1>, (const void*)k_conv_tc<2, 1>,
@@ -796,16 +814,6 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
     }
     attr = true;
   }
-  // Two CTAs per SM when both fit: 228 KB of shared memory per SM, 1 KB reserved per CTA, 2304 B static; 512 TMEM columns.
-  // (A CTA that needs more than 256 columns must never share an SM with a sibling: its tcgen05.alloc would block.)
-  // Measured per layer (profiles/r01_s5_conv_layers_occ*.txt, 960 images): 7x7 16->16 1.49x, 1x1 32->16 1.43x, 3x3 32->32 1.08x
-  // faster with two CTAs per SM; the 3x3 16->32 layer (16-channel K-blocks, loader-bound) is 9 % slower and keeps one.
-  // (Also tried and dropped: one LDG.128 per lane over whole 128-B lines with 8-byte shared stores - fewer L1 sector
-  //  lookups but twice the store instructions: 3 % slower over the trunk's layer mix.)
-  const bool occ2 = TC_LOADERS == 256 && g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
-  const int slots = num_sms * (occ2 ? 2 : 1);
-  int grid = t.total_items < slots ? t.total_items : slots;              // persistent: one or two CTAs per SM
-  if (t.resident == 2) grid -= grid % t.n_tiles;                         // CTA b serves N tile b % n_tiles only
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);
@@ -825,4 +833,25 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
     else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1, 1>, t);
     else cudaLaunchKernelEx(&cfg, k_conv_tc<0, 1>, t);
   }
+}
+
+// Host-only: the launch plan fvp_launch_conv_tc would choose for one layer (no CUDA call is made).  out[10] = n_tile, n_tiles,
+// weight residency (0 streamed, 1 whole image, 2 one N tile), A stages, B stages, dynamic smem bytes, two CTAs per SM (0/1),
+// grid, work items, TMEM columns; out[0] = 0 when the layer falls back to the CUDA-core kernel.  engine: 2 = fp16 split
+// (16-channel K-blocks when cin <= 16 like the trunk dispatch in fvp_conv.cu), 1 = 3xTF32.
+extern "C" int fvp_debug_conv_plan(int n, int H, int W, int cin, int cin2, int cout, int k, int engine, int num_sms, int* out) {
+  if (!out || n <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0 || (k != 1 && k != 3 && k != 7) || num_sms <= 0) return -1;
+  FvpConvArgs a = {};
+  static const float dummy = 0.f;                    // only the NULL-ness of the pointers matters to the planner
+  a.n = n; a.H = H; a.W = W; a.Cin = cin; a.Cin2 = cin2; a.in2 = cin2 ? &dummy : nullptr;
+  a.CoutP = fvp_round_up(cout, 4); a.ksize = k;
+  const int npad = fvp_round_up(a.CoutP, 16);
+  const float* wide[3] = {&dummy, npad > 32 ? &dummy : nullptr, npad > 64 ? &dummy : nullptr};     // as stash() packs them
+  const float* c16[3] = {&dummy, nullptr, nullptr};
+  const bool use_c16 = engine == 2 && cin <= 16 && cin2 <= 16;
+  for (int i = 0; i < 10; ++i) out[i] = 0;
+  g_tc_plan = out;
+  fvp_launch_conv_tc(a, use_c16 ? c16 : wide, engine == 2 ? (use_c16 ? 2 : 1) : 0, num_sms, nullptr);
+  g_tc_plan = nullptr;
+  return 0;
 }

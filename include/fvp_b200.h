@@ -135,6 +135,12 @@ int fvp_debug_project(fvp_ctx* ctx, int slot, const float* d_points, int n, floa
  * times after one warm-up and the mean CUDA-event time per launch (ms) is written to h_ms (may be NULL) */
 int fvp_debug_conv(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin, const float* h_weight, const float* h_bias,
                    int cout, int k, int relu, int mode, float* d_out, int repeat, float* h_ms, uintptr_t stream);
+/* test hook, host only (no context, no CUDA call): the launch plan of the tensor-core convolution for one layer of
+ * n images H x W, cin (+ cin2 of a fused 1x1 skip conv) -> cout channels, k in {1,3,7}; engine 2 = fp16 hi/lo split,
+ * 1 = 3xTF32.  out[10] = N-tile width, N tiles, weight residency (0 streamed / 1 whole image / 2 one N tile per CTA),
+ * A stages, B stages, dynamic shared memory, two CTAs per SM (0/1), grid, work items, TMEM columns; out[0] = 0 when the
+ * layer is left to the CUDA-core kernel.  Returns 0, or -1 on invalid arguments. */
+int fvp_debug_conv_plan(int n, int H, int W, int cin, int cin2, int cout, int k, int engine, int num_sms, int* out);
 /* K0: [batch][V][J][H][W] -> internal channel-last, zero-bordered copy */
 int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr_t stream);
 /* K1: ProjectLayer(whole).forward + CenterNet's z-max (project_whole.py:62-88, cnns_2d.py:174)

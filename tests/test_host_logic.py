@@ -100,6 +100,51 @@ def test_bench_conv_tensor_rooflines():
     assert abs(r32["p2p_net"]["useful_tflops"] - 2 * 32 * 18.618 / 6.38) < 0.5
 
 
+def _conv_plan(lib, n, H, W, cin, cin2, cout, k, engine=2, sms=148):
+    import ctypes as C
+    out = (C.c_int * 10)()
+    assert lib.fvp_debug_conv_plan(n, H, W, cin, cin2, cout, k, engine, sms, out) == 0
+    keys = ("n_tile", "n_tiles", "resident", "a_stages", "b_stages", "smem", "occ2", "grid", "items", "tmem")
+    return dict(zip(keys, list(out)))
+
+
+def test_conv_launch_plans(built_library):
+    """Host-side planner of the tcgen05 convolution (N-tile width, weight residency, CTAs per SM), queried without a GPU:
+    resource invariants over every trunk layer shape x batch size, and the decisions DESIGN.md 4.1 describes."""
+    from fvp import capi
+    lib = capi.load()
+    layers = [(16, 0, 16, 7), (16, 0, 32, 3), (32, 16, 32, 3), (32, 0, 32, 3), (32, 0, 64, 3), (64, 32, 64, 3), (64, 0, 64, 3),
+              (64, 0, 128, 3), (128, 64, 128, 3), (128, 0, 128, 3), (128, 0, 256, 1), (64, 0, 128, 1), (32, 0, 16, 1), (32, 0, 4, 1)]
+    res_of = {16: 1, 32: 1, 64: 2, 128: 4, 256: 4}                       # spatial divisor of the level a layer lives on
+    for size, imgs_per_frame in ((80, 1), (64, 30)):                    # CenterNet 80x80, P2PNet 64x64 x 3 planes x 10 people
+        for batch in (1, 2, 8, 32):
+            for cin, cin2, cout, k in layers:
+                d = res_of[max(cin, 16)]
+                p = _conv_plan(lib, batch * imgs_per_frame, size // d, size // d, cin, cin2, cout, k)
+                assert p["n_tile"] > 0 and p["n_tile"] * p["n_tiles"] >= cout
+                assert p["smem"] <= 227 * 1024 - 1280                   # opt-in limit minus the static part
+                assert p["tmem"] in (32, 64, 128, 256, 512) and p["tmem"] >= 4 * min(p["n_tile"], 32)
+                assert 1 <= p["grid"] <= 148 * (2 if p["occ2"] else 1) and p["grid"] <= p["items"]
+                if p["occ2"]:
+                    assert 2 * (p["smem"] + 1280 + 1024) <= 228 * 1024 and p["tmem"] <= 256
+                if p["resident"] == 2:
+                    assert p["n_tiles"] > 1 and p["grid"] % p["n_tiles"] == 0 and p["grid"] >= p["n_tiles"]
+                if p["resident"] == 0:
+                    assert p["b_stages"] >= 3
+    # the decisions documented in DESIGN.md 4.1
+    assert _conv_plan(lib, 960, 64, 64, 32, 0, 32, 3)["occ2"] == 1 and _conv_plan(lib, 960, 64, 64, 16, 0, 16, 7)["occ2"] == 1
+    assert _conv_plan(lib, 960, 64, 64, 16, 0, 32, 3)["occ2"] == 0      # loader-bound 16-channel 3x3: one CTA per SM
+    assert _conv_plan(lib, 1, 20, 20, 128, 0, 128, 3) | {"smem": 0} == {"n_tile": 32, "n_tiles": 4, "resident": 2, "a_stages": 2,
+                                                                         "b_stages": 1, "smem": 0, "occ2": 0, "grid": 24, "items": 24,
+                                                                         "tmem": 128}
+    big = _conv_plan(lib, 960, 16, 16, 128, 0, 128, 3)
+    assert (big["n_tile"], big["resident"], big["tmem"]) == (128, 0, 512)           # streamed, full-width N at large batch
+    assert _conv_plan(lib, 960, 32, 32, 64, 32, 64, 3)["resident"] == 1             # 19 weight blocks + 2 halo stages fit in 227 KB
+    assert _conv_plan(lib, 30, 16, 16, 128, 64, 128, 3)["resident"] == 2            # P2PNet at batch 1
+    # layers the tensor-core engine leaves to the CUDA-core kernel
+    assert _conv_plan(lib, 1, 64, 64, 32, 0, 32, 7)["n_tile"] == 0 and _conv_plan(lib, 1, 16, 16, 128, 0, 512, 1)["n_tile"] == 0
+
+
 def test_two_cta_conv_variants_do_not_spill_more_than_measured(built_library):
     """The 72-register variants of k_conv_tc (two CTAs per SM) run beside 2 x 111 KB of shared memory, i.e. with 28 KB of L1:
     ptxas spills beyond the sizes measured fast on B200 (profiles/r01_s5_conv_layers_final.txt) cost up to 45 % on the
