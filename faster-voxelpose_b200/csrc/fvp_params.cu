@@ -327,6 +327,27 @@ void bind_trunk(const float* base, const std::vector<PendingConv>& v, FvpTrunkW&
 
 }  // namespace
 
+// Host-only test hook: the fp16 hi/lo weight image pack_tc16 builds for the tensor-core convolution, from a BN-folded GEMM
+// matrix w_rows [(k*k*round_up(cin,16) + round_up(cin2,16))][coutp] (rows = (tap, input channel), then the fused skip conv's
+// channels).  variant 0/1/2 = N tiles of up to 128/32/64 columns, cb = channels per K-block (32, or 16 for <= 16-channel
+// layers).  Writes the image as halves; returns 0, -1 on bad arguments, -2 when `capacity` halves are not enough.
+extern "C" int fvp_debug_pack_tc16(const float* w_rows, int cin, int cin2, int coutp, int k, int variant, int cb,
+                                   unsigned short* out, long long capacity, long long* n_halves) {
+  if (!w_rows || !n_halves || cin <= 0 || cin2 < 0 || coutp <= 0 || (k != 1 && k != 3 && k != 7) || variant < 0 || variant > 2 ||
+      (cb != 16 && cb != 32))
+    return -1;
+  Packed p;
+  p.cin = cin; p.cin2 = cin2; p.coutp = coutp; p.k = k;
+  const size_t rows = (size_t)k * k * fvp_round_up(cin, 16) + (cin2 ? fvp_round_up(cin2, 16) : 0);
+  p.w.assign(w_rows, w_rows + rows * coutp);
+  p.b.assign(coutp, 0.f);
+  const std::vector<float> img = pack_tc16(p, variant, cb);
+  *n_halves = (long long)img.size() * 2;
+  if (!out || capacity < *n_halves) return -2;
+  std::memcpy(out, img.data(), img.size() * sizeof(float));
+  return 0;
+}
+
 int fvp_pack_params(fvp_ctx* ctx) {
   for (const FvpParam& p : ctx->params)
     if (!p.set) return fvp_fail(ctx, FVP_E_STATE, "parameter '%s' was never set", p.name.c_str());

@@ -65,6 +65,7 @@ SYMBOLS = {
     "fvp_debug_conv": (C.c_int, [_CTX, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_float), C.c_size_t]),
     "fvp_debug_project": (C.c_int, [_CTX, C.c_int, _P, C.c_int, _P, _P, C.c_size_t]),
     "fvp_debug_conv_plan": (C.c_int, [C.c_int] * 9 + [C.POINTER(C.c_int)]),
+    "fvp_debug_pack_tc16": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_longlong, C.POINTER(C.c_longlong)]),
     "fvp_stage_heatmaps": (C.c_int, [_CTX, _P, C.c_int, C.c_size_t]),
     "fvp_hdn_project": (C.c_int, [_CTX, C.c_int, _P, _P, C.c_size_t]),
     "fvp_center_net": (C.c_int, [_CTX, _P, C.c_int, _P, _P, C.c_size_t]),

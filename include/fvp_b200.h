@@ -141,6 +141,14 @@ int fvp_debug_conv(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin
  * A stages, B stages, dynamic shared memory, two CTAs per SM (0/1), grid, work items, TMEM columns; out[0] = 0 when the
  * layer is left to the CUDA-core kernel.  Returns 0, or -1 on invalid arguments. */
 int fvp_debug_conv_plan(int n, int H, int W, int cin, int cin2, int cout, int k, int engine, int num_sms, int* out);
+/* test hook, host only: the fp16 hi/lo weight image of the tensor-core convolution (csrc/fvp_params.cu pack_tc16) for a
+ * BN-folded GEMM matrix w_rows [(k*k*round_up(cin,16) + round_up(cin2,16))][coutp]; variant 0/1/2 = N tiles of up to
+ * 128/32/64 columns, cb = 32 or 16 channels per K-block.  Layout contract (what k_conv_tc's descriptors read): blocks in the
+ * order [phase][K-block][tap][N tile][hi, lo]; a block = n_tile rows of cb halves, the 16-byte chunks of row n XOR-ed with
+ * (n >> 1) & 3 (cb = 32, SWIZZLE_64B) or (n >> 2) & 1 (cb = 16, SWIZZLE_32B); hi = fp16(w), lo = fp16((w - hi) * 2^11).
+ * Returns 0, -1 on bad arguments, -2 (with *n_halves set) when capacity is too small. */
+int fvp_debug_pack_tc16(const float* w_rows, int cin, int cin2, int coutp, int k, int variant, int cb, unsigned short* out,
+                        long long capacity, long long* n_halves);
 /* K0: [batch][V][J][H][W] -> internal channel-last, zero-bordered copy */
 int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr_t stream);
 /* K1: ProjectLayer(whole).forward + CenterNet's z-max (project_whole.py:62-88, cnns_2d.py:174)

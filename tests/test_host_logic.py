@@ -145,6 +145,61 @@ def test_conv_launch_plans(built_library):
     assert _conv_plan(lib, 1, 64, 64, 32, 0, 32, 7)["n_tile"] == 0 and _conv_plan(lib, 1, 16, 16, 128, 0, 512, 1)["n_tile"] == 0
 
 
+@pytest.mark.parametrize("cin,cin2,cout,k,variant,cb", [(64, 32, 64, 3, 0, 32), (128, 0, 128, 3, 1, 32), (32, 16, 32, 3, 0, 32),
+                                                        (16, 0, 16, 7, 0, 16), (16, 0, 32, 3, 0, 16), (128, 0, 256, 1, 2, 32),
+                                                        (32, 0, 15, 1, 0, 32)])
+def test_tensor_core_weight_image_layout(built_library, cin, cin2, cout, k, variant, cb):
+    """The host packer's shared-memory image against an independent statement of the layout k_conv_tc's descriptors read
+    (include/fvp_b200.h, fvp_debug_pack_tc16), and the hi/lo split against NumPy float16 arithmetic."""
+    import ctypes as C
+    from fvp import capi
+    lib = capi.load()
+    rng = np.random.default_rng(cin * 7 + cout + k)
+    ru = lambda a, b: -(-a // b) * b
+    coutp, cinp, cin2p = ru(cout, 4), ru(cin, 16), (ru(cin2, 16) if cin2 else 0)
+    rows = k * k * cinp + cin2p
+    w = np.zeros((rows, coutp), np.float32)
+    for tap in range(k * k):
+        w[tap * cinp: tap * cinp + cin, :cout] = rng.normal(0, 0.2, (cin, cout)) * 10.0 ** rng.integers(-3, 1, (cin, cout))
+    if cin2:
+        w[k * k * cinp: k * k * cinp + cin2, :cout] = rng.normal(0, 0.2, (cin2, cout))
+    n = C.c_longlong(0)
+    assert lib.fvp_debug_pack_tc16(w.ctypes.data, cin, cin2, coutp, k, variant, cb, None, 0, C.byref(n)) == -2
+    img = np.zeros(n.value, np.uint16)
+    assert lib.fvp_debug_pack_tc16(w.ctypes.data, cin, cin2, coutp, k, variant, cb, img.ctypes.data, n.value, C.byref(n)) == 0
+    # independent reconstruction of the contract
+    npad = ru(coutp, 16)
+    cap = {0: 128, 1: 32, 2: 64}[variant]
+    n_tile = npad if npad <= cap else cap
+    n_tiles = -(-npad // n_tile)
+    chunks, shift = cb // 8, (1 if cb == 32 else 2)
+    hi = w.astype(np.float16)
+    lo = ((w - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+    expect = np.zeros(n.value, np.uint16)
+    pos = 0
+    for taps, cp, rowbase in ((k * k, cinp, 0),) + (((1, cin2p, k * k * cinp),) if cin2 else ()):
+        for c0 in range(0, ru(cp, cb), cb):
+            for tap in range(taps):
+                for nt in range(n_tiles):
+                    for part in (hi, lo):
+                        blk = np.zeros((n_tile, cb), np.uint16)
+                        for r in range(n_tile):
+                            col = nt * n_tile + r
+                            for cc in range(cb):
+                                ci = c0 + cc
+                                v = part[rowbase + tap * cp + ci, col] if (col < coutp and ci < cp) else np.float16(0)
+                                chunk = (cc >> 3) ^ ((r >> shift) & (chunks - 1))
+                                blk[r, chunk * 8 + (cc & 7)] = np.float16(v).view(np.uint16)
+                        expect[pos: pos + blk.size] = blk.ravel()
+                        pos += blk.size
+    assert pos == n.value
+    assert np.array_equal(img, expect)
+    # the pair carries 22 significant bits of every weight
+    back = hi.astype(np.float64) + lo.astype(np.float64) / 2048.0
+    nz = np.abs(w) > 1e-4                      # below fp16's normal range of the lo term the split degrades gracefully
+    assert np.max(np.abs(back - w)[nz] / np.abs(w)[nz]) < 2.0 ** -20
+
+
 def test_two_cta_conv_variants_do_not_spill_more_than_measured(built_library):
     """The 72-register variants of k_conv_tc (two CTAs per SM) run beside 2 x 111 KB of shared memory, i.e. with 28 KB of L1:
     ptxas spills beyond the sizes measured fast on B200 (profiles/r01_s5_conv_layers_final.txt) cost up to 45 % on the
