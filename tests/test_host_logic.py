@@ -147,7 +147,7 @@ def test_conv_launch_plans(built_library):
 
 @pytest.mark.parametrize("cin,cin2,cout,k,variant,cb", [(64, 32, 64, 3, 0, 32), (128, 0, 128, 3, 1, 32), (32, 16, 32, 3, 0, 32),
                                                         (16, 0, 16, 7, 0, 16), (16, 0, 32, 3, 0, 16), (128, 0, 256, 1, 2, 32),
-                                                        (32, 0, 15, 1, 0, 32)])
+                                                        (32, 0, 15, 1, 0, 32), (256, 0, 512, 1, 0, 32)])   # last: a backbone-sized layer (N2)
 def test_tensor_core_weight_image_layout(built_library, cin, cin2, cout, k, variant, cb):
     """The host packer's shared-memory image against an independent statement of the layout k_conv_tc's descriptors read
     (include/fvp_b200.h, fvp_debug_pack_tc16), and the hi/lo split against NumPy float16 arithmetic."""
