@@ -469,6 +469,20 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
           const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
           const int CinP = (Cin + CB - 1) / CB * CB;
           for (int c0 = 0; c0 < CinP; c0 += CB) {
+#ifdef FVP_TC_STREAM_ROWS
+            // Experimental (off by default, not yet measured on a B200): one ring stage = the K blocks of one tap ROW,
+            // i.e. one barrier wait + one commit per K taps on the issuing lane instead of per tap (the streamed path costs
+            // ~157 cycles per MMA against ~87 on the unrolled resident path).
+            for (int dy = 0; dy < K; ++dy) {
+              const int bs = b_it % B_ST;
+              if (b_it >= B_ST) mbar_wait(b_empty + bs, ((b_it / B_ST) - 1) & 1);
+              mbar_arrive_expect_tx(b_full + bs, (uint32_t)K * t.blk_bytes);
+              for (int dx = 0; dx < K; ++dx)
+                tma_bulk_g2s(sB + (size_t)bs * t.b_stage_bytes + (size_t)dx * t.blk_bytes,
+                             wsrc + ((size_t)(dy * K + dx) * t.n_tiles + w.nt) * t.blk_bytes, t.blk_bytes, b_full + bs);
+              ++b_it;
+            }
+#else
             for (int tap = 0; tap < K * K; ++tap) {
               const int bs = b_it % B_ST;
               if (b_it >= B_ST) mbar_wait(b_empty + bs, ((b_it / B_ST) - 1) & 1);
@@ -477,6 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
                            t.blk_bytes, b_full + bs);
               ++b_it;
             }
+#endif
             wsrc += (size_t)K * K * t.n_tiles * t.blk_bytes;
           }
         }
@@ -529,17 +544,30 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
             accumulate = 1;
           } else
           for (int dy = 0; dy < K; ++dy) {
+#ifdef FVP_TC_STREAM_ROWS
+            int bs = 0;                                              // ring stage of this tap row (streamed weights)
+#endif
             for (int dx = 0; dx < K; ++dx) {
               uint64_t bd_hi;
+#ifndef FVP_TC_STREAM_ROWS
               int bs = 0;
+#endif
               if (t.resident) {
                 if (!b_ready) { TC_TIMED(2, mbar_wait(b_full, 0)); b_ready = true; }
                 bd_hi = bd_res0 + bidx;
                 bidx += nts_img * blk16;
               } else {
+#ifdef FVP_TC_STREAM_ROWS
+                if (dx == 0) {
+                  bs = b_it % B_ST;
+                  TC_TIMED(2, mbar_wait(b_full + bs, (b_it / B_ST) & 1));
+                }
+                bd_hi = bd_res0 + (uint32_t)bs * (t.b_stage_bytes >> 4) + (uint32_t)dx * blk16;
+#else
                 bs = b_it % B_ST;
                 TC_TIMED(2, mbar_wait(b_full + bs, (b_it / B_ST) & 1));
                 bd_hi = bd_res0 + (uint32_t)bs * (t.b_stage_bytes >> 4);
+#endif
               }
               tc_fence_after();
               const uint64_t ad_hi = ad0 + (uint32_t)((dy * HWP + dx) * (ROWB >> 4));
@@ -564,10 +592,17 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
                 }
               }
               accumulate = 1;
+#ifdef FVP_TC_STREAM_ROWS
+              if (!t.resident && dx == K - 1) {
+                if (elect_one()) umma_commit(b_empty + bs);          // the row's stage is reusable when its MMAs retire
+                ++b_it;
+              }
+#else
               if (!t.resident) {
                 if (elect_one()) umma_commit(b_empty + bs);          // B slot reusable when these MMAs retire
                 ++b_it;
               }
+#endif
             }
           }
           blk += (uint32_t)K * K * nts_img;
@@ -757,19 +792,26 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   t.blk_bytes = (uint32_t)t.n_tile * rowb * 2;
   const uint32_t image_bytes = (uint32_t)nblocks * t.n_tiles * t.blk_bytes;
   const int res = residency(t.n_tile, t.n_tiles);
-  const int stream2 = (2 * t.a_stage_bytes + 4 * t.blk_bytes <= budget) ? (int)((budget - 2 * t.a_stage_bytes) / t.blk_bytes) : 0;
+#ifdef FVP_TC_STREAM_ROWS
+  const uint32_t stage_bytes = (uint32_t)k * t.blk_bytes;         // experiment: one ring stage per tap row
+  const int min_stages = 2;
+#else
+  const uint32_t stage_bytes = t.blk_bytes;
+  const int min_stages = 4;
+#endif
+  const int stream2 = (2 * t.a_stage_bytes + min_stages * stage_bytes <= budget) ? (int)((budget - 2 * t.a_stage_bytes) / stage_bytes) : 0;
   if (res == 1) {                                                  // weights resident, double-buffered halo
     t.resident = 1; t.a_stages = 2; t.b_stages = 1; t.b_stage_bytes = image_bytes;
   } else if (res == 2) {                                           // one N tile's weights resident per CTA
     t.resident = 2; t.a_stages = 2; t.b_stages = 1; t.b_stage_bytes = (uint32_t)nblocks * t.blk_bytes;
-  } else if (stream2 >= 4) {                                       // streamed weights, double-buffered halo
-    t.resident = 0; t.a_stages = 2; t.b_stage_bytes = t.blk_bytes;
+  } else if (stream2 >= min_stages) {                              // streamed weights, double-buffered halo
+    t.resident = 0; t.a_stages = 2; t.b_stage_bytes = stage_bytes;
     t.b_stages = stream2 > TC_MAX_B ? TC_MAX_B : stream2;
   } else if (image_bytes + t.a_stage_bytes <= budget) {
     t.resident = 1; t.a_stages = 1; t.b_stages = 1; t.b_stage_bytes = image_bytes;
   } else {
-    t.resident = 0; t.a_stages = 1; t.b_stage_bytes = t.blk_bytes;
-    const int bs = (int)((budget - t.a_stage_bytes) / t.blk_bytes);
+    t.resident = 0; t.a_stages = 1; t.b_stage_bytes = stage_bytes;
+    const int bs = (int)((budget - t.a_stage_bytes) / stage_bytes);
     t.b_stages = bs > TC_MAX_B ? TC_MAX_B : bs;
   }
   t.acc_stride = (uint32_t)fvp_round_up(t.n_tile, 32);          // accumulators side by side in TMEM: 2 buffers x (D1[,D2])
