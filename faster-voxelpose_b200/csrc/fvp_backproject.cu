@@ -197,8 +197,12 @@ __device__ __forceinline__ void fvp_k3_bar_arrive(uint64_t* bar) {      // relea
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 __device__ __forceinline__ void fvp_k3_bar_wait(uint64_t* bar, unsigned parity) {
-  unsigned ok;
+  unsigned ok, spins = 0;
   do {
+    if (++spins > (1u << 26)) {          // watchdog: a protocol bug must abort the kernel, never hang the GPU
+      printf("k3_jln_patch: split-phase barrier timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
   } while (!ok);
