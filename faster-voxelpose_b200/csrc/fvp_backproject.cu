@@ -322,6 +322,16 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
 #ifdef FVP_K3_PREFETCH_GRID
         const float2 q = q_next;
         if (q_ok && v + 1 < V) q_next = __ldg(grid_s + (size_t)(v + 1) * nfine + col + cz);
+#elif defined(FVP_K3_INKERNEL_PROJ)
+        // Experimental (off by default, not yet measured in this kernel): recompute the position from the camera block
+        // instead of reading the 8-byte cache entry - DRAM traffic falls from ~57 MB to ~22 MB per frame (the algorithmic
+        // bytes) at the price of ~75 FP instructions per lane and view.  Same fvp_project, same axis values: bit-identical.
+        float2 q = make_float2(0.f, 0.f);
+        if (q_ok) {
+          const FvpSeq& sq = g.seqs[pd.seq];
+          fvp_project(sq.cam[v], sq.A, P, __ldg(g.fine_axes + pd.tl[0] + a), __ldg(g.fine_axes + g.fine[0] + pd.tl[1] + b),
+                      __ldg(g.fine_axes + g.fine[0] + F1 + pd.tl[2] + cz), q.x, q.y);
+        }
 #else
         float2 q = make_float2(0.f, 0.f);
         if (q_ok) q = __ldg(grid_s + (size_t)v * nfine + col + cz);
