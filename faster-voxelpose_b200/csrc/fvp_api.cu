@@ -6,7 +6,14 @@
 
 #include "fvp_ctx.h"
 
+#include <mutex>
+
 static std::string g_create_error;
+
+// Range-guard status word of every device (mapped pinned host memory the conv kernels write through a __device__ pointer):
+// allocated when the first context of a device is created, shared by all contexts of that device, never freed.
+static std::mutex g_status_mutex;
+static int* g_status_host[64] = {nullptr};
 
 int fvp_fail(fvp_ctx* ctx, int code, const char* fmt, ...) {
   char buf[1024];
@@ -46,6 +53,13 @@ int check_stage_ready(fvp_ctx* ctx, int batch) {
   return FVP_OK;
 }
 
+int refuse_if_tickets_open(fvp_ctx* ctx);
+// stage entry points share d_hm_cl and the workspaces with in-flight fvp_submit_host tickets: refuse before any enqueue
+int check_stage_entry(fvp_ctx* ctx, int batch) {
+  const int rc = check_stage_ready(ctx, batch);
+  return rc != FVP_OK ? rc : refuse_if_tickets_open(ctx);
+}
+
 int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaStream_t st) {
   bool same = true;
   std::vector<int> want(batch);
@@ -77,6 +91,25 @@ int fvp_k3_parts(const fvp_ctx* ctx, int batch) {
   return parts;
 }
 
+FvpLaunchEnv launch_env(const fvp_ctx* ctx) { return FvpLaunchEnv{ctx->num_sms, ctx->conv_mode, nullptr, nullptr}; }
+
+// Other entry points must not touch the shared workspaces while fvp_submit_host tickets are in flight.
+int refuse_if_tickets_open(fvp_ctx* ctx) {
+  if (ctx->tickets != ctx->waited)
+    return fvp_fail(ctx, FVP_E_STATE, "fvp_submit_host tickets are outstanding: call fvp_wait before other entry points");
+  return FVP_OK;
+}
+
+// After a synchronise: did any convolution of this device store an activation outside the fp16 range of the hi/lo engine?
+int check_range_status(fvp_ctx* ctx) {
+  if (ctx->h_status && *(volatile int*)ctx->h_status) {
+    *(volatile int*)ctx->h_status = 0;
+    return fvp_fail(ctx, FVP_E_RANGE, "a convolution produced an activation outside the fp16 range (|x| >= 65504 or NaN): the "
+                    "fp16 hi/lo tensor-core engine cannot represent it; use fvp_set_conv_mode(ctx, 1) (3xTF32) or 0 (fp32)");
+  }
+  return FVP_OK;
+}
+
 FvpPropArgs prop_args(fvp_ctx* ctx) {
   FvpPropArgs a = ctx->prop;
   a.g = ctx->geom;
@@ -103,7 +136,7 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
   fvp_launch_hdn_project(g, ctx->d_hm_cl, ctx->d_frame_seq, ctx->d_plane_cl, batch, st); ++*launches;
   T.mark(2);
   fvp_run_trunk2d(ctx->w_center, ctx->d_plane_cl, g.proj.JP, batch, g.X, g.Y, ctx->cn_buf, nullptr, true,
-                  ctx->d_hmsize, 3, launches, st, ctx->conv_mode);
+                  ctx->d_hmsize, 3, launches, st, launch_env(ctx));
   T.mark(3);
   fvp_launch_nms_topk(ctx->d_hmsize, (size_t)3 * XY, g.X, g.Y, g.P, batch, ctx->d_conf2d, ctx->d_flat, st); ++*launches;
   T.mark(4);
@@ -126,7 +159,7 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
   ++*launches;                                   // (+ one memset node)
   T.mark(6);
   fvp_run_trunk2d(ctx->w_p2p, ctx->d_planes_cl, g.proj.JP, 3 * n, 64, 64, ctx->p2p_buf, ctx->d_img_valid, false,
-                  ctx->d_feat, g.J, launches, st, ctx->conv_mode);
+                  ctx->d_feat, g.J, launches, st, launch_env(ctx));
   T.mark(7);
   fvp_launch_pose_head(g, ctx->w_pose, ctx->d_feat, ctx->d_people, nullptr, n, ctx->cfg.beta, ctx->d_pose,
                        ctx->d_maxw, ctx->d_wts, ctx->d_fused, st); *launches += 2;   // k_pose_head + k_fuse
@@ -181,9 +214,36 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   if (e != cudaSuccess) return fvp_fail(nullptr, FVP_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
   if (prop.major != 10) return fvp_fail(nullptr, FVP_E_CUDA, "libfvp_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
 
+  if (device < 0 || device >= 64) return fvp_fail(nullptr, FVP_E_INVALID, "device index %d outside [0, 64)", device);
+  // per-DEVICE kernel setup (function attributes are per device; repeated for every context, which is harmless)
+  e = fvp_conv_tc_init_device();
+  if (e == cudaSuccess) e = fvp_conv_init_device();
+  if (e != cudaSuccess) return fvp_fail(nullptr, FVP_E_CUDA, "kernel attribute setup on device %d: %s", device, cudaGetErrorString(e));
+  e = fvp_proposal_init_device(c.voxels[0], c.voxels[1]);
+  if (e == cudaErrorInvalidConfiguration)
+    return fvp_fail(nullptr, FVP_E_INVALID, "VOXELS_PER_AXIS %dx%d: the NMS / top-k kernel stages the whole X*Y map (%d B) in shared "
+                    "memory, limit 227 KB per CTA", c.voxels[0], c.voxels[1], c.voxels[0] * c.voxels[1] * 4);
+  if (e != cudaSuccess) return fvp_fail(nullptr, FVP_E_CUDA, "kernel attribute setup on device %d: %s", device, cudaGetErrorString(e));
+  int* h_status = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_status_mutex);
+    if (!g_status_host[device]) {
+      int* h = nullptr;
+      int* d = nullptr;
+      e = cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped);
+      if (e == cudaSuccess) { *h = 0; e = cudaHostGetDevicePointer((void**)&d, h, 0); }
+      if (e == cudaSuccess) e = fvp_conv_tc_set_status_ptr(d);
+      if (e == cudaSuccess) e = fvp_conv_set_status_ptr(d);
+      if (e != cudaSuccess) return fvp_fail(nullptr, FVP_E_CUDA, "range-guard status word on device %d: %s", device, cudaGetErrorString(e));
+      g_status_host[device] = h;
+    }
+    h_status = g_status_host[device];
+  }
+
   fvp_ctx* ctx = new fvp_ctx();
   ctx->cfg = c;
   ctx->device = device;
+  ctx->h_status = h_status;
   fvp_build_param_table(ctx);
 
   FvpGeom& g = ctx->geom;
@@ -497,18 +557,29 @@ static int forward_device(fvp_ctx* ctx, const float* d_heatmaps, int batch, cons
     for (int b = 0; b < batch; ++b) sig_same = sig_same && ctx->graph_seqs[b] == ctx->h_frame_seq[b];
   if (ctx->use_graph && !ctx->profiling) {
     if (!sig_same) {
-      // first call with this signature: run eagerly (also performs one-time function attribute setup),
-      // then capture the same sequence into a graph bound to the internal output buffers
+      // first call with this signature: run eagerly, then capture the same sequence into a graph bound to the internal
+      // output buffers.  Whatever fails inside the capture, the stream is taken OUT of capture mode again (an unfinished
+      // capture would poison every later call on it, the caller's PyTorch work included) and the previous executable
+      // graph is only replaced once the new one was instantiated.
       rc = run_pipeline(ctx, batch, ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, st, &launches);
       if (rc != FVP_OK) return rc;
-      if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
       cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
       int cap_launches = 0;
       FVP_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      run_pipeline(ctx, batch, ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, st, &cap_launches);
-      FVP_CUDA_OK(cudaStreamEndCapture(st, &graph));
-      FVP_CUDA_OK(cudaGraphInstantiate(&ctx->graph_exec, graph, 0));
-      cudaGraphDestroy(graph);
+      const int cap_rc = run_pipeline(ctx, batch, ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, st, &cap_launches);
+      const cudaError_t launch_err = cudaGetLastError();
+      cudaError_t cap_err = cudaStreamEndCapture(st, &graph);       // always ends the capture (graph = NULL on failure)
+      if (cap_err == cudaSuccess && (cap_rc != FVP_OK || launch_err != cudaSuccess)) cap_err = launch_err != cudaSuccess ? launch_err : cudaErrorUnknown;
+      if (cap_err == cudaSuccess) cap_err = cudaGraphInstantiate(&exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (cap_err != cudaSuccess) {
+        if (exec) cudaGraphExecDestroy(exec);
+        cudaGetLastError();                                         // clear the sticky-free error state of the failed capture
+        return fvp_fail(ctx, FVP_E_CUDA, "CUDA graph capture of the forward failed: %s", cudaGetErrorString(cap_err));
+      }
+      if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+      ctx->graph_exec = exec;
       ctx->graph_batch = batch;
       ctx->graph_seqs.assign(ctx->h_frame_seq, ctx->h_frame_seq + batch);
       ctx->graph_launches = cap_launches;
@@ -546,6 +617,8 @@ int fvp_forward_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int
   int rc = check_stage_ready(ctx, batch);
   if (rc != FVP_OK) return rc;
   if (!h_heatmaps) return fvp_fail(ctx, FVP_E_INVALID, "null heat maps");
+  rc = refuse_if_tickets_open(ctx);             // before ANY enqueue: the H2D below would overwrite a ticket's input
+  if (rc != FVP_OK) return rc;
   cudaSetDevice(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   const FvpGeom& g = ctx->geom;
@@ -558,7 +631,7 @@ int fvp_forward_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int
   if (h_plane) FVP_CUDA_OK(cudaMemcpyAsync(h_plane, ctx->d_out_plane, (size_t)3 * n * g.J * 2 * 4, cudaMemcpyDeviceToHost, st));
   if (h_centers) FVP_CUDA_OK(cudaMemcpyAsync(h_centers, ctx->d_out_centers, (size_t)n * 7 * 4, cudaMemcpyDeviceToHost, st));
   FVP_CUDA_OK(cudaStreamSynchronize(st));
-  return FVP_OK;
+  return check_range_status(ctx);
 }
 
 // Pipelined host entry: fvp_submit_host enqueues H2D (copy stream) -> forward (context stream) -> D2H and returns a
@@ -602,14 +675,21 @@ int fvp_wait(fvp_ctx* ctx, long long ticket) {
   cudaSetDevice(ctx->device);
   for (long long t = ctx->waited; t <= ticket; ++t) FVP_CUDA_OK(cudaEventSynchronize(ctx->ev_done[t & 1]));
   ctx->waited = ticket + 1;
-  return FVP_OK;
+  return check_range_status(ctx);
+}
+
+int fvp_fp16_fallback_layers(const fvp_ctx* ctx) { return ctx ? ctx->fp16_fallback_layers : 0; }
+
+int fvp_check_range(fvp_ctx* ctx) {
+  if (!ctx) return FVP_E_INVALID;
+  return check_range_status(ctx);
 }
 
 // ------------------------------------------------------------------------------------------------
 // stage entry points
 // ------------------------------------------------------------------------------------------------
 int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr_t stream) {
-  int rc = check_stage_ready(ctx, batch);
+  int rc = check_stage_entry(ctx, batch);
   if (rc != FVP_OK) return rc;
   cudaSetDevice(ctx->device);
   fvp_launch_stage_heatmaps(ctx->geom, d_heatmaps, ctx->d_hm_cl, batch, (cudaStream_t)stream);
@@ -635,7 +715,7 @@ int fvp_debug_project(fvp_ctx* ctx, int slot, const float* d_points, int n, floa
 }
 
 int fvp_hdn_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, float* d_plane, uintptr_t stream) {
-  int rc = check_stage_ready(ctx, batch);
+  int rc = check_stage_entry(ctx, batch);
   if (rc != FVP_OK) return rc;
   cudaSetDevice(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -649,7 +729,7 @@ int fvp_hdn_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, float* 
 }
 
 int fvp_center_net(fvp_ctx* ctx, const float* d_plane_in, int batch, float* d_hm, float* d_size, uintptr_t stream) {
-  int rc = check_stage_ready(ctx, batch);
+  int rc = check_stage_entry(ctx, batch);
   if (rc != FVP_OK) return rc;
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");
   cudaSetDevice(ctx->device);
@@ -659,7 +739,7 @@ int fvp_center_net(fvp_ctx* ctx, const float* d_plane_in, int batch, float* d_hm
   if (d_plane_in) fvp_launch_nchw_to_nhwc(d_plane_in, ctx->d_plane_cl, batch, XY, g.proj.JP, g.J, st);
   int launches = 0;
   fvp_run_trunk2d(ctx->w_center, ctx->d_plane_cl, g.proj.JP, batch, g.X, g.Y, ctx->cn_buf, nullptr, true,
-                  ctx->d_hmsize, 3, &launches, st, ctx->conv_mode);
+                  ctx->d_hmsize, 3, &launches, st, launch_env(ctx));
   for (int b = 0; b < batch; ++b) {
     if (d_hm) FVP_CUDA_OK(cudaMemcpyAsync(d_hm + (size_t)b * XY, ctx->d_hmsize + (size_t)b * 3 * XY, XY * 4, cudaMemcpyDeviceToDevice, st));
     if (d_size) FVP_CUDA_OK(cudaMemcpyAsync(d_size + (size_t)b * 2 * XY, ctx->d_hmsize + (size_t)b * 3 * XY + XY, 2 * XY * 4, cudaMemcpyDeviceToDevice, st));
@@ -669,7 +749,7 @@ int fvp_center_net(fvp_ctx* ctx, const float* d_plane_in, int batch, float* d_hm
 }
 
 int fvp_nms_topk(fvp_ctx* ctx, const float* d_hm, int batch, float* d_conf2d, int32_t* d_flat, uintptr_t stream) {
-  int rc = check_stage_ready(ctx, batch);
+  int rc = check_stage_entry(ctx, batch);
   if (rc != FVP_OK) return rc;
   if (!d_hm || !d_conf2d || !d_flat) return fvp_fail(ctx, FVP_E_INVALID, "null argument");
   cudaSetDevice(ctx->device);
@@ -681,7 +761,7 @@ int fvp_nms_topk(fvp_ctx* ctx, const float* d_hm, int batch, float* d_conf2d, in
 
 int fvp_proposals(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const float* d_conf2d, const int32_t* d_flat,
                   const float* d_size, float* d_cols, float* d_hm1d, float* d_centers, uintptr_t stream) {
-  int rc = check_stage_ready(ctx, batch);
+  int rc = check_stage_entry(ctx, batch);
   if (rc != FVP_OK) return rc;
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");
   if (!d_conf2d || !d_flat || !d_size) return fvp_fail(ctx, FVP_E_INVALID, "null argument");
@@ -705,6 +785,7 @@ int fvp_proposals(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const flo
 
 int fvp_c2c_net(fvp_ctx* ctx, const float* d_cols, int n, float* d_hm1d, uintptr_t stream) {
   if (!ctx || !d_cols || !d_hm1d || n < 1) return FVP_E_INVALID;
+  if (int trc = refuse_if_tickets_open(ctx)) return trc;
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");
   cudaSetDevice(ctx->device);
   FvpPropArgs a = prop_args(ctx);
@@ -718,7 +799,7 @@ int fvp_c2c_net(fvp_ctx* ctx, const float* d_cols, int n, float* d_hm1d, uintptr
 
 int fvp_jln_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const float* d_centers, float* d_planes,
                     float* d_offset, uintptr_t stream) {
-  int rc = check_stage_ready(ctx, batch);
+  int rc = check_stage_entry(ctx, batch);
   if (rc != FVP_OK) return rc;
   if (!d_centers) return fvp_fail(ctx, FVP_E_INVALID, "null centers");
   cudaSetDevice(ctx->device);
@@ -742,6 +823,7 @@ int fvp_jln_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const f
 
 int fvp_p2p_net(fvp_ctx* ctx, const float* d_planes, int n, const int32_t* d_valid, float* d_feat, uintptr_t stream) {
   if (!ctx || n < 1 || !d_feat) return FVP_E_INVALID;
+  if (int trc = refuse_if_tickets_open(ctx)) return trc;
   if (n > 3 * ctx->cfg.max_batch * ctx->geom.P) return fvp_fail(ctx, FVP_E_INVALID, "too many images (%d)", n);
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");
   cudaSetDevice(ctx->device);
@@ -753,7 +835,7 @@ int fvp_p2p_net(fvp_ctx* ctx, const float* d_planes, int n, const int32_t* d_val
     in = ctx->d_tmp;
   }
   int launches = 0;
-  fvp_run_trunk2d(ctx->w_p2p, in, g.proj.JP, n, 64, 64, ctx->p2p_buf, d_valid, false, d_feat, g.J, &launches, st, ctx->conv_mode);
+  fvp_run_trunk2d(ctx->w_p2p, in, g.proj.JP, n, 64, 64, ctx->p2p_buf, d_valid, false, d_feat, g.J, &launches, st, launch_env(ctx));
   FVP_CUDA_OK(cudaGetLastError());
   return FVP_OK;
 }
@@ -761,6 +843,7 @@ int fvp_p2p_net(fvp_ctx* ctx, const float* d_planes, int n, const int32_t* d_val
 int fvp_pose_head(fvp_ctx* ctx, const float* d_feat, const float* d_offset, int n, float* d_pose, float* d_conf,
                   float* d_weights, float* d_fused, uintptr_t stream) {
   if (!ctx || !d_feat || !d_offset || n < 1) return FVP_E_INVALID;
+  if (int trc = refuse_if_tickets_open(ctx)) return trc;
   if (n > ctx->cfg.max_batch * ctx->geom.P) return fvp_fail(ctx, FVP_E_INVALID, "too many persons (%d)", n);
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");
   cudaSetDevice(ctx->device);
@@ -793,7 +876,7 @@ int fvp_pose_head(fvp_ctx* ctx, const float* d_feat, const float* d_offset, int 
 // ------------------------------------------------------------------------------------------------
 int fvp_render_heatmaps(fvp_ctx* ctx, const double* h_joints, const int32_t* h_num_people, const uint8_t* h_vis, int batch,
                         int max_people, double sigma, float* d_heatmaps, uintptr_t stream) {
-  int rc = check_stage_ready(ctx, batch);
+  int rc = check_stage_entry(ctx, batch);
   if (rc != FVP_OK) return rc;
   if (!h_joints || !h_num_people || !d_heatmaps) return fvp_fail(ctx, FVP_E_INVALID, "null joints / counts / output");
   if (max_people < 1 || max_people > FVP_MAX_PEOPLE)

@@ -7,7 +7,12 @@
 //                         The [B,J,X,Y,Z] volume never exists.
 //   K3  JLN            : ProjectLayer(individual).forward (project_individual.py:96-136) + the three
 //                         orthographic max planes (joint_localization_net.py:80-81).  The [N,J,64^3] cubes
-//                         never exist; the 164 MB cached fine sample grid is replaced by in-kernel projection.
+//                         never exist.
+//   Sample positions: K1 / K3 look up per-calibration sample-grid caches (k_build_sample_grid, the same bit-exact
+//   fvp_project chain evaluated once per calibration slot, like the reference's own per-sequence grids).  Measured on
+//   B200 in round 2 (profiles/r02_k3_experiments.txt): recomputing the projection inside K3 cuts its DRAM traffic to
+//   the algorithmic bytes but makes it 20 % slower (0.135 -> 0.162 ms at batch 1, 3.50 -> 4.22 ms at batch 32) - the
+//   kernel is bound by the L1 gather and its issue slots, not by HBM - so the cache stays and that variant was removed.
 //
 // Lane layout of K1/K3: CG consecutive lanes own one voxel column, lane s of the group holds channel
 // group s (4 joints, one float4).  One tap of one voxel is therefore a single contiguous 16*JG byte
@@ -189,25 +194,6 @@ __device__ __forceinline__ void fvp_red_max4(float4* dst, float4 m) {
   if (m.w > 0.0f) atomicMax(p + 3, __float_as_uint(m.w));
 }
 
-#ifdef FVP_K3_SPLIT_BARRIER
-__device__ __forceinline__ void fvp_k3_bar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void fvp_k3_bar_arrive(uint64_t* bar) {      // release: the chunk image written before is visible
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void fvp_k3_bar_wait(uint64_t* bar, unsigned parity) {
-  unsigned ok, spins = 0;
-  do {
-    if (++spins > (1u << 26)) {          // watchdog: a protocol bug must abort the kernel, never hang the GPU
-      printf("k3_jln_patch: split-phase barrier timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // One CTA = one person x one compact patch of 8 cube rows a (one per warp) x BPW = 32/CG cube columns b x one depth
@@ -268,35 +254,6 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
   const bool sample_ok = ch_ok && b_ok && a_ok;
   const int s_me = ch_ok ? s : JG - 1;           // idle channel-group lanes re-read the last group (same sectors)
 
-#ifdef FVP_K3_SPLIT_BARRIER
-  // the two cross-thread maxima of one chunk image (depths cc0 .. cc0+CCH-1), folded into the planes
-  auto reduce_chunk = [&](float4(*yzb)[8][32], int cc0) {
-    constexpr int N_YZ = CCH * 32;               // yz outputs of the chunk: (depth, b, channel group)
-    constexpr int N_XZ = 8 * CCH * CG;           // xz outputs of the chunk: (row, depth, channel group)
-    for (int o = tid; o < N_YZ + N_XZ; o += 256) {
-      if (o < N_YZ) {                            // yz[b][cc0 + c] = max over the 8 rows of the patch
-        const int c = o >> 5, l = o & 31, ss = l % CG;
-        if (ss < JG) {
-          float4 m = yzb[c][0][l];
-#pragma unroll
-          for (int w = 1; w < 8; ++w) m = fvp_max4(m, yzb[c][w][l]);
-          fvp_red_max4(yz_img + ((size_t)(bblk * BPW + l / CG) * 64 + cc0 + c) * JG + ss, m);
-        }
-      } else {                                   // xz[a][cc0 + c] = max over the BPW columns of the patch
-        const int x = o - N_YZ, ss = x % CG, c = (x / CG) % CCH, w = x / (CG * CCH);
-        if (ss < JG) {
-          float4 m = yzb[c][w][ss];
-#pragma unroll
-          for (int i = 1; i < BPW; ++i) m = fvp_max4(m, yzb[c][w][i * CG + ss]);
-          fvp_red_max4(xz_img + ((size_t)(ablk * 8 + w) * 64 + cc0 + c) * JG + ss, m);
-        }
-      }
-    }
-  };
-  __shared__ uint64_t s_bar[2];
-  if (tid == 0) { fvp_k3_bar_init(&s_bar[0], 256); fvp_k3_bar_init(&s_bar[1], 256); }
-  __syncthreads();
-#endif
   float4 xy_m = zero4;
   int it = 0;
   for (int cc = c_begin; cc < c_end; cc += CCH, ++it) {
@@ -309,33 +266,16 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
     if (row_live) {
       const int cz = cc + s;                     // the depth this lane looks up for its column
       const bool q_ok = b_ok && cz >= pd.lo[2] && cz < pd.hi[2];
-#ifdef FVP_K3_PREFETCH_GRID
-      // Experimental (off by default, not yet measured on a B200): fetch the next view's cached position one view early.
-      // ncu's source page attributes 9 % of K3's stall samples to the first use of this load (F2I.FLOOR in fvp_taps).
+      // The next view's cached position is fetched one view early (ncu attributed 9 % of K3's stall samples to the first
+      // use of this load; measured +1 % at batch 32, profiles/r02_k3_experiments.txt).
       float2 q_next = make_float2(0.f, 0.f);
       if (q_ok) q_next = __ldg(grid_s + col + cz);
-#endif
       for (int v = 0; v < V; ++v) {
         FvpTapRegs tr;
         tr.off = -1;
         tr.a = tr.b = tr.c = tr.d = zero4;
-#ifdef FVP_K3_PREFETCH_GRID
         const float2 q = q_next;
         if (q_ok && v + 1 < V) q_next = __ldg(grid_s + (size_t)(v + 1) * nfine + col + cz);
-#elif defined(FVP_K3_INKERNEL_PROJ)
-        // Experimental (off by default, not yet measured in this kernel): recompute the position from the camera block
-        // instead of reading the 8-byte cache entry - DRAM traffic falls from ~57 MB to ~22 MB per frame (the algorithmic
-        // bytes) at the price of ~75 FP instructions per lane and view.  Same fvp_project, same axis values: bit-identical.
-        float2 q = make_float2(0.f, 0.f);
-        if (q_ok) {
-          const FvpSeq& sq = g.seqs[pd.seq];
-          fvp_project(sq.cam[v], sq.A, P, __ldg(g.fine_axes + pd.tl[0] + a), __ldg(g.fine_axes + g.fine[0] + pd.tl[1] + b),
-                      __ldg(g.fine_axes + g.fine[0] + F1 + pd.tl[2] + cz), q.x, q.y);
-        }
-#else
-        float2 q = make_float2(0.f, 0.f);
-        if (q_ok) q = __ldg(grid_s + (size_t)v * nfine + col + cz);
-#endif
         const FvpTaps t = fvp_taps(P, q.x, q.y);
         const int my_off = t.off + frame_off + v * vs4;
 #pragma unroll
@@ -353,44 +293,6 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
     // mean + clamp + the three maxima of this chunk.  Both cross-thread maxima go through ONE shared-memory image of
     // the chunk ([depth][row][lane]): a partial-mask REDUX per channel group costs a serialised collective per mask
     // (CREDUX + ENDCOLLECTIVE + BSSY/BSYNC were ~20 % of the instructions and ~35 % of the stall samples in ncu).
-#ifdef FVP_K3_SPLIT_BARRIER
-    // Experimental (off by default, not yet measured on a B200): split-phase barrier.  The values of chunk i stay in
-    // registers while the thread waits for and reduces chunk i-1 (whose writers arrived a whole sampling pass ago), then
-    // they are written and the thread arrives for chunk i: nobody waits for the slowest warp of the CURRENT chunk
-    // (ncu: 14 % of K3's stall samples sit on the per-chunk __syncthreads).  Two buffers suffice: a thread overwrites
-    // buffer b only after its wait for the other buffer's phase, which completes after every thread has left reduce(b).
-    // (the 8-lane-group instantiation has a single buffer and keeps the classic barrier)
-    float4 vals[CCH];
-#pragma unroll
-    for (int c = 0; c < CCH; ++c) {
-      const bool c_in = (cc + c) >= pd.lo[2] && (cc + c) < pd.hi[2];
-      vals[c] = (sample_ok && c_in) ? fvp_mean_clamp4(acc[c], fV, rV) : zero4;
-      xy_m = fvp_max4(xy_m, vals[c]);
-    }
-    if constexpr (NBUF == 2) {
-      if (it > 0) {
-        fvp_k3_bar_wait(&s_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-        reduce_chunk(s_yz[(it - 1) & 1], cc - CCH);
-      }
-      float4(*yzw)[8][32] = s_yz[it & 1];
-#pragma unroll
-      for (int c = 0; c < CCH; ++c) yzw[c][warp][lane] = vals[c];
-      fvp_k3_bar_arrive(&s_bar[it & 1]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < CCH; ++c) s_yz[0][c][warp][lane] = vals[c];
-      __syncthreads();
-      reduce_chunk(s_yz[0], cc);
-      __syncthreads();
-    }
-  }
-  if constexpr (NBUF == 2) {
-    if (it > 0) {                                // the last chunk
-      fvp_k3_bar_wait(&s_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-      reduce_chunk(s_yz[(it - 1) & 1], c_end - CCH);
-    }
-  }
-#else
     float4(*yzb)[8][32] = s_yz[NBUF == 2 ? (it & 1) : 0];
 #pragma unroll
     for (int c = 0; c < CCH; ++c) {
@@ -423,7 +325,6 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
     }
     if (NBUF == 1) __syncthreads();
   }
-#endif
   if (ch_ok) {
     if (ncpart == 1) xy_img[((size_t)a * 64 + b) * JG + s] = xy_m;           // complete: plain store
     else fvp_red_max4(xy_img + ((size_t)a * 64 + b) * JG + s, xy_m);          // partial over the depth parts

@@ -8,6 +8,9 @@
 // This is the exact-fp32 path (summation order differs from cuDNN/oneDNN, nothing else).
 #include "fvp_kernels.h"
 
+// range guard twin of fvp_conv_tc.cu's g_tc_status: this kernel's outputs may feed a layer of the fp16 hi/lo engine
+__device__ int* g_conv_status = nullptr;
+
 namespace {
 
 constexpr int TH = 8, TW = 8;          // output pixels per CTA
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_nhwc(FvpConvArgs a) {
       const float4 r = __ldg((const float4*)(a.res + opix * a.CoutS + ch));
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
+    if (!(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))) < 65504.0f) && g_conv_status) *g_conv_status = 1;
     if (!a.nchw) {
       *(float4*)(a.out + opix * a.CoutS + ch) = v;
     } else {
@@ -181,14 +185,17 @@ __global__ void __launch_bounds__(256) k_maxpool2(const float4* __restrict__ in,
 
 }  // namespace
 
+cudaError_t fvp_conv_set_status_ptr(int* d_status) { return cudaMemcpyToSymbol(g_conv_status, &d_status, sizeof(d_status)); }
+
+// per-device: the 7x7 variants need more than the default 48 KB of dynamic shared memory (called by fvp_create)
+cudaError_t fvp_conv_init_device() {
+  cudaError_t e = cudaFuncSetAttribute(k_conv_nhwc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(7, 16));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_conv_nhwc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(7, 32));
+}
+
 void fvp_launch_conv(const FvpConvArgs& a, cudaStream_t st) {
   const int tiles = fvp_cdiv(a.H, TH) * fvp_cdiv(a.W, TW);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_conv_nhwc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(7, 16));
-    cudaFuncSetAttribute(k_conv_nhwc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(7, 32));
-    attr_done = true;
-  }
   if (a.CoutP <= 16) {
     dim3 grid(tiles, 1, a.n);
     k_conv_nhwc<16><<<grid, NTHREADS, conv_smem_bytes(a.ksize, 16), st>>>(a);
@@ -206,18 +213,22 @@ void fvp_launch_maxpool2(const float* in, float* out, int n, int H, int W, int C
 // ------------------------------------------------------------------------------------------------
 // trunk program: front_layers + EncoderDecorder (+ heads), cnns_2d.py:94-135,173-178
 // ------------------------------------------------------------------------------------------------
-static int g_tc = 0;   // set by fvp_run_trunk2d for the duration of one (single-threaded) trunk enqueue
-static int num_sms() {                       // SM count of the current device (148 on B200), queried once
-  static const int n = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-    return v;
-  }();
-  return n;
-}
-static void conv(const FvpConvW& w, const float* in, int H, int W, const float* in2, float* out, int couts,
-                 const float* res, int res_mode, int relu, int upsample, int n, const int* valid, int* launches,
-                 cudaStream_t st, int nchw = 0, int cout_real = 0) {
+namespace {
+struct TrunkRun {            // what every conv of one trunk enqueue shares (no process-global launcher state)
+  const FvpLaunchEnv& env;
+  int n;
+  const int* valid;
+  int* launches;
+  cudaStream_t st;
+};
+}  // namespace
+static void conv(const TrunkRun& r, const FvpConvW& w, const float* in, int H, int W, const float* in2, float* out, int couts,
+                 const float* res, int res_mode, int relu, int upsample, int nchw = 0, int cout_real = 0) {
+  const int n = r.n;
+  const int* valid = r.valid;
+  int* launches = r.launches;
+  cudaStream_t st = r.st;
+  const int tc = r.env.conv_mode;
   FvpConvArgs a;
   a.in = in; a.H = H; a.W = W; a.Cin = w.cin;
   a.in2 = in2; a.Cin2 = w.cin2;
@@ -227,54 +238,56 @@ static void conv(const FvpConvW& w, const float* in, int H, int W, const float* 
   a.nchw = nchw; a.n = n; a.valid = valid;
   // engine 2: fp16-split tcgen05 kernel (all layers); engine 1: 3xTF32 tcgen05 kernel, where the 7x7 front conv (49 taps
   // of half-empty 32-channel K-blocks, measured 6.6 vs 11.4 TMAC/s) stays on the CUDA-core kernel; engine 0: CUDA cores.
+  // A layer whose BN-folded weights leave the fp16 range has no fp16 image (fvp_params.cu: stash) and drops to the 3xTF32
+  // engine (fp32 exponent range) or, for a 7x7, to the CUDA cores.
   const float* const c16[3] = {w.wtc16_c16, nullptr, nullptr};
-  if (g_tc == 2 && w.wtc16_c16) fvp_launch_conv_tc(a, c16, 2, num_sms(), st);                       // <= 16 input channels
-  else if (g_tc == 2 && w.wtc16[0]) fvp_launch_conv_tc(a, w.wtc16, 1, num_sms(), st);
-  else if (g_tc == 1 && w.wtc[0] && w.k != 7) fvp_launch_conv_tc(a, w.wtc, 0, num_sms(), st);
+  if (tc == 2 && w.wtc16_c16) fvp_launch_conv_tc(a, c16, 2, r.env, st);             // 16-channel K-blocks (<= 16 channels, 7x7)
+  else if (tc == 2 && w.wtc16[0] && w.k != 7) fvp_launch_conv_tc(a, w.wtc16, 1, r.env, st);
+  else if (tc >= 1 && w.wtc[0] && w.k != 7) fvp_launch_conv_tc(a, w.wtc, 0, r.env, st);
   else fvp_launch_conv(a, st);
   if (launches) ++*launches;
 }
 
 void fvp_run_trunk2d(const FvpTrunkW& t, const float* d_in, int cin, int n, int H, int W, float* const buf[6],
                      const int* valid, bool center_heads, float* d_out, int out_real, int* launches, cudaStream_t st,
-                     int tensor_cores) {
+                     const FvpLaunchEnv& env) {
   (void)cin;
-  g_tc = tensor_cores;
+  const TrunkRun r{env, n, valid, launches, st};
   float *B0 = buf[0], *B1 = buf[1], *B2 = buf[2], *B3 = buf[3], *B4 = buf[4], *B5 = buf[5];
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
   // front_layers
-  conv(t.front, d_in, H, W, nullptr, B0, 16, nullptr, 0, 1, 0, n, valid, launches, st);          // t16
-  conv(t.r1a, B0, H, W, nullptr, B1, 32, nullptr, 0, 1, 0, n, valid, launches, st);
-  conv(t.r1b, B1, H, W, B0, B2, 32, nullptr, 0, 1, 0, n, valid, launches, st);                     // f1 (conv skip fused)
+  conv(r, t.front, d_in, H, W, nullptr, B0, 16, nullptr, 0, 1, 0);          // t16
+  conv(r, t.r1a, B0, H, W, nullptr, B1, 32, nullptr, 0, 1, 0);
+  conv(r, t.r1b, B1, H, W, B0, B2, 32, nullptr, 0, 1, 0);                     // f1 (conv skip fused)
   // skip_res1 @ full
-  conv(t.s1a, B2, H, W, nullptr, B0, 32, nullptr, 0, 1, 0, n, valid, launches, st);
-  conv(t.s1b, B0, H, W, nullptr, B3, 32, B2, 1, 1, 0, n, valid, launches, st);                     // skip1
+  conv(r, t.s1a, B2, H, W, nullptr, B0, 32, nullptr, 0, 1, 0);
+  conv(r, t.s1b, B0, H, W, nullptr, B3, 32, B2, 1, 1, 0);                     // skip1
   // encoder_res1 @ half
   fvp_launch_maxpool2(B2, B0, n, H, W, 32, valid, st); if (launches) ++*launches;
-  conv(t.e1a, B0, H2, W2, nullptr, B1, 64, nullptr, 0, 1, 0, n, valid, launches, st);
-  conv(t.e1b, B1, H2, W2, B0, B4, 64, nullptr, 0, 1, 0, n, valid, launches, st);                   // e1
+  conv(r, t.e1a, B0, H2, W2, nullptr, B1, 64, nullptr, 0, 1, 0);
+  conv(r, t.e1b, B1, H2, W2, B0, B4, 64, nullptr, 0, 1, 0);                   // e1
   // skip_res2 @ half
-  conv(t.s2a, B4, H2, W2, nullptr, B0, 64, nullptr, 0, 1, 0, n, valid, launches, st);
-  conv(t.s2b, B0, H2, W2, nullptr, B5, 64, B4, 1, 1, 0, n, valid, launches, st);                   // skip2
+  conv(r, t.s2a, B4, H2, W2, nullptr, B0, 64, nullptr, 0, 1, 0);
+  conv(r, t.s2b, B0, H2, W2, nullptr, B5, 64, B4, 1, 1, 0);                   // skip2
   // encoder_res2 @ quarter
   fvp_launch_maxpool2(B4, B0, n, H2, W2, 64, valid, st); if (launches) ++*launches;
-  conv(t.e2a, B0, H4, W4, nullptr, B1, 128, nullptr, 0, 1, 0, n, valid, launches, st);
-  conv(t.e2b, B1, H4, W4, B0, B2, 128, nullptr, 0, 1, 0, n, valid, launches, st);                  // e2
+  conv(r, t.e2a, B0, H4, W4, nullptr, B1, 128, nullptr, 0, 1, 0);
+  conv(r, t.e2b, B1, H4, W4, B0, B2, 128, nullptr, 0, 1, 0);                  // e2
   // mid_res, decoder_res2
-  conv(t.ma, B2, H4, W4, nullptr, B0, 128, nullptr, 0, 1, 0, n, valid, launches, st);
-  conv(t.mb, B0, H4, W4, nullptr, B1, 128, B2, 1, 1, 0, n, valid, launches, st);                   // m
-  conv(t.d2a, B1, H4, W4, nullptr, B0, 128, nullptr, 0, 1, 0, n, valid, launches, st);
-  conv(t.d2b, B0, H4, W4, nullptr, B2, 128, B1, 1, 1, 0, n, valid, launches, st);                  // d2
+  conv(r, t.ma, B2, H4, W4, nullptr, B0, 128, nullptr, 0, 1, 0);
+  conv(r, t.mb, B0, H4, W4, nullptr, B1, 128, B2, 1, 1, 0);                   // m
+  conv(r, t.d2a, B1, H4, W4, nullptr, B0, 128, nullptr, 0, 1, 0);
+  conv(r, t.d2b, B0, H4, W4, nullptr, B2, 128, B1, 1, 1, 0);                  // d2
   // decoder_upsample2 (+ skip2 after ReLU), decoder_res1
-  conv(t.up2, B2, H4, W4, nullptr, B0, 64, B5, 2, 1, 1, n, valid, launches, st);                   // u2 @ half
-  conv(t.d1a, B0, H2, W2, nullptr, B1, 64, nullptr, 0, 1, 0, n, valid, launches, st);
-  conv(t.d1b, B1, H2, W2, nullptr, B2, 64, B0, 1, 1, 0, n, valid, launches, st);                   // d1
+  conv(r, t.up2, B2, H4, W4, nullptr, B0, 64, B5, 2, 1, 1);                   // u2 @ half
+  conv(r, t.d1a, B0, H2, W2, nullptr, B1, 64, nullptr, 0, 1, 0);
+  conv(r, t.d1b, B1, H2, W2, nullptr, B2, 64, B0, 1, 1, 0);                   // d1
   // decoder_upsample1 (+ skip1)
-  conv(t.up1, B2, H2, W2, nullptr, B0, 32, B3, 2, 1, 1, n, valid, launches, st);                   // u1 @ full
+  conv(r, t.up1, B2, H2, W2, nullptr, B0, 32, B3, 2, 1, 1);                   // u1 @ full
   if (center_heads) {
-    conv(t.head_a, B0, H, W, nullptr, B1, 64, nullptr, 0, 1, 0, n, valid, launches, st);           // both 3x3 heads + ReLU
-    conv(t.head_b, B1, H, W, nullptr, d_out, 0, nullptr, 0, 0, 0, n, valid, launches, st, 1, out_real);
+    conv(r, t.head_a, B0, H, W, nullptr, B1, 64, nullptr, 0, 1, 0);           // both 3x3 heads + ReLU
+    conv(r, t.head_b, B1, H, W, nullptr, d_out, 0, nullptr, 0, 0, 0, 1, out_real);
   } else {
-    conv(t.head_b, B0, H, W, nullptr, d_out, 0, nullptr, 0, 0, 0, n, valid, launches, st, 1, out_real);
+    conv(r, t.head_b, B0, H, W, nullptr, d_out, 0, nullptr, 0, 0, 0, 1, out_real);
   }
 }

@@ -34,13 +34,16 @@
 
 #include "fvp_kernels.h"
 
+// Range guard of the fp16 hi/lo engine (per device, set by fvp_create): every stored activation is the next layer's
+// operand and must convert to a finite fp16 "hi" part (network inputs are back-projected planes clamped to [0,1]).  An output with |x| >= 65504 (or NaN) raises bit 0 of the status
+// word in mapped pinned host memory; the host entry points turn it into FVP_E_RANGE after their next synchronise.
+__device__ int* g_tc_status = nullptr;
+
 namespace {
 
 constexpr int TC_TH = 16, TC_TW = 8;       // output tile (pixels)
-#ifndef FVP_TC_LOADERS
-#define FVP_TC_LOADERS 256                 // experiment switch: -DFVP_TC_LOADERS=512 = 16 loader warps (one CTA per SM only)
-#endif
-constexpr int TC_LOADERS = FVP_TC_LOADERS; // warps 0..7: A staging
+constexpr int TC_LOADERS = 256;            // warps 0..7: A staging (16 loader warps in the one-CTA variant measured 13-32 % slower
+                                           // on every layer, profiles/r02_conv_experiments.txt)
 constexpr int TC_LW = TC_LOADERS / 32;     // warp 8 = MMA issuer / TMEM owner, warp 9 = weight TMA producer, warps 10-13 = epilogue
 constexpr int TC_THREADS = TC_LOADERS + 64 + 128;
 constexpr int TC_EPI = 128;
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
       mbar_arrive(a_full + as);
       ++a_it;
     };
-    if constexpr (OCC == 1 && TC_LOADERS == 256) {
+    if constexpr (OCC == 1) {
       float4 va[EPT][NV], vb[EPT][NV];
       KBlock ka, kb;
       bool more = advance(ka);
@@ -469,10 +472,9 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
           const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
           const int CinP = (Cin + CB - 1) / CB * CB;
           for (int c0 = 0; c0 < CinP; c0 += CB) {
-#ifdef FVP_TC_STREAM_ROWS
-            // Experimental (off by default, not yet measured on a B200): one ring stage = the K blocks of one tap ROW,
-            // i.e. one barrier wait + one commit per K taps on the issuing lane instead of per tap (the streamed path costs
-            // ~157 cycles per MMA against ~87 on the unrolled resident path).
+            // One ring stage = the K weight blocks of one tap ROW: one barrier wait + one commit per K taps on the issuing
+            // lane instead of per tap (measured on the streamed 128-channel layers at 960 images: 229 -> 184 us for
+            // 128->128, 128 -> 104 us for 64->128; profiles/r02_conv_experiments.txt).
             for (int dy = 0; dy < K; ++dy) {
               const int bs = b_it % B_ST;
               if (b_it >= B_ST) mbar_wait(b_empty + bs, ((b_it / B_ST) - 1) & 1);
@@ -482,16 +484,6 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
                              wsrc + ((size_t)(dy * K + dx) * t.n_tiles + w.nt) * t.blk_bytes, t.blk_bytes, b_full + bs);
               ++b_it;
             }
-#else
-            for (int tap = 0; tap < K * K; ++tap) {
-              const int bs = b_it % B_ST;
-              if (b_it >= B_ST) mbar_wait(b_empty + bs, ((b_it / B_ST) - 1) & 1);
-              mbar_arrive_expect_tx(b_full + bs, t.blk_bytes);
-              tma_bulk_g2s(sB + (size_t)bs * t.b_stage_bytes, wsrc + ((size_t)tap * t.n_tiles + w.nt) * t.blk_bytes,
-                           t.blk_bytes, b_full + bs);
-              ++b_it;
-            }
-#endif
             wsrc += (size_t)K * K * t.n_tiles * t.blk_bytes;
           }
         }
@@ -544,30 +536,19 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
             accumulate = 1;
           } else
           for (int dy = 0; dy < K; ++dy) {
-#ifdef FVP_TC_STREAM_ROWS
             int bs = 0;                                              // ring stage of this tap row (streamed weights)
-#endif
             for (int dx = 0; dx < K; ++dx) {
               uint64_t bd_hi;
-#ifndef FVP_TC_STREAM_ROWS
-              int bs = 0;
-#endif
               if (t.resident) {
                 if (!b_ready) { TC_TIMED(2, mbar_wait(b_full, 0)); b_ready = true; }
                 bd_hi = bd_res0 + bidx;
                 bidx += nts_img * blk16;
               } else {
-#ifdef FVP_TC_STREAM_ROWS
                 if (dx == 0) {
                   bs = b_it % B_ST;
                   TC_TIMED(2, mbar_wait(b_full + bs, (b_it / B_ST) & 1));
                 }
                 bd_hi = bd_res0 + (uint32_t)bs * (t.b_stage_bytes >> 4) + (uint32_t)dx * blk16;
-#else
-                bs = b_it % B_ST;
-                TC_TIMED(2, mbar_wait(b_full + bs, (b_it / B_ST) & 1));
-                bd_hi = bd_res0 + (uint32_t)bs * (t.b_stage_bytes >> 4);
-#endif
               }
               tc_fence_after();
               const uint64_t ad_hi = ad0 + (uint32_t)((dy * HWP + dx) * (ROWB >> 4));
@@ -592,17 +573,10 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
                 }
               }
               accumulate = 1;
-#ifdef FVP_TC_STREAM_ROWS
               if (!t.resident && dx == K - 1) {
                 if (elect_one()) umma_commit(b_empty + bs);          // the row's stage is reusable when its MMAs retire
                 ++b_it;
               }
-#else
-              if (!t.resident) {
-                if (elect_one()) umma_commit(b_empty + bs);          // B slot reusable when these MMAs retire
-                ++b_it;
-              }
-#endif
             }
           }
           blk += (uint32_t)K * K * nts_img;
@@ -650,7 +624,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
         ch = co - q * Co;
         return (px_plain + (size_t)(q >> 1) * Wo + (q & 1)) * a.CoutS;
       };
-      constexpr int CW = (OCC == 2 || TC_LOADERS != 256) ? 8 : 16, G4 = CW / 4;         // columns per chunk (8 keeps the 2-CTA variant in 72 registers)
+      constexpr int CW = OCC == 2 ? 8 : 16, G4 = CW / 4;         // columns per chunk (8 keeps the 2-CTA variant in 72 registers)
       auto fetch_res = [&](int cb, float4* rr) {                   // residuals of one chunk, issued early
 #pragma unroll
         for (int g4 = 0; g4 < G4; ++g4) rr[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -698,6 +672,8 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
           if (a.res_mode == 1) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
           if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           if (a.res_mode == 2) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+          // range guard (NaN fails the comparison too); also in the 3xTF32 variant, whose outputs may feed an fp16 layer
+          if (!(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))) < 65504.0f) && g_tc_status) *g_tc_status = 1;
           const int ch = ch0 + g4 * 4;
           if (!a.nchw) {
             *(float4*)(a.out + off + ch) = o;
@@ -738,22 +714,49 @@ void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
   *n_tiles = fvp_cdiv(npad, *n_tile);
 }
 
-static int* g_tc_plan = nullptr;   // set by fvp_debug_conv_plan: fvp_launch_conv_tc records its decisions here and returns before touching the GPU
-static unsigned long long* g_tc_prof = nullptr;
-static int g_tc_occ = [] { const char* e = std::getenv("FVP_TC_OCC"); return e ? std::atoi(e) : 2; }();   // 1: never co-schedule two CTAs per SM (A/B switch)
-void fvp_tc_set_prof(unsigned long long* d_counters) { g_tc_prof = d_counters; }   // debug hook (fvp_debug_conv)
+// read-only after start-up: FVP_TC_OCC=1 never co-schedules two CTAs per SM (A/B switch of tools/gpu_conv_check.sh)
+static const int g_tc_occ = [] { const char* e = std::getenv("FVP_TC_OCC"); return e ? std::atoi(e) : 2; }();
+// read-only after start-up: FVP_TC_VARIANT=0/1/2 forces the N-tile cap (128 / 32 / 64 columns) where that image exists (A/B switch)
+static const int g_tc_variant = [] { const char* e = std::getenv("FVP_TC_VARIANT"); return e ? std::atoi(e) : -1; }();
+
+// Per-device setup (fvp_create): opt-in shared memory of all six instantiations, carve-out of the two-CTA variants.
+cudaError_t fvp_conv_tc_init_device() {
+  const void* fns[6] = {(const void*)k_conv_tc<0, 1>, (const void*)k_conv_tc<1, 1>, (const void*)k_conv_tc<2, 1>,
+                        (const void*)k_conv_tc<0, 2>, (const void*)k_conv_tc<1, 2>, (const void*)k_conv_tc<2, 2>};
+  for (int i = 0; i < 6; ++i) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, fns[i]);
+    if (e != cudaSuccess) return e;
+    if (fa.sharedSizeBytes > (size_t)TC_STATIC_SMEM) {
+      fprintf(stderr, "fvp_conv_tc_init_device: static shared memory %zu B exceeds TC_STATIC_SMEM\n", fa.sharedSizeBytes);
+      return cudaErrorInvalidValue;
+    }
+    e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_DYN_SMEM_MAX);
+    if (e != cudaSuccess) return e;
+    if (i >= 3) {
+      e = cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  return cudaSuccess;
+}
+cudaError_t fvp_conv_tc_set_status_ptr(int* d_status) {
+  return cudaMemcpyToSymbol(g_tc_status, &d_status, sizeof(d_status));
+}
 
 // mode: 0 = 3xTF32, 1 = fp16 split with 32-channel K-blocks, 2 = fp16 split with 16-channel K-blocks
 // wtc[3]: weight images tiled for N tiles of up to 128 / 32 / 64 columns (NULL where not packed)
-void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st) {
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, const FvpLaunchEnv& env, cudaStream_t st) {
+  const int num_sms = env.num_sms;
+  int* const plan_out = env.tc_plan;
   if ((mode != 2 && a.ksize > 3) || a.CoutP > TC_MAX_COUT) {     // the loaders of the 32-channel K-block variants hold a 3x3 halo at most (EPT); 7x7 layers
-    if (g_tc_plan) { g_tc_plan[0] = 0; return; }      // plan query: "not handled by the tensor-core engine"
-    fvp_launch_conv(a, st);           // of this network have <= 16 input channels and run in mode 2
+    if (plan_out) { plan_out[0] = 0; return; }        // plan query: "not handled by the tensor-core engine"
+    fvp_launch_conv(a, st);           // of this network run in mode 2 (16-channel K-blocks)
     return;
   }
   TcArgs t;
   t.c = a;
-  t.prof = g_tc_prof;
+  t.prof = env.tc_prof;
   const uint32_t rowb = mode == 0 ? 128 : (mode == 1 ? 64 : 32);
   const int cb = mode == 2 ? 16 : 32, f16 = mode != 0;
   const int tiles = fvp_cdiv(a.H, TC_TH) * fvp_cdiv(a.W, TC_TW) * a.n;
@@ -787,18 +790,14 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
     const double cost = (double)fvp_cdiv(tiles * nts, num_sms) * per_item * (residency(nt, nts) ? 1.0 : 1.8) + 1.0 * nts;   // ties: wider tile
     if (cost < best_cost) { best_cost = cost; best = v; }
   }
+  if (g_tc_variant >= 0 && g_tc_variant < 3 && wtc[g_tc_variant]) best = g_tc_variant;
   fvp_tc_geometry(a.CoutP, best, &t.n_tile, &t.n_tiles);
   t.wtc = wtc[best];
   t.blk_bytes = (uint32_t)t.n_tile * rowb * 2;
   const uint32_t image_bytes = (uint32_t)nblocks * t.n_tiles * t.blk_bytes;
   const int res = residency(t.n_tile, t.n_tiles);
-#ifdef FVP_TC_STREAM_ROWS
-  const uint32_t stage_bytes = (uint32_t)k * t.blk_bytes;         // experiment: one ring stage per tap row
+  const uint32_t stage_bytes = (uint32_t)k * t.blk_bytes;         // streamed weights: one ring stage per tap row
   const int min_stages = 2;
-#else
-  const uint32_t stage_bytes = t.blk_bytes;
-  const int min_stages = 4;
-#endif
   const int stream2 = (2 * t.a_stage_bytes + min_stages * stage_bytes <= budget) ? (int)((budget - 2 * t.a_stage_bytes) / stage_bytes) : 0;
   if (res == 1) {                                                  // weights resident, double-buffered halo
     t.resident = 1; t.a_stages = 2; t.b_stages = 1; t.b_stage_bytes = image_bytes;
@@ -831,30 +830,15 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   // faster with two CTAs per SM; the 3x3 16->32 layer (16-channel K-blocks, loader-bound) is 9 % slower and keeps one.
   // (Also tried and dropped: one LDG.128 per lane over whole 128-B lines with 8-byte shared stores - fewer L1 sector
   //  lookups but twice the store instructions: 3 % slower over the trunk's layer mix.)
-  const bool occ2 = TC_LOADERS == 256 && g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
+  const bool occ2 = g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
   const int slots = num_sms * (occ2 ? 2 : 1);
   int grid = t.total_items < slots ? t.total_items : slots;              // persistent: one or two CTAs per SM
   if (t.resident == 2) grid -= grid % t.n_tiles;                         // CTA b serves N tile b % n_tiles only
-  if (g_tc_plan) {                                                       // host-only query of the decisions above (tests)
+  if (plan_out) {                                                        // host-only query of the decisions above (tests)
     const int plan[10] = {t.n_tile, t.n_tiles, t.resident, t.a_stages, t.b_stages, (int)smem, occ2 ? 1 : 0, grid, t.total_items,
                           (int)t.tmem_cols};
-    for (int i = 0; i < 10; ++i) g_tc_plan[i] = plan[i];
+    for (int i = 0; i < 10; ++i) plan_out[i] = plan[i];
     return;
-  }
-  static bool attr = false;
-  if (!attr) {
-    const void* fns[6] = {(const void*)k_conv_tc<0, 1>, (const void*)k_conv_tc<1, 1>, (const void*)k_conv_tc<2, 1>,
-                          (const void*)k_conv_tc<0, 2>, (const void*)k_conv_tc<1, 2>, (const void*)k_conv_tc<2, 2>};
-    for (int i = 0; i < 6; ++i) {
-      cudaFuncAttributes fa;
-      if (cudaFuncGetAttributes(&fa, fns[i]) != cudaSuccess || fa.sharedSizeBytes > (size_t)TC_STATIC_SMEM) {
-        fprintf(stderr, "fvp_launch_conv_tc: static shared memory %zu B exceeds TC_STATIC_SMEM\n", fa.sharedSizeBytes);
-        abort();
-      }
-      cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_DYN_SMEM_MAX);
-      if (i >= 3) cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
-    attr = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -890,10 +874,9 @@ extern "C" int fvp_debug_conv_plan(int n, int H, int W, int cin, int cin2, int c
   const int npad = fvp_round_up(a.CoutP, 16);
   const float* wide[3] = {&dummy, npad > 32 ? &dummy : nullptr, npad > 64 ? &dummy : nullptr};     // as stash() packs them
   const float* c16[3] = {&dummy, nullptr, nullptr};
-  const bool use_c16 = engine == 2 && cin <= 16 && cin2 <= 16;
+  const bool use_c16 = engine == 2 && ((cin <= 16 && cin2 <= 16) || (k == 7 && cin <= 32));     // as stash() packs them
   for (int i = 0; i < 10; ++i) out[i] = 0;
-  g_tc_plan = out;
-  fvp_launch_conv_tc(a, use_c16 ? c16 : wide, engine == 2 ? (use_c16 ? 2 : 1) : 0, num_sms, nullptr);
-  g_tc_plan = nullptr;
+  const FvpLaunchEnv env{num_sms, engine, nullptr, out};
+  fvp_launch_conv_tc(a, use_c16 ? c16 : wide, engine == 2 ? (use_c16 ? 2 : 1) : 0, env, nullptr);
   return 0;
 }

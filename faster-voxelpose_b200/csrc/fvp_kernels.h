@@ -85,10 +85,26 @@ struct FvpConvW {         // one packed conv
   const float* wtc16[3];    // fp16 hi / scaled-lo split (engine 2)
   const float* wtc16_c16;   // fp16 split with 16-channel K-blocks (layers with <= 16 input channels), NULL otherwise
 };
+// Everything a conv launch needs to know about its context.  Handed down from fvp_ctx on every call: the launchers keep NO
+// process-global mutable state, so contexts on different devices / host threads do not interfere.
+struct FvpLaunchEnv {
+  int num_sms;                      // SM count of the context's device
+  int conv_mode;                    // 0 CUDA cores, 1 tcgen05 3xTF32, 2 tcgen05 fp16 hi/lo split
+  unsigned long long* tc_prof;      // debug: 12 role counters of k_conv_tc (fvp_debug_conv), NULL in production
+  int* tc_plan;                     // host-only plan query (fvp_debug_conv_plan): decisions are recorded, nothing is launched
+};
 // tcgen05 / TMEM implicit-GEMM conv (fvp_conv_tc.cu); same arguments as fvp_launch_conv plus the tiled weights
-void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, int num_sms, cudaStream_t st);
-void fvp_tc_set_prof(unsigned long long* d_counters);   // debug: 9 role counters (see fvp_debug_conv)
+void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, const FvpLaunchEnv& env, cudaStream_t st);
 void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles);
+// Per-DEVICE one-time setup (function attributes are per device: opt-in shared-memory sizes, carve-outs); fvp_create calls
+// every one of these on the context's device, so a second context on another GPU of the same process is set up as well.
+cudaError_t fvp_conv_tc_init_device();
+cudaError_t fvp_conv_init_device();
+cudaError_t fvp_proposal_init_device(int X, int Y);
+// Range guard of the fp16 hi/lo engine: a conv output outside the fp16 range (the next layer's operand) sets *status |= 1
+// through this per-device pointer (mapped pinned host memory, read by the host after a synchronise).
+cudaError_t fvp_conv_tc_set_status_ptr(int* d_status);
+cudaError_t fvp_conv_set_status_ptr(int* d_status);    // same word, CUDA-core kernel (its outputs may feed an fp16 layer)
 struct FvpTrunkW {
   FvpConvW front, r1a, r1b, s1a, s1b, e1a, e1b, s2a, s2b, e2a, e2b, ma, mb, d2a, d2b, up2, d1a, d1b, up1;
   FvpConvW head_a, head_b;   // CenterNet: merged 3x3 (32->64) + block-diagonal 1x1 (64->3); P2PNet: head_b only
@@ -96,7 +112,7 @@ struct FvpTrunkW {
 // buf[6]: scratch units of n*H*W*64 floats each
 void fvp_run_trunk2d(const FvpTrunkW& t, const float* d_in, int cin, int n, int H, int W, float* const buf[6],
                      const int* valid, bool center_heads, float* d_out, int out_real, int* launches, cudaStream_t st,
-                     int tensor_cores);
+                     const FvpLaunchEnv& env);
 
 // ---- proposals -------------------------------------------------------------------------------
 // nms2D + top-k: hm planar with image stride `img_stride` floats -> conf [B][P], flat [B][P]

@@ -264,18 +264,33 @@ std::vector<float> pack_tc16(const Packed& p, int narrow, int cb = 32) {
   return f;
 }
 
+// Largest magnitude the fp16 hi/lo engine may be handed as a weight: fp16(w) must be finite (|w| < 65520 rounds to <= 65504).
+// Real checkpoints can exceed it after BN folding (small running_var, large gamma); such a layer gets no fp16 image and
+// runs on the 3xTF32 engine (fp32 exponent range) instead - see conv() in fvp_conv.cu.
+constexpr float FVP_FP16_WEIGHT_LIMIT = 65504.0f;
+bool fits_fp16(const Packed& p) {
+  float m = 0.f;
+  for (float w : p.w) m = std::fmax(m, std::fabs(w));                 // NaN-safe: fmax ignores NaN, caught below
+  for (float w : p.w) if (!(std::fabs(w) < INFINITY)) return false;
+  return m < FVP_FP16_WEIGHT_LIMIT;
+}
+
 PendingConv stash(Arena& A, const Packed& p, bool tc = false, int cin_act = 0) {
   PendingConv pc;
   pc.w_off = A.put(p.w);
   pc.b_off = A.put(p.b);
   const int npad = fvp_round_up(p.coutp, 16);
+  const bool f16_ok = fits_fp16(p);
   for (int v = 0; v < 3; ++v) {                      // N-tile caps 128 / 32 / 64 (only where they differ from the wide image)
     const bool need = tc && (v == 0 || (v == 1 && npad > 32) || (v == 2 && npad > 64));
     pc.tc_off[v] = need ? A.put(pack_tc(p, cin_act ? cin_act : p.cin, v)) : (size_t)-1;
-    pc.t16_off[v] = need ? A.put(pack_tc16(p, v)) : (size_t)-1;
+    pc.t16_off[v] = need && f16_ok ? A.put(pack_tc16(p, v)) : (size_t)-1;
   }
-  // layers whose (activation) input has <= 16 channels also get a 16-channel K-block image (32-B rows)
-  const bool c16 = tc && (cin_act ? cin_act : p.cin) <= 16 && p.cin2 <= 16;
+  // layers whose (activation) input has <= 16 channels also get a 16-channel K-block image (32-B rows); so does the 7x7
+  // front conv with up to 32 input channels (J = 17 -> JP = 20: Campus / Shelf), as two 16-channel K-blocks - the 32-channel
+  // K-block loaders hold a 3x3 halo at most
+  const int cact = cin_act ? cin_act : p.cin;
+  const bool c16 = tc && f16_ok && ((cact <= 16 && p.cin2 <= 16) || (p.k == 7 && cact <= 32 && p.cin2 == 0));
   pc.t16c_off = c16 ? A.put(pack_tc16(p, 0, 16)) : (size_t)-1;
   pc.cin = p.cin; pc.cin2 = p.cin2; pc.coutp = p.coutp; pc.k = p.k;
   return pc;
@@ -448,6 +463,10 @@ int fvp_pack_params(fvp_ctx* ctx) {
   ctx->w_pose.fc2_b = base + o_f2b;
   ctx->w_pose.feat = F;
   ctx->w_pose.hidden = ctx->cfg.hidden_channels;
+  ctx->fp16_fallback_layers = 0;                     // tensor-core layers whose folded weights left the fp16 range
+  for (const std::vector<PendingConv>* v : {&cn, &p2p})
+    for (const PendingConv& pc : *v)
+      if (pc.tc_off[0] != (size_t)-1 && pc.t16_off[0] == (size_t)-1) ++ctx->fp16_fallback_layers;
   ctx->params_ready = true;
   return FVP_OK;
 }
@@ -468,7 +487,8 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
     p.b[co] = h_b[co];
   }
   Arena A;
-  const size_t ow = A.put(p.w), ob = A.put(p.b), ot = A.put(pack_tc(p, cin, 0)), ot16 = A.put(pack_tc16(p, 0)), ot16c = cin <= 16 ? A.put(pack_tc16(p, 0, 16)) : 0;
+  const bool c16 = cin <= 16 || (k == 7 && cin <= 32);               // 16-channel K-blocks, as stash() decides for the trunks
+  const size_t ow = A.put(p.w), ob = A.put(p.b), ot = A.put(pack_tc(p, cin, 0)), ot16 = A.put(pack_tc16(p, 0)), ot16c = c16 ? A.put(pack_tc16(p, 0, 16)) : 0;
   float* d = nullptr;
   FVP_CUDA_OK(cudaMalloc(&d, A.host.size() * sizeof(float)));
   FVP_CUDA_OK(cudaMemcpy(d, A.host.data(), A.host.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -482,22 +502,22 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   mode &= 0xff;
   unsigned long long* d_prof = nullptr;
   if (prof) { FVP_CUDA_OK(cudaMalloc(&d_prof, 12 * sizeof(unsigned long long))); }
+  FvpLaunchEnv env{ctx->num_sms, mode, nullptr, nullptr};
   for (int it = 0; it < 1 + (repeat > 0 ? repeat : 1); ++it) {     // first launch = warm-up
     if (it == 1) {
       cudaEventRecord(e0, st);
-      if (prof) { cudaMemsetAsync(d_prof, 0, 12 * sizeof(unsigned long long), st); fvp_tc_set_prof(d_prof); }
+      if (prof) { cudaMemsetAsync(d_prof, 0, 12 * sizeof(unsigned long long), st); env.tc_prof = d_prof; }
     }
     const float* const i16c[3] = {d + ot16c, nullptr, nullptr};
     const float* const i16[3] = {d + ot16, nullptr, nullptr};
     const float* const i32[3] = {d + ot, nullptr, nullptr};
-    if (mode == 2 && cin <= 16) fvp_launch_conv_tc(a, i16c, 2, ctx->num_sms, st);
-    else if (mode == 2 || mode == 3) fvp_launch_conv_tc(a, i16, 1, ctx->num_sms, st);
-    else if (mode == 1) fvp_launch_conv_tc(a, i32, 0, ctx->num_sms, st);
+    if (mode == 2 && c16) fvp_launch_conv_tc(a, i16c, 2, env, st);
+    else if (mode == 2 || mode == 3) fvp_launch_conv_tc(a, i16, 1, env, st);
+    else if (mode == 1) fvp_launch_conv_tc(a, i32, 0, env, st);
     else fvp_launch_conv(a, st);
   }
   cudaEventRecord(e1, st);
   FVP_CUDA_OK(cudaStreamSynchronize(st));
-  fvp_tc_set_prof(nullptr);
   if (ms_out) { cudaEventElapsedTime(ms_out, e0, e1); *ms_out /= (float)(repeat > 0 ? repeat : 1); }
   if (prof && ms_out) {                                             // kilo-cycles per launch, summed over CTAs
     unsigned long long h[12];

@@ -74,12 +74,7 @@ __global__ void __launch_bounds__(1024) k_nms_topk(const float* __restrict__ hm,
 
 void fvp_launch_nms_topk(const float* d_hm, size_t img_stride, int X, int Y, int P, int batch, float* d_conf,
                          int* d_flat, cudaStream_t st) {
-  const size_t smem = (size_t)X * Y * sizeof(float);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(k_nms_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
+  const size_t smem = (size_t)X * Y * sizeof(float);               // opt-in size set per device by fvp_proposal_init_device
   k_nms_topk<<<batch, 1024, smem, st>>>(d_hm, img_stride, X, Y, P, d_conf, d_flat);
 }
 
@@ -103,6 +98,7 @@ struct C2CNet {
 // The layer's packed weights are streamed global(L2) -> shared in 32 KB chunks with cp.async, double buffered, so the
 // inner loop reads only shared memory (round 1 read every weight straight from L2 inside the FMA loop: 0.45 ms).
 constexpr int C2C_WCHUNK = 8192;    // floats per weight buffer (32 KB)
+constexpr size_t C2C_SMEM_BYTES = (size_t)(2 * C2C_WCHUNK + 6 * C2C_BUF + 24 * C2C_MAXZ + 4 * C2C_MAXZ + C2C_THREADS * C2C_MAXZ) * sizeof(float);
 
 __device__ __forceinline__ void c2c_cp16(float* dst_smem, const float* src_gmem) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -514,18 +510,27 @@ __global__ void k_people_from_centers(FvpPropArgs a, const float* __restrict__ c
     for (int q = 0; q < 3; ++q) a.img_valid[q * a.n_slots + slot] = pd.valid;
 }
 
+// Per-device setup (fvp_create): dynamic shared memory opt-ins of the NMS kernel (the whole X*Y map) and the proposal kernel.
+// A grid whose NMS map does not fit the 227 KB per-CTA limit is refused here, at create time, with a clear error.
+cudaError_t fvp_proposal_init_device(int X, int Y) {
+  const size_t nms = (size_t)X * Y * sizeof(float);
+  if (nms + 1024 > 227 * 1024) return cudaErrorInvalidConfiguration;
+  cudaFuncAttributes fa;                         // several contexts may share the device: never lower an earlier opt-in
+  cudaError_t e = cudaFuncGetAttributes(&fa, k_nms_topk);
+  if (e != cudaSuccess) return e;
+  if (nms > 48 * 1024 && nms > (size_t)fa.maxDynamicSharedSizeBytes)
+    e = cudaFuncSetAttribute(k_nms_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_proposals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2C_SMEM_BYTES);
+}
+
 void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, cudaStream_t st) {
   C2CNet net;
   for (int i = 0; i < 20; ++i) {
     net.l[i].w = w.w[i];
     net.l[i].b = w.b[i];
   }
-  const size_t smem = (size_t)(2 * C2C_WCHUNK + 6 * C2C_BUF + 24 * C2C_MAXZ + 4 * C2C_MAXZ + C2C_THREADS * C2C_MAXZ) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_proposals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
+  const size_t smem = C2C_SMEM_BYTES;
   C2CNet2 net2;
   for (int i = 0; i < 20; ++i) {
     net2.w[i] = w.w2[i];

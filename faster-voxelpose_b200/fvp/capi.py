@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # ...
 LIB_NAME = "libfvp_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
 
-FVP_OK, FVP_E_INVALID, FVP_E_CUDA, FVP_E_STATE, FVP_E_NOTFOUND, FVP_E_CALIB = 0, -1, -2, -3, -4, -5
+FVP_OK, FVP_E_INVALID, FVP_E_CUDA, FVP_E_STATE, FVP_E_NOTFOUND, FVP_E_CALIB, FVP_E_RANGE = 0, -1, -2, -3, -4, -5, -6
 ABI_VERSION = 1
 
 
@@ -77,6 +77,8 @@ SYMBOLS = {
     "fvp_c2c_net": (C.c_int, [_CTX, _P, C.c_int, _P, C.c_size_t]),
     "fvp_render_heatmaps": (C.c_int, [_CTX, _P, _P, _P, C.c_int, C.c_int, C.c_double, _P, C.c_size_t]),
     "fvp_set_conv_mode": (C.c_int, [_CTX, C.c_int]),
+    "fvp_check_range": (C.c_int, [_CTX]),
+    "fvp_fp16_fallback_layers": (C.c_int, [_CTX]),
     "fvp_last_launch_count": (C.c_int, [_CTX]),
     "fvp_set_profiling": (C.c_int, [_CTX, C.c_int]),
     "fvp_stage_times_ms": (C.c_int, [_CTX, C.POINTER(C.c_float * 9)]),

@@ -247,6 +247,18 @@ class Engine:
     def use_cuda_graph(self, on: bool = True) -> None:
         self._ck(self.lib.fvp_use_cuda_graph(self.ctx, 1 if on else 0))
 
+    def check_range(self, synchronize: bool = True) -> None:
+        """Raise ``FvpError(FVP_E_RANGE)`` if a convolution stored an activation outside the fp16 range of the default
+        hi/lo engine since the last check (the host entry points check by themselves; the stream-ordered ``forward`` cannot
+        without a synchronise)."""
+        if synchronize:
+            torch.cuda.synchronize(self.device)
+        self._ck(self.lib.fvp_check_range(self.ctx))
+
+    def fp16_fallback_layers(self) -> int:
+        """Conv layers whose BN-folded weights left the fp16 range and therefore run on the 3xTF32 engine."""
+        return int(self.lib.fvp_fp16_fallback_layers(self.ctx))
+
     def set_conv_mode(self, mode: int) -> None:
         """0 = fp32 CUDA-core convolutions, 1 = tcgen05 3xTF32, 2 = tcgen05 fp16 hi/lo split (default)."""
         self._ck(self.lib.fvp_set_conv_mode(self.ctx, int(mode)))

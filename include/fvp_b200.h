@@ -32,8 +32,10 @@ enum {
   FVP_E_CUDA = -2,      /* CUDA runtime error (message has cudaGetErrorString)    */
   FVP_E_STATE = -3,     /* call order (e.g. forward before finalize_params)       */
   FVP_E_NOTFOUND = -4,  /* unknown parameter / sequence slot                      */
-  FVP_E_CALIB = -5      /* calibration missing / wrong camera count (reference: AssertionError,
+  FVP_E_CALIB = -5,     /* calibration missing / wrong camera count (reference: AssertionError,
                            lib/models/project_whole.py:73-74)                     */
+  FVP_E_RANGE = -6      /* an activation left the fp16 range of the hi/lo tensor-core engine (results are invalid;
+                           select conv mode 1 or 0).  Reported by the host entry points and fvp_check_range.   */
 };
 
 /* Geometry + network constants: the keys FasterVoxelPoseNet reads from cfg (SURVEY.md section 5,
@@ -197,6 +199,16 @@ int fvp_render_heatmaps(fvp_ctx* ctx, const double* h_joints, const int32_t* h_n
 /* convolution engine of CenterNet / P2PNet: 0 = exact-fp32 CUDA-core implicit GEMM, 1 = tcgen05/TMEM implicit GEMM with
  * the error-compensated 3xTF32 split (default set at build time) */
 int fvp_set_conv_mode(fvp_ctx* ctx, int mode);
+
+/* Range guard of the default convolution engine (fp16 hi/lo split: operands must stay below 65504).  BN-folded weights
+ * are checked when they are packed (a layer outside the range silently runs on the 3xTF32 engine); activations are checked
+ * by the kernels as they are stored.  fvp_forward_host / fvp_wait report a violation as FVP_E_RANGE; after the
+ * stream-ordered fvp_forward call fvp_check_range once the stream was synchronised (it does not synchronise itself).
+ * Returns FVP_OK or FVP_E_RANGE (and clears the flag, which is shared by all contexts of a device). */
+int fvp_check_range(fvp_ctx* ctx);
+/* number of CenterNet / P2PNet layers whose BN-folded weights left the fp16 range at the last fvp_finalize_params and
+ * therefore run on the 3xTF32 engine (0 for well-conditioned checkpoints) */
+int fvp_fp16_fallback_layers(const fvp_ctx* ctx);
 
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* number of kernel launches the last fvp_forward enqueued (graph replay counts its kernel nodes) */
