@@ -46,8 +46,10 @@ void linspace_plus(float start, float end, int n, float center, float* out) {
   }
 }
 
+fvp_ctx* sync_shared(fvp_ctx* ctx);
 int check_stage_ready(fvp_ctx* ctx, int batch) {
   if (!ctx) return FVP_E_INVALID;
+  sync_shared(ctx);                               // a lane picks up its root's current weights / tables
   if (batch < 1 || batch > ctx->cfg.max_batch)
     return fvp_fail(ctx, FVP_E_INVALID, "batch %d outside [1, max_batch=%d]", batch, ctx->cfg.max_batch);
   return FVP_OK;
@@ -63,17 +65,13 @@ int check_stage_entry(fvp_ctx* ctx, int batch) {
 int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaStream_t st) {
   bool same = true;
   std::vector<int> want(batch);
+  const fvp_ctx* owner = ctx->root ? ctx->root : ctx;        // calibrations and sample grids live in the root context
   for (int b = 0; b < batch; ++b) {
     const int s = h_seq_slots ? h_seq_slots[b] : 0;
-    if (s < 0 || s >= ctx->cfg.max_sequences || !ctx->seq_set[s])
+    if (s < 0 || s >= owner->cfg.max_sequences || !owner->seq_set[s] || !owner->grid_ready[s])
       return fvp_fail(ctx, FVP_E_CALIB, "missing camera parameters for the current sequence (slot %d of frame %d)", s, b);
     if (ctx->h_frame_seq[b] != s || b >= ctx->frame_seq_uploaded) same = false;
     want[b] = s;
-    if (!ctx->grid_ready[s]) {                     // sample-grid cache of this calibration (two small kernels, once)
-      fvp_launch_build_sample_grids(ctx->geom, s, st);
-      FVP_CUDA_OK(cudaGetLastError());
-      ctx->grid_ready[s] = 1;
-    }
   }
   if (same) return FVP_OK;                       // device copy already holds these slots
   FVP_CUDA_OK(cudaStreamSynchronize(st));        // the pinned staging buffer may still be in flight
@@ -91,6 +89,83 @@ int fvp_k3_parts(const fvp_ctx* ctx, int batch) {
   return parts;
 }
 
+// Per-context workspaces, streams and events (everything a lane owns), sized for ctx->cfg.max_batch.
+cudaError_t alloc_workspaces(fvp_ctx* ctx) {
+  const fvp_config& c = ctx->cfg;
+  const FvpGeom& g = ctx->geom;
+  const FvpProj& P = g.proj;
+  const int MB = c.max_batch, n = MB * g.P, XY = g.X * g.Y, JP = P.JP;
+  cudaError_t e = cudaSuccess;
+  bool ok = true;
+  auto A = [&](cudaError_t r) { if (r != cudaSuccess && ok) { ok = false; e = r; } };
+  A(dalloc(&ctx->d_hm_in, (size_t)MB * g.V * g.J * P.H * P.W));
+  A(dalloc(&ctx->d_hm_cl, (size_t)MB * g.V * g.view_stride4 * 4));
+  A(dalloc(&ctx->d_plane_cl, (size_t)MB * XY * JP));
+  A(dalloc(&ctx->d_hmsize, (size_t)MB * 3 * XY));
+  A(dalloc(&ctx->d_conf2d, (size_t)n));
+  A(dalloc(&ctx->d_flat, (size_t)n));
+  A(dalloc(&ctx->d_centers, (size_t)n * 7));
+  A(dalloc(&ctx->d_people, (size_t)n));
+  A(dalloc(&ctx->d_img_valid, (size_t)3 * n));
+  A(dalloc(&ctx->d_planes_cl, (size_t)3 * n * 4096 * JP));
+  A(dalloc(&ctx->d_feat, (size_t)3 * n * g.J * 4096));
+  A(dalloc(&ctx->d_pose, (size_t)3 * n * g.J * 2));
+  A(dalloc(&ctx->d_maxw, (size_t)3 * n * g.J));
+  A(dalloc(&ctx->d_wts, (size_t)3 * n * g.J));
+  A(dalloc(&ctx->d_fused, (size_t)n * g.J * 3));
+  A(dalloc(&ctx->d_conf, (size_t)n));
+  A(dalloc(&ctx->d_out_fused, (size_t)n * g.J * 5));
+  A(dalloc(&ctx->d_out_plane, (size_t)3 * n * g.J * 2));
+  A(dalloc(&ctx->d_out_centers, (size_t)n * 7));
+  ctx->tmp_floats = (size_t)3 * n * 4096 * JP;
+  if ((size_t)MB * XY * JP > ctx->tmp_floats) ctx->tmp_floats = (size_t)MB * XY * JP;
+  A(dalloc(&ctx->d_tmp, ctx->tmp_floats));
+  for (int i = 0; i < 6; ++i) {
+    A(dalloc(&ctx->cn_buf[i], (size_t)MB * XY * 64));
+    A(dalloc(&ctx->p2p_buf[i], (size_t)3 * n * 4096 * 64));
+  }
+  A(dalloc(&ctx->d_frame_seq, (size_t)MB));
+  A(cudaMallocHost((void**)&ctx->h_frame_seq, MB * sizeof(int)));
+  for (int i = 0; i < 10; ++i) A(cudaEventCreate(&ctx->ev[i]));
+  A(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  A(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  A(dalloc(&ctx->d_hm_in_b, (size_t)MB * g.V * g.J * P.H * P.W));
+  for (int i = 0; i < 2; ++i) {
+    A(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&ctx->ev_k0[i], cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+  }
+  if (ok) {
+    A(cudaMemset(ctx->d_hm_cl, 0, (size_t)MB * g.V * g.view_stride4 * 16));   // zero borders (never written again)
+    A(cudaMemset(ctx->d_people, 0, (size_t)n * sizeof(FvpPerson)));
+    A(cudaMemset(ctx->d_img_valid, 0, (size_t)3 * n * sizeof(int)));
+    A(cudaMemset(ctx->d_feat, 0, (size_t)3 * n * g.J * 4096 * sizeof(float)));
+  }
+  return e;
+}
+
+// A lane mirrors the read-only tables of its root; the root bumps shared_gen whenever weights, axes or calibrations change.
+// Called at the start of every entry point that launches kernels.  Returns the context that owns the shared state.
+fvp_ctx* sync_shared(fvp_ctx* ctx) {
+  fvp_ctx* r = ctx->root;
+  if (!r) return ctx;
+  if (ctx->shared_gen != r->shared_gen) {
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }   // may hold stale weight pointers
+    ctx->w_center = r->w_center; ctx->w_p2p = r->w_p2p; ctx->w_c2c = r->w_c2c; ctx->w_pose = r->w_pose;
+    ctx->params_ready = r->params_ready;
+    ctx->geom = r->geom;
+    ctx->prop = r->prop;
+    ctx->frame_seq_uploaded = 0;
+    ctx->shared_gen = r->shared_gen;
+  }
+  return r;
+}
+
+int refuse_on_lane(fvp_ctx* ctx, const char* what) {
+  if (ctx->root) return fvp_fail(ctx, FVP_E_STATE, "%s must be called on the root context, not on a lane", what);
+  return FVP_OK;
+}
+
 FvpLaunchEnv launch_env(const fvp_ctx* ctx) { return FvpLaunchEnv{ctx->num_sms, ctx->conv_mode, nullptr, nullptr}; }
 
 // Other entry points must not touch the shared workspaces while fvp_submit_host tickets are in flight.
@@ -104,6 +179,7 @@ int refuse_if_tickets_open(fvp_ctx* ctx) {
 int check_range_status(fvp_ctx* ctx) {
   if (ctx->h_status && *(volatile int*)ctx->h_status) {
     *(volatile int*)ctx->h_status = 0;
+    if (ctx->conv_mode != 2) return FVP_OK;       // no layer of this context uses fp16 operands: the mark is irrelevant
     return fvp_fail(ctx, FVP_E_RANGE, "a convolution produced an activation outside the fp16 range (|x| >= 65504 or NaN): the "
                     "fp16 hi/lo tensor-core engine cannot represent it; use fvp_set_conv_mode(ctx, 1) (3xTF32) or 0 (fp32)");
   }
@@ -287,7 +363,8 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
     pa.whole[d] = c.space_size[d]; pa.ind[d] = c.ind_space_size[d]; pa.ind_vox[d] = c.ind_voxels[d];
   }
 
-  const int MB = c.max_batch, n = MB * g.P, XY = g.X * g.Y, JP = P.JP;
+  ctx->num_sms = prop.multiProcessorCount;
+  // shared (read-only during forwards) state: axis tables, calibration blocks, sample-grid caches
   const size_t n_axes = (size_t)g.X + g.Y + g.Z + g.fine[0] + g.fine[1] + g.fine[2] + 192;
   bool ok = true;
   auto A = [&](cudaError_t r) { if (r != cudaSuccess && ok) { ok = false; e = r; } };
@@ -295,50 +372,8 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   A(dalloc(&ctx->d_coarse_grid, (size_t)c.max_sequences * g.V * g.X * g.Y * g.Z));
   A(dalloc(&ctx->d_fine_grid, (size_t)c.max_sequences * g.V * g.fine[0] * g.fine[1] * g.fine[2]));
   A(dalloc(&ctx->d_seqs, (size_t)c.max_sequences));
-  A(dalloc(&ctx->d_hm_in, (size_t)MB * g.V * g.J * P.H * P.W));
-  A(dalloc(&ctx->d_hm_cl, (size_t)MB * g.V * g.view_stride4 * 4));
-  A(dalloc(&ctx->d_plane_cl, (size_t)MB * XY * JP));
-  A(dalloc(&ctx->d_hmsize, (size_t)MB * 3 * XY));
-  A(dalloc(&ctx->d_conf2d, (size_t)n));
-  A(dalloc(&ctx->d_flat, (size_t)n));
-  A(dalloc(&ctx->d_centers, (size_t)n * 7));
-  A(dalloc(&ctx->d_people, (size_t)n));
-  A(dalloc(&ctx->d_img_valid, (size_t)3 * n));
-  A(dalloc(&ctx->d_planes_cl, (size_t)3 * n * 4096 * JP));
-  A(dalloc(&ctx->d_feat, (size_t)3 * n * g.J * 4096));
-  A(dalloc(&ctx->d_pose, (size_t)3 * n * g.J * 2));
-  A(dalloc(&ctx->d_maxw, (size_t)3 * n * g.J));
-  A(dalloc(&ctx->d_wts, (size_t)3 * n * g.J));
-  A(dalloc(&ctx->d_fused, (size_t)n * g.J * 3));
-  A(dalloc(&ctx->d_conf, (size_t)n));
-  A(dalloc(&ctx->d_out_fused, (size_t)n * g.J * 5));
-  A(dalloc(&ctx->d_out_plane, (size_t)3 * n * g.J * 2));
-  A(dalloc(&ctx->d_out_centers, (size_t)n * 7));
-  ctx->tmp_floats = (size_t)3 * n * 4096 * JP;
-  if ((size_t)MB * XY * JP > ctx->tmp_floats) ctx->tmp_floats = (size_t)MB * XY * JP;
-  A(dalloc(&ctx->d_tmp, ctx->tmp_floats));
-  for (int i = 0; i < 6; ++i) {
-    A(dalloc(&ctx->cn_buf[i], (size_t)MB * XY * 64));
-    A(dalloc(&ctx->p2p_buf[i], (size_t)3 * n * 4096 * 64));
-  }
-  A(dalloc(&ctx->d_frame_seq, (size_t)MB));
-  A(cudaMallocHost((void**)&ctx->h_frame_seq, MB * sizeof(int)));
-  for (int i = 0; i < 10; ++i) A(cudaEventCreate(&ctx->ev[i]));
-  A(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-  A(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  A(dalloc(&ctx->d_hm_in_b, (size_t)MB * g.V * g.J * P.H * P.W));
-  for (int i = 0; i < 2; ++i) {
-    A(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-    A(cudaEventCreateWithFlags(&ctx->ev_k0[i], cudaEventDisableTiming));
-    A(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
-  }
-  if (ok) {
-    A(cudaMemset(ctx->d_hm_cl, 0, (size_t)MB * g.V * g.view_stride4 * 16));   // zero borders (never written again)
-    A(cudaMemset(ctx->d_seqs, 0, (size_t)c.max_sequences * sizeof(FvpSeq)));
-    A(cudaMemset(ctx->d_people, 0, (size_t)n * sizeof(FvpPerson)));
-    A(cudaMemset(ctx->d_img_valid, 0, (size_t)3 * n * sizeof(int)));
-    A(cudaMemset(ctx->d_feat, 0, (size_t)3 * n * g.J * 4096 * sizeof(float)));
-  }
+  if (ok) A(cudaMemset(ctx->d_seqs, 0, (size_t)c.max_sequences * sizeof(FvpSeq)));
+  if (ok) A(alloc_workspaces(ctx));
   if (!ok) {
     fvp_fail(nullptr, FVP_E_CUDA, "allocation failed: %s", cudaGetErrorString(e));
     fvp_destroy(ctx);
@@ -352,7 +387,6 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   g.coarse_grid = ctx->d_coarse_grid;
   g.fine_grid = ctx->d_fine_grid;
   g.seqs = ctx->d_seqs;
-  ctx->num_sms = prop.multiProcessorCount;
   int rc = fvp_set_axes(ctx, nullptr, nullptr, nullptr);
   if (rc != FVP_OK) {
     g_create_error = ctx->err;
@@ -363,14 +397,59 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   return FVP_OK;
 }
 
+int fvp_create_lane(fvp_ctx* root, int max_batch, fvp_ctx** out) {
+  if (!root || !out) return fvp_fail(root, FVP_E_INVALID, "null argument");
+  *out = nullptr;
+  if (root->root) return fvp_fail(root, FVP_E_STATE, "fvp_create_lane: the parent must be a root context, not a lane");
+  if (max_batch < 1) return fvp_fail(root, FVP_E_INVALID, "max_batch must be >= 1");
+  {
+    const fvp_config& c = root->cfg;
+    const double per_view = (c.hm_w * 1.1 + 6.0) * (c.hm_h * 1.1 + 6.0) * ((c.num_joints + 3) / 4);
+    if (per_view * c.num_views * max_batch > 2.6e8)
+      return fvp_fail(root, FVP_E_INVALID, "max_batch x views x heat-map size exceeds the 32-bit tap index range");
+  }
+  cudaError_t e = cudaSetDevice(root->device);
+  if (e != cudaSuccess) return fvp_fail(root, FVP_E_CUDA, "cudaSetDevice(%d): %s", root->device, cudaGetErrorString(e));
+  fvp_ctx* ctx = new fvp_ctx();
+  ctx->cfg = root->cfg;
+  ctx->cfg.max_batch = max_batch;
+  ctx->device = root->device;
+  ctx->h_status = root->h_status;
+  ctx->num_sms = root->num_sms;
+  ctx->conv_mode = root->conv_mode;
+  ctx->root = root;
+  ctx->shared_gen = -1;                            // mirrors nothing yet: the first forward copies the root's tables
+  ctx->geom = root->geom;
+  ctx->prop = root->prop;
+  e = alloc_workspaces(ctx);
+  if (e != cudaSuccess) {
+    fvp_fail(root, FVP_E_CUDA, "lane allocation failed: %s", cudaGetErrorString(e));
+    fvp_destroy(ctx);
+    return FVP_E_CUDA;
+  }
+  ++root->lanes_alive;
+  *out = ctx;
+  return FVP_OK;
+}
+
 void fvp_destroy(fvp_ctx* ctx) {
   if (!ctx) return;
+  if (!ctx->root && ctx->lanes_alive > 0) {      // lanes point into this context's weights / grids
+    fvp_fail(ctx, FVP_E_STATE, "fvp_destroy: %d lane(s) of this context are still alive; destroy them first", ctx->lanes_alive);
+    return;
+  }
   cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
-  void* ptrs[] = {ctx->d_weights, ctx->d_axes, ctx->d_seqs, ctx->d_hm_in, ctx->d_hm_cl, ctx->d_plane_cl, ctx->d_hmsize,
+  // shared state belongs to the root; a lane frees its workspaces only
+  void* shared[] = {ctx->d_weights, ctx->d_axes, ctx->d_seqs, ctx->d_coarse_grid, ctx->d_fine_grid};
+  if (!ctx->root)
+    for (void* p : shared)
+      if (p) cudaFree(p);
+  void* ptrs[] = {ctx->d_hm_in, ctx->d_hm_cl, ctx->d_plane_cl, ctx->d_hmsize,
                   ctx->d_conf2d, ctx->d_flat, ctx->d_centers, ctx->d_people, ctx->d_img_valid, ctx->d_planes_cl,
                   ctx->d_feat, ctx->d_pose, ctx->d_maxw, ctx->d_wts, ctx->d_fused, ctx->d_conf,
-                  ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq, ctx->d_hm_in_b, ctx->d_coarse_grid, ctx->d_fine_grid,
+                  ctx->d_out_fused, ctx->d_out_plane, ctx->d_out_centers, ctx->d_tmp, ctx->d_frame_seq, ctx->d_hm_in_b,
                   ctx->d_rj, ctx->d_rn, ctx->d_rv, ctx->d_rp};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -388,6 +467,7 @@ void fvp_destroy(fvp_ctx* ctx) {
   }
   for (int i = 0; i < 10; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->root) --ctx->root->lanes_alive;
   delete ctx;
 }
 
@@ -401,6 +481,7 @@ int64_t fvp_param_numel(const fvp_ctx* ctx, int i) {
 
 int fvp_set_param(fvp_ctx* ctx, const char* name, const float* h_data, int64_t numel) {
   if (!ctx || !name) return FVP_E_INVALID;
+  if (int lrc = refuse_on_lane(ctx, "fvp_set_param")) return lrc;
   auto it = ctx->param_index.find(name);
   if (it == ctx->param_index.end()) return fvp_fail(ctx, FVP_E_NOTFOUND, "unexpected key '%s' in state_dict", name);
   FvpParam& p = ctx->params[it->second];
@@ -415,8 +496,10 @@ int fvp_set_param(fvp_ctx* ctx, const char* name, const float* h_data, int64_t n
 
 int fvp_finalize_params(fvp_ctx* ctx) {
   if (!ctx) return FVP_E_INVALID;
+  if (int lrc = refuse_on_lane(ctx, "fvp_finalize_params")) return lrc;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  ++ctx->shared_gen;                               // lanes re-mirror the weight tables (and drop their graphs)
   if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
   int rc = fvp_pack_params(ctx);
   if (rc != FVP_OK) return rc;
@@ -433,6 +516,7 @@ int fvp_fine_voxels(const fvp_ctx* ctx, int32_t out[3]) {
 
 int fvp_set_axes(fvp_ctx* ctx, const float* h_coarse, const float* h_fine, const float* h_individual) {
   if (!ctx) return FVP_E_INVALID;
+  if (int lrc = refuse_on_lane(ctx, "fvp_set_axes")) return lrc;
   cudaSetDevice(ctx->device);
   const FvpGeom& g = ctx->geom;
   const fvp_config& c = ctx->cfg;
@@ -458,12 +542,23 @@ int fvp_set_axes(fvp_ctx* ctx, const float* h_coarse, const float* h_fine, const
       linspace_plus(-c.ind_space_size[d] / 2, c.ind_space_size[d] / 2, 64, c.space_center[d], q + 64 * d);
   cudaDeviceSynchronize();
   FVP_CUDA_OK(cudaMemcpy(ctx->d_axes, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
-  ctx->grid_ready.assign(ctx->cfg.max_sequences, 0);      // sample grids depend on the axes
+  // the sample grids depend on the axes: rebuild those of every populated calibration slot now (setup path, synchronous),
+  // so that forwards - of this context or of its lanes - only ever read finished grids
+  for (int slot = 0; slot < ctx->cfg.max_sequences; ++slot) {
+    ctx->grid_ready[slot] = 0;
+    if (!ctx->seq_set[slot]) continue;
+    fvp_launch_build_sample_grids(ctx->geom, slot, nullptr);
+    FVP_CUDA_OK(cudaGetLastError());
+    ctx->grid_ready[slot] = 1;
+  }
+  FVP_CUDA_OK(cudaDeviceSynchronize());
+  ++ctx->shared_gen;
   return FVP_OK;
 }
 
 int fvp_set_sequence(fvp_ctx* ctx, int slot, const float* h_cameras, int num_views, const float* h_resize) {
   if (!ctx || !h_cameras || !h_resize) return FVP_E_INVALID;
+  if (int lrc = refuse_on_lane(ctx, "fvp_set_sequence")) return lrc;
   if (slot < 0 || slot >= ctx->cfg.max_sequences) return fvp_fail(ctx, FVP_E_NOTFOUND, "sequence slot %d outside [0,%d)", slot, ctx->cfg.max_sequences);
   if (num_views != ctx->cfg.num_views) return fvp_fail(ctx, FVP_E_CALIB, "inconsistent number of cameras (%d given, model built for %d)", num_views, ctx->cfg.num_views);
   cudaSetDevice(ctx->device);
@@ -482,7 +577,13 @@ int fvp_set_sequence(fvp_ctx* ctx, int slot, const float* h_cameras, int num_vie
   cudaDeviceSynchronize();
   FVP_CUDA_OK(cudaMemcpy(ctx->d_seqs + slot, &s, sizeof(s), cudaMemcpyHostToDevice));
   ctx->seq_set[slot] = 1;
-  ctx->grid_ready[slot] = 0;                               // rebuilt on first use (upload_frame_seq)
+  // sample-grid caches of this calibration (two kernels over 5 + 164 MB, once per calibration; synchronous like the upload)
+  ctx->grid_ready[slot] = 0;
+  fvp_launch_build_sample_grids(ctx->geom, slot, nullptr);
+  FVP_CUDA_OK(cudaGetLastError());
+  FVP_CUDA_OK(cudaDeviceSynchronize());
+  ctx->grid_ready[slot] = 1;
+  ++ctx->shared_gen;
   return FVP_OK;
 }
 
@@ -700,13 +801,15 @@ int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr
 int fvp_debug_conv(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin, const float* h_weight, const float* h_bias,
                    int cout, int k, int relu, int mode, float* d_out, int repeat, float* h_ms, uintptr_t stream) {
   if (!ctx || !d_in || !h_weight || !h_bias || !d_out || (k != 1 && k != 3 && k != 7) || cin % 4 || mode < 0 || (mode & 0xff) > 3) return FVP_E_INVALID;
+  sync_shared(ctx);
   cudaSetDevice(ctx->device);
   return fvp_debug_conv_impl(ctx, d_in, n, H, W, cin, h_weight, h_bias, cout, k, relu, mode, d_out, repeat, h_ms, (cudaStream_t)stream);
 }
 
 int fvp_debug_project(fvp_ctx* ctx, int slot, const float* d_points, int n, float* d_ix, float* d_iy, uintptr_t stream) {
   if (!ctx || !d_points || !d_ix || !d_iy || n < 1) return FVP_E_INVALID;
-  if (slot < 0 || slot >= ctx->cfg.max_sequences || !ctx->seq_set[slot])
+  const fvp_ctx* owner = sync_shared(ctx);
+  if (slot < 0 || slot >= owner->cfg.max_sequences || !owner->seq_set[slot])
     return fvp_fail(ctx, FVP_E_CALIB, "missing camera parameters for the current sequence (slot %d)", slot);
   cudaSetDevice(ctx->device);
   fvp_launch_debug_project(ctx->geom, slot, d_points, n, d_ix, d_iy, (cudaStream_t)stream);
@@ -785,6 +888,7 @@ int fvp_proposals(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const flo
 
 int fvp_c2c_net(fvp_ctx* ctx, const float* d_cols, int n, float* d_hm1d, uintptr_t stream) {
   if (!ctx || !d_cols || !d_hm1d || n < 1) return FVP_E_INVALID;
+  sync_shared(ctx);
   if (int trc = refuse_if_tickets_open(ctx)) return trc;
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");
   cudaSetDevice(ctx->device);
@@ -823,6 +927,7 @@ int fvp_jln_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const f
 
 int fvp_p2p_net(fvp_ctx* ctx, const float* d_planes, int n, const int32_t* d_valid, float* d_feat, uintptr_t stream) {
   if (!ctx || n < 1 || !d_feat) return FVP_E_INVALID;
+  sync_shared(ctx);
   if (int trc = refuse_if_tickets_open(ctx)) return trc;
   if (n > 3 * ctx->cfg.max_batch * ctx->geom.P) return fvp_fail(ctx, FVP_E_INVALID, "too many images (%d)", n);
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");
@@ -843,6 +948,7 @@ int fvp_p2p_net(fvp_ctx* ctx, const float* d_planes, int n, const int32_t* d_val
 int fvp_pose_head(fvp_ctx* ctx, const float* d_feat, const float* d_offset, int n, float* d_pose, float* d_conf,
                   float* d_weights, float* d_fused, uintptr_t stream) {
   if (!ctx || !d_feat || !d_offset || n < 1) return FVP_E_INVALID;
+  sync_shared(ctx);
   if (int trc = refuse_if_tickets_open(ctx)) return trc;
   if (n > ctx->cfg.max_batch * ctx->geom.P) return fvp_fail(ctx, FVP_E_INVALID, "too many persons (%d)", n);
   if (!ctx->params_ready) return fvp_fail(ctx, FVP_E_STATE, "fvp_finalize_params has not been called");

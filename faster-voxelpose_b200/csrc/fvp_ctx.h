@@ -24,6 +24,13 @@ struct fvp_ctx {
   int device;
   std::string err;
 
+  // Lanes (fvp_create_lane): a lane is a context with its OWN workspaces, streams, events and CUDA graph that SHARES the
+  // read-only state of its root context - packed weights, axis tables, calibration blocks, sample-grid caches.  Several
+  // frames can then be in flight on one GPU (one lane each) with one copy of the weights and of the 164 MB fine grid.
+  fvp_ctx* root = nullptr;            // NULL for a root context
+  int lanes_alive = 0;                // root only: lanes created and not yet destroyed
+  long long shared_gen = 0;           // root: bumped whenever weights / axes / calibrations change; lane: generation it mirrors
+
   // parameters
   std::vector<FvpLayer> layers;
   std::vector<FvpParam> params;

@@ -46,6 +46,7 @@ _CTX = C.c_void_p
 # name -> (restype, argtypes): every symbol include/fvp_b200.h declares
 SYMBOLS = {
     "fvp_create": (C.c_int, [C.POINTER(FvpConfig), C.c_int, C.POINTER(_CTX)]),
+    "fvp_create_lane": (C.c_int, [_CTX, C.c_int, C.POINTER(_CTX)]),
     "fvp_destroy": (None, [_CTX]),
     "fvp_last_error": (C.c_char_p, [_CTX]),
     "fvp_abi_version": (C.c_int, []),

@@ -38,6 +38,22 @@ def shard_bounds(num_frames: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def gather_shards(shard: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """THE collective of the path: one all-gather of equally sized per-rank row blocks [n,...] into one contiguous
+    [world*n,...] tensor (rank-major = frame order for contiguous frame blocks) - ``ncclAllGather`` on GPUs.  Under gloo
+    (CPU tests, or several ranks sharing one GPU) the rows are staged through host memory: gloo has no CUDA all-gather."""
+    world = dist.get_world_size()
+    if out is None:
+        out = torch.empty((world * shard.shape[0],) + tuple(shard.shape[1:]), dtype=shard.dtype, device=shard.device)
+    if dist.get_backend() == "gloo" and shard.is_cuda:
+        host = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(host, shard.cpu().contiguous())
+        out.copy_(host)
+    else:
+        dist.all_gather_into_tensor(out, shard.contiguous())
+    return out
+
+
 def gather_frames(local_rows: torch.Tensor, num_frames: int, rank: int, world: int) -> torch.Tensor:
     """all_gather of per-rank result rows ([n_local, ...]) into frame order [num_frames, ...].
     Blocks may be ragged (num_frames % world != 0): rows are padded to the largest block."""
@@ -47,9 +63,23 @@ def gather_frames(local_rows: torch.Tensor, num_frames: int, rank: int, world: i
     mx = max(hi - lo for lo, hi in sizes)
     pad = torch.zeros((mx,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
     pad[: local_rows.shape[0]] = local_rows
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad)
-    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+    out = gather_shards(pad).view((world, mx) + tuple(local_rows.shape[1:]))
+    return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+def pin_rank_to_cores(local_rank: int, local_world: int) -> list:
+    """Give every rank of a node its own block of host cores (8 ranks x 7 pinned-copy pipelines otherwise migrate over
+    all cores and contend).  Returns the cores this process may now run on ([] when affinity is not available)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(1, local_world)
+        if local_world > 1 and per >= 2:
+            mine = cores[local_rank * per:(local_rank + 1) * per]
+            os.sched_setaffinity(0, mine)
+            return mine
+        return cores
+    except (AttributeError, OSError):
+        return []
 
 
 def sharded_forward(run_frames: Callable[[int, int], torch.Tensor], num_frames: int, rank: int, world: int) -> torch.Tensor:

@@ -56,9 +56,16 @@ def reference_axes(cfg) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
 
 
 class Engine:
+    """One ``fvp_ctx``.  With ``parent`` given the context is a *lane* of that engine (``fvp_create_lane``): it owns
+    workspaces, streams and a CUDA graph for one more frame in flight and shares the parent's weights, axis tables,
+    calibrations and sample-grid caches; parameters and calibrations are then managed through the parent only."""
+
     def __init__(self, cfg, device: Optional[torch.device] = None, max_batch: int = 8, max_sequences: int = 8,
-                 axes: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None):
+                 axes: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None, parent: Optional["Engine"] = None):
         self.lib = capi.load()
+        self.parent = parent
+        if parent is not None:
+            cfg, device, max_sequences = parent.cfg, parent.device, parent.max_sequences
         if not torch.cuda.is_available():
             raise RuntimeError("faster-voxelpose_b200 needs a CUDA (sm_100a) device; there is no CPU path")
         self.device = torch.device(device if device is not None else getattr(cfg, "DEVICE", "cuda:0"))
@@ -90,6 +97,16 @@ class Engine:
         self.X, self.Y, self.Z = c.voxels[0], c.voxels[1], c.voxels[2]
         self.max_batch, self.max_sequences = int(max_batch), int(max_sequences)
         ctx = C.c_void_p()
+        self._seq_slots: Dict[str, int] = {}     # calibration fingerprint -> slot
+        self._seq_lru: List[str] = []
+        self._params_loaded = False
+        self._lanes: List["Engine"] = []
+        if parent is not None:
+            capi.check(self.lib, parent.ctx, self.lib.fvp_create_lane(parent.ctx, int(max_batch), C.byref(ctx)))
+            self.ctx = ctx
+            self.fine = list(parent.fine)
+            parent._lanes.append(self)
+            return
         rc = self.lib.fvp_create(C.byref(c), idx, C.byref(ctx))
         if rc != capi.FVP_OK:
             raise capi.FvpError(rc, (self.lib.fvp_last_error(None) or b"?").decode())
@@ -102,18 +119,24 @@ class Engine:
         self._ck(self.lib.fvp_set_axes(self.ctx, _f32_ptr(np.ascontiguousarray(coarse, np.float32)),
                                        _f32_ptr(np.ascontiguousarray(fine, np.float32)),
                                        _f32_ptr(np.ascontiguousarray(indiv, np.float32))))
-        self._seq_slots: Dict[str, int] = {}     # calibration fingerprint -> slot
-        self._seq_lru: List[str] = []
-        self._params_loaded = False
 
     # ------------------------------------------------------------------------------------------
     def _ck(self, rc: int) -> None:
         capi.check(self.lib, self.ctx, rc)
 
+    def new_lane(self, max_batch: Optional[int] = None) -> "Engine":
+        """A lane of this engine: own workspaces / stream / graph, shared weights, calibrations and sample grids."""
+        assert self.parent is None, "lanes hang off a root engine"
+        return Engine(None, parent=self, max_batch=int(max_batch or self.max_batch))
+
     def close(self) -> None:
         if getattr(self, "ctx", None):
+            for lane in list(getattr(self, "_lanes", [])):      # lanes point into this context: they go first
+                lane.close()
             self.lib.fvp_destroy(self.ctx)
             self.ctx = None
+            if self.parent is not None and self in self.parent._lanes:
+                self.parent._lanes.remove(self)
 
     def __del__(self):  # pragma: no cover
         try:
@@ -131,6 +154,8 @@ class Engine:
 
     def load_state_dict(self, sd: Mapping[str, object]) -> None:
         """Reference ``state_dict`` (torch tensors or numpy arrays, any device) -> folded, packed, uploaded."""
+        if self.parent is not None:
+            raise RuntimeError("load_state_dict: a lane shares its parent's weights; load them into the parent engine")
         names = self.param_names()
         missing = [k for k in names if k not in sd]
         unexpected = [k for k in sd if k not in set(names)]
@@ -152,6 +177,8 @@ class Engine:
     def sequence_slot(self, cams: Sequence[Mapping], resize) -> int:
         """Slot of a calibration; uploads it on first use.  Keyed on the calibration *values* (the
         reference keys its grid cache on the sequence name only, SURVEY.md 3.3 - a stale-cache hazard)."""
+        if self.parent is not None:
+            return self.parent.sequence_slot(cams, resize)
         rows = camera_rows(cams)
         rz = np.ascontiguousarray(np.asarray(resize.detach().cpu() if isinstance(resize, torch.Tensor) else resize,
                                              np.float64).astype(np.float32).reshape(6))
@@ -181,11 +208,18 @@ class Engine:
             raise ValueError("batch %d exceeds max_batch %d" % (hm.shape[0], self.max_batch))
         return int(hm.shape[0])
 
-    def forward(self, heatmaps: torch.Tensor, slots: Sequence[int]):
-        """[B,V,J,H,W] fp32 on this device -> (fused_poses [B,P,J,5], plane_poses [3,B,P,J,2], proposal_centers [B,P,7])."""
+    def forward(self, heatmaps: torch.Tensor, slots: Sequence[int], out_fused: Optional[torch.Tensor] = None):
+        """[B,V,J,H,W] fp32 on this device -> (fused_poses [B,P,J,5], plane_poses [3,B,P,J,2], proposal_centers [B,P,7]).
+        ``out_fused``: optional preallocated contiguous [B,P,J,5] destination (e.g. this frame's rows of a rank's shard
+        buffer, so the multi-GPU gather needs no extra copy)."""
         B = self._check_hm(heatmaps)
         hm = heatmaps.to(device=self.device, dtype=torch.float32).contiguous()
-        fused = torch.empty((B, self.P, self.J, 5), device=self.device, dtype=torch.float32)
+        if out_fused is None:
+            fused = torch.empty((B, self.P, self.J, 5), device=self.device, dtype=torch.float32)
+        else:
+            fused = out_fused
+            assert fused.is_contiguous() and fused.dtype == torch.float32 and fused.device == self.device
+            assert tuple(fused.shape) == (B, self.P, self.J, 5)
         plane = torch.empty((3, B, self.P, self.J, 2), device=self.device, dtype=torch.float32)
         centers = torch.empty((B, self.P, 7), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
@@ -374,7 +408,8 @@ class Engine:
 
 
 class EngineLanes:
-    """Several independent contexts ("lanes") on ONE GPU for a stream of frames.
+    """Several frames in flight on ONE GPU: a root context plus ``lanes - 1`` lane contexts (``fvp_create_lane``) that
+    share its weights, calibrations and sample-grid caches - L workspaces, one weight set, one 164 MB fine grid.
 
     A batch-1 forward is a chain of ~55 kernels of which many cannot fill 148 SMs (CenterNet on one 80x80 plane is
     <= 50 CTAs, the proposal kernel is one CTA per slot, ...).  Consecutive frames are independent
@@ -386,8 +421,9 @@ class EngineLanes:
 
     def __init__(self, cfg, device=None, lanes: int = 2, max_batch: int = 1, max_sequences: int = 8, axes=None):
         assert lanes >= 1
-        self.engines = [Engine(cfg, device, max_batch=max_batch, max_sequences=max_sequences, axes=axes) for _ in range(lanes)]
-        e0 = self.engines[0]
+        root = Engine(cfg, device, max_batch=max_batch, max_sequences=max_sequences, axes=axes)
+        self.engines = [root] + [root.new_lane(max_batch) for _ in range(lanes - 1)]
+        e0 = root
         self.device, self.P, self.J, self.V = e0.device, e0.P, e0.J, e0.V
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(lanes)]
         self._next = 0
@@ -398,18 +434,15 @@ class EngineLanes:
         return len(self.engines)
 
     def close(self) -> None:
-        for e in self.engines:
-            e.close()
+        self.engines[0].close()                             # closes its lanes first
 
-    # ---- setup is broadcast to every lane ---------------------------------------------------------
+    # ---- weights and calibrations live in the root context, every lane reads them ------------------
     def load_state_dict(self, sd) -> None:
-        for e in self.engines:
-            e.load_state_dict(sd)
+        torch.cuda.synchronize(self.device)                 # no forward of any lane may be in flight
+        self.engines[0].load_state_dict(sd)
 
     def sequence_slot(self, cams, resize) -> int:
-        slots = [e.sequence_slot(cams, resize) for e in self.engines]
-        assert len(set(slots)) == 1                         # same call history on every lane -> same slot
-        return slots[0]
+        return self.engines[0].sequence_slot(cams, resize)
 
     def use_cuda_graph(self, on: bool = True) -> None:
         for e in self.engines:
@@ -423,16 +456,16 @@ class EngineLanes:
         return self.engines[0].last_launch_count()
 
     # ---- device-resident frames -------------------------------------------------------------------
-    def submit(self, heatmaps: torch.Tensor, slots: Sequence[int]) -> int:
+    def submit(self, heatmaps: torch.Tensor, slots: Sequence[int], out_fused: Optional[torch.Tensor] = None) -> int:
         """Enqueue one forward on the next lane (ordered after the work already queued on the caller's current
-        stream); returns a ticket for collect().  Nothing blocks the host."""
+        stream); returns a ticket for collect().  Nothing blocks the host.  ``out_fused``: see Engine.forward."""
         lane = self._next
         self._next = (lane + 1) % len(self.engines)
         cur = torch.cuda.current_stream(self.device)
         st = self.streams[lane]
         st.wait_stream(cur)
         with torch.cuda.stream(st):
-            out = self.engines[lane].forward(heatmaps, slots)
+            out = self.engines[lane].forward(heatmaps, slots, out_fused)
             ev = torch.cuda.Event()
             ev.record(st)
         heatmaps.record_stream(st)

@@ -66,6 +66,13 @@ typedef struct fvp_ctx fvp_ctx;
 /* ---- lifetime ------------------------------------------------------------------------------ */
 /* replaces models.faster_voxelpose.get(cfg) (lib/models/faster_voxelpose.py:108-110) */
 int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out);
+/* A lane of `root`: a context for one more frame in flight on the same GPU.  It owns workspaces, streams and a CUDA graph
+ * (sized for max_batch frames) and shares root's weights, axis tables, calibrations and sample-grid caches, so L frames in
+ * flight cost L workspaces but ONE weight set and ONE grid cache.  Parameters, axes and calibrations are set on the root
+ * only (FVP_E_STATE on a lane) and are picked up by the lanes at their next forward; the caller must not change them
+ * while forwards of any lane are in flight.  Destroy lanes before their root (fvp_destroy(root) refuses otherwise -
+ * it then returns without freeing and fvp_last_error(root) explains). */
+int fvp_create_lane(fvp_ctx* root, int max_batch, fvp_ctx** out);
 void fvp_destroy(fvp_ctx* ctx);
 const char* fvp_last_error(const fvp_ctx* ctx);   /* ctx may be NULL: error of the last failed fvp_create */
 int fvp_abi_version(void);

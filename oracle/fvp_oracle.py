@@ -420,6 +420,59 @@ def fuse(pose: Tensor, weights: Tensor) -> Tensor:
 
 
 # =============================================================================================
+# float64 yardstick of a14-a19 ("measure the reference's own fp32-vs-fp64 noise floor in the same run")
+# =============================================================================================
+def jln_fp64(cfg, sd: Dict[str, Tensor], heatmaps_b: Tensor, cams: Sequence[dict], resize: Tensor,
+             centers_valid: Tensor) -> Dict[str, Tensor]:
+    """JointLocalizationNet for the valid proposals [n,7] of one frame, evaluated in float64 downstream of everything
+    that is bit-exact on both sides of the parity tests: proposal centres, crop parameters and the fp32 sample positions
+    (ix, iy) of every fine voxel are the reference's own fp32 values; the bilinear taps, view mean, clamp, three-plane
+    max, P2PNet, soft-argmax, WeightNet and fusion run in float64 on float64 copies of the weights.  |reference_fp32 -
+    this| is the reference's own rounding noise; an implementation is "as good as the reference" when it is at most
+    that far from this result (tests/test_gpu_parity.py prints and asserts both)."""
+    K = JlnConstants(cfg)
+    crop = jln_crop_params(K, centers_valid)
+    V, J, H, W = heatmaps_b.shape
+    n = crop["tl"].shape[0]
+    hm64 = heatmaps_b.double().numpy()
+    vx = [int(v) for v in K.vox]
+    cubes = np.zeros((n, J, vx[0], vx[1], vx[2]), np.float64)
+    for i in range(n):
+        s, e, tl = crop["start"][i].tolist(), crop["end"][i].tolist(), crop["tl"][i].tolist()
+        if any(s[d] >= e[d] for d in range(3)):
+            continue
+        ax = [K.fine_axes[d][s[d]:e[d]] for d in range(3)]
+        gx, gy, gz = torch.meshgrid(ax[0], ax[1], ax[2], indexing="ij")
+        pts = torch.stack([gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)], dim=1).contiguous()
+        acc = np.zeros((J, pts.shape[0]), np.float64)
+        for v, cam in enumerate(cams):
+            g = sample_grid(pts, cam, resize, cfg.DATASET.ORI_IMAGE_SIZE, cfg.DATASET.IMAGE_SIZE, cfg.DATASET.HEATMAP_SIZE)
+            # ATen grid_sampler_unnormalize, align_corners: ((g + 1) / 2) * (size - 1), in fp32 like the reference
+            ix = (((g[:, 0] + 1.0) / 2.0) * float(W - 1)).numpy().astype(np.float64)
+            iy = (((g[:, 1] + 1.0) / 2.0) * float(H - 1)).numpy().astype(np.float64)
+            x0, y0 = np.floor(ix), np.floor(iy)
+            fx, fy = ix - x0, iy - y0
+            for xx, yy, ww in ((x0, y0, (1 - fx) * (1 - fy)), (x0 + 1, y0, fx * (1 - fy)), (x0, y0 + 1, (1 - fx) * fy),
+                               (x0 + 1, y0 + 1, fx * fy)):
+                xi, yi = xx.astype(np.int64), yy.astype(np.int64)
+                ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+                acc += np.where(ok[None, :], hm64[v][:, np.clip(yi, 0, H - 1), np.clip(xi, 0, W - 1)], 0.0) * ww[None, :]
+        cubes[i, :, s[0] - tl[0]:e[0] - tl[0], s[1] - tl[1]:e[1] - tl[1], s[2] - tl[2]:e[2] - tl[2]] = \
+            (acc / V).reshape(J, e[0] - s[0], e[1] - s[1], e[2] - s[2])
+    cubes_t = torch.from_numpy(cubes).clamp(0.0, 1.0)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    planes = three_planes(cubes_t)
+    feat = torch.stack(torch.chunk(p2p_net(sd64, planes), 3), dim=0)
+    pose, confs = soft_argmax(feat, K.center_grid.double(), float(cfg.NETWORK.BETA))
+    off = crop["offset"].double().reshape(-1, 1, 3)
+    pose[0] += off[:, :, :2]
+    pose[1] += off[:, :, ::2]
+    pose[2] += off[:, :, 1:]
+    w = weight_net(sd64, feat)
+    return {"planes": planes, "feat": feat, "pose": pose, "confs": confs, "weights": w, "fused": fuse(pose, w)}
+
+
+# =============================================================================================
 # a12  whole forward (eval branch)                      faster_voxelpose.py:34-48,99-105
 # =============================================================================================
 def forward(cfg, sd: Dict[str, Tensor], heatmaps: Tensor, seqs: Sequence[str], cameras: Dict[str, Sequence[dict]],

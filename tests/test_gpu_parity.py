@@ -215,10 +215,12 @@ def test_single_conv_layers_both_engines(built_library, golden):
 
 
 def test_pose_head_softargmax_weightnet_fusion(case):
-    """Soft-argmax + WeightNet + fusion on golden features.
-    * vs an fp64 evaluation of the same formulas: each plane coordinate within max(1e-4 mm, 1 fp32 ulp of the
-      coordinate) - the north-star tolerance (1e-4 abs) is below one ulp above 1024 mm;
-    * vs the reference's fp32 result: <= 5e-2 mm (its own 4096-term fp32 summation noise; measured <= 1.8e-2);
+    """Soft-argmax + WeightNet + fusion on golden features, with the reference's own noise floor measured in the same run
+    (SURVEY.md H1).  The north-star tolerance on joints (1e-4 mm abs) is below one fp32 ulp above 1024 mm and 20-200x below
+    what the reference's fp32 4096-term soft-argmax sum achieves against a float64 evaluation, so the bar is stated as:
+    * ours vs float64: each plane coordinate within max(1e-4 mm, 1 fp32 ulp of the coordinate);
+    * ours vs float64 <= reference_fp32 vs float64 (both printed), per case;
+    * ours vs the reference's fp32 result <= 1.5 x that measured reference noise floor;
     * fusion weights <= 2e-6, confidences <= 1e-8."""
     g, eng, slots = case
     beta = float(g.cfg.NETWORK.BETA)
@@ -231,6 +233,7 @@ def test_pose_head_softargmax_weightnet_fusion(case):
         offs = g["b%d_crop_offset" % b][:n]
         pose, confs, w, fused = eng.pose_head(torch.from_numpy(fk), torch.from_numpy(offs))
         pose = pose.cpu().numpy()
+        ref_pose = g["b%d_pose" % b][:, :n]
         # fp64 evaluation (the softmax argument is the fp32 product beta*x, as in the reference)
         t = (np.float32(beta) * fk).astype(np.float32).astype(np.float64).reshape(3, n, g.J, 4096)
         e = np.exp(t - t.max(axis=3, keepdims=True))
@@ -238,22 +241,64 @@ def test_pose_head_softargmax_weightnet_fusion(case):
         first = [np.repeat(ind[0], 64), np.repeat(ind[0], 64), np.repeat(ind[1], 64)]
         second = [np.tile(ind[1], 64), np.tile(ind[2], 64), np.tile(ind[2], 64)]
         osel = [(0, 1), (0, 2), (1, 2)]
+        ours_err = ref_err = 0.0
         for q in range(3):
-            p0 = (wgt[q] * first[q]).sum(axis=2).astype(np.float32) + offs[:, None, osel[q][0]]
-            p1 = (wgt[q] * second[q]).sum(axis=2).astype(np.float32) + offs[:, None, osel[q][1]]
+            p0 = (wgt[q] * first[q]).sum(axis=2) + offs[:, None, osel[q][0]].astype(np.float64)
+            p1 = (wgt[q] * second[q]).sum(axis=2) + offs[:, None, osel[q][1]].astype(np.float64)
             exact = np.stack([p0, p1], axis=-1)
             tol = np.maximum(1e-4, np.spacing(np.abs(exact).astype(np.float32)).astype(np.float64))
             assert (np.abs(pose[q].astype(np.float64) - exact) <= tol).all()
-        assert _maxerr(pose, g["b%d_pose" % b][:, :n]) <= 5e-2
+            ours_err = max(ours_err, float(np.abs(pose[q].astype(np.float64) - exact).max()))
+            ref_err = max(ref_err, float(np.abs(ref_pose[q].astype(np.float64) - exact).max()))
+        print("\n[noise floor, pose head] %s b%d: |ours - fp64| = %.3g mm, |reference_fp32 - fp64| = %.3g mm" % (g.name, b, ours_err, ref_err))
+        assert ours_err <= ref_err
+        assert _maxerr(pose, ref_pose) <= 1.5 * ref_err
         assert _maxerr(confs.cpu(), g["b%d_confs" % b][:n]) <= 1e-8
         wr = g["b%d_weights" % b].reshape(3, -1, g.J)[:, :n]
         assert _maxerr(w.cpu(), wr) <= 2e-6
-        assert _maxerr(fused.cpu(), g["b%d_fused" % b][:n]) <= 5e-2
+        assert _maxerr(fused.cpu(), g["b%d_fused" % b][:n]) <= 1.5 * ref_err
+
+
+def _noise_floor(cfg, weights, heatmaps, cams, resize, hdn_centers, ref_fused, ref_plane, ours_fused, ours_plane, label):
+    """Same-run noise floor of the joint coordinates (mm): max |ours - fp64| and max |reference_fp32 - fp64| over the valid
+    people of every frame, for the fused joints and for the three plane poses.  The float64 yardstick is oracle.jln_fp64
+    (float64 downstream of the bit-exact proposals / crop parameters / fp32 sample positions)."""
+    from oracle import fvp_oracle as O
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()}
+    hc = torch.as_tensor(np.asarray(hdn_centers))
+    r = {"ours_fused": 0.0, "ref_fused": 0.0, "ours_plane": 0.0, "ref_plane": 0.0}
+    for b in range(heatmaps.shape[0]):
+        valid = hc[b, :, 3] >= 0
+        if int(valid.sum()) == 0:
+            continue
+        with torch.no_grad():
+            y = O.jln_fp64(cfg, sd, torch.as_tensor(heatmaps[b]), cams, torch.as_tensor(np.asarray(resize), dtype=torch.float), hc[b, valid])
+        v = valid.numpy()
+        ef, ep = y["fused"].numpy(), y["pose"].numpy()
+        d = lambda a, e: float(np.abs(np.asarray(a, np.float64) - e).max())
+        r["ours_fused"] = max(r["ours_fused"], d(ours_fused[b][v][..., :3], ef))
+        r["ref_fused"] = max(r["ref_fused"], d(ref_fused[b][v][..., :3], ef))
+        r["ours_plane"] = max(r["ours_plane"], d(ours_plane[:, b][:, v], ep))
+        r["ref_plane"] = max(r["ref_plane"], d(ref_plane[:, b][:, v], ep))
+    print("\n[noise floor, %s] fused joints: |ours - fp64| = %.3g mm, |reference_fp32 - fp64| = %.3g mm; plane poses: %.3g / %.3g mm"
+          % (label, r["ours_fused"], r["ref_fused"], r["ours_plane"], r["ref_plane"]))
+    return r
+
+
+def _assert_joints_within_reference_noise(r, ours_fused, ref_fused, ours_plane, ref_plane):
+    """ours is at most as far from float64 as the reference's own fp32 path, and within 1.5 x that floor of the reference."""
+    if r["ref_fused"] == 0.0:                      # no valid person in the case: nothing to compare
+        return
+    assert r["ours_fused"] <= r["ref_fused"] and r["ours_plane"] <= r["ref_plane"]
+    assert _maxerr(np.asarray(ours_fused)[..., :3], np.asarray(ref_fused)[..., :3]) <= 1.5 * r["ref_fused"]
+    assert _maxerr(ours_plane, ref_plane) <= 1.5 * r["ref_plane"]
 
 
 def test_end_to_end_plugin_forward(case):
     """models.faster_voxelpose.get(cfg) called like run/validate.py:102-105 does: proposal cells, flags and bbox
-    bit-exact; joint coordinates <= 5e-2 mm of the reference (measured <= 8e-3)."""
+    bit-exact; joint coordinates: the reference's own fp32-vs-float64 noise floor is measured in the same run
+    (oracle.jln_fp64) - ours must be at most that far from the float64 result, and within 1.5 x the floor of the
+    reference's fp32 result (1e-4 mm, the north-star figure, is 20-200x below what the reference itself achieves)."""
     import models
     g, _, _ = case
     cfg = g.cfg
@@ -277,8 +322,10 @@ def test_end_to_end_plugin_forward(case):
     assert np.array_equal(f[..., 3], g["fused_poses"][..., 3])
     assert _maxerr(c[..., 4], g["proposal_centers"][..., 4]) <= 1e-6
     assert _maxerr(f[..., 4], g["fused_poses"][..., 4]) <= 1e-6
-    assert _maxerr(f[..., :3], g["fused_poses"][..., :3]) <= 5e-2
-    assert _maxerr(plane.cpu(), g["plane_poses"]) <= 5e-2
+    pl = plane.cpu().numpy()
+    r = _noise_floor(g.cfg, g.weights, g.heatmaps, g.cams, g.resize, g["hdn_centers"], g["fused_poses"], g["plane_poses"], f, pl,
+                     "plugin forward, " + g.name)
+    _assert_joints_within_reference_noise(r, f, g["fused_poses"], pl, g["plane_poses"])
     invalid = g["fused_poses"][..., 0, 3] < 0
     assert np.abs(f[invalid][..., :3]).max(initial=0.0) == 0.0
     model._engine.close()
@@ -392,7 +439,87 @@ def test_live_oracle_parity_on_fresh_inputs(built_library):
         ref = O.forward(cfg, {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, torch.from_numpy(hm), ["s"],
                         {"s": cams}, torch.as_tensor(resize, dtype=torch.float))
     assert np.array_equal(centers.cpu().numpy()[..., :4], ref["proposal_centers"].numpy()[..., :4])
-    assert _maxerr(fused.cpu()[..., :3], ref["fused_poses"][..., :3]) <= 5e-2
+    f, pl = fused.cpu().numpy(), plane.cpu().numpy()
+    r = _noise_floor(cfg, sd, hm, cams, resize, ref["hdn_centers"].numpy(), ref["fused_poses"].numpy(), ref["plane_poses"].numpy(),
+                     f, pl, "live oracle, shelf ring")
+    _assert_joints_within_reference_noise(r, f, ref["fused_poses"].numpy(), pl, ref["plane_poses"].numpy())
+    eng.close()
+
+
+def test_full_pipeline_eight_views_high_resolution_grid(built_library):
+    """BASELINE configs[4] as a FULL forward (round 1 tested K0+K1 only there): 8-view synthetic ring calibration,
+    160x160x40 coarse grid, 256x192 heat maps, live oracle on this host vs the CUDA path - proposal cells / flags
+    bit-exact, bbox <= 4e-6, joints inside the reference's own fp32 noise floor."""
+    from fvp import config as fcfg, synth
+    from fvp.engine import Engine
+    from oracle import fvp_oracle as O
+    cfg = fcfg.preset("ring8_160")
+    cfg.CAPTURE_SPEC.MIN_SCORE = -1e30
+    cfg.CAPTURE_SPEC.MAX_PEOPLE = 4
+    J = int(cfg.DATASET.NUM_JOINTS)
+    cams = synth.ring_cameras(8, cfg.CAPTURE_SPEC.SPACE_CENTER)
+    resize = synth.resize_transform(cfg.DATASET.ORI_IMAGE_SIZE, cfg.DATASET.IMAGE_SIZE)
+    hm = synth.render_heatmaps(cfg, cams, synth.make_skeletons(cfg, 4, seed=19), sigma=3.0)[None]
+    sd = synth.make_weights(J, seed=99)
+    eng = Engine(cfg, torch.device("cuda:0"), max_batch=1, max_sequences=1)
+    eng.load_state_dict(sd)
+    slot = eng.sequence_slot(cams, resize)
+    fused, plane, centers = eng.forward(torch.from_numpy(hm).cuda(), [slot])
+    eng.check_range()
+    with torch.no_grad():
+        ref = O.forward(cfg, {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, torch.from_numpy(hm), ["s"],
+                        {"s": cams}, torch.as_tensor(resize, dtype=torch.float))
+    c, rc = centers.cpu().numpy(), ref["proposal_centers"].numpy()
+    assert np.array_equal(c[..., :4], rc[..., :4])
+    assert _maxerr(c[..., 5:], rc[..., 5:]) <= 4e-6
+    f, pl = fused.cpu().numpy(), plane.cpu().numpy()
+    assert np.array_equal(f[..., 3], ref["fused_poses"].numpy()[..., 3])
+    r = _noise_floor(cfg, sd, hm, cams, resize, ref["hdn_centers"].numpy(), ref["fused_poses"].numpy(), ref["plane_poses"].numpy(),
+                     f, pl, "8 views, 160x160x40")
+    _assert_joints_within_reference_noise(r, f, ref["fused_poses"].numpy(), pl, ref["plane_poses"].numpy())
+    eng.close()
+
+
+def test_fp16_range_guard(built_library, golden):
+    """The default conv engine splits operands into fp16 hi/lo parts.  (a) A checkpoint whose BN-folded weights leave the
+    fp16 range must not produce inf/NaN: those layers run on the 3xTF32 engine and agree with the exact-fp32 engine.
+    (b) Activations outside the fp16 range are reported loudly (FVP_E_RANGE), never propagated silently."""
+    from fvp import capi
+    g = golden("panoptic_none_valid")
+    eng, slots = _engine(g)
+    assert eng.fp16_fallback_layers() == 0
+    plane = torch.from_numpy(g["hdn_plane"])
+    base = [t.cpu().numpy() for t in eng.center_net(plane, g.B)]
+    eng.check_range()
+    # BatchNorm gamma x 1e7 on one mid-network conv (the next conv divides it out again; ReLU is positively homogeneous):
+    # the same function, but that layer's BN-folded weights (~1e5) and its output activations (~1e7) leave the fp16 range
+    bn = "pose_net.center_net.encoder_decoder.encoder_res1.res_branch.1"
+    sd2 = {k: np.array(v, copy=True) for k, v in g.weights.items()}
+    sd2[bn + ".weight"] = sd2[bn + ".weight"] * np.float32(1.0e7)
+    sd2[bn + ".bias"] = sd2[bn + ".bias"] * np.float32(1.0e7)
+    nxt = "pose_net.center_net.encoder_decoder.encoder_res1.res_branch.3"
+    sd2[nxt + ".weight"] = sd2[nxt + ".weight"] / np.float32(1.0e7)
+    eng.load_state_dict(sd2)
+    assert eng.fp16_fallback_layers() >= 1
+    eng.center_net(plane, g.B)
+    # the activation between the two layers is ~1e7, 150 x what fp16 holds: the result is garbage and the guard says so
+    with pytest.raises(capi.FvpError) as ei:
+        eng.check_range()
+    assert ei.value.code == capi.FVP_E_RANGE
+    # with the 3xTF32 engine (fp32 exponent range) the same checkpoint matches the exact-fp32 engine
+    eng.set_conv_mode(0)
+    exact = [t.cpu().numpy() for t in eng.center_net(plane, g.B)]
+    eng.set_conv_mode(1)
+    tf32 = [t.cpu().numpy() for t in eng.center_net(plane, g.B)]
+    eng.check_range()                                # modes 0 / 1 have no fp16 operands: nothing to report
+    assert all(np.isfinite(a).all() for a in tf32)
+    assert _maxerr(tf32[0], exact[0]) <= 2e-4 and _maxerr(tf32[1], exact[1]) <= 2e-4
+    assert _maxerr(exact[0], base[0]) <= 1e-3        # (and it is the same function as the unscaled checkpoint)
+    eng.set_conv_mode(2)
+    eng.load_state_dict(g.weights)
+    again = [t.cpu().numpy() for t in eng.center_net(plane, g.B)]
+    eng.check_range()
+    assert all(np.array_equal(a, b) for a, b in zip(base, again))
     eng.close()
 
 

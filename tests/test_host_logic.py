@@ -301,6 +301,15 @@ N = int(sys.argv[2])
 full = torch.arange(N * 10 * 15 * 5, dtype=torch.float32).view(N, 10, 15, 5) * 0.5      # stands for fused_poses
 out = fdist.sharded_forward(lambda lo, hi: full[lo:hi].clone(), N, rank, world)
 assert torch.equal(out, full), (rank, out.shape)
+# the bench's form: equal shards of S rows, ONE all_gather_into_tensor into one contiguous rank-major buffer
+S = 4
+mine = full[:S] + 1000.0 * rank
+buf = torch.empty((world * S, 10, 15, 5))
+got = fdist.gather_shards(mine, buf)
+assert got.data_ptr() == buf.data_ptr() and got.is_contiguous()
+assert all(torch.equal(got[r * S:(r + 1) * S], full[:S] + 1000.0 * r) for r in range(world))
+cores = fdist.pin_rank_to_cores(rank, world)
+assert len(cores) >= 1 and set(cores) == set(os.sched_getaffinity(0))
 if rank == 0: print("GATHER_OK", N, world)
 dist.destroy_process_group()
 '''

@@ -22,7 +22,6 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-import bench  # noqa: E402
 from oracle import fvp_oracle as O  # noqa: E402
 
 
@@ -92,6 +91,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--check", action="store_true", help="compare with O.forward on the CPU (first frame)")
     args = ap.parse_args()
+    import bench                                              # (lazily: bench.py imports CachedReference from this module)
     cfg, cams, resize = bench.workload("panoptic_256x192")
     from fvp import synth
     J = int(cfg.DATASET.NUM_JOINTS)
