@@ -442,7 +442,7 @@ void fvp_destroy(fvp_ctx* ctx) {
   cudaDeviceSynchronize();
   if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   // shared state belongs to the root; a lane frees its workspaces only
-  void* shared[] = {ctx->d_weights, ctx->d_axes, ctx->d_seqs, ctx->d_coarse_grid, ctx->d_fine_grid};
+  void* shared[] = {ctx->d_weights, ctx->d_c2c_plan, ctx->d_axes, ctx->d_seqs, ctx->d_coarse_grid, ctx->d_fine_grid};
   if (!ctx->root)
     for (void* p : shared)
       if (p) cudaFree(p);

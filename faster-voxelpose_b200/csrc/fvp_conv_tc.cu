@@ -38,6 +38,9 @@
 // operand and must convert to a finite fp16 "hi" part (network inputs are back-projected planes clamped to [0,1]).  An output with |x| >= 65504 (or NaN) raises bit 0 of the status
 // word in mapped pinned host memory; the host entry points turn it into FVP_E_RANGE after their next synchronise.
 __device__ int* g_tc_status = nullptr;
+#ifndef FVP_RANGE_CHECK
+#define FVP_RANGE_CHECK 1                  // 1: per-item running maximum (shipped); 0 / 2: A/B switches (none / per-store test)
+#endif
 
 namespace {
 
@@ -267,6 +270,14 @@ __device__ __forceinline__ bool tc_decode(const TcArgs& t, int item, TcItem& w) 
 template <int MODE, int OCC>
 __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
   constexpr bool F16 = MODE != 0;
+  // Streamed weights fill the whole shared memory, so they only ever occur with one CTA per SM.  The register allocation
+  // of the two-CTA (72-register) instantiations is fragile: with the streaming code present the 16-channel K-block variant
+  // (7x7 layer) spills 108 B instead of 88 B and ran 17 % slower, so it compiles that path out (rule 2; rules 0 / 1 = keep
+  // it everywhere / drop it from every two-CTA variant are A/B switches, profiles/r02_conv_ab.txt).
+#ifndef FVP_CAN_STREAM_RULE
+#define FVP_CAN_STREAM_RULE 2
+#endif
+  constexpr bool CAN_STREAM = FVP_CAN_STREAM_RULE == 0 ? true : (FVP_CAN_STREAM_RULE == 1 ? OCC == 1 : !(OCC == 2 && MODE == 2));
   constexpr int ROWB = MODE == 0 ? 128 : (MODE == 1 ? 64 : 32);   // bytes of one pixel row of a K-block in shared memory
   constexpr int CB = MODE == 2 ? 16 : 32;                          // channels per K-block
   constexpr uint32_t LAYOUT = MODE == 0 ? 2u : (MODE == 1 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
@@ -462,7 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
     }
   } else if (tid == TC_LOADERS + 32) {
     // =============================== B producer (TMA bulk copies) =====================================
-    if (!t.resident) {                                            // (resident image: already requested above)
+    if (CAN_STREAM && !t.resident) {                              // (resident image: already requested above)
       int b_it = 0;
       for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
         TcItem w;
@@ -539,7 +550,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
             int bs = 0;                                              // ring stage of this tap row (streamed weights)
             for (int dx = 0; dx < K; ++dx) {
               uint64_t bd_hi;
-              if (t.resident) {
+              if (!CAN_STREAM || t.resident) {
                 if (!b_ready) { TC_TIMED(2, mbar_wait(b_full, 0)); b_ready = true; }
                 bd_hi = bd_res0 + bidx;
                 bidx += nts_img * blk16;
@@ -573,7 +584,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
                 }
               }
               accumulate = 1;
-              if (!t.resident && dx == K - 1) {
+              if (CAN_STREAM && !t.resident && dx == K - 1) {
                 if (elect_one()) umma_commit(b_empty + bs);          // the row's stage is reusable when its MMAs retire
                 ++b_it;
               }
@@ -638,6 +649,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
       };
       float4 rnext[G4];
       fetch_res(0, rnext);
+      float amax = 0.0f;                                           // range guard: largest stored magnitude of this item
       for (int cb = 0; cb < t.n_tile; cb += CW) {
         float4 rcur[G4];
 #pragma unroll
@@ -672,8 +684,11 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
           if (a.res_mode == 1) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
           if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
           if (a.res_mode == 2) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-          // range guard (NaN fails the comparison too); also in the 3xTF32 variant, whose outputs may feed an fp16 layer
+#if FVP_RANGE_CHECK == 2
           if (!(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))) < 65504.0f) && g_tc_status) *g_tc_status = 1;
+#elif FVP_RANGE_CHECK == 1
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+#endif
           const int ch = ch0 + g4 * 4;
           if (!a.nchw) {
             *(float4*)(a.out + off + ch) = o;
@@ -687,6 +702,11 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
           }
         }
       }
+#if FVP_RANGE_CHECK == 1
+      // Range guard (also in the 3xTF32 variant, whose outputs may feed an fp16 layer).  A maximum ignores NaN, but a NaN
+      // needs an infinite operand, and the first value that cannot become a finite fp16 "hi" part is caught here.
+      if (amax >= 65504.0f && g_tc_status) *g_tc_status = 1;
+#endif
       ++it;
     }
     if (t.prof && tid == TC_LOADERS + 64) {
@@ -830,7 +850,7 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   // faster with two CTAs per SM; the 3x3 16->32 layer (16-channel K-blocks, loader-bound) is 9 % slower and keeps one.
   // (Also tried and dropped: one LDG.128 per lane over whole 128-B lines with 8-byte shared stores - fewer L1 sector
   //  lookups but twice the store instructions: 3 % slower over the trunk's layer mix.)
-  const bool occ2 = g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
+  const bool occ2 = t.resident && g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
   const int slots = num_sms * (occ2 ? 2 : 1);
   int grid = t.total_items < slots ? t.total_items : slots;              // persistent: one or two CTAs per SM
   if (t.resident == 2) grid -= grid % t.n_tiles;                         // CTA b serves N tile b % n_tiles only

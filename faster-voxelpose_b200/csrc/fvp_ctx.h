@@ -37,6 +37,7 @@ struct fvp_ctx {
   std::map<std::string, int> param_index;
   bool params_ready = false;
   float* d_weights = nullptr;
+  void* d_c2c_plan = nullptr;         // chunk table of the C2CNet weight ring (device)
   FvpTrunkW w_center, w_p2p;
   FvpC2CW w_c2c;
   FvpPoseW w_pose;

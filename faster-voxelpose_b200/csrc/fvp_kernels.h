@@ -123,7 +123,12 @@ struct FvpC2CW {            // packed 1-D trunk, weights [tap][ci][co] per conv
   const float* w[24];
   const float* b[24];
   const float* w2[24];      // same, ci-major ([ci][tap][co], then the fused-skip rows) for the split-K kernel
+  const void* plan;         // device copy of the weight-ring chunk table (fvp_c2c_build_plan)
 };
+size_t fvp_c2c_plan_bytes();
+// chunk table of the network-wide weight ring of k_proposals from the DEVICE addresses of the ci-major weights; returns
+// the number of chunks or < 0 (table too small / misaligned chunk)
+int fvp_c2c_build_plan(const float* const w2[20], int J, void* h_plan);
 struct FvpPropArgs {
   FvpGeom g;
   const float* hm_cl;

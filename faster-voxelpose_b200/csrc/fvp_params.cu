@@ -455,6 +455,16 @@ int fvp_pack_params(fvp_ctx* ctx) {
     ctx->w_c2c.b[i] = base + c2c[i].b_off;
     ctx->w_c2c.w2[i] = base + c2c_cimajor[i];
   }
+  {  // chunk table of k_proposals' network-wide weight ring (device addresses of the ci-major weights)
+    std::vector<char> plan(fvp_c2c_plan_bytes(), 0);
+    const int nchunks = fvp_c2c_build_plan(ctx->w_c2c.w2, ctx->cfg.num_joints, plan.data());
+    if (nchunks <= 0) return fvp_fail(ctx, FVP_E_INVALID, "C2CNet weight-ring plan failed (%d)", nchunks);
+    if (ctx->d_c2c_plan) cudaFree(ctx->d_c2c_plan);
+    ctx->d_c2c_plan = nullptr;
+    FVP_CUDA_OK(cudaMalloc(&ctx->d_c2c_plan, plan.size()));
+    FVP_CUDA_OK(cudaMemcpy(ctx->d_c2c_plan, plan.data(), plan.size(), cudaMemcpyHostToDevice));
+    ctx->w_c2c.plan = ctx->d_c2c_plan;
+  }
   ctx->w_pose.conv_w = base + o_cw;
   ctx->w_pose.conv_b = base + o_cb;
   ctx->w_pose.fc1_w = base + o_f1w;

@@ -98,7 +98,11 @@ struct C2CNet {
 // The layer's packed weights are streamed global(L2) -> shared in 32 KB chunks with cp.async, double buffered, so the
 // inner loop reads only shared memory (round 1 read every weight straight from L2 inside the FMA loop: 0.45 ms).
 constexpr int C2C_WCHUNK = 8192;    // floats per weight buffer (32 KB)
-constexpr size_t C2C_SMEM_BYTES = (size_t)(2 * C2C_WCHUNK + 6 * C2C_BUF + 24 * C2C_MAXZ + 4 * C2C_MAXZ + C2C_THREADS * C2C_MAXZ) * sizeof(float);
+constexpr int C2C_NST_MAX = 4;      // weight ring stages: 4 for Z <= 20, 3 for Z = 40 (the split-K scratch grows with Z)
+static inline int c2c_nst(int Z) { return Z <= 20 ? 4 : 3; }
+static inline size_t c2c_smem_bytes(int Z) {
+  return (size_t)(c2c_nst(Z) * C2C_WCHUNK + 6 * C2C_BUF + 24 * C2C_MAXZ + 4 * C2C_MAXZ + C2C_THREADS * (Z <= 20 ? 20 : C2C_MAXZ)) * sizeof(float);
+}
 
 __device__ __forceinline__ void c2c_cp16(float* dst_smem, const float* src_gmem) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -234,18 +238,76 @@ __device__ void c2c_forward(const C2CNet& net, const float* x0, int J, int Z, fl
   c2c_conv(B0, 32, L, nullptr, 0, net.l[19], 1, out, 4, nullptr, 0, false, false, wbuf);    // head (row 0 of 4)
 }
 
+// ---- network-wide weight ring -------------------------------------------------------------------------------------
+// The ~1.5 MB of C2CNet weights stream through every column's CTA once.  Round 1 restarted a cp.async double buffer
+// in every (layer, part): 26 exposed L2 latencies plus 2 block barriers per 32 KB chunk - 94 us per column for 2.5 MMAC.
+// Now the whole net is ONE sequence of chunks (host-built table, consumption order) that thread 0 keeps NST - 1 chunks
+// ahead of the consumers with TMA bulk copies (cp.async.bulk -> mbarrier complete_tx), across layer boundaries: a
+// layer's first chunk is already in shared memory when the previous layer's epilogue ends.
+struct C2CChunk {
+  const float* src;
+  int nfloats;
+  int pad;
+};
+constexpr int C2C_MAX_CHUNKS = 80;
+struct C2CPlan {
+  C2CChunk chunk[C2C_MAX_CHUNKS];
+  int n;
+};
+struct C2CRing {
+  float* stage;           // [nst][C2C_WCHUNK]
+  uint64_t* full;         // [nst] mbarriers
+  int nst;
+  int next;               // chunk the consumers wait for next (uniform across the block)
+};
+__device__ __forceinline__ unsigned c2c_s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void c2c_ring_issue(const C2CPlan& plan, const C2CRing& r, int g) {     // one thread
+  if (g >= plan.n) return;
+  const int st = g % r.nst;
+  const unsigned bytes = (unsigned)plan.chunk[g].nfloats * 4u, bar = c2c_s32(r.full + st);
+  asm volatile("{\n\t.reg .b64 s;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 s, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   c2c_s32(r.stage + (size_t)st * C2C_WCHUNK)),
+               "l"(plan.chunk[g].src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ const float* c2c_ring_wait(const C2CRing& r) {                          // all threads
+  const int st = r.next % r.nst;
+  const unsigned bar = c2c_s32(r.full + st), parity = (unsigned)(r.next / r.nst) & 1u;
+  unsigned ok, spins = 0;
+  do {
+    if (++spins > (1u << 26)) {          // watchdog: a protocol bug must abort the kernel, never hang the GPU
+      printf("k_proposals: weight ring wait timed out (block %d thread %d chunk %d)\n", blockIdx.x, threadIdx.x, r.next);
+      __trap();
+    }
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+  return r.stage + (size_t)st * C2C_WCHUNK;
+}
+// after the block barrier that ends the use of chunk r.next: refill its stage with chunk r.next + nst
+__device__ __forceinline__ void c2c_ring_release(const C2CPlan& plan, C2CRing& r) {
+  if (threadIdx.x == 0) c2c_ring_issue(plan, r, r.next + r.nst);
+  ++r.next;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Register-tiled 1-D conv with K split across the thread block (round-1 profile: the row-major c2c_conv above
 // spends ~20 instructions per weight row and predicated position; 0.35 ms per column).  Thread (co, ks) owns ALL L
 // output positions of channel co for the input channels ci = ks, ks+KS, ...: per ci it loads the L+K-1 inputs once
 // into registers (warp-broadcast) and runs K*L FMAs; the KS partial sums meet in shared memory in fixed order.
-// Weights are packed ci-major ([ci][tap][CoutG], then the fused 1x1 skip rows [ci][CoutG]) and streamed through the
-// same cp.async double buffer.
+// Weights are packed ci-major ([ci][tap][CoutG], then the fused 1x1 skip rows [ci][CoutG]) and arrive through the
+// network-wide ring above; the chunking (input channels per chunk) here must match c2c_build_plan on the host.
 // ------------------------------------------------------------------------------------------------
+__host__ __device__ inline int c2c_cpc(int C, int taps, int CoutG) {      // input channels per weight chunk
+  int cpc = C2C_WCHUNK / (taps * CoutG);
+  return cpc > C ? C : cpc;
+}
+
 template <int L, int K>
-__device__ void c2c_conv2(const float* __restrict__ in, int Cin, const float* __restrict__ in2, int Cin2, const float* w2,
+__device__ void c2c_conv2(const float* __restrict__ in, int Cin, const float* __restrict__ in2, int Cin2,
                           const float* bias_p, float* __restrict__ out, int CoutG, const float* __restrict__ res,
-                          int res_mode, bool relu, bool upsample, float* __restrict__ wbuf, float* __restrict__ red) {
+                          int res_mode, bool relu, bool upsample, const C2CPlan& plan, C2CRing& ring, float* __restrict__ red) {
   constexpr int PAD = (K - 1) / 2;
   const int tid = threadIdx.x;
   const int KS = C2C_THREADS / CoutG;
@@ -259,28 +321,11 @@ __device__ void c2c_conv2(const float* __restrict__ in, int Cin, const float* __
     if (src == nullptr) break;
     const int C = part == 0 ? Cin : Cin2;
     const int taps = part == 0 ? K : 1;
-    const float* wsrc = part == 0 ? w2 : w2 + (size_t)Cin * K * CoutG;
-    int cpc = C2C_WCHUNK / (taps * CoutG);               // input channels per weight chunk
-    if (cpc > C) cpc = C;
+    const int cpc = c2c_cpc(C, taps, CoutG);
     const int nchunks = (C + cpc - 1) / cpc;
-    auto issue = [&](int ch) {
-      const int c_lo = ch * cpc, nc = min(cpc, C - c_lo);
-      const float* g = wsrc + (size_t)c_lo * taps * CoutG;
-      float* d = wbuf + (ch & 1) * C2C_WCHUNK;
-      for (int i = tid * 4; i < nc * taps * CoutG; i += C2C_THREADS * 4) c2c_cp16(d + i, g + i);
-      asm volatile("cp.async.commit_group;\n" ::);
-    };
-    issue(0);
     for (int ch = 0; ch < nchunks; ++ch) {
-      if (ch + 1 < nchunks) {
-        issue(ch + 1);
-        asm volatile("cp.async.wait_group 1;\n" ::);
-      } else {
-        asm volatile("cp.async.wait_group 0;\n" ::);
-      }
-      __syncthreads();
+      const float* wb = c2c_ring_wait(ring) + co;
       const int c_lo = ch * cpc, c_hi = min(C, c_lo + cpc);
-      const float* wb = wbuf + (ch & 1) * C2C_WCHUNK + co;
       for (int ci = c_lo + ks; ci < c_hi; ci += KS) {
         const float* xr_src = src + ci * L;
         const float* wr = wb + (size_t)(ci - c_lo) * taps * CoutG;
@@ -300,7 +345,8 @@ __device__ void c2c_conv2(const float* __restrict__ in, int Cin, const float* __
           for (int l = 0; l < L; ++l) acc[l] = fmaf(wv, xr_src[l], acc[l]);
         }
       }
-      __syncthreads();                                   // buffer (ch&1) may be refilled by chunk ch+2
+      __syncthreads();                                   // every thread is done with this chunk's stage
+      c2c_ring_release(plan, ring);
     }
   }
   // ---- fixed-order reduction over the K split, then the epilogue ----
@@ -338,18 +384,39 @@ __device__ void c2c_pool2(const float* __restrict__ in, int C, float* __restrict
   __syncthreads();
 }
 
-struct C2CNet2 {          // ci-major weights (w2) + bias per layer
-  const float* w[20];
+struct C2CNet2 {          // bias per layer (the ci-major weights arrive through the ring, see C2CPlan)
   const float* b[20];
 };
+// (layer index, K, Cin, Cin2, CoutG) of the 20 convolutions in execution order: the single source of truth for the chunk
+// plan on the host and the call sequence in c2c_forward2
+struct C2CLayerShape { int K, Cin, Cin2, CoutG; };
+__host__ __device__ inline C2CLayerShape c2c_shape(int i, int J) {
+  switch (i) {
+    case 0: return {7, J, 0, 16};
+    case 1: return {3, 16, 0, 32};
+    case 2: return {3, 32, 16, 32};
+    case 3: case 4: return {3, 32, 0, 32};
+    case 5: return {3, 32, 0, 64};
+    case 6: return {3, 64, 32, 64};
+    case 7: case 8: return {3, 64, 0, 64};
+    case 9: return {3, 64, 0, 128};
+    case 10: return {3, 128, 64, 128};
+    case 11: case 12: case 13: case 14: return {3, 128, 0, 128};
+    case 15: return {1, 128, 0, 128};
+    case 16: case 17: return {3, 64, 0, 64};
+    case 18: return {1, 64, 0, 64};
+    default: return {1, 32, 0, 4};
+  }
+}
 
 template <int Z>
-__device__ void c2c_forward2(const C2CNet2& n, const float* x0, int J, float* buf, float* out, float* wbuf, float* red) {
+__device__ void c2c_forward2(const C2CNet2& n, const C2CPlan& plan, C2CRing& ring, const float* x0, int J, float* buf, float* out,
+                             float* red) {
   float *B0 = buf, *B1 = buf + C2C_BUF, *B2 = buf + 2 * C2C_BUF, *B3 = buf + 3 * C2C_BUF, *B4 = buf + 4 * C2C_BUF,
         *B5 = buf + 5 * C2C_BUF;
   constexpr int L = Z, L2 = Z / 2, L4 = Z / 4;
 #define CV(Lx, Kx, i, inp, cin, inp2, cin2, outp, cg, resp, rm, up) \
-  c2c_conv2<Lx, Kx>(inp, cin, inp2, cin2, n.w[i], n.b[i], outp, cg, resp, rm, true, up, wbuf, red)
+  c2c_conv2<Lx, Kx>(inp, cin, inp2, cin2, n.b[i], outp, cg, resp, rm, true, up, plan, ring, red)
   CV(L, 7, 0, x0, J, nullptr, 0, B0, 16, nullptr, 0, false);
   CV(L, 3, 1, B0, 16, nullptr, 0, B1, 32, nullptr, 0, false);
   CV(L, 3, 2, B1, 32, B0, 16, B2, 32, nullptr, 0, false);
@@ -372,7 +439,7 @@ __device__ void c2c_forward2(const C2CNet2& n, const float* x0, int J, float* bu
   CV(L2, 3, 17, B1, 64, nullptr, 0, B2, 64, B0, 1, false);         // d1
   CV(L2, 1, 18, B2, 64, nullptr, 0, B0, 64, B3, 2, true);          // u1 = relu(convT)+skip1
 #undef CV
-  c2c_conv2<L, 1>(B0, 32, nullptr, 0, n.w[19], n.b[19], out, 4, nullptr, 0, false, false, wbuf, red);   // head (row 0 of 4)
+  c2c_conv2<L, 1>(B0, 32, nullptr, 0, n.b[19], out, 4, nullptr, 0, false, false, plan, ring, red);   // head (row 0 of 4)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,10 +474,13 @@ __device__ void fvp_make_person(const FvpPropArgs& a, const float* c7, int seq, 
 }
 
 // one CTA per proposal slot
-__global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet net, C2CNet2 net2) {
-  extern __shared__ __align__(16) float c2c_smem[];
-  float* s_wbuf = c2c_smem;                       // 2 x C2C_WCHUNK weight staging
-  float* s_buf = s_wbuf + 2 * C2C_WCHUNK;         // 6 activation buffers
+__global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet net, C2CNet2 net2, const C2CPlan* __restrict__ plan_g,
+                                                           int nst) {
+  extern __shared__ __align__(128) float c2c_smem[];
+  __shared__ C2CPlan s_plan;
+  __shared__ uint64_t s_full[4];
+  float* s_wbuf = c2c_smem;                       // nst x C2C_WCHUNK weight ring (>= 2: the generic path double-buffers in it)
+  float* s_buf = s_wbuf + nst * C2C_WCHUNK;       // 6 activation buffers
   float* s_x0 = s_buf + 6 * C2C_BUF;              // [JP][Z] input columns
   float* s_out = s_x0 + 24 * C2C_MAXZ;            // [4][Z] head output
   float* s_red = s_out + 4 * C2C_MAXZ;            // [KS][CoutG][L] split-K partial sums (512 * L floats)
@@ -420,6 +490,19 @@ __global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet
   const int tid = threadIdx.x;
   const int J = g.J, Z = g.Z, JP = g.proj.JP;
   int flat = 0;
+  // weight ring: copy the chunk table, arm the barriers, start the first nst chunks - all under the column sampling below
+  C2CRing ring{s_wbuf, s_full, nst, 0};
+  if (Z == 20 || Z == 40) {
+    for (int i = tid; i < (int)(sizeof(C2CPlan) / 4); i += C2C_THREADS) ((int*)&s_plan)[i] = ((const int*)plan_g)[i];
+    if (tid == 0) {
+      for (int i = 0; i < nst; ++i)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(c2c_s32(s_full + i)));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int i = 0; i < nst; ++i) c2c_ring_issue(s_plan, ring, i);
+  }
 
   if (a.mode == 0) {
     // ---- K2: sample the z column of the selected (x,y) cell straight from the heat maps ----------
@@ -461,8 +544,8 @@ __global__ void __launch_bounds__(C2C_THREADS) k_proposals(FvpPropArgs a, C2CNet
     for (int i = tid; i < J * Z; i += C2C_THREADS) a.cols_out[(size_t)slot * J * Z + i] = s_x0[i];
   (void)JP;
 
-  if (Z == 20) c2c_forward2<20>(net2, s_x0, J, s_buf, s_out, s_wbuf, s_red);        // s_out[0..Z) = 1-D heat map
-  else if (Z == 40) c2c_forward2<40>(net2, s_x0, J, s_buf, s_out, s_wbuf, s_red);
+  if (Z == 20) c2c_forward2<20>(net2, s_plan, ring, s_x0, J, s_buf, s_out, s_red);        // s_out[0..Z) = 1-D heat map
+  else if (Z == 40) c2c_forward2<40>(net2, s_plan, ring, s_x0, J, s_buf, s_out, s_red);
   else c2c_forward(net, s_x0, J, Z, s_buf, s_out, s_wbuf);
 
   if (a.hm1d_out)
@@ -521,7 +604,36 @@ cudaError_t fvp_proposal_init_device(int X, int Y) {
   if (nms > 48 * 1024 && nms > (size_t)fa.maxDynamicSharedSizeBytes)
     e = cudaFuncSetAttribute(k_nms_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_proposals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2C_SMEM_BYTES);
+  const size_t c2c = c2c_smem_bytes(20) > c2c_smem_bytes(40) ? c2c_smem_bytes(20) : c2c_smem_bytes(40);
+  return cudaFuncSetAttribute(k_proposals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2c);
+}
+
+// Chunk table of the network-wide weight ring: (layer, part, chunk) in the order c2c_forward2 consumes them.  Written to
+// `h_plan` (host) - fvp_pack_params uploads it next to the weights and passes the device copy back in FvpC2CW::plan.
+size_t fvp_c2c_plan_bytes() { return sizeof(C2CPlan); }
+int fvp_c2c_build_plan(const float* const w2[20], int J, void* h_plan) {
+  C2CPlan& p = *reinterpret_cast<C2CPlan*>(h_plan);
+  p.n = 0;
+  for (int i = 0; i < 20; ++i) {
+    const C2CLayerShape sh = c2c_shape(i, J);
+    const float* base = w2[i];
+    for (int part = 0; part < 2; ++part) {
+      const int C = part == 0 ? sh.Cin : sh.Cin2, taps = part == 0 ? sh.K : 1;
+      if (C == 0) continue;
+      const float* src = part == 0 ? base : base + (size_t)sh.Cin * sh.K * sh.CoutG;
+      const int cpc = c2c_cpc(C, taps, sh.CoutG);
+      for (int c_lo = 0; c_lo < C; c_lo += cpc) {
+        if (p.n >= C2C_MAX_CHUNKS) return -1;
+        const int nc = C - c_lo < cpc ? C - c_lo : cpc;
+        p.chunk[p.n].src = src + (size_t)c_lo * taps * sh.CoutG;
+        p.chunk[p.n].nfloats = nc * taps * sh.CoutG;
+        p.chunk[p.n].pad = 0;
+        if ((p.chunk[p.n].nfloats & 3) || ((uintptr_t)p.chunk[p.n].src & 15)) return -2;     // TMA bulk: 16-byte granules
+        ++p.n;
+      }
+    }
+  }
+  return p.n;
 }
 
 void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, cudaStream_t st) {
@@ -530,13 +642,10 @@ void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, cudaStr
     net.l[i].w = w.w[i];
     net.l[i].b = w.b[i];
   }
-  const size_t smem = C2C_SMEM_BYTES;
+  const size_t smem = c2c_smem_bytes(a.g.Z);
   C2CNet2 net2;
-  for (int i = 0; i < 20; ++i) {
-    net2.w[i] = w.w2[i];
-    net2.b[i] = w.b[i];
-  }
-  k_proposals<<<n, C2C_THREADS, smem, st>>>(a, net, net2);
+  for (int i = 0; i < 20; ++i) net2.b[i] = w.b[i];
+  k_proposals<<<n, C2C_THREADS, smem, st>>>(a, net, net2, reinterpret_cast<const C2CPlan*>(w.plan), c2c_nst(a.g.Z));
 }
 
 void fvp_launch_people_from_centers(const FvpPropArgs& a, const float* d_centers, int n, cudaStream_t st) {
