@@ -2,6 +2,7 @@
 // the forward pipeline (optionally replayed as a CUDA graph) and the per-stage entry points.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "fvp_ctx.h"
@@ -166,7 +167,7 @@ int refuse_on_lane(fvp_ctx* ctx, const char* what) {
   return FVP_OK;
 }
 
-FvpLaunchEnv launch_env(const fvp_ctx* ctx) { return FvpLaunchEnv{ctx->num_sms, ctx->conv_mode, nullptr, nullptr}; }
+FvpLaunchEnv launch_env(const fvp_ctx* ctx) { return FvpLaunchEnv{ctx->num_sms, ctx->conv_mode, nullptr, nullptr, ctx->split_activations}; }
 
 // Other entry points must not touch the shared workspaces while fvp_submit_host tickets are in flight.
 int refuse_if_tickets_open(fvp_ctx* ctx) {
@@ -320,6 +321,7 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   ctx->cfg = c;
   ctx->device = device;
   ctx->h_status = h_status;
+  if (const char* sa = std::getenv("FVP_SPLIT_ACT")) ctx->split_activations = std::atoi(sa) != 0;   // A/B switch (tools only)
   fvp_build_param_table(ctx);
 
   FvpGeom& g = ctx->geom;
@@ -417,6 +419,7 @@ int fvp_create_lane(fvp_ctx* root, int max_batch, fvp_ctx** out) {
   ctx->h_status = root->h_status;
   ctx->num_sms = root->num_sms;
   ctx->conv_mode = root->conv_mode;
+  ctx->split_activations = root->split_activations;
   ctx->root = root;
   ctx->shared_gen = -1;                            // mirrors nothing yet: the first forward copies the root's tables
   ctx->geom = root->geom;
@@ -800,7 +803,7 @@ int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr
 
 int fvp_debug_conv(fvp_ctx* ctx, const float* d_in, int n, int H, int W, int cin, const float* h_weight, const float* h_bias,
                    int cout, int k, int relu, int mode, float* d_out, int repeat, float* h_ms, uintptr_t stream) {
-  if (!ctx || !d_in || !h_weight || !h_bias || !d_out || (k != 1 && k != 3 && k != 7) || cin % 4 || mode < 0 || (mode & 0xff) > 3) return FVP_E_INVALID;
+  if (!ctx || !d_in || !h_weight || !h_bias || !d_out || (k != 1 && k != 3 && k != 7) || cin % 4 || mode < 0 || (mode & 0xff) > 4) return FVP_E_INVALID;
   sync_shared(ctx);
   cudaSetDevice(ctx->device);
   return fvp_debug_conv_impl(ctx, d_in, n, H, W, cin, h_weight, h_bias, cout, k, relu, mode, d_out, repeat, h_ms, (cudaStream_t)stream);

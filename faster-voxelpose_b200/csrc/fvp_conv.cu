@@ -6,6 +6,8 @@
 //   * ConvTranspose2d(k=2,s=2) (cnns_2d.py:58-71) = 1x1 conv to 4*Co channels + pixel-shuffle store
 //   * planar (NCHW) store for the final layers the reference-layout consumers read
 // This is the exact-fp32 path (summation order differs from cuDNN/oneDNN, nothing else).
+#include <cuda_fp16.h>
+
 #include "fvp_kernels.h"
 
 // range guard twin of fvp_conv_tc.cu's g_tc_status: this kernel's outputs may feed a layer of the fp16 hi/lo engine
@@ -183,7 +185,67 @@ __global__ void __launch_bounds__(256) k_maxpool2(const float4* __restrict__ in,
                   fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
 }
 
+// 2x2 max-pool on a split tensor: 8 channels (one uint4 of hi halves + one of lo halves) per thread.  The winner is chosen
+// on the reconstructed values hi + lo * 2^-11 and its (hi, lo) pair is copied, so pooling a split tensor is exact.
+__global__ void __launch_bounds__(256) k_maxpool2_split(const uint4* __restrict__ in, uint4* __restrict__ out, int n, int H, int W,
+                                                        int C8, const int* __restrict__ valid) {
+  const int img = blockIdx.y;
+  if (valid && !valid[img]) return;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= Ho * Wo * C8) return;
+  const int c = i % C8, p = i / C8;
+  const int oy = p / Wo, ox = p - oy * Wo;
+  const size_t plane_in = (size_t)n * H * W * C8, plane_out = (size_t)n * Ho * Wo * C8;
+  const size_t base = ((size_t)img * H * W + (size_t)(2 * oy) * W + 2 * ox) * C8 + c;
+  const size_t offs[4] = {0, (size_t)C8, (size_t)W * C8, (size_t)W * C8 + C8};
+  uint4 bh = in[base], bl = in[plane_in + base];
+#pragma unroll
+  for (int q = 1; q < 4; ++q) {
+    const uint4 h = in[base + offs[q]], l = in[plane_in + base + offs[q]];
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&h);
+    const uint32_t* lw = reinterpret_cast<const uint32_t*>(&l);
+    uint32_t* bhw = reinterpret_cast<uint32_t*>(&bh);
+    uint32_t* blw = reinterpret_cast<uint32_t*>(&bl);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 xh = __half22float2(*reinterpret_cast<const __half2*>(&hw[e])), xl = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+      const float2 yh = __half22float2(*reinterpret_cast<const __half2*>(&bhw[e])), yl = __half22float2(*reinterpret_cast<const __half2*>(&blw[e]));
+      const bool t0 = fmaf(xl.x, 1.0f / 2048.0f, xh.x) > fmaf(yl.x, 1.0f / 2048.0f, yh.x);
+      const bool t1 = fmaf(xl.y, 1.0f / 2048.0f, xh.y) > fmaf(yl.y, 1.0f / 2048.0f, yh.y);
+      const uint32_t m = (t0 ? 0x0000ffffu : 0u) | (t1 ? 0xffff0000u : 0u);
+      bhw[e] = (hw[e] & m) | (bhw[e] & ~m);
+      blw[e] = (lw[e] & m) | (blw[e] & ~m);
+    }
+  }
+  const size_t o = (size_t)img * Ho * Wo * C8 + i;
+  out[o] = bh;
+  out[plane_out + o] = bl;
+}
+
+// test / transition helpers: fp32 <-> split (hi, scaled lo) element-wise over `count` values
+__global__ void k_split(const float* __restrict__ in, __half* __restrict__ out, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float x = in[i];
+  const __half h = __float2half_rn(x);
+  out[i] = h;
+  out[count + i] = __float2half_rn((x - __half2float(h)) * 2048.0f);
+}
+__global__ void k_unsplit(const __half* __restrict__ in, float* __restrict__ out, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  out[i] = fmaf(__half2float(in[count + i]), 1.0f / 2048.0f, __half2float(in[i]));
+}
+
 }  // namespace
+
+void fvp_launch_split(const float* in, void* out, size_t count, cudaStream_t st) {
+  k_split<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(in, (__half*)out, count);
+}
+void fvp_launch_unsplit(const void* in, float* out, size_t count, cudaStream_t st) {
+  k_unsplit<<<(unsigned)((count + 255) / 256), 256, 0, st>>>((const __half*)in, out, count);
+}
 
 cudaError_t fvp_conv_set_status_ptr(int* d_status) { return cudaMemcpyToSymbol(g_conv_status, &d_status, sizeof(d_status)); }
 
@@ -209,6 +271,10 @@ void fvp_launch_maxpool2(const float* in, float* out, int n, int H, int W, int C
   dim3 grid(fvp_cdiv((H / 2) * (W / 2) * (C / 4), 256), n);
   k_maxpool2<<<grid, 256, 0, st>>>((const float4*)in, (float4*)out, H, W, C / 4, valid);
 }
+void fvp_launch_maxpool2_split(const void* in, void* out, int n, int H, int W, int C, const int* valid, cudaStream_t st) {
+  dim3 grid(fvp_cdiv((H / 2) * (W / 2) * (C / 8), 256), n);
+  k_maxpool2_split<<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, n, H, W, C / 8, valid);
+}
 
 // ------------------------------------------------------------------------------------------------
 // trunk program: front_layers + EncoderDecorder (+ heads), cnns_2d.py:94-135,173-178
@@ -223,7 +289,7 @@ struct TrunkRun {            // what every conv of one trunk enqueue shares (no 
 };
 }  // namespace
 static void conv(const TrunkRun& r, const FvpConvW& w, const float* in, int H, int W, const float* in2, float* out, int couts,
-                 const float* res, int res_mode, int relu, int upsample, int nchw = 0, int cout_real = 0) {
+                 const float* res, int res_mode, int relu, int upsample, int nchw = 0, int cout_real = 0, int fmt = 0) {
   const int n = r.n;
   const int* valid = r.valid;
   int* launches = r.launches;
@@ -236,6 +302,14 @@ static void conv(const TrunkRun& r, const FvpConvW& w, const float* in, int H, i
   a.out = out; a.CoutP = w.coutp; a.CoutS = couts; a.CoutReal = cout_real;
   a.res = res; a.res_mode = res_mode; a.relu = relu; a.ksize = w.k; a.upsample = upsample;
   a.nchw = nchw; a.n = n; a.valid = valid;
+  a.fmt = fmt;
+  if (fmt & FVP_FMT_IN_SPLIT) {                     // TMA-fed layer of a split-activation trunk (fp16 engine by construction)
+    const float* const c16s[3] = {w.wtc16_c16, nullptr, nullptr};
+    if (w.wtc16_c16 && w.cin <= 16 && w.k != 7) fvp_launch_conv_tc(a, c16s, 2, r.env, st);
+    else fvp_launch_conv_tc(a, w.wtc16, 1, r.env, st);
+    if (launches) ++*launches;
+    return;
+  }
   // engine 2: fp16-split tcgen05 kernel (all layers); engine 1: 3xTF32 tcgen05 kernel, where the 7x7 front conv (49 taps
   // of half-empty 32-channel K-blocks, measured 6.6 vs 11.4 TMAC/s) stays on the CUDA-core kernel; engine 0: CUDA cores.
   // A layer whose BN-folded weights leave the fp16 range has no fp16 image (fvp_params.cu: stash) and drops to the 3xTF32
@@ -255,6 +329,46 @@ void fvp_run_trunk2d(const FvpTrunkW& t, const float* d_in, int cin, int n, int 
   const TrunkRun r{env, n, valid, launches, st};
   float *B0 = buf[0], *B1 = buf[1], *B2 = buf[2], *B3 = buf[3], *B4 = buf[4], *B5 = buf[5];
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
+  // Engine 2 with an fp16 image for every layer (the normal case): activations travel between layers as SPLIT tensors -
+  // every epilogue stores hi / scaled-lo fp16 planes once, every consumer fetches its halos with TMA tensor loads (no
+  // loader warps, no conversions, zero padding = TMA out-of-bounds fill).  Only the first layer reads fp32 (the
+  // back-projected planes) through the legacy loaders and only the last one writes fp32.  Scratch units hold either form
+  // (2 x fp16 = 1 x fp32 per element).
+  const FvpConvW* all[21] = {&t.front, &t.r1a, &t.r1b, &t.s1a, &t.s1b, &t.e1a, &t.e1b, &t.s2a, &t.s2b, &t.e2a, &t.e2b,
+                             &t.ma, &t.mb, &t.d2a, &t.d2b, &t.up2, &t.d1a, &t.d1b, &t.up1, &t.head_b, center_heads ? &t.head_a : &t.head_b};
+  bool split = env.conv_mode == 2 && env.split_activations && t.front.wtc16_c16 != nullptr;
+  for (int i = 1; i < 21 && split; ++i) split = all[i]->wtc16[0] != nullptr;
+  if (split) {
+    const int S = FVP_FMT_IN_SPLIT | FVP_FMT_OUT_SPLIT, SR = S | FVP_FMT_RES_SPLIT;
+    conv(r, t.front, d_in, H, W, nullptr, B0, 16, nullptr, 0, 1, 0, 0, 0, FVP_FMT_OUT_SPLIT);   // fp32 in (legacy loaders), split out
+    conv(r, t.r1a, B0, H, W, nullptr, B1, 32, nullptr, 0, 1, 0, 0, 0, S);
+    conv(r, t.r1b, B1, H, W, B0, B2, 32, nullptr, 0, 1, 0, 0, 0, S);                             // f1 (conv skip fused)
+    conv(r, t.s1a, B2, H, W, nullptr, B0, 32, nullptr, 0, 1, 0, 0, 0, S);
+    conv(r, t.s1b, B0, H, W, nullptr, B3, 32, B2, 1, 1, 0, 0, 0, SR);                            // skip1
+    fvp_launch_maxpool2_split(B2, B0, n, H, W, 32, valid, st); if (launches) ++*launches;
+    conv(r, t.e1a, B0, H2, W2, nullptr, B1, 64, nullptr, 0, 1, 0, 0, 0, S);
+    conv(r, t.e1b, B1, H2, W2, B0, B4, 64, nullptr, 0, 1, 0, 0, 0, S);                           // e1
+    conv(r, t.s2a, B4, H2, W2, nullptr, B0, 64, nullptr, 0, 1, 0, 0, 0, S);
+    conv(r, t.s2b, B0, H2, W2, nullptr, B5, 64, B4, 1, 1, 0, 0, 0, SR);                          // skip2
+    fvp_launch_maxpool2_split(B4, B0, n, H2, W2, 64, valid, st); if (launches) ++*launches;
+    conv(r, t.e2a, B0, H4, W4, nullptr, B1, 128, nullptr, 0, 1, 0, 0, 0, S);
+    conv(r, t.e2b, B1, H4, W4, B0, B2, 128, nullptr, 0, 1, 0, 0, 0, S);                          // e2
+    conv(r, t.ma, B2, H4, W4, nullptr, B0, 128, nullptr, 0, 1, 0, 0, 0, S);
+    conv(r, t.mb, B0, H4, W4, nullptr, B1, 128, B2, 1, 1, 0, 0, 0, SR);                          // m
+    conv(r, t.d2a, B1, H4, W4, nullptr, B0, 128, nullptr, 0, 1, 0, 0, 0, S);
+    conv(r, t.d2b, B0, H4, W4, nullptr, B2, 128, B1, 1, 1, 0, 0, 0, SR);                         // d2
+    conv(r, t.up2, B2, H4, W4, nullptr, B0, 64, B5, 2, 1, 1, 0, 0, SR);                          // u2 @ half
+    conv(r, t.d1a, B0, H2, W2, nullptr, B1, 64, nullptr, 0, 1, 0, 0, 0, S);
+    conv(r, t.d1b, B1, H2, W2, nullptr, B2, 64, B0, 1, 1, 0, 0, 0, SR);                          // d1
+    conv(r, t.up1, B2, H2, W2, nullptr, B0, 32, B3, 2, 1, 1, 0, 0, SR);                          // u1 @ full
+    if (center_heads) {
+      conv(r, t.head_a, B0, H, W, nullptr, B1, 64, nullptr, 0, 1, 0, 0, 0, S);                   // both 3x3 heads + ReLU
+      conv(r, t.head_b, B1, H, W, nullptr, d_out, 0, nullptr, 0, 0, 0, 1, out_real, FVP_FMT_IN_SPLIT);
+    } else {
+      conv(r, t.head_b, B0, H, W, nullptr, d_out, 0, nullptr, 0, 0, 0, 1, out_real, FVP_FMT_IN_SPLIT);
+    }
+    return;
+  }
   // front_layers
   conv(r, t.front, d_in, H, W, nullptr, B0, 16, nullptr, 0, 1, 0);          // t16
   conv(r, t.r1a, B0, H, W, nullptr, B1, 32, nullptr, 0, 1, 0);

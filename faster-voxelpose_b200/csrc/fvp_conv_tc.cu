@@ -27,10 +27,12 @@
 // Warp roles (14 warps, see the kernel): 8 loader warps | MMA issuer + TMEM owner | weight TMA producer | 4 epilogue warps,
 // connected by mbarrier full/empty rings; MMA completion frees a slot through tcgen05.commit.
 // DESIGN.md 4.1 has the measured hardware facts this layout rests on and what bounds the kernel.
+#include <cuda.h>          // CUtensorMap + enums only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 #include <cuda_fp16.h>
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "fvp_kernels.h"
 
@@ -72,6 +74,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// 4-D tiled TMA tensor load global -> shared (SASS UTMALDG): box = (channels of one K-block, halo width padded to the
+// row pitch, halo height, 1 image), out-of-bounds elements arrive as zeros (= the convolution's zero padding), the
+// 16-byte chunks land swizzled exactly as the UMMA descriptors of this kernel read them.
+__device__ __forceinline__ void tma_tensor4d_g2s(void* dst_smem, const CUtensorMap* map, int c0, int x, int y, int img, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(map), "r"(c0), "r"(x), "r"(y), "r"(img), "r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -227,6 +239,11 @@ struct TcArgs {
   unsigned long long* prof;                  // debug: per-role wait / busy cycle counters (NULL in production)
 };
 
+// TMA descriptors of a launch whose inputs are split tensors (fp16 hi / lo planes): main input and fused-skip input
+struct alignas(64) TcMaps {
+  CUtensorMap in_hi, in_lo, in2_hi, in2_lo;
+};
+
 // debug instrumentation: add the cycles spent in `stmt` to counter `slot` when profiling is on
 #define TC_TIMED(slot, stmt)                                   \
   do {                                                         \
@@ -267,17 +284,18 @@ __device__ __forceinline__ bool tc_decode(const TcArgs& t, int item, TcItem& w) 
 // OCC = CTAs per SM the kernel is compiled for: 2 caps the registers at 72 so that two persistent CTAs (each with its own
 // loaders / MMA issuer / epilogue) share an SM when the launch needs <= ~110 KB of shared memory and <= 256 TMEM columns -
 // every role of this kernel is latency-bound per item, a second CTA fills the idle issue slots and tensor-pipe gaps.
-template <int MODE, int OCC>
-__global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
+// TMA = true: the input (and fused-skip input) are split tensors fetched by TMA tensor loads from the producer lane - the 8
+// loader warps do not exist (192 threads: MMA warp, producer warp, 4 epilogue warps).
+template <int MODE, int OCC, bool TMA>
+__global__ void __launch_bounds__(TMA ? 192 : TC_THREADS, OCC) k_conv_tc(TcArgs t, const __grid_constant__ TcMaps maps) {
   constexpr bool F16 = MODE != 0;
-  // Streamed weights fill the whole shared memory, so they only ever occur with one CTA per SM.  The register allocation
-  // of the two-CTA (72-register) instantiations is fragile: with the streaming code present the 16-channel K-block variant
-  // (7x7 layer) spills 108 B instead of 88 B and ran 17 % slower, so it compiles that path out (rule 2; rules 0 / 1 = keep
-  // it everywhere / drop it from every two-CTA variant are A/B switches, profiles/r02_conv_ab.txt).
-#ifndef FVP_CAN_STREAM_RULE
-#define FVP_CAN_STREAM_RULE 2
-#endif
-  constexpr bool CAN_STREAM = FVP_CAN_STREAM_RULE == 0 ? true : (FVP_CAN_STREAM_RULE == 1 ? OCC == 1 : !(OCC == 2 && MODE == 2));
+  static_assert(!TMA || F16, "split tensors are the operand format of the fp16 engine");
+  constexpr int LW = TMA ? 0 : TC_LW;                               // warps in front of the MMA warp (the loaders)
+  constexpr int NTHREADS = LW * 32 + 64 + TC_EPI;
+  // (Measured, profiles/r02_conv_ab.txt: compiling the streamed-weight path out of the two-CTA instantiations - which can
+  // never stream, streaming fills the shared memory - lowers their spill counts but made the 7x7 layer 11 % SLOWER; the
+  // 72-register variants are a register-allocation lottery, only measurements count.  The path stays in every variant.)
+  constexpr bool CAN_STREAM = true;
   constexpr int ROWB = MODE == 0 ? 128 : (MODE == 1 ? 64 : 32);   // bytes of one pixel row of a K-block in shared memory
   constexpr int CB = MODE == 2 ? 16 : 32;                          // channels per K-block
   constexpr uint32_t LAYOUT = MODE == 0 ? 2u : (MODE == 1 ? 4u : 6u);   // SWIZZLE_128B / 64B / 32B
@@ -307,13 +325,13 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
   // and run OUR prologue (barriers, TMEM allocation, resident weight fetch) under the tail of the previous kernel.
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   if (tid == 0) {
-    for (int i = 0; i < A_ST; ++i) { mbar_init(a_full + i, TC_LOADERS); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < A_ST; ++i) { mbar_init(a_full + i, TMA ? 1 : TC_LOADERS); mbar_init(a_empty + i, 1); }
     for (int i = 0; i < B_ST; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  for (int i = tid; i < a.CoutP; i += TC_THREADS) s_bias[i] = a.bias[i];   // weights: independent of the previous kernel
-  if (warp == TC_LW) {                                             // TMEM allocation (power of two >= 32 columns)
+  for (int i = tid; i < a.CoutP; i += NTHREADS) s_bias[i] = a.bias[i];   // weights: independent of the previous kernel
+  if (warp == LW) {                                                // TMEM allocation (power of two >= 32 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&s_tmem)), "r"(t.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
@@ -322,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
   tc_fence_after();
   const uint32_t tmem = s_tmem;
   const int nph = a.in2 ? 2 : 1;
-  const bool is_producer = tid == TC_LOADERS + 32;
+  const bool is_producer = tid == LW * 32 + 32;
   if (is_producer && t.resident) {                                // weights do not depend on the previous kernel
     mbar_arrive_expect_tx(b_full, t.b_stage_bytes);
     if (per_nt) {                                         // my N tile's blocks, compacted: block b -> sB + b * blk_bytes
@@ -339,7 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
   }
   asm volatile("griddepcontrol.wait;\n" ::: "memory");           // activations of the previous kernel are now visible
 
-  if (warp < TC_LW) {
+  if (!TMA && warp < TC_LW) {
     // =============================== A staging (256 threads) ========================================
     // Thread (q = tid & 7, p0 = tid >> 3) always handles channel quad q of halo pixels p0, p0+32, p0+64, ...:
     // their halo coordinates, shared-memory destinations and global offsets do not depend on the work item, so they
@@ -471,10 +489,10 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
       atomicAdd(t.prof + 0, (unsigned long long)pc[0]);
       atomicAdd(t.prof + 1, (unsigned long long)(clock64() - lt0));
     }
-  } else if (tid == TC_LOADERS + 32) {
-    // =============================== B producer (TMA bulk copies) =====================================
-    if (CAN_STREAM && !t.resident) {                              // (resident image: already requested above)
-      int b_it = 0;
+  } else if (tid == LW * 32 + 32) {
+    // ============== producer lane: weight TMA bulk copies (+ the activation halos when TMA) ==============
+    if (TMA || (CAN_STREAM && !t.resident)) {                     // (resident image: already requested above)
+      int b_it = 0, a_it = 0;
       for (int item = blockIdx.x; item < t.total_items; item += gridDim.x) {
         TcItem w;
         if (!tc_decode(t, item, w)) continue;
@@ -483,6 +501,20 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
           const int K = ph == 0 ? a.ksize : 1, Cin = ph == 0 ? a.Cin : a.Cin2;
           const int CinP = (Cin + CB - 1) / CB * CB;
           for (int c0 = 0; c0 < CinP; c0 += CB) {
+            if constexpr (TMA) {
+              // halo of this K-block: hi plane then lo plane, one tensor load each.  Order A(kb), B(kb, rows), A(kb+1), ...:
+              // the MMA warp needs them in exactly this order, so waiting for a free A stage can never starve it of weights.
+              const int HH = TC_TH + K - 1, HWP = K == 1 ? 8 : 16, pad = (K - 1) / 2;
+              const uint32_t plane = (uint32_t)HH * HWP * ROWB;
+              const int as = a_it % A_ST;
+              if (a_it >= A_ST) mbar_wait(a_empty + as, ((a_it / A_ST) - 1) & 1);
+              uint8_t* dst = sA + (size_t)as * t.a_stage_bytes;
+              mbar_arrive_expect_tx(a_full + as, 2 * plane);
+              tma_tensor4d_g2s(dst, ph == 0 ? &maps.in_hi : &maps.in2_hi, c0, w.x0 - pad, w.y0 - pad, w.img, a_full + as);
+              tma_tensor4d_g2s(dst + plane, ph == 0 ? &maps.in_lo : &maps.in2_lo, c0, w.x0 - pad, w.y0 - pad, w.img, a_full + as);
+              ++a_it;
+            }
+            if (!(CAN_STREAM && !t.resident)) continue;
             // One ring stage = the K weight blocks of one tap ROW: one barrier wait + one commit per K taps on the issuing
             // lane instead of per tap (measured on the streamed 128-channel layers at 960 images: 229 -> 184 us for
             // 128->128, 128 -> 104 us for 64->128; profiles/r02_conv_experiments.txt).
@@ -500,7 +532,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
         }
       }
     }
-  } else if (warp == TC_LW) {
+  } else if (warp == LW) {
     // ======================= MMA issue (whole warp converged, one elected lane issues) ===============
     const uint32_t idesc = F16 ? umma_idesc_f16(128, t.n_tile) : umma_idesc_tf32(128, t.n_tile);
     const uint32_t idesc2 = umma_idesc_f16(128, 2 * t.n_tile);   // fp16 engine: A_hi x [B_hi ; B_lo]
@@ -605,7 +637,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
       atomicAdd(t.prof + 5, (unsigned long long)(clock64() - mt0));
       atomicAdd(t.prof + 8, (unsigned long long)it);
     }
-  } else if (warp >= TC_LW + 2) {
+  } else if (warp >= LW + 2) {
     // =================================== epilogue (4 warps) ===========================================
     const int quarter = warp & 3;                                  // TMEM lanes this warp may read
     const int r = quarter * 32 + (tid & 31);                       // accumulator row = output pixel of the tile
@@ -636,22 +668,48 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
         return (px_plain + (size_t)(q >> 1) * Wo + (q & 1)) * a.CoutS;
       };
       constexpr int CW = OCC == 2 ? 8 : 16, G4 = CW / 4;         // columns per chunk (8 keeps the 2-CTA variant in 72 registers)
-      auto fetch_res = [&](int cb, float4* rr) {                   // residuals of one chunk, issued early
+      // Split tensors (fp16 hi plane, then the scaled-lo plane): residuals only reach the TMA variants, split outputs also
+      // leave the 16-channel legacy variant (the 7x7 front layer feeds the first TMA layer).
+      constexpr bool SPLIT_RES_OK = TMA, SPLIT_OUT_OK = TMA || MODE == 2;
+      const bool res_split = SPLIT_RES_OK && (a.fmt & FVP_FMT_RES_SPLIT), out_split = SPLIT_OUT_OK && (a.fmt & FVP_FMT_OUT_SPLIT);
+      const size_t out_plane = (size_t)a.n * Ho * Wo * a.CoutS;    // halves per plane of the output / residual tensor
+      // residuals of one chunk, issued early and kept RAW (converted at their use): fp32 = G4 float4; split = CW/8 uint4 of
+      // hi halves followed by CW/8 uint4 of lo halves
+      auto fetch_res = [&](int cb, uint4* rr) {
 #pragma unroll
-        for (int g4 = 0; g4 < G4; ++g4) rr[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g4 = 0; g4 < G4; ++g4) rr[g4] = make_uint4(0u, 0u, 0u, 0u);
         if (a.res_mode && px_ok && cb < t.n_tile) {
           int ch;
           const size_t off = chunk_offset(co_base + cb, ch);
+          if (res_split) {
+            const __half* rh = reinterpret_cast<const __half*>(a.res) + off + ch;
 #pragma unroll
-          for (int g4 = 0; g4 < G4; ++g4)
-            if (co_base + cb + g4 * 4 < a.CoutP) rr[g4] = __ldg((const float4*)(a.res + off + ch + g4 * 4));
+            for (int g8 = 0; g8 < CW / 8; ++g8)
+              if (co_base + cb + g8 * 8 < a.CoutP) {
+                rr[g8] = __ldg((const uint4*)(rh + g8 * 8));
+                rr[CW / 8 + g8] = __ldg((const uint4*)(rh + out_plane + g8 * 8));
+              }
+          } else {
+#pragma unroll
+            for (int g4 = 0; g4 < G4; ++g4)
+              if (co_base + cb + g4 * 4 < a.CoutP) rr[g4] = __ldg((const uint4*)(a.res + off + ch + g4 * 4));
+          }
         }
       };
-      float4 rnext[G4];
+      auto res_value = [&](const uint4* rr, int i) -> float {      // residual of column i of the chunk (i is a constant after unrolling)
+        if (res_split) {
+          const uint32_t wh = reinterpret_cast<const uint32_t*>(&rr[i / 8])[(i % 8) / 2];
+          const uint32_t wl = reinterpret_cast<const uint32_t*>(&rr[CW / 8 + i / 8])[(i % 8) / 2];
+          const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&wh)), l = __half22float2(*reinterpret_cast<const __half2*>(&wl));
+          return (i & 1) ? fmaf(l.y, 1.0f / 2048.0f, h.y) : fmaf(l.x, 1.0f / 2048.0f, h.x);
+        }
+        return __uint_as_float(reinterpret_cast<const uint32_t*>(&rr[i / 4])[i % 4]);
+      };
+      uint4 rnext[G4];
       fetch_res(0, rnext);
       float amax = 0.0f;                                           // range guard: largest stored magnitude of this item
       for (int cb = 0; cb < t.n_tile; cb += CW) {
-        float4 rcur[G4];
+        uint4 rcur[G4];
 #pragma unroll
         for (int g4 = 0; g4 < G4; ++g4) rcur[g4] = rnext[g4];
         uint32_t u1[CW], u2[CW];
@@ -674,31 +732,62 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
         if (!px_ok) continue;
         int ch0;
         const size_t off = chunk_offset(co_base + cb, ch0);
+        // bias, residual, ReLU - in place in v[]
 #pragma unroll
         for (int g4 = 0; g4 < G4; ++g4) {
           const int co = co_base + cb + g4 * 4;
           if (co >= a.CoutP) break;
           const float4 bias = *(const float4*)(s_bias + co);
-          float4 o = make_float4(v[g4 * 4] + bias.x, v[g4 * 4 + 1] + bias.y, v[g4 * 4 + 2] + bias.z, v[g4 * 4 + 3] + bias.w);
-          const float4 rr = rcur[g4];
-          if (a.res_mode == 1) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-          if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          if (a.res_mode == 2) { o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+          const float bb[4] = {bias.x, bias.y, bias.z, bias.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float o = v[g4 * 4 + e] + bb[e];
+            if (a.res_mode == 1) o += res_value(rcur, g4 * 4 + e);
+            if (a.relu) o = fmaxf(o, 0.f);
+            if (a.res_mode == 2) o += res_value(rcur, g4 * 4 + e);
+            v[g4 * 4 + e] = o;
+          }
 #if FVP_RANGE_CHECK == 2
-          if (!(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))) < 65504.0f) && g_tc_status) *g_tc_status = 1;
+          if (!(fmaxf(fmaxf(fabsf(v[g4 * 4]), fabsf(v[g4 * 4 + 1])), fmaxf(fabsf(v[g4 * 4 + 2]), fabsf(v[g4 * 4 + 3]))) < 65504.0f) && g_tc_status) *g_tc_status = 1;
 #elif FVP_RANGE_CHECK == 1
-          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[g4 * 4]), fabsf(v[g4 * 4 + 1])), fmaxf(fabsf(v[g4 * 4 + 2]), fabsf(v[g4 * 4 + 3]))));
 #endif
+        }
+        if (out_split) {
+          // one 16-byte store of 8 hi halves and one of 8 scaled-lo halves per 8 channels: the operand form the next
+          // layer's TMA loads drop into shared memory as they are (x = hi + lo * 2^-11, 22 significant bits)
+          __half* oh = reinterpret_cast<__half*>(a.out) + off + ch0;
+#pragma unroll
+          for (int g8 = 0; g8 < CW / 8; ++g8) {
+            if (co_base + cb + g8 * 8 >= a.CoutP) break;
+            uint32_t ph_[4], pl_[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = v[g8 * 8 + 2 * e], x1 = v[g8 * 8 + 2 * e + 1];
+              const __half2 h2 = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+              ph_[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              pl_[e] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            *(uint4*)(oh + g8 * 8) = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
+            *(uint4*)(oh + out_plane + g8 * 8) = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
+          }
+          continue;
+        }
+#pragma unroll
+        for (int g4 = 0; g4 < G4; ++g4) {
+          const int co = co_base + cb + g4 * 4;
+          if (co >= a.CoutP) break;
           const int ch = ch0 + g4 * 4;
           if (!a.nchw) {
-            *(float4*)(a.out + off + ch) = o;
+            *(float4*)(a.out + off + ch) = make_float4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
           } else {                                                 // planar [n][CoutReal][Ho][Wo] (final layers, no upsample)
             const size_t plane = (size_t)Ho * Wo;
             float* op = a.out + (size_t)w.img * a.CoutReal * plane + (size_t)oy * Wo + ox;
-            const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (ch + e < a.CoutReal) op[(size_t)(ch + e) * plane] = ov[e];
+              if (ch + e < a.CoutReal) op[(size_t)(ch + e) * plane] = v[g4 * 4 + e];
           }
         }
       }
@@ -709,7 +798,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
 #endif
       ++it;
     }
-    if (t.prof && tid == TC_LOADERS + 64) {
+    if (t.prof && tid == LW * 32 + 64) {
       atomicAdd(t.prof + 6, (unsigned long long)pc[0]);
       atomicAdd(t.prof + 7, (unsigned long long)(clock64() - et0));
       atomicAdd(t.prof + 9, (unsigned long long)pc[1]);
@@ -717,13 +806,41 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) k_conv_tc(TcArgs t) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_LW) {
+  if (warp == LW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(t.tmem_cols));
   }
 }
 
 }  // namespace
+
+// ---- TMA descriptors of split activation tensors -------------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver (libcuda); fetched at run time so that the library has no link-time
+// dependency on libcuda (it must load - and export its symbols - on hosts without a driver).
+typedef CUresult (*FvpEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static FvpEncodeTiled fvp_encode_tiled() {
+  static const FvpEncodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (FvpEncodeTiled)p;
+  }();
+  return fn;
+}
+// one plane [n][H][W][C] of fp16; box = (cb channels, halo pitch, halo height, 1 image), swizzle = the K-block row size
+static bool fvp_make_map(CUtensorMap* m, const void* base, int n, int H, int W, int C, int cb, int hwp, int hh) {
+  FvpEncodeTiled enc = fvp_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)hwp, (cuuint32_t)hh, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             cb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // host: geometry of the tiled weight image (must match pack_tc in fvp_params.cu).  narrow = 32-column N tiles
 // (more CTAs for small launches), otherwise up to 128 columns per CTA.  K-blocks are always 32 channels.
@@ -741,9 +858,12 @@ static const int g_tc_variant = [] { const char* e = std::getenv("FVP_TC_VARIANT
 
 // Per-device setup (fvp_create): opt-in shared memory of all six instantiations, carve-out of the two-CTA variants.
 cudaError_t fvp_conv_tc_init_device() {
-  const void* fns[6] = {(const void*)k_conv_tc<0, 1>, (const void*)k_conv_tc<1, 1>, (const void*)k_conv_tc<2, 1>,
-                        (const void*)k_conv_tc<0, 2>, (const void*)k_conv_tc<1, 2>, (const void*)k_conv_tc<2, 2>};
-  for (int i = 0; i < 6; ++i) {
+  const void* fns[10] = {(const void*)k_conv_tc<0, 1, false>, (const void*)k_conv_tc<1, 1, false>, (const void*)k_conv_tc<2, 1, false>,
+                         (const void*)k_conv_tc<0, 2, false>, (const void*)k_conv_tc<1, 2, false>, (const void*)k_conv_tc<2, 2, false>,
+                         (const void*)k_conv_tc<1, 1, true>,  (const void*)k_conv_tc<2, 1, true>,
+                         (const void*)k_conv_tc<1, 2, true>,  (const void*)k_conv_tc<2, 2, true>};
+  const bool two_cta[10] = {false, false, false, true, true, true, false, false, true, true};
+  for (int i = 0; i < 10; ++i) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, fns[i]);
     if (e != cudaSuccess) return e;
@@ -753,7 +873,7 @@ cudaError_t fvp_conv_tc_init_device() {
     }
     e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, TC_DYN_SMEM_MAX);
     if (e != cudaSuccess) return e;
-    if (i >= 3) {
+    if (two_cta[i]) {
       e = cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (e != cudaSuccess) return e;
     }
@@ -850,7 +970,9 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   // faster with two CTAs per SM; the 3x3 16->32 layer (16-channel K-blocks, loader-bound) is 9 % slower and keeps one.
   // (Also tried and dropped: one LDG.128 per lane over whole 128-B lines with 8-byte shared stores - fewer L1 sector
   //  lookups but twice the store instructions: 3 % slower over the trunk's layer mix.)
-  const bool occ2 = t.resident && g_tc_occ != 1 && !(mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
+  // split (TMA-fed) input: no loader warps, so the loader-bound exception of the 16-channel 3x3 layer does not apply
+  const bool tma = (a.fmt & FVP_FMT_IN_SPLIT) != 0;
+  const bool occ2 = t.resident && g_tc_occ != 1 && !(!tma && mode == 2 && k == 3 && g_tc_occ != 3) && 2 * (smem + TC_STATIC_SMEM + 1024) <= 228 * 1024 && t.tmem_cols <= 256 && t.total_items > num_sms;
   const int slots = num_sms * (occ2 ? 2 : 1);
   int grid = t.total_items < slots ? t.total_items : slots;              // persistent: one or two CTAs per SM
   if (t.resident == 2) grid -= grid % t.n_tiles;                         // CTA b serves N tile b % n_tiles only
@@ -860,9 +982,24 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
     for (int i = 0; i < 10; ++i) plan_out[i] = plan[i];
     return;
   }
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (tma) {
+    if (mode == 0) { fprintf(stderr, "fvp_launch_conv_tc: split input needs the fp16 engine\n"); abort(); }
+    const int hh = TC_TH + k - 1, hwp = k == 1 ? 8 : 16;
+    const __half* in_hi = reinterpret_cast<const __half*>(a.in);
+    bool ok = fvp_make_map(&maps.in_hi, in_hi, a.n, a.H, a.W, a.Cin, cb, hwp, hh) &&
+              fvp_make_map(&maps.in_lo, in_hi + (size_t)a.n * a.H * a.W * a.Cin, a.n, a.H, a.W, a.Cin, cb, hwp, hh);
+    if (ok && a.in2) {
+      const __half* in2_hi = reinterpret_cast<const __half*>(a.in2);
+      ok = fvp_make_map(&maps.in2_hi, in2_hi, a.n, a.H, a.W, a.Cin2, cb, 8, TC_TH) &&
+           fvp_make_map(&maps.in2_lo, in2_hi + (size_t)a.n * a.H * a.W * a.Cin2, a.n, a.H, a.W, a.Cin2, cb, 8, TC_TH);
+    }
+    if (!ok) { fprintf(stderr, "fvp_launch_conv_tc: cuTensorMapEncodeTiled failed (n=%d %dx%d C=%d/%d k=%d)\n", a.n, a.H, a.W, a.Cin, a.Cin2, k); abort(); }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(tma ? 192 : TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[1];
@@ -870,14 +1007,22 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  if (occ2) {
-    if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2, 2>, t);
-    else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1, 2>, t);
-    else cudaLaunchKernelEx(&cfg, k_conv_tc<0, 2>, t);
+  if (tma) {
+    if (occ2) {
+      if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2, 2, true>, t, maps);
+      else cudaLaunchKernelEx(&cfg, k_conv_tc<1, 2, true>, t, maps);
+    } else {
+      if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2, 1, true>, t, maps);
+      else cudaLaunchKernelEx(&cfg, k_conv_tc<1, 1, true>, t, maps);
+    }
+  } else if (occ2) {
+    if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2, 2, false>, t, maps);
+    else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1, 2, false>, t, maps);
+    else cudaLaunchKernelEx(&cfg, k_conv_tc<0, 2, false>, t, maps);
   } else {
-    if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2, 1>, t);
-    else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1, 1>, t);
-    else cudaLaunchKernelEx(&cfg, k_conv_tc<0, 1>, t);
+    if (mode == 2) cudaLaunchKernelEx(&cfg, k_conv_tc<2, 1, false>, t, maps);
+    else if (mode == 1) cudaLaunchKernelEx(&cfg, k_conv_tc<1, 1, false>, t, maps);
+    else cudaLaunchKernelEx(&cfg, k_conv_tc<0, 1, false>, t, maps);
   }
 }
 
@@ -896,7 +1041,7 @@ extern "C" int fvp_debug_conv_plan(int n, int H, int W, int cin, int cin2, int c
   const float* c16[3] = {&dummy, nullptr, nullptr};
   const bool use_c16 = engine == 2 && ((cin <= 16 && cin2 <= 16) || (k == 7 && cin <= 32));     // as stash() packs them
   for (int i = 0; i < 10; ++i) out[i] = 0;
-  const FvpLaunchEnv env{num_sms, engine, nullptr, out};
+  const FvpLaunchEnv env{num_sms, engine, nullptr, out, 0};
   fvp_launch_conv_tc(a, use_c16 ? c16 : wide, engine == 2 ? (use_c16 ? 2 : 1) : 0, env, nullptr);
   return 0;
 }

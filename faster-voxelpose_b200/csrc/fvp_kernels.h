@@ -71,9 +71,19 @@ struct FvpConvArgs {
   int nchw;
   int n;
   const int* valid;   // optional per-image gate
+  // Activation format (tensor-core engine 2 only; 0 = everything fp32 as described above).  A *split* tensor holds the
+  // fp16 hi plane [n][H][W][C] followed by the fp16 scaled-lo plane (x = hi + lo * 2^-11, the operand form of the MMAs):
+  // the producing epilogue splits once, consumers fetch halos with TMA tensor loads (no loader warps, no conversions).
+  int fmt;            // FVP_FMT_* bits
 };
+enum { FVP_FMT_IN_SPLIT = 1, FVP_FMT_OUT_SPLIT = 2, FVP_FMT_RES_SPLIT = 4 };   // in / in2 share IN_SPLIT
 void fvp_launch_conv(const FvpConvArgs& a, cudaStream_t st);
 void fvp_launch_maxpool2(const float* in, float* out, int n, int H, int W, int C, const int* valid, cudaStream_t st);
+// same on split tensors (hi/lo fp16 planes): the pair of the largest reconstructed value is copied, so the result is exact
+void fvp_launch_maxpool2_split(const void* in, void* out, int n, int H, int W, int C, const int* valid, cudaStream_t st);
+// element-wise fp32 <-> split conversion of `count` values (test hooks: a split tensor of `count` elements is 2*count halves)
+void fvp_launch_split(const float* in, void* out, size_t count, cudaStream_t st);
+void fvp_launch_unsplit(const void* in, float* out, size_t count, cudaStream_t st);
 
 // ---- 2-D trunk program (CenterNet / P2PNet) ------------------------------------------------------
 struct FvpConvW {         // one packed conv
@@ -92,6 +102,7 @@ struct FvpLaunchEnv {
   int conv_mode;                    // 0 CUDA cores, 1 tcgen05 3xTF32, 2 tcgen05 fp16 hi/lo split
   unsigned long long* tc_prof;      // debug: 12 role counters of k_conv_tc (fvp_debug_conv), NULL in production
   int* tc_plan;                     // host-only plan query (fvp_debug_conv_plan): decisions are recorded, nothing is launched
+  int split_activations;            // engine 2: activations travel as split (fp16 hi / lo) tensors fetched by TMA (default on)
 };
 // tcgen05 / TMEM implicit-GEMM conv (fvp_conv_tc.cu); same arguments as fvp_launch_conv plus the tiled weights
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, const FvpLaunchEnv& env, cudaStream_t st);

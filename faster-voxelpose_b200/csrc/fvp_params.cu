@@ -506,13 +506,27 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   a.in = d_in; a.H = H; a.W = W; a.Cin = cin; a.in2 = nullptr; a.Cin2 = 0;
   a.w = d + ow; a.bias = d + ob; a.out = d_out; a.CoutP = coutP; a.CoutS = coutP; a.CoutReal = cout;
   a.res = nullptr; a.res_mode = 0; a.relu = relu; a.ksize = k; a.upsample = 0; a.nchw = 0; a.n = n; a.valid = nullptr;
+  a.fmt = 0;
+  // mode 4: the TMA-fed form of engine 2 - input converted to a split tensor first, split output converted back afterwards
+  // (both conversions outside the timed launches), so the same fp32 NHWC interface tests the split path in isolation
+  void *d_split_in = nullptr, *d_split_out = nullptr;
+  const size_t n_in = (size_t)n * H * W * cin, n_out = (size_t)n * H * W * coutP;
+  if ((mode & 0xff) == 4) {
+    if (cin % 16 || coutP % 16) { cudaFree(d); return fvp_fail(ctx, FVP_E_INVALID, "debug conv mode 4 needs cin and cout multiples of 16"); }
+    FVP_CUDA_OK(cudaMalloc(&d_split_in, n_in * 4));
+    FVP_CUDA_OK(cudaMalloc(&d_split_out, n_out * 4));
+    fvp_launch_split(d_in, d_split_in, n_in, st);
+    a.in = (const float*)d_split_in;
+    a.out = (float*)d_split_out;
+    a.fmt = FVP_FMT_IN_SPLIT | FVP_FMT_OUT_SPLIT;
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   const bool prof = (mode & 0x100) != 0;                            // role counters: ms_out must hold 1 + 12 floats
   mode &= 0xff;
   unsigned long long* d_prof = nullptr;
   if (prof) { FVP_CUDA_OK(cudaMalloc(&d_prof, 12 * sizeof(unsigned long long))); }
-  FvpLaunchEnv env{ctx->num_sms, mode, nullptr, nullptr};
+  FvpLaunchEnv env{ctx->num_sms, mode, nullptr, nullptr, 0};
   for (int it = 0; it < 1 + (repeat > 0 ? repeat : 1); ++it) {     // first launch = warm-up
     if (it == 1) {
       cudaEventRecord(e0, st);
@@ -521,13 +535,17 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
     const float* const i16c[3] = {d + ot16c, nullptr, nullptr};
     const float* const i16[3] = {d + ot16, nullptr, nullptr};
     const float* const i32[3] = {d + ot, nullptr, nullptr};
-    if (mode == 2 && c16) fvp_launch_conv_tc(a, i16c, 2, env, st);
+    if (mode == 4) fvp_launch_conv_tc(a, (cin <= 16 && k != 7) ? i16c : i16, (cin <= 16 && k != 7) ? 2 : 1, env, st);
+    else if (mode == 2 && c16) fvp_launch_conv_tc(a, i16c, 2, env, st);
     else if (mode == 2 || mode == 3) fvp_launch_conv_tc(a, i16, 1, env, st);
     else if (mode == 1) fvp_launch_conv_tc(a, i32, 0, env, st);
     else fvp_launch_conv(a, st);
   }
   cudaEventRecord(e1, st);
+  if (d_split_out) fvp_launch_unsplit(d_split_out, d_out, n_out, st);
   FVP_CUDA_OK(cudaStreamSynchronize(st));
+  if (d_split_in) cudaFree(d_split_in);
+  if (d_split_out) cudaFree(d_split_out);
   if (ms_out) { cudaEventElapsedTime(ms_out, e0, e1); *ms_out /= (float)(repeat > 0 ? repeat : 1); }
   if (prof && ms_out) {                                             // kilo-cycles per launch, summed over CTAs
     unsigned long long h[12];

@@ -196,6 +196,10 @@ def test_single_conv_layers_both_engines(built_library, golden):
         assert float((eng.debug_conv(x, w, b, False, 0) - ref).abs().max()) <= 2e-5      # fp32 FFMA
         assert float((eng.debug_conv(x, w, b, False, 1) - ref).abs().max()) <= 1e-4      # 3xTF32 on O(1) outputs
         assert float((eng.debug_conv(x, w, b, False, 2) - ref).abs().max()) <= 3e-5      # fp16 split (measured <= 7e-6)
+        if cin % 16 == 0 and cout % 16 == 0 and k != 7:
+            # the TMA-fed form of the same engine: split (fp16 hi / lo) input tensor fetched by tensor loads, split output
+            assert float((eng.debug_conv(x, w, b, False, 4) - ref).abs().max()) <= 3e-5
+            assert float((eng.debug_conv(x, w, b, True, 4) - ref.clamp_min(0)).abs().max()) <= 3e-5
 
     check(1, 16, 8, 32, 32, 1)
     check(2, 32, 32, 64, 128, 1)
@@ -211,6 +215,9 @@ def test_single_conv_layers_both_engines(built_library, golden):
     check(1, 80, 80, 32, 32, 3)
     check(1, 20, 20, 32, 64, 3)
     check(1, 64, 64, 16, 16, 7)
+    check(1, 64, 64, 20, 16, 7)          # J = 17 front layer: two 16-channel K-blocks on tcgen05
+    check(3, 40, 40, 64, 64, 3)          # partial tiles in both directions (40 = 2.5 x 16 = 5 x 8)
+    check(2, 20, 20, 128, 128, 3)        # CenterNet quarter resolution: tile rows beyond the image
     eng.close()
 
 

@@ -210,10 +210,19 @@ def test_two_cta_conv_variants_do_not_spill_more_than_measured(built_library):
     import re
     log = open(os.path.join(os.path.dirname(built_library), "csrc", "build", "fvp_conv_tc.log")).read()
     spills = {}
-    for m in re.finditer(r"k_conv_tcILi(\d)ELi(\d)EE.*?\n.*?(\d+) bytes spill stores", log):
-        spills[(int(m.group(1)), int(m.group(2)))] = int(m.group(3))
-    assert set(spills) == {(m, o) for m in (0, 1, 2) for o in (1, 2)}, spills
-    assert spills[(1, 2)] <= 32 and spills[(2, 2)] <= 128 and spills[(1, 1)] <= 32, spills
+    for m in re.finditer(r"k_conv_tcILi(\d)ELi(\d)ELb(\d)EE.*?\n.*?(\d+) bytes spill stores", log):
+        spills[(int(m.group(1)), int(m.group(2)), int(m.group(3)))] = int(m.group(4))
+    legacy = {(m, o, 0) for m in (0, 1, 2) for o in (1, 2)}              # fp32 activations staged by loader warps
+    tma = {(m, o, 1) for m in (1, 2) for o in (1, 2)}                    # split activations fetched by TMA tensor loads
+    assert set(spills) == legacy | tma, spills
+    assert spills[(1, 2, 0)] <= 32 and spills[(2, 2, 0)] <= 128 and spills[(1, 1, 0)] <= 32, spills
+    assert spills[(1, 2, 1)] <= 32 and spills[(1, 1, 1)] <= 32 and spills[(2, 2, 1)] <= 64, spills
+    # the split-activation path is real TMA: tensor-map loads (UTMALDG) next to the bulk weight copies (UBLKCP)
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump"):
+        sass = subprocess.run(["cuobjdump", "-sass", built_library], capture_output=True, text=True).stdout
+        assert sass.count("UTMALDG") >= 8 and "UBLKCP" in sass and "UTCHMMA" in sass
 
 
 # ---- reference-facing module -----------------------------------------------------------------------
