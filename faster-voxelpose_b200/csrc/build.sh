@@ -8,7 +8,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        -Xptxas -v)
 # experiments: extra -D switches (e.g. FVP_NVCC_DEFS="-DFVP_K3_PREFETCH_GRID" csrc/build.sh); empty in every shipped build
 if [ -n "${FVP_NVCC_DEFS:-}" ]; then read -r -a EXTRA <<< "$FVP_NVCC_DEFS"; FLAGS+=("${EXTRA[@]}"); fi
-SRCS=(fvp_api.cu fvp_params.cu fvp_backproject.cu fvp_conv.cu fvp_conv_tc.cu fvp_proposal.cu fvp_pose.cu fvp_render.cu)
+SRCS=(fvp_api.cu fvp_params.cu fvp_backproject.cu fvp_conv.cu fvp_conv_tc.cu fvp_proposal.cu fvp_pose.cu fvp_render.cu fvp_backbone.cu)
 mkdir -p "$HERE/build"
 pids=()
 for s in "${SRCS[@]}"; do
