@@ -9,9 +9,10 @@ from fvp import synth
 from fvp.engine import Engine
 n_iter = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-cfg, cams, resize = bench.workload("panoptic_256x192")
+PRESET = os.environ.get("FVP_PROFILE_PRESET", "panoptic_256x192")
+cfg, cams, resize = bench.workload(PRESET)
 eng = Engine(cfg, torch.device("cuda:0"), max_batch=batch, max_sequences=1)
-eng.load_state_dict(synth.make_weights(15, seed=2024))
+eng.load_state_dict(synth.make_weights(int(cfg.DATASET.NUM_JOINTS), seed=2024))
 if 'FVP_CONV_MODE' in os.environ:
     eng.set_conv_mode(int(os.environ['FVP_CONV_MODE']))
 slot = eng.sequence_slot(cams, resize)
