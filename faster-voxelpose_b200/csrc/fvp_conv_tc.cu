@@ -909,8 +909,10 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   const int nblocks = k * k * (fvp_round_up(a.Cin, cb) / cb) + (a.in2 ? fvp_round_up(a.Cin2, cb) / cb : 0);
   const uint32_t budget = TC_DYN_SMEM_MAX - 1024;                  // dynamic smem we may use (1 KB alignment slack)
   // Weight residency of a variant: 1 = the whole image fits beside a double-buffered halo; 2 = only one N tile's blocks fit
-  // (small launches: every CTA then serves a single N tile); 0 = streamed per tap (measured ~1.8x the per-MMA cost of the
-  // unrolled resident issue path: per-tap barrier waits and commits on the issuing lane).
+  // (small launches: every CTA then serves a single N tile); 0 = streamed per tap row (charged 1.4x the per-MMA cost of the
+  // unrolled resident issue path; 1.8x before the row-wise ring - with 1.4 the 128-channel layers of P2PNet at batch 1 take
+  // 64-column streamed tiles instead of 32-column resident ones: measured 0.351 -> 0.338 ms for the trunk,
+  // profiles/r02_bench_b1_serial_ntile64.json, while CenterNet's single image keeps the 32-column tiles).
   auto residency = [&](int nt, int nts) -> int {
     const uint32_t blk = (uint32_t)nt * rowb * 2;
     if ((uint64_t)nblocks * nts * blk + 2 * t.a_stage_bytes <= budget) return 1;
@@ -927,7 +929,7 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
     fvp_tc_geometry(a.CoutP, v, &nt, &nts);
     const double per_item = f16 ? (48 + (128 + 2 * nt) / 4.0 + nt) + (48 + (128 + nt) / 4.0 + nt / 2.0)
                                 : 3.0 * (48 + (128 + nt) / 4.0 + nt / 2.0);
-    const double cost = (double)fvp_cdiv(tiles * nts, num_sms) * per_item * (residency(nt, nts) ? 1.0 : 1.8) + 1.0 * nts;   // ties: wider tile
+    const double cost = (double)fvp_cdiv(tiles * nts, num_sms) * per_item * (residency(nt, nts) ? 1.0 : 1.4) + 1.0 * nts;   // ties: wider tile
     if (cost < best_cost) { best_cost = cost; best = v; }
   }
   if (g_tc_variant >= 0 && g_tc_variant < 3 && wtc[g_tc_variant]) best = g_tc_variant;

@@ -140,7 +140,8 @@ def test_conv_launch_plans(built_library):
     big = _conv_plan(lib, 960, 16, 16, 128, 0, 128, 3)
     assert (big["n_tile"], big["resident"], big["tmem"]) == (128, 0, 512)           # streamed, full-width N at large batch
     assert _conv_plan(lib, 960, 32, 32, 64, 32, 64, 3)["resident"] == 1             # 19 weight blocks + 2 halo stages fit in 227 KB
-    assert _conv_plan(lib, 30, 16, 16, 128, 64, 128, 3)["resident"] == 2            # P2PNet at batch 1
+    p30 = _conv_plan(lib, 30, 16, 16, 128, 64, 128, 3)                              # P2PNet at batch 1: 64-column tiles, weights
+    assert (p30["n_tile"], p30["resident"], p30["grid"]) == (64, 0, 120)            # streamed row-wise (measured faster, round 2)
     # the 7x7 front conv of the J = 17 datasets (JP = 20 channels): two 16-channel K-blocks, 98 resident weight blocks
     j17 = _conv_plan(lib, 30, 64, 64, 20, 0, 16, 7)
     assert (j17["n_tile"], j17["resident"], j17["a_stages"]) == (16, 1, 2) and j17["smem"] <= 227 * 1024 - 1280
