@@ -77,7 +77,9 @@ SYMBOLS = {
     "fvp_pose_head": (C.c_int, [_CTX, _P, _P, C.c_int, _P, _P, _P, _P, C.c_size_t]),
     "fvp_c2c_net": (C.c_int, [_CTX, _P, C.c_int, _P, C.c_size_t]),
     "fvp_render_heatmaps": (C.c_int, [_CTX, _P, _P, _P, C.c_int, C.c_int, C.c_double, _P, C.c_size_t]),
-    "fvp_backbone_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_CTX)]),
+    "fvp_backbone_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_CTX)]),
+    "fvp_backbone_forward": (C.c_int, [_CTX, _P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
+    "fvp_backbone_num_stages": (C.c_int, [_CTX]),
     "fvp_backbone_destroy": (None, [_CTX]),
     "fvp_backbone_last_error": (C.c_char_p, [_CTX]),
     "fvp_backbone_set_param": (C.c_int, [_CTX, C.c_char_p, _P, C.c_int64]),

@@ -203,19 +203,26 @@ int fvp_c2c_net(fvp_ctx* ctx, const float* d_cols, int n, float* d_hm1d, uintptr
 int fvp_render_heatmaps(fvp_ctx* ctx, const double* h_joints, const int32_t* h_num_people, const uint8_t* h_vis, int batch,
                         int max_people, double sigma, float* d_heatmaps, uintptr_t stream);
 
-/* ---- N2: PoseResNet backbone, first slice -------------------------------------------------------------------
+/* ---- N2: PoseResNet backbone ------------------------------------------------------------------------------
  * The step in front of the hot path when TEST_HEATMAP_SRC = 'image': faster_voxelpose.py:36-38 calls backbone(views[:, c]) per
- * camera (lib/models/resnet.py:188-201).  Built so far: stem (conv 7x7 s2 + BN + ReLU), MaxPool(3,2,1) and layer1 (Bottleneck
- * or BasicBlock, resnet.py:22-95) - layer1 on the tcgen05 engine.  The object takes the reference's backbone state_dict
- * (338 keys for ResNet-50; keys of layers that are not built yet are accepted and ignored). */
+ * camera; the backbone is models.resnet.get(cfg) (lib/models/resnet.py:98-215, run/validate.py:69-74).  The object takes the
+ * reference's backbone state_dict (338 keys for ResNet-50) as it is.  Supported: NUM_LAYERS 18/34/50/101/152, three 4x4
+ * transposed convolutions, 1x1 final layer (the reference's configs); image sides multiples of 32. */
 typedef struct fvp_backbone fvp_backbone;
-int fvp_backbone_create(int num_layers, int max_images, int max_h, int max_w, int device, fvp_backbone** out);
+/* replaces models.resnet.get(cfg) (resnet.py:211-215) */
+int fvp_backbone_create(int num_layers, int num_joints, int max_images, int max_h, int max_w, int device, fvp_backbone** out);
 void fvp_backbone_destroy(fvp_backbone* bb);
 const char* fvp_backbone_last_error(const fvp_backbone* bb);   /* bb may be NULL: error of the last failed create */
+/* replaces load_state_dict (run/validate.py:72): one fp32 tensor of the reference's state_dict, reference shape */
 int fvp_backbone_set_param(fvp_backbone* bb, const char* name, const float* h_data, int64_t numel);
-int fvp_backbone_finalize(fvp_backbone* bb);                   /* fold BatchNorm, pack, upload */
-/* d_images [n][3][h][w] fp32 (normalised as the reference's transform does) -> d_out NCHW fp32 of tap `stage`:
- * 0 = after the max-pool [n][64][h/4][w/4]; k >= 1 = after layer1 block k-1 ([n][256][h/4][w/4], 64 channels for ResNet-18/34) */
+int fvp_backbone_finalize(fvp_backbone* bb);                   /* fold BatchNorm, pack for the tensor-core engine, upload */
+/* replaces ResNet.forward (resnet.py:188-201): d_images [n][3][h][w] fp32 (normalised as the reference's transform does)
+ * -> d_heatmaps [n][J][h/4][w/4] fp32 */
+int fvp_backbone_forward(fvp_backbone* bb, const float* d_images, int n, int h, int w, float* d_heatmaps, uintptr_t stream);
+/* taps for the parity tests: number of stages, and the NCHW fp32 output of one stage - 0 = after the max-pool
+ * [n][64][h/4][w/4]; 1..B = after residual block stage-1 in network order (B blocks in all); B+1..B+3 = after a transposed
+ * convolution (+BN+ReLU); B+4 = the heat maps (= fvp_backbone_forward).  Valid after fvp_backbone_finalize. */
+int fvp_backbone_num_stages(const fvp_backbone* bb);
 int fvp_backbone_forward_slice(fvp_backbone* bb, const float* d_images, int n, int h, int w, int stage, float* d_out, uintptr_t stream);
 
 /* convolution engine of CenterNet / P2PNet: 0 = exact-fp32 CUDA-core implicit GEMM, 1 = tcgen05/TMEM implicit GEMM with
