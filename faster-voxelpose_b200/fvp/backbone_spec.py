@@ -6,10 +6,8 @@ The reference builds it as nested ``nn.Module`` classes (lib/models/resnet.py:22
 execution order, keyed by the reference ``state_dict`` prefix, so that the parameter holder, the weight generator, the
 CPU oracle (oracle/backbone_oracle.py) and - next - the CUDA engine enumerate one list.
 
-Status: the table, the oracle and its pin against the unmodified reference are in; the first slice of the network
-(stem + max-pool + layer1) runs on the GPU (csrc/fvp_backbone.cu, fvp/backbone.py, tests/test_gpu_backbone.py); layer2-4,
-the transposed convolutions and the final layer need stride 2, channel counts up to 2048 and 4x4 stride-2 transposed
-convolutions in the tcgen05 engine first (DESIGN.md sections 4.5 and 7).
+Status: the table, the oracle and its pin against the unmodified reference are in, and the whole network runs on the GPU
+(csrc/fvp_backbone.cu, fvp/backbone.py, lib/models/resnet.py, tests/test_gpu_backbone.py).
 """
 from __future__ import annotations
 

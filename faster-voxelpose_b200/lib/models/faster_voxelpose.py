@@ -105,7 +105,7 @@ class FasterVoxelPoseNet(nn.Module):
         if self.training:
             raise NotImplementedError("training branch (faster_voxelpose.py:51-98) is out of scope of the B200 path; "
                                       "call model.eval()")
-        if views is not None:      # faster_voxelpose.py:36-38 (backbone is a pass-through callable)
+        if views is not None:      # faster_voxelpose.py:36-38 (backbone: any callable; models.resnet.get(cfg) is the B200 one)
             num_views = views.shape[1]
             input_heatmaps = torch.stack([backbone(views[:, c]) for c in range(num_views)], dim=1)
         eng = self.engine()
