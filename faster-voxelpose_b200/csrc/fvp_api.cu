@@ -167,7 +167,7 @@ int refuse_on_lane(fvp_ctx* ctx, const char* what) {
   return FVP_OK;
 }
 
-FvpLaunchEnv launch_env(const fvp_ctx* ctx) { return FvpLaunchEnv{ctx->num_sms, ctx->conv_mode, nullptr, nullptr, ctx->split_activations}; }
+FvpLaunchEnv launch_env(fvp_ctx* ctx) { return FvpLaunchEnv{ctx->num_sms, ctx->conv_mode, nullptr, nullptr, ctx->split_activations, &ctx->launch_error}; }
 
 // Other entry points must not touch the shared workspaces while fvp_submit_host tickets are in flight.
 int refuse_if_tickets_open(fvp_ctx* ctx) {
@@ -243,6 +243,10 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
   fvp_launch_finalize(g, ctx->d_people, ctx->d_maxw, ctx->d_pose, ctx->d_fused, ctx->d_centers, batch, ctx->d_conf,
                       d_fused_poses, d_plane_poses, d_centers_out, st); ++*launches;
   T.mark(8);
+  if (ctx->launch_error) {
+    ctx->launch_error = 0;
+    return fvp_fail(ctx, FVP_E_CUDA, "a convolution launch could not be prepared (TMA descriptor encode failed; see stderr)");
+  }
   return FVP_OK;
 }
 
@@ -846,6 +850,7 @@ int fvp_center_net(fvp_ctx* ctx, const float* d_plane_in, int batch, float* d_hm
   int launches = 0;
   fvp_run_trunk2d(ctx->w_center, ctx->d_plane_cl, g.proj.JP, batch, g.X, g.Y, ctx->cn_buf, nullptr, true,
                   ctx->d_hmsize, 3, &launches, st, launch_env(ctx));
+  if (ctx->launch_error) { ctx->launch_error = 0; return fvp_fail(ctx, FVP_E_CUDA, "a convolution launch could not be prepared (TMA descriptor)"); }
   for (int b = 0; b < batch; ++b) {
     if (d_hm) FVP_CUDA_OK(cudaMemcpyAsync(d_hm + (size_t)b * XY, ctx->d_hmsize + (size_t)b * 3 * XY, XY * 4, cudaMemcpyDeviceToDevice, st));
     if (d_size) FVP_CUDA_OK(cudaMemcpyAsync(d_size + (size_t)b * 2 * XY, ctx->d_hmsize + (size_t)b * 3 * XY + XY, 2 * XY * 4, cudaMemcpyDeviceToDevice, st));
@@ -944,6 +949,7 @@ int fvp_p2p_net(fvp_ctx* ctx, const float* d_planes, int n, const int32_t* d_val
   }
   int launches = 0;
   fvp_run_trunk2d(ctx->w_p2p, in, g.proj.JP, n, 64, 64, ctx->p2p_buf, d_valid, false, d_feat, g.J, &launches, st, launch_env(ctx));
+  if (ctx->launch_error) { ctx->launch_error = 0; return fvp_fail(ctx, FVP_E_CUDA, "a convolution launch could not be prepared (TMA descriptor)"); }
   FVP_CUDA_OK(cudaGetLastError());
   return FVP_OK;
 }

@@ -128,6 +128,7 @@ struct fvp_backbone {
   std::string err;
   std::map<std::string, std::vector<float>> params;     // raw state_dict entries
   bool ready = false;
+  int launch_error = 0;
   float *d_stem_w = nullptr, *d_stem_b = nullptr;
   std::vector<BbConv> convs;
   std::vector<BbBlock> blocks;
@@ -287,7 +288,7 @@ void run_conv(const fvp_backbone* bb, const BbConv& c, const float* in, const fl
     a.CoutP = ch.cols; a.CoutS = c.cout; a.CoutReal = cout_real;
     a.res = res ? res + ch.ch0 : nullptr; a.res_mode = res ? 1 : 0; a.relu = relu; a.ksize = c.k;
     a.upsample = c.upsample; a.nchw = nchw_out ? 1 : 0; a.n = n; a.valid = nullptr; a.fmt = 0;
-    const FvpLaunchEnv env{bb->num_sms, 2, nullptr, nullptr, 0};
+    const FvpLaunchEnv env{bb->num_sms, 2, nullptr, nullptr, 0, const_cast<int*>(&bb->launch_error)};
     fvp_launch_conv_tc(a, ch.wtc16, 1, env, st);
   }
 }
@@ -483,6 +484,7 @@ int fvp_backbone_forward_slice(fvp_backbone* bb, const float* d_images, int n, i
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return bb_fail(bb, FVP_E_CUDA, "CUDA error: %s", cudaGetErrorString(e));
+  if (bb->launch_error) { bb->launch_error = 0; return bb_fail(bb, FVP_E_CUDA, "a convolution launch could not be prepared"); }
   return FVP_OK;
 }
 

@@ -987,7 +987,11 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   if (tma) {
-    if (mode == 0) { fprintf(stderr, "fvp_launch_conv_tc: split input needs the fp16 engine\n"); abort(); }
+    if (mode == 0) {                   // split tensors are the operand format of the fp16 engine: a caller bug, reported, never launched
+      fprintf(stderr, "fvp_launch_conv_tc: split input needs the fp16 engine\n");
+      if (env.error) *env.error = 1;
+      return;
+    }
     const int hh = TC_TH + k - 1, hwp = k == 1 ? 8 : 16;
     const __half* in_hi = reinterpret_cast<const __half*>(a.in);
     bool ok = fvp_make_map(&maps.in_hi, in_hi, a.n, a.H, a.W, a.Cin, cb, hwp, hh) &&
@@ -997,7 +1001,11 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
       ok = fvp_make_map(&maps.in2_hi, in2_hi, a.n, a.H, a.W, a.Cin2, cb, 8, TC_TH) &&
            fvp_make_map(&maps.in2_lo, in2_hi + (size_t)a.n * a.H * a.W * a.Cin2, a.n, a.H, a.W, a.Cin2, cb, 8, TC_TH);
     }
-    if (!ok) { fprintf(stderr, "fvp_launch_conv_tc: cuTensorMapEncodeTiled failed (n=%d %dx%d C=%d/%d k=%d)\n", a.n, a.H, a.W, a.Cin, a.Cin2, k); abort(); }
+    if (!ok) {                         // no descriptor, no launch: the entry point that built `env` turns the mark into FVP_E_CUDA
+      fprintf(stderr, "fvp_launch_conv_tc: cuTensorMapEncodeTiled failed (n=%d %dx%d C=%d/%d k=%d)\n", a.n, a.H, a.W, a.Cin, a.Cin2, k);
+      if (env.error) *env.error = 1;
+      return;
+    }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -1043,7 +1051,7 @@ extern "C" int fvp_debug_conv_plan(int n, int H, int W, int cin, int cin2, int c
   const float* c16[3] = {&dummy, nullptr, nullptr};
   const bool use_c16 = engine == 2 && ((cin <= 16 && cin2 <= 16) || (k == 7 && cin <= 32));     // as stash() packs them
   for (int i = 0; i < 10; ++i) out[i] = 0;
-  const FvpLaunchEnv env{num_sms, engine, nullptr, out, 0};
+  const FvpLaunchEnv env{num_sms, engine, nullptr, out, 0, nullptr};
   fvp_launch_conv_tc(a, use_c16 ? c16 : wide, engine == 2 ? (use_c16 ? 2 : 1) : 0, env, nullptr);
   return 0;
 }

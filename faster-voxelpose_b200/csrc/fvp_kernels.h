@@ -103,6 +103,7 @@ struct FvpLaunchEnv {
   unsigned long long* tc_prof;      // debug: 12 role counters of k_conv_tc (fvp_debug_conv), NULL in production
   int* tc_plan;                     // host-only plan query (fvp_debug_conv_plan): decisions are recorded, nothing is launched
   int split_activations;            // engine 2: activations travel as split (fp16 hi / lo) tensors fetched by TMA (default on)
+  int* error;                       // set to 1 when a launch could not be prepared (TMA descriptor encode failed); may be NULL
 };
 // tcgen05 / TMEM implicit-GEMM conv (fvp_conv_tc.cu); same arguments as fvp_launch_conv plus the tiled weights
 void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mode, const FvpLaunchEnv& env, cudaStream_t st);

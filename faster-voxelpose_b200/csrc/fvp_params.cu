@@ -526,7 +526,7 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   mode &= 0xff;
   unsigned long long* d_prof = nullptr;
   if (prof) { FVP_CUDA_OK(cudaMalloc(&d_prof, 12 * sizeof(unsigned long long))); }
-  FvpLaunchEnv env{ctx->num_sms, mode, nullptr, nullptr, 0};
+  FvpLaunchEnv env{ctx->num_sms, mode, nullptr, nullptr, 0, &ctx->launch_error};
   for (int it = 0; it < 1 + (repeat > 0 ? repeat : 1); ++it) {     // first launch = warm-up
     if (it == 1) {
       cudaEventRecord(e0, st);
@@ -556,5 +556,6 @@ int fvp_debug_conv_impl(fvp_ctx* ctx, const float* d_in, int n, int H, int W, in
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   FVP_CUDA_OK(cudaGetLastError());
   cudaFree(d);
+  if (ctx->launch_error) { ctx->launch_error = 0; return fvp_fail(ctx, FVP_E_CUDA, "a convolution launch could not be prepared (TMA descriptor)"); }
   return FVP_OK;
 }
