@@ -7,7 +7,9 @@
 //   max-pool  3x3 stride 2 pad 1                                                  resnet.py:108,192
 //   layer1-4  Bottleneck (1x1, 3x3 [stride on the 3x3], 1x1 x4, + 1x1 downsample of the block input in a stage's first
 //             block; out += residual; ReLU, resnet.py:57-95,118-146) or BasicBlock (resnet.py:22-54) on the tcgen05 engine
-//             of fvp_conv_tc.cu (fp16 hi/lo split, fp32 accumulation): BN folded, the downsample conv fused as the second K
+//             of fvp_conv_tc.cu (fp16 hi/lo split, fp32 accumulation) in its TMA-fed form: from the max-pool on, every
+//             activation is a split tensor (fp16 hi plane + scaled-lo plane) written once by the producing epilogue and
+//             fetched by cp.async.bulk.tensor; BN folded, the downsample conv fused as the second K
 //             segment of the block's last conv, the identity residual added in its epilogue; output channels beyond 256
 //             (the engine's bias table) run as 256-column launches into one NHWC tensor.
 //             Stride 2 (first version): a stride-2 3x3 is the stride-1 convolution kept at the even positions
@@ -23,6 +25,8 @@
 #include <map>
 #include <string>
 #include <vector>
+
+#include <cuda_fp16.h>
 
 #include "fvp_kernels.h"
 
@@ -76,9 +80,11 @@ __global__ void __launch_bounds__(256) k_stem7x7s2(const float* __restrict__ img
   }
 }
 
-// MaxPool2d(3, 2, 1) on NHWC, 4 channels per thread (padding = -inf, i.e. ignored)
-__global__ void __launch_bounds__(256) k_maxpool3s2(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int Ho, int Wo,
-                                                    int C4) {
+// MaxPool2d(3, 2, 1) on NHWC, 4 channels per thread (padding = -inf, i.e. ignored).  The result is written as a SPLIT
+// tensor (fp16 hi plane, then the scaled-lo plane: the operand form of the tensor-core engine, see fvp_conv_tc.cu) -
+// everything downstream of the max-pool is fed by TMA.
+__global__ void __launch_bounds__(256) k_maxpool3s2(const float4* __restrict__ in, __half* __restrict__ out, int H, int W, int Ho, int Wo,
+                                                    int C4, size_t plane) {
   const int n = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
   if (i >= Ho * Wo * C4) return;
   const int c = i % C4, p = i / C4, oy = p / Wo, ox = p - oy * Wo;
@@ -90,15 +96,25 @@ __global__ void __launch_bounds__(256) k_maxpool3s2(const float4* __restrict__ i
       const float4 v = in[(((size_t)n * H + y) * W + x) * C4 + c];
       m = make_float4(fmaxf(m.x, v.x), fmaxf(m.y, v.y), fmaxf(m.z, v.z), fmaxf(m.w, v.w));
     }
-  out[(size_t)n * Ho * Wo * C4 + i] = m;
+  const __half2 h01 = __floats2half2_rn(m.x, m.y), h23 = __floats2half2_rn(m.z, m.w);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn((m.x - f01.x) * 2048.0f, (m.y - f01.y) * 2048.0f);
+  const __half2 l23 = __floats2half2_rn((m.z - f23.x) * 2048.0f, (m.w - f23.y) * 2048.0f);
+  __half* o = out + ((size_t)n * Ho * Wo * C4 + i) * 4;
+  *reinterpret_cast<uint2*>(o) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  *reinterpret_cast<uint2*>(o + plane) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
 
-// keep the even positions of an NHWC tensor: [n][H][W][C] -> [n][ceil(H/2)][ceil(W/2)][C]
-__global__ void __launch_bounds__(256) k_decimate2(const float4* __restrict__ in, float4* __restrict__ out, int H, int W, int Ho, int Wo, int C4) {
+// keep the even positions of a split NHWC tensor: [n][H][W][C] -> [n][ceil(H/2)][ceil(W/2)][C], 8 channels (16 bytes of
+// either plane) per thread
+__global__ void __launch_bounds__(256) k_decimate2(const uint4* __restrict__ in, uint4* __restrict__ out, int H, int W, int Ho, int Wo, int C8,
+                                                   size_t plane_in, size_t plane_out) {
   const int n = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= Ho * Wo * C4) return;
-  const int c = i % C4, p = i / C4, oy = p / Wo, ox = p - oy * Wo;
-  out[(size_t)n * Ho * Wo * C4 + i] = in[(((size_t)n * H + 2 * oy) * W + 2 * ox) * C4 + c];
+  if (i >= Ho * Wo * C8) return;
+  const int c = i % C8, p = i / C8, oy = p / Wo, ox = p - oy * Wo;
+  const size_t src = (((size_t)n * H + 2 * oy) * W + 2 * ox) * C8 + c, dst = (size_t)n * Ho * Wo * C8 + i;
+  out[dst] = in[src];
+  out[plane_out + dst] = in[plane_in + src];
 }
 
 struct BbChunk {                // <= 256 GEMM columns of one convolution: its own weight images and bias slice
@@ -278,23 +294,28 @@ int pack_deconv(fvp_backbone* bb, const std::string& key, const std::string& bn,
   return FVP_OK;
 }
 
-// one convolution = one launch per <= 256-column chunk into the same NHWC tensor (channel stride = all output channels)
+// One convolution = one launch per <= 256-column chunk into the same NHWC tensor (channel stride = all output channels).
+// All activations are SPLIT tensors (fp16 hi plane + scaled-lo plane) fetched by TMA; only the heat maps leave as fp32 NCHW.
 void run_conv(const fvp_backbone* bb, const BbConv& c, const float* in, const float* in2, const float* res, float* out, int n, int H, int W,
               int relu, cudaStream_t st, float* nchw_out = nullptr, int cout_real = 0) {
   for (const BbChunk& ch : c.chunks) {
     FvpConvArgs a;
     a.in = in; a.H = H; a.W = W; a.Cin = c.cin; a.in2 = in2; a.Cin2 = c.cin2; a.w = nullptr; a.bias = ch.d_bias;
-    a.out = nchw_out ? nchw_out : out + ch.ch0;
+    // channel offsets of a chunk are in ELEMENTS of the split planes (halves)
+    a.out = nchw_out ? nchw_out : reinterpret_cast<float*>(reinterpret_cast<__half*>(out) + ch.ch0);
     a.CoutP = ch.cols; a.CoutS = c.cout; a.CoutReal = cout_real;
-    a.res = res ? res + ch.ch0 : nullptr; a.res_mode = res ? 1 : 0; a.relu = relu; a.ksize = c.k;
-    a.upsample = c.upsample; a.nchw = nchw_out ? 1 : 0; a.n = n; a.valid = nullptr; a.fmt = 0;
+    a.res = res ? reinterpret_cast<const float*>(reinterpret_cast<const __half*>(res) + ch.ch0) : nullptr;
+    a.res_mode = res ? 1 : 0; a.relu = relu; a.ksize = c.k;
+    a.upsample = c.upsample; a.nchw = nchw_out ? 1 : 0; a.n = n; a.valid = nullptr;
+    a.fmt = FVP_FMT_IN_SPLIT | (nchw_out ? 0 : FVP_FMT_OUT_SPLIT) | (res ? FVP_FMT_RES_SPLIT : 0);
     const FvpLaunchEnv env{bb->num_sms, 2, nullptr, nullptr, 0, const_cast<int*>(&bb->launch_error)};
     fvp_launch_conv_tc(a, ch.wtc16, 1, env, st);
   }
 }
 void decimate(const float* in, float* out, int n, int H, int W, int C, cudaStream_t st) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  k_decimate2<<<dim3(fvp_cdiv(Ho * Wo * (C / 4), 256), n), 256, 0, st>>>((const float4*)in, (float4*)out, H, W, Ho, Wo, C / 4);
+  k_decimate2<<<dim3(fvp_cdiv(Ho * Wo * (C / 8), 256), n), 256, 0, st>>>((const uint4*)in, (uint4*)out, H, W, Ho, Wo, C / 8,
+                                                                        (size_t)n * H * W * (C / 8), (size_t)n * Ho * Wo * (C / 8));
 }
 
 void free_convs(fvp_backbone* bb) {
@@ -449,7 +470,7 @@ int fvp_backbone_forward_slice(fvp_backbone* bb, const float* d_images, int n, i
   int H = h / 4, W = w / 4;
   float *X = bb->buf[0], *Y = bb->buf[1], *T1 = bb->buf[2], *T2 = bb->buf[3], *T3 = bb->buf[4], *XS = bb->buf[5];
   k_stem7x7s2<<<dim3(fvp_cdiv(wo, ST_T), fvp_cdiv(ho, ST_T), n), 256, 0, st>>>(d_images, bb->d_stem_w, bb->d_stem_b, Y, h, w, ho, wo);
-  k_maxpool3s2<<<dim3(fvp_cdiv(H * W * 16, 256), n), 256, 0, st>>>((const float4*)Y, (float4*)X, ho, wo, H, W, 16);
+  k_maxpool3s2<<<dim3(fvp_cdiv(H * W * 16, 256), n), 256, 0, st>>>((const float4*)Y, (__half*)X, ho, wo, H, W, 16, (size_t)n * H * W * 64);
   int cx = 64;
   for (int b = 0; b < nb && b < stage; ++b) {
     const BbBlock& k = bb->blocks[b];
@@ -479,8 +500,9 @@ int fvp_backbone_forward_slice(fvp_backbone* bb, const float* d_images, int n, i
   }
   if (stage == last) {
     run_conv(bb, bb->convs[bb->final_conv], X, nullptr, nullptr, nullptr, n, H, W, 0, st, d_out, bb->num_joints);
-  } else {
-    fvp_launch_nhwc_to_nchw(X, d_out, n, H * W, cx, cx, st);
+  } else {                                                 // a tap for the parity tests: split NHWC -> fp32 NHWC -> fp32 NCHW
+    fvp_launch_unsplit(X, Y, (size_t)n * H * W * cx, st);
+    fvp_launch_nhwc_to_nchw(Y, d_out, n, H * W, cx, cx, st);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return bb_fail(bb, FVP_E_CUDA, "CUDA error: %s", cudaGetErrorString(e));
