@@ -25,6 +25,10 @@ class Backbone:
         self.device = torch.device("cuda", idx)
         self.num_layers, self.num_joints = int(num_layers), int(num_joints)
         self.max_images, self.max_h, self.max_w = int(max_images), int(max_h), int(max_w)
+        ctx = C.c_void_p()
+        rc = self.lib.fvp_backbone_create(self.num_layers, self.num_joints, self.max_images, self.max_h, self.max_w, idx, C.byref(ctx))
+        if rc != capi.FVP_OK:
+            raise capi.FvpError(rc, (self.lib.fvp_backbone_last_error(None) or b"?").decode())
         kind, blocks = BS.RESNET_SPEC[self.num_layers]
         exp = 4 if kind == "bottleneck" else 1
         # (channels, log2 of the down-sampling factor) of every stage output: max-pool, residual blocks, deconvs, heat maps
@@ -32,10 +36,6 @@ class Backbone:
         for li, (planes, n) in enumerate(zip((64, 128, 256, 512), blocks)):
             self.stage_shapes += [(planes * exp, 2 + li)] * n
         self.stage_shapes += [(256, 4), (256, 3), (256, 2), (self.num_joints, 2)]
-        ctx = C.c_void_p()
-        rc = self.lib.fvp_backbone_create(self.num_layers, self.num_joints, self.max_images, self.max_h, self.max_w, idx, C.byref(ctx))
-        if rc != capi.FVP_OK:
-            raise capi.FvpError(rc, (self.lib.fvp_backbone_last_error(None) or b"?").decode())
         self.ctx = ctx
 
     def _ck(self, rc: int) -> None:

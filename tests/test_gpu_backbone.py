@@ -112,3 +112,30 @@ def test_backbone_plugin_module_and_image_source_forward(built_library, golden):
         b = model(backbone=None, meta={"seq": [g.seq]}, input_heatmaps=hms, cameras=g.cameras, resize_transform=rz)
     assert tuple(a[3].shape) == (1, V, J, H, W)
     assert torch.equal(a[3], hms) and all(torch.equal(p, q) for p, q in zip(a[:3], b[:3]))
+
+
+def test_backbone_error_behaviour(built_library):
+    from fvp.backbone import Backbone
+    from fvp.capi import FvpError
+    with pytest.raises(FvpError):
+        Backbone(50, 15, "cuda:0", max_images=1, max_h=100, max_w=96)          # sides must be multiples of 32
+    with pytest.raises(FvpError):
+        Backbone(42, 15, "cuda:0", max_images=1, max_h=96, max_w=96)           # not a ResNet depth of resnet.py:204-208
+    bb = Backbone(18, 15, "cuda:0", max_images=1, max_h=96, max_w=96)
+    x = torch.zeros(1, 3, 96, 96)
+    with pytest.raises(FvpError):
+        bb.forward(x)                                                          # nothing loaded
+    cfg = fcfg.preset("panoptic")
+    cfg.RESNET.NUM_LAYERS = 18
+    sd = synth.make_backbone_weights(BS.from_cfg(cfg), 3)
+    part = {k: v for k, v in sd.items() if not k.startswith("layer3.1.")}
+    with pytest.raises(FvpError):
+        bb.load_state_dict(part)                                               # a missing layer is named, never skipped
+    bb.load_state_dict(sd)
+    assert tuple(bb.forward(x).shape) == (1, 15, 24, 24)
+    with pytest.raises(FvpError):
+        bb.forward(torch.zeros(1, 3, 128, 96))                                 # larger than the object was created for
+    with pytest.raises(FvpError):
+        bb.forward(torch.zeros(2, 3, 96, 96)[:, :, :80])                       # not a multiple of 32
+    bb.close()
+

@@ -646,3 +646,54 @@ def test_k1_config5_ring_sweep_points_match_oracle(built_library, views, voxels)
     assert plane.shape == ref.shape == (2, int(cfg.DATASET.NUM_JOINTS), voxels[0], voxels[1])
     assert float((plane - ref).abs().max()) <= 1e-6
     assert float(ref[0].max()) > 0.5                     # the blobs are visible: the comparison is not zeros vs zeros
+
+
+def test_lane_contexts_share_weights_calibrations_and_grids(bench_setup):
+    """fvp_create_lane: a lane owns workspaces / streams / graph and reads the root's weights, calibrations and sample grids.
+    Parameters and calibrations are managed on the root only; a lane follows the root when they change (its CUDA graph,
+    which holds the old weight pointers, is dropped); the root cannot be destroyed under its lanes."""
+    import ctypes as C
+    from fvp import capi
+    from fvp.engine import Engine
+    g, eng, slots = bench_setup
+    hm = torch.from_numpy(g.heatmaps).cuda()
+    root = Engine(g.cfg, torch.device("cuda:0"), max_batch=g.B, max_sequences=2, axes=g.axes)
+    lane = root.new_lane()
+    with pytest.raises(capi.FvpError):                       # nothing loaded on the root yet
+        lane.forward(hm, [0] * g.B)
+    root.load_state_dict(g.weights)
+    with pytest.raises(RuntimeError):
+        lane.load_state_dict(g.weights)
+    a = np.zeros(4, np.float32)
+    assert root.lib.fvp_set_param(lane.ctx, b"pose_net.center_net.output_hm.2.bias", a.ctypes.data, 1) == capi.FVP_E_STATE
+    assert root.lib.fvp_finalize_params(lane.ctx) == capi.FVP_E_STATE
+    with pytest.raises(AssertionError):                      # calibration not set yet: the reference's assertion, through the lane
+        lane.forward(hm, [0] * g.B)
+    slot = lane.sequence_slot(g.cams, g.resize)              # forwarded to the root
+    assert slot == root.sequence_slot(g.cams, g.resize)
+    want = eng.forward(hm, slots)
+    lane.use_cuda_graph(True)
+    for _ in range(3):
+        got = lane.forward(hm, [slot] * g.B)
+    assert all(torch.equal(x, y) for x, y in zip(want, got))
+    # the root gets new weights: the lane must follow (and re-capture its graph)
+    sd2 = {k: np.array(v, copy=True) for k, v in g.weights.items()}
+    sd2["joint_net.conv_net.output_layer.bias"] = sd2["joint_net.conv_net.output_layer.bias"] + np.float32(0.01)
+    root.load_state_dict(sd2)
+    fresh = Engine(g.cfg, torch.device("cuda:0"), max_batch=g.B, max_sequences=2, axes=g.axes)
+    fresh.load_state_dict(sd2)
+    s2 = fresh.sequence_slot(g.cams, g.resize)
+    want2 = fresh.forward(hm, [s2] * g.B)
+    for _ in range(2):
+        got2 = lane.forward(hm, [slot] * g.B)
+    assert all(torch.equal(x, y) for x, y in zip(want2, got2))
+    assert not torch.equal(want[0], want2[0])
+    fresh.close()
+    # destroying the root under a live lane is refused (nothing is freed), the lane keeps working
+    root.lib.fvp_destroy(root.ctx)
+    assert b"lane" in (root.lib.fvp_last_error(root.ctx) or b"")
+    got3 = lane.forward(hm, [slot] * g.B)
+    assert all(torch.equal(x, y) for x, y in zip(want2, got3))
+    root.close()                                             # closes the lane first, then the root
+    assert lane.ctx is None and root.ctx is None
+
