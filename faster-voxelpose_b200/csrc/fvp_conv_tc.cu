@@ -40,9 +40,6 @@
 // operand and must convert to a finite fp16 "hi" part (network inputs are back-projected planes clamped to [0,1]).  An output with |x| >= 65504 (or NaN) raises bit 0 of the status
 // word in mapped pinned host memory; the host entry points turn it into FVP_E_RANGE after their next synchronise.
 __device__ int* g_tc_status = nullptr;
-#ifndef FVP_RANGE_CHECK
-#define FVP_RANGE_CHECK 1                  // 1: per-item running maximum (shipped); 0 / 2: A/B switches (none / per-store test)
-#endif
 
 namespace {
 
@@ -747,11 +744,7 @@ __global__ void __launch_bounds__(TMA ? 192 : TC_THREADS, OCC) k_conv_tc(TcArgs 
             if (a.res_mode == 2) o += res_value(rcur, g4 * 4 + e);
             v[g4 * 4 + e] = o;
           }
-#if FVP_RANGE_CHECK == 2
-          if (!(fmaxf(fmaxf(fabsf(v[g4 * 4]), fabsf(v[g4 * 4 + 1])), fmaxf(fabsf(v[g4 * 4 + 2]), fabsf(v[g4 * 4 + 3]))) < 65504.0f) && g_tc_status) *g_tc_status = 1;
-#elif FVP_RANGE_CHECK == 1
           amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[g4 * 4]), fabsf(v[g4 * 4 + 1])), fmaxf(fabsf(v[g4 * 4 + 2]), fabsf(v[g4 * 4 + 3]))));
-#endif
         }
         if (out_split) {
           // one 16-byte store of 8 hi halves and one of 8 scaled-lo halves per 8 channels: the operand form the next
@@ -791,11 +784,10 @@ __global__ void __launch_bounds__(TMA ? 192 : TC_THREADS, OCC) k_conv_tc(TcArgs 
           }
         }
       }
-#if FVP_RANGE_CHECK == 1
       // Range guard (also in the 3xTF32 variant, whose outputs may feed an fp16 layer).  A maximum ignores NaN, but a NaN
-      // needs an infinite operand, and the first value that cannot become a finite fp16 "hi" part is caught here.
+      // needs an infinite operand, and the first value that cannot become a finite fp16 "hi" part is caught here.  (A test
+      // per store instead of this per-item maximum measured 17 % slower on the 3x3 32->32 layer, profiles/r02_conv_ab.txt.)
       if (amax >= 65504.0f && g_tc_status) *g_tc_status = 1;
-#endif
       ++it;
     }
     if (t.prof && tid == LW * 32 + 64) {
@@ -853,8 +845,6 @@ void fvp_tc_geometry(int coutp, int narrow, int* n_tile, int* n_tiles) {
 
 // read-only after start-up: FVP_TC_OCC=1 never co-schedules two CTAs per SM (A/B switch of tools/gpu_conv_check.sh)
 static const int g_tc_occ = [] { const char* e = std::getenv("FVP_TC_OCC"); return e ? std::atoi(e) : 2; }();
-// read-only after start-up: FVP_TC_VARIANT=0/1/2 forces the N-tile cap (128 / 32 / 64 columns) where that image exists (A/B switch)
-static const int g_tc_variant = [] { const char* e = std::getenv("FVP_TC_VARIANT"); return e ? std::atoi(e) : -1; }();
 
 // Per-device setup (fvp_create): opt-in shared memory of all six instantiations, carve-out of the two-CTA variants.
 cudaError_t fvp_conv_tc_init_device() {
@@ -932,7 +922,6 @@ void fvp_launch_conv_tc(const FvpConvArgs& a, const float* const wtc[3], int mod
     const double cost = (double)fvp_cdiv(tiles * nts, num_sms) * per_item * (residency(nt, nts) ? 1.0 : 1.4) + 1.0 * nts;   // ties: wider tile
     if (cost < best_cost) { best_cost = cost; best = v; }
   }
-  if (g_tc_variant >= 0 && g_tc_variant < 3 && wtc[g_tc_variant]) best = g_tc_variant;
   fvp_tc_geometry(a.CoutP, best, &t.n_tile, &t.n_tiles);
   t.wtc = wtc[best];
   t.blk_bytes = (uint32_t)t.n_tile * rowb * 2;
