@@ -21,60 +21,89 @@ __device__ __forceinline__ ValIdx vi_best(ValIdx a, ValIdx b) {
   return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
 }
 
+// Round 2: the P selection rounds no longer rescan the map with the whole block.  The cells are split into 32 groups (the
+// warps' strided cells); each group's best sits in shared memory; a round is one warp reduction over the 32 group bests
+// and one re-scan of the winner's group, all in warp 0 without block barriers.  Same order as before: value descending,
+// flat index ascending among equals (the tie rule of the tests), so the result is bit-identical.
 __global__ void __launch_bounds__(1024) k_nms_topk(const float* __restrict__ hm, size_t img_stride, int X, int Y,
                                                    int P, float* __restrict__ conf, int* __restrict__ flat) {
-  extern __shared__ float s_nms[];               // [X*Y]
-  __shared__ ValIdx s_red[32];
-  __shared__ ValIdx s_win;
-  const int b = blockIdx.x, n = X * Y, tid = threadIdx.x;
+  extern __shared__ float s_nms[];               // [X*Y] map, then [ceil(X*Y/32)] keep bits
+  __shared__ ValIdx s_warp[32];                  // best of every group of cells (group w = the cells warp w strides over)
+  const int b = blockIdx.x, n = X * Y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   const float* h = hm + (size_t)b * img_stride;
-  for (int i = tid; i < n; i += blockDim.x) {
-    const int x = i / Y, y = i - x * Y;
-    const float v = h[i];
-    float m = v;
-    for (int dx = -1; dx <= 1; ++dx)
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int xx = x + dx, yy = y + dy;
-        if (xx >= 0 && xx < X && yy >= 0 && yy < Y) m = fmaxf(m, h[xx * Y + yy]);
-      }
-    s_nms[i] = (v == m) ? v : 0.0f;
+  unsigned* s_keep = reinterpret_cast<unsigned*>(s_nms + n);
+  // The map is staged with independent coalesced loads first: reading the 3x3 neighbourhoods straight from global memory
+  // made every thread wait for ~60 dependent L2 round trips (ncu: 44 K warp instructions in 38 K cycles, 19 us).
+  for (int i = tid; i < n; i += nthreads) s_nms[i] = h[i];
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += nthreads) {     // warp-uniform trip count: every lane takes part in the ballot
+    const int i = i0 + tid;
+    bool keep = false;
+    if (i < n) {
+      const int x = i / Y, y = i - x * Y;
+      const float v = s_nms[i];
+      float m = v;
+      for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int xx = x + dx, yy = y + dy;
+          if (xx >= 0 && xx < X && yy >= 0 && yy < Y) m = fmaxf(m, s_nms[xx * Y + yy]);
+        }
+      keep = v == m;
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0 && i < n) s_keep[i >> 5] = bits;   // i is a multiple of 32 for lane 0
   }
   __syncthreads();
-  for (int r = 0; r < P; ++r) {
-    ValIdx best = {-INFINITY, 0x7fffffff};
-    for (int i = tid; i < n; i += blockDim.x) best = vi_best(best, ValIdx{s_nms[i], i});
+  for (int i = tid; i < n; i += nthreads)
+    if (!((s_keep[i >> 5] >> (i & 31)) & 1u)) s_nms[i] = 0.0f;
+  __syncthreads();
+  const ValIdx none = {-INFINITY, 0x7fffffff};
+  auto warp_best = [&](ValIdx v) {               // all lanes get the warp's best
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       ValIdx other;
-      other.v = __shfl_xor_sync(0xffffffffu, best.v, o);
-      other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-      best = vi_best(best, other);
+      other.v = __shfl_xor_sync(0xffffffffu, v.v, o);
+      other.i = __shfl_xor_sync(0xffffffffu, v.i, o);
+      v = vi_best(v, other);
     }
-    if ((tid & 31) == 0) s_red[tid >> 5] = best;
-    __syncthreads();
-    if (tid < 32) {
-      ValIdx v2 = tid < (int)(blockDim.x >> 5) ? s_red[tid] : ValIdx{-INFINITY, 0x7fffffff};
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        ValIdx other;
-        other.v = __shfl_xor_sync(0xffffffffu, v2.v, o);
-        other.i = __shfl_xor_sync(0xffffffffu, v2.i, o);
-        v2 = vi_best(v2, other);
-      }
-      if (tid == 0) {
-        s_win = v2;
-        conf[b * P + r] = v2.v;
-        flat[b * P + r] = v2.i;
-        s_nms[v2.i] = -INFINITY;                 // remove from later rounds
-      }
-    }
-    __syncthreads();
+    return v;
+  };
+  auto best_of_warp_cells = [&](int w) {         // best of the cells i with (i % nthreads) / 32 == w, computed by one whole warp
+    ValIdx best = none;
+    for (int i = w * 32 + lane; i < n; i += nthreads) best = vi_best(best, ValIdx{s_nms[i], i});
+    return warp_best(best);
+  };
+  {
+    const ValIdx wb = best_of_warp_cells(warp);
+    if (lane == 0) s_warp[warp] = wb;
   }
+  __syncthreads();
+  if (warp != 0) return;
+  // The P rounds run in warp 0 alone, without block barriers: reduce the 32 group bests, emit the winner, remove it, re-scan
+  // the winner's group (<= ceil(n / 32) cells over 32 lanes).  Same order as a global arg-max per round.
+  const int nwarps = nthreads >> 5;
+  for (int r = 0; r < P; ++r) {
+    const ValIdx v2 = warp_best(lane < nwarps ? s_warp[lane] : none);
+    if (lane == 0) {
+      conf[b * P + r] = v2.v;
+      flat[b * P + r] = v2.i;
+      s_nms[v2.i] = -INFINITY;                   // remove from later rounds
+    }
+    __syncwarp();
+    const int w = (v2.i % nthreads) >> 5;        // the group that owned the winner has a new best
+    const ValIdx nb = best_of_warp_cells(w);
+    if (lane == 0) s_warp[w] = nb;
+    __syncwarp();
+  }
+}
+
+static inline size_t fvp_nms_smem_bytes(int X, int Y) {           // the map + one keep bit per cell
+  return (size_t)X * Y * sizeof(float) + (size_t)((X * Y + 31) / 32) * sizeof(unsigned);
 }
 
 void fvp_launch_nms_topk(const float* d_hm, size_t img_stride, int X, int Y, int P, int batch, float* d_conf,
                          int* d_flat, cudaStream_t st) {
-  const size_t smem = (size_t)X * Y * sizeof(float);               // opt-in size set per device by fvp_proposal_init_device
+  const size_t smem = fvp_nms_smem_bytes(X, Y);                   // opt-in size set per device by fvp_proposal_init_device
   k_nms_topk<<<batch, 1024, smem, st>>>(d_hm, img_stride, X, Y, P, d_conf, d_flat);
 }
 
@@ -596,7 +625,7 @@ __global__ void k_people_from_centers(FvpPropArgs a, const float* __restrict__ c
 // Per-device setup (fvp_create): dynamic shared memory opt-ins of the NMS kernel (the whole X*Y map) and the proposal kernel.
 // A grid whose NMS map does not fit the 227 KB per-CTA limit is refused here, at create time, with a clear error.
 cudaError_t fvp_proposal_init_device(int X, int Y) {
-  const size_t nms = (size_t)X * Y * sizeof(float);
+  const size_t nms = fvp_nms_smem_bytes(X, Y);
   if (nms + 1024 > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaFuncAttributes fa;                         // several contexts may share the device: never lower an earlier opt-in
   cudaError_t e = cudaFuncGetAttributes(&fa, k_nms_topk);
