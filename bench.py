@@ -381,6 +381,9 @@ def main():
     eng.check_range()                            # synchronises; raises if an activation left the fp16 range
 
     # ---- serial forwards on one lane (one frame in flight): the per-frame latency ------------------------------
+    # From here on lane 0 runs alone, so it uses the latency kernels (fvp_set_latency_mode; an engine without lanes picks them
+    # by itself): C2CNet on one 8-CTA cluster per column.  The pipelined `value` above ran the throughput kernels.
+    eng.set_latency_mode(1)
     ser_steps = max(10, args.steps // 4)
     for i in range(3):
         eng.forward(pool_dev[i % POOL], slots)
@@ -394,6 +397,7 @@ def main():
     serial_ms = marks[0].elapsed_time(marks[-1]) / ser_steps
     per_step = np.array([marks[i].elapsed_time(marks[i + 1]) for i in range(ser_steps)])     # per-frame latency distribution
     serial_p50, serial_p95 = float(np.percentile(per_step, 50)), float(np.percentile(per_step, 95))
+    eng.set_latency_mode(-1)                     # back to automatic (throughput kernels while the lanes exist) for the e2e pipeline
 
     # ---- the reference-facing plugin: models.faster_voxelpose.get(cfg)(...) as run/validate.py:102-105 calls it ----
     plugin = None
@@ -517,6 +521,7 @@ def main():
 
     # ---- per-stage CUDA-event times (same stream, graph off) -> roofline of the back-projection ----
     eng.use_cuda_graph(False)
+    eng.set_latency_mode(1)                      # lane 0 alone again: the stage times belong to the serial figure
     eng.set_profiling(True)
     acc = np.zeros(9)
     prof_steps = min(args.steps, 50)
@@ -525,6 +530,7 @@ def main():
         if i >= 3:
             acc += np.array(eng.stage_times_ms())
     eng.set_profiling(False)
+    eng.set_latency_mode(-1)
     stage = acc / prof_steps
     k1_bytes, k3_bytes = eng.algorithmic_bytes(max(1, n_valid // B))
     peaks = {}
@@ -609,6 +615,8 @@ def main():
                 "blocking_call_ms": sync_call_ms},
         "roofline": roofline, "roofline_k1": roofline_k1, "cpu_baseline": cpu_base, "gpu_reference_port": gpu_port,
         "plugin_forward": plugin, "kernels": extra_kernels, "valid_people_last_step": n_valid,
+        "kernel_modes": {"value_and_e2e": "throughput" if L > 1 else "latency", "serial_and_stage_ms": "latency",
+                         "what": "fvp_set_latency_mode: proposal stage on one CTA per column (throughput) or one 8-CTA cluster per column (latency)"},
         "cuda_graph": not args.no_graph, "serial_ms_per_step": serial_ms, "serial_fps": world * B / (serial_ms * 1e-3),
         "serial_ms_p50": serial_p50, "serial_ms_p95": serial_p95,
         "collective": None if world == 1 else {

@@ -167,6 +167,17 @@ int refuse_on_lane(fvp_ctx* ctx, const char* what) {
   return FVP_OK;
 }
 
+// per-frame latency before SM efficiency?  Automatic: yes while the context runs alone, no once it shares the device with lanes
+static int prefer_latency(const fvp_ctx* ctx) {
+  if (ctx->latency_mode >= 0) return ctx->latency_mode;
+  return ctx->root == nullptr && ctx->lanes_alive == 0;
+}
+
+// a captured graph holds the kernel choice: drop it when the automatic choice may have changed
+static void drop_auto_graph(fvp_ctx* ctx) {
+  if (ctx->latency_mode < 0 && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+}
+
 FvpLaunchEnv launch_env(fvp_ctx* ctx) { return FvpLaunchEnv{ctx->num_sms, ctx->conv_mode, nullptr, nullptr, ctx->split_activations, &ctx->launch_error}; }
 
 // Other entry points must not touch the shared workspaces while fvp_submit_host tickets are in flight.
@@ -229,7 +240,7 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
     a.img_valid = ctx->d_img_valid;
     a.n_slots = n;
     a.mode = 0;
-    fvp_launch_proposals(a, ctx->w_c2c, n, st); ++*launches;
+    fvp_launch_proposals(a, ctx->w_c2c, n, prefer_latency(ctx), st); ++*launches;
   }
   T.mark(5);
   fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, batch, fvp_k3_parts(ctx, batch), st);
@@ -435,6 +446,7 @@ int fvp_create_lane(fvp_ctx* root, int max_batch, fvp_ctx** out) {
     return FVP_E_CUDA;
   }
   ++root->lanes_alive;
+  drop_auto_graph(root);                           // the automatic latency mode of the root has just changed
   *out = ctx;
   return FVP_OK;
 }
@@ -474,7 +486,10 @@ void fvp_destroy(fvp_ctx* ctx) {
   }
   for (int i = 0; i < 10; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-  if (ctx->root) --ctx->root->lanes_alive;
+  if (ctx->root) {
+    --ctx->root->lanes_alive;
+    drop_auto_graph(ctx->root);
+  }
   delete ctx;
 }
 
@@ -605,6 +620,13 @@ int fvp_set_conv_mode(fvp_ctx* ctx, int mode) {
   if (!ctx || mode < 0 || mode > 2) return FVP_E_INVALID;
   if (mode != ctx->conv_mode && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
   ctx->conv_mode = mode;
+  return FVP_OK;
+}
+
+int fvp_set_latency_mode(fvp_ctx* ctx, int mode) {
+  if (!ctx || mode < -1 || mode > 1) return FVP_E_INVALID;
+  if (mode != ctx->latency_mode && ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+  ctx->latency_mode = mode;
   return FVP_OK;
 }
 
@@ -889,7 +911,7 @@ int fvp_proposals(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const flo
   a.centers = d_centers ? d_centers : ctx->d_centers;
   a.people = ctx->d_people; a.img_valid = ctx->d_img_valid; a.n_slots = n;
   a.mode = 0;
-  fvp_launch_proposals(a, ctx->w_c2c, n, st);
+  fvp_launch_proposals(a, ctx->w_c2c, n, prefer_latency(ctx), st);
   FVP_CUDA_OK(cudaGetLastError());
   return FVP_OK;
 }
@@ -904,7 +926,7 @@ int fvp_c2c_net(fvp_ctx* ctx, const float* d_cols, int n, float* d_hm1d, uintptr
   a.cols_in = d_cols; a.cols_out = nullptr; a.hm1d_out = d_hm1d;
   a.centers = nullptr; a.people = nullptr; a.img_valid = nullptr; a.n_slots = n;
   a.mode = 1;
-  fvp_launch_proposals(a, ctx->w_c2c, n, (cudaStream_t)stream);
+  fvp_launch_proposals(a, ctx->w_c2c, n, prefer_latency(ctx), (cudaStream_t)stream);
   FVP_CUDA_OK(cudaGetLastError());
   return FVP_OK;
 }

@@ -78,6 +78,7 @@ struct fvp_ctx {
   int frame_seq_uploaded = 0;         // how many leading entries of d_frame_seq mirror h_frame_seq
   int num_sms = 148;
   int conv_mode = 2;                  // 0 = fp32 CUDA cores, 1 = tcgen05 3xTF32 (7x7 on CUDA cores), 2 = tcgen05 fp16 split
+  int latency_mode = -1;              // fvp_set_latency_mode: -1 auto (on when the context has no lanes), 0 off, 1 on
   int launch_error = 0;               // set by a conv launcher that could not prepare its launch (FvpLaunchEnv::error)
   int split_activations = 1;          // engine 2: split (fp16 hi / lo) activations between layers, TMA-fed convolutions
   int fp16_fallback_layers = 0;       // conv layers packed without an fp16 image (weights outside the fp16 range)

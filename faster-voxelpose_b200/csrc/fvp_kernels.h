@@ -136,7 +136,12 @@ struct FvpC2CW {            // packed 1-D trunk, weights [tap][ci][co] per conv
   const float* b[24];
   const float* w2[24];      // same, ci-major ([ci][tap][co], then the fused-skip rows) for the split-K kernel
   const void* plan;         // device copy of the weight-ring chunk table (fvp_c2c_build_plan)
+  const float* w3;          // per-rank weight slices of the cluster kernel (fvp_c2c_pack_cluster); NULL = one CTA per column
+  int max_clusters;         // clusters per launch of the cluster kernel (columns beyond that are looped over)
 };
+size_t fvp_c2c_cluster_floats(int J);
+void fvp_c2c_pack_cluster(const float* const w2_host[20], const float* const b_host[20], int J, float* out);
+int fvp_c2c_max_clusters(int J);       // co-resident 8-CTA clusters of the cluster kernel on the current device
 size_t fvp_c2c_plan_bytes();
 // chunk table of the network-wide weight ring of k_proposals from the DEVICE addresses of the ci-major weights; returns
 // the number of chunks or < 0 (table too small / misaligned chunk)
@@ -163,7 +168,9 @@ struct FvpPropArgs {
   int ind_vox[3];
   int mode;                 // 0 full (sample + c2c + proposal), 1 c2c only on cols_in
 };
-void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, cudaStream_t st);
+// prefer_latency: one 8-CTA cluster per column when the columns fit one wave of clusters (2.4x shorter at batch 1, ~2x the
+// SM time); otherwise, and always for other Z than 20, one CTA per column
+void fvp_launch_proposals(const FvpPropArgs& a, const FvpC2CW& w, int n, int prefer_latency, cudaStream_t st);
 // proposal_centers [B][P][7] -> FvpPerson (stage API for K3)
 void fvp_launch_people_from_centers(const FvpPropArgs& a, const float* d_centers, int n, cudaStream_t st);
 

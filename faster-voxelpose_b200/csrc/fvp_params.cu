@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 
 #include "fvp_ctx.h"
+#include <cstdlib>
 
 namespace {
 
@@ -417,6 +418,22 @@ int fvp_pack_params(fvp_ctx* ctx) {
       std::memcpy(&v[(size_t)(pc.cin * taps + ci) * pc.coutp], src + (size_t)(taps * cinP + ci) * pc.coutp, pc.coutp * sizeof(float));
     c2c_cimajor.push_back(A.put(v));
   }
+  // per-rank slices for the 8-CTA cluster form of the column kernel (FVP_C2C_CLUSTER=0 keeps one CTA per column, for A/B)
+  size_t c2c_cluster_off = (size_t)-1;
+  {
+    const char* sw = std::getenv("FVP_C2C_CLUSTER");
+    const size_t nfl = fvp_c2c_cluster_floats(ctx->cfg.num_joints);
+    if (nfl > 0 && !(sw && sw[0] == '0')) {
+      const float *w2h[20], *bh[20];
+      for (int i = 0; i < 20; ++i) {
+        w2h[i] = A.host.data() + c2c_cimajor[i];
+        bh[i] = A.host.data() + c2c[i].b_off;
+      }
+      std::vector<float> v(nfl, 0.f);
+      fvp_c2c_pack_cluster(w2h, bh, ctx->cfg.num_joints, v.data());
+      c2c_cluster_off = A.put(v);
+    }
+  }
   // ---- P2PNet --------------------------------------------------------------------------------
   pack_trunk(ctx, "joint_net.conv_net", A, p2p, true);
   p2p.push_back(stash(A, pack_conv(ctx, "joint_net.conv_net.output_layer"), true));
@@ -455,6 +472,8 @@ int fvp_pack_params(fvp_ctx* ctx) {
     ctx->w_c2c.b[i] = base + c2c[i].b_off;
     ctx->w_c2c.w2[i] = base + c2c_cimajor[i];
   }
+  ctx->w_c2c.w3 = c2c_cluster_off == (size_t)-1 ? nullptr : base + c2c_cluster_off;
+  ctx->w_c2c.max_clusters = fvp_c2c_max_clusters(ctx->cfg.num_joints);
   {  // chunk table of k_proposals' network-wide weight ring (device addresses of the ci-major weights)
     std::vector<char> plan(fvp_c2c_plan_bytes(), 0);
     const int nchunks = fvp_c2c_build_plan(ctx->w_c2c.w2, ctx->cfg.num_joints, plan.data());

@@ -86,6 +86,7 @@ SYMBOLS = {
     "fvp_backbone_finalize": (C.c_int, [_CTX]),
     "fvp_backbone_forward_slice": (C.c_int, [_CTX, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
     "fvp_set_conv_mode": (C.c_int, [_CTX, C.c_int]),
+    "fvp_set_latency_mode": (C.c_int, [_CTX, C.c_int]),
     "fvp_check_range": (C.c_int, [_CTX]),
     "fvp_fp16_fallback_layers": (C.c_int, [_CTX]),
     "fvp_last_launch_count": (C.c_int, [_CTX]),

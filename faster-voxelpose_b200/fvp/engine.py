@@ -297,6 +297,11 @@ class Engine:
         """0 = fp32 CUDA-core convolutions, 1 = tcgen05 3xTF32, 2 = tcgen05 fp16 hi/lo split (default)."""
         self._ck(self.lib.fvp_set_conv_mode(self.ctx, int(mode)))
 
+    def set_latency_mode(self, mode: int) -> None:
+        """1 = latency kernels (C2CNet on one 8-CTA cluster per column), 0 = throughput kernels (one CTA per column),
+        -1 = automatic: latency while this engine runs alone, throughput once lanes share its device."""
+        self._ck(self.lib.fvp_set_latency_mode(self.ctx, int(mode)))
+
     def set_profiling(self, on: bool) -> None:
         self._ck(self.lib.fvp_set_profiling(self.ctx, 1 if on else 0))
 

@@ -229,6 +229,12 @@ int fvp_backbone_forward_slice(fvp_backbone* bb, const float* d_images, int n, i
  * the error-compensated 3xTF32 split (default set at build time) */
 int fvp_set_conv_mode(fvp_ctx* ctx, int mode);
 
+/* Latency or throughput kernels where the two differ (today: the proposal stage, lib/models/human_detection_net.py:88-102 -
+ * C2CNet on one 8-CTA cluster per column, 2.4x shorter at batch 1, or on one CTA per column, half the SM time).
+ * mode 1 = latency, 0 = throughput, -1 = automatic (default): latency while the context runs alone, throughput once lanes
+ * (fvp_create_lane) share its device.  Results are identical within the fp32 reassociation of the C2CNet sums. */
+int fvp_set_latency_mode(fvp_ctx* ctx, int mode);
+
 /* Range guard of the default convolution engine (fp16 hi/lo split: operands must stay below 65504).  BN-folded weights
  * are checked when they are packed (a layer outside the range silently runs on the 3xTF32 engine); activations are checked
  * by the kernels as they are stored.  fvp_forward_host / fvp_wait report a violation as FVP_E_RANGE; after the

@@ -110,20 +110,30 @@ def test_nms_topk_tie_rule_and_suppression(case):
 
 def test_proposals_columns_c2c_and_assembly(case):
     """K2 column re-sampling + C2CNet + ProposalLayer given the golden top-k: columns <= 1e-6, 1-D heat map
-    <= 2e-6, proposal xyz / flag / bbox bit-exact, confidence <= 1e-6."""
+    <= 2e-6, proposal xyz / flag / bbox bit-exact, confidence <= 1e-6.  Both kernel forms (fvp_set_latency_mode): 0 = one
+    CTA per column, 1 = one 8-CTA cluster per column (taken when the columns fit one wave of clusters; the 8-column
+    c2c_net call below always does)."""
     g, eng, slots = case
     eng.stage_heatmaps(torch.from_numpy(g.heatmaps))
-    cols, hm1d, centers = eng.proposals(g.B, slots, torch.from_numpy(g["conf2d"]), torch.from_numpy(g["flat"]).int(),
-                                        torch.from_numpy(g["size"]))
-    assert _maxerr(cols.cpu().view(g.B, g.P, g.J, -1), g["cols"]) <= 1e-6
-    assert _maxerr(hm1d.cpu().view(g.B, g.P, -1), g["hm1d"]) <= 2e-6
-    c = centers.cpu().numpy()
     ref = g["hdn_centers"]
-    assert np.array_equal(c[..., :4], ref[..., :4])          # xyz (mm) and validity flag
-    assert np.array_equal(c[..., 5:], ref[..., 5:])          # bbox
-    assert _maxerr(c[..., 4], ref[..., 4]) <= 1e-6
-    hm1d2 = eng.c2c_net(torch.from_numpy(g["cols"]).view(-1, g.J, g["cols"].shape[-1]))
-    assert _maxerr(hm1d2.cpu().view(g.B, g.P, -1), g["hm1d"]) <= 2e-6
+    try:
+        for mode in (0, 1):
+            eng.set_latency_mode(mode)
+            cols, hm1d, centers = eng.proposals(g.B, slots, torch.from_numpy(g["conf2d"]), torch.from_numpy(g["flat"]).int(),
+                                                torch.from_numpy(g["size"]))
+            assert _maxerr(cols.cpu().view(g.B, g.P, g.J, -1), g["cols"]) <= 1e-6, mode
+            assert _maxerr(hm1d.cpu().view(g.B, g.P, -1), g["hm1d"]) <= 2e-6, mode
+            c = centers.cpu().numpy()
+            assert np.array_equal(c[..., :4], ref[..., :4]), mode    # xyz (mm) and validity flag
+            assert np.array_equal(c[..., 5:], ref[..., 5:]), mode    # bbox
+            assert _maxerr(c[..., 4], ref[..., 4]) <= 1e-6, mode
+            gc = torch.from_numpy(g["cols"]).view(-1, g.J, g["cols"].shape[-1])
+            hm1d2 = eng.c2c_net(gc)
+            assert _maxerr(hm1d2.cpu().view(g.B, g.P, -1), g["hm1d"]) <= 2e-6, mode
+            hm1d3 = eng.c2c_net(gc[:8].contiguous())                 # 8 columns: one cluster each in mode 1
+            assert _maxerr(hm1d3.cpu(), g["hm1d"].reshape(-1, hm1d3.shape[-1])[:8]) <= 2e-6, mode
+    finally:
+        eng.set_latency_mode(-1)
 
 
 def test_k3_jln_backprojection_three_planes(case):
