@@ -3,7 +3,7 @@
 //   WeightNet (weight_net.py:48-80: conv3x3(1->F)+BN, MaxPool2, ReLU, global average, MLP, sigmoid),
 //   fuse_pose_preds, offset add, confidence mean and the final [B,P,J,5] packing
 //   (faster_voxelpose.py:102-103).
-// One CTA per (joint, person, plane) - 3*J*n CTAs, three per SM at batch 1 instead of one; the 64x64 map is staged once
+// One CTA per (joint, person, plane) - 3*J*n CTAs, four per SM; the 64x64 map is staged once
 // in shared memory and used by both the soft-argmax and the WeightNet; k_fuse blends the three planes per joint.  Expectations are accumulated in fp64 (joint
 // coordinates are ~1e3 mm where one fp32 ulp is 1.2e-4 mm; see DESIGN.md "numerics").
 #include "fvp_kernels.h"
@@ -37,7 +37,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 template <int F>
-__global__ void __launch_bounds__(PT, 3) k_pose_head(FvpGeom g, FvpPoseW w, const float* __restrict__ feat,
+__global__ void __launch_bounds__(PT, 4) k_pose_head(FvpGeom g, FvpPoseW w, const float* __restrict__ feat,
                                                   const FvpPerson* __restrict__ people,
                                                   const float* __restrict__ offsets, int n, float beta,
                                                   float* __restrict__ pose, float* __restrict__ maxw,
@@ -94,44 +94,49 @@ __global__ void __launch_bounds__(PT, 3) k_pose_head(FvpGeom g, FvpPoseW w, cons
     s1 = block_sum(s1, s_dred);
 
     // ---- WeightNet on the staged map ------------------------------------------------------------
-    // each thread owns 4 pooled pixels (a 4x4 input patch each); channels are a runtime loop so the
-    // patches stay in registers and each channel's pooled sum is warp-reduced immediately
-    float in[4][4][4];
+    // each thread owns 4 pooled pixels (a 4x4 input patch each), two per pass: 32 patch registers instead of 64 keep the
+    // kernel at 64 registers = 4 CTAs per SM, so the 3 * J * P = 450 CTAs of a batch-1 frame are ONE wave (592 slots; at 3 per
+    // SM, 444 slots, six CTAs ran alone in a second wave).  Channels are a runtime loop so the patches stay in registers and
+    // each channel's pooled sum is warp-reduced immediately.
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float in[2][4][4];
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp) {
-      const int pix = tid + PT * pp;              // pooled pixel 0..1023
-      const int py = pix >> 5, px = pix & 31;
+      for (int pp = 0; pp < 2; ++pp) {
+        const int pix = tid + PT * (2 * pass + pp);              // pooled pixel 0..1023
+        const int py = pix >> 5, px = pix & 31;
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) in[pp][r][c] = s_map[(2 * py + r) * MS + 2 * px + c];
-    }
-#pragma unroll 2
-    for (int c = 0; c < F; ++c) {
-      float k[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) k[i] = s_cw[c * 9 + i];
-      const float cb = s_cb[c];
-      float v = 0.f;
-#pragma unroll
-      for (int pp = 0; pp < 4; ++pp) {
-        float best = -INFINITY;
-#pragma unroll
-        for (int oy = 0; oy < 2; ++oy)
-#pragma unroll
-          for (int ox = 0; ox < 2; ++ox) {
-            float a = cb;
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int cc = 0; cc < 3; ++cc) a = fmaf(k[r * 3 + cc], in[pp][oy + r][ox + cc], a);
-            best = fmaxf(best, a);
-          }
-        v += fmaxf(best, 0.f);
+          for (int c = 0; c < 4; ++c) in[pp][r][c] = s_map[(2 * py + r) * MS + 2 * px + c];
       }
+#pragma unroll 2
+      for (int c = 0; c < F; ++c) {
+        float k[9];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((tid & 31) == 0) s_gap[tid >> 5][c] = v;
+        for (int i = 0; i < 9; ++i) k[i] = s_cw[c * 9 + i];
+        const float cb = s_cb[c];
+        float v = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          float best = -INFINITY;
+#pragma unroll
+          for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox) {
+              float a = cb;
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) a = fmaf(k[r * 3 + cc], in[pp][oy + r][ox + cc], a);
+              best = fmaxf(best, a);
+            }
+          v += fmaxf(best, 0.f);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) s_gap[tid >> 5][c] = pass ? s_gap[tid >> 5][c] + v : v;
+      }
     }
     __syncthreads();
     if (tid < F) {

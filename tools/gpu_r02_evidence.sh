@@ -16,6 +16,8 @@ stamp "ncu full, back-projection kernels at batch 1"
 timeout 300 ncu --set full --clock-control none -k regex:'k3_jln|k1_hdn|k0_stage' -s 3 -c 3 -f -o gpurun_out/r02_prof_bp_b1 python tools/profile_driver.py 2 1 > gpurun_out/ncu_bp.log 2>&1; tail -1 gpurun_out/ncu_bp.log
 stamp "ncu full + source, TMA-fed 3x3 32->32 at 960 images"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_conv_tc -s 1 -c 1 -f -o gpurun_out/r02_prof_conv_32_tma python tools/conv_ncu.py 960 64 64 32 32 3 4 2>&1 | tail -2
+stamp "ncu full + source, proposal stage (8-CTA cluster per column) at batch 1"
+timeout 300 ncu --set full --clock-control none --import-source on --warp-sampling-interval 0 -k regex:k_proposals_cluster --launch-skip 2 -c 1 -f -o gpurun_out/r02_prof_c2c_cluster python tools/profile_driver.py 4 1 2>&1 | tail -1
 stamp "backbone (N2): 5 views of 960x512"; timeout 300 python tools/backbone_bench.py 50 5 512 960 10 2>&1 | tail -1
 stamp "ncu full, TMA-fed 3x3 64->64 at 960 images"
 timeout 300 ncu --set full --clock-control none -k regex:k_conv_tc -s 1 -c 1 -f -o gpurun_out/r02_prof_conv_64_tma python tools/conv_ncu.py 960 32 32 64 64 3 4 2>&1 | tail -2
