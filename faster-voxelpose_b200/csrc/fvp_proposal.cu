@@ -719,6 +719,7 @@ __device__ __forceinline__ void c2cl_conv(const float* __restrict__ in, int inC,
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[l][q] = 0.f;
     const float4* wg = w4 + (size_t)g * Cin * K;
+#pragma unroll 1
     for (int ci = lane; ci < Cin; ci += 32) {
       float xr[NX];
 #pragma unroll
@@ -740,6 +741,7 @@ __device__ __forceinline__ void c2cl_conv(const float* __restrict__ in, int inC,
     }
     const float4* ws = w4 + (size_t)G * Cin * K;
     if (in2 != nullptr) {
+#pragma unroll 1
       for (int ci = lane; ci < Cin2; ci += 32) {
         const float4 wv = ws[g * Cin2 + ci];
 #pragma unroll
@@ -762,7 +764,7 @@ __device__ __forceinline__ void c2cl_conv(const float* __restrict__ in, int inC,
     __syncwarp();
     float s0 = 0.f, s1 = 0.f;
     if (lane < NV) {
-#pragma unroll
+#pragma unroll 4
       for (int r = 0; r < 32; r += 2) {
         s0 += sc[r * NV + lane];
         s1 += sc[(r + 1) * NV + lane];
