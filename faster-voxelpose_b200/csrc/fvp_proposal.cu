@@ -2,7 +2,9 @@
 //   * nms2D + top-k                       (lib/core/proposal.py:13-33)
 //   * z-column re-sampling (K2)           (replaces the torch.gather on the never-materialised volume,
 //                                          lib/models/human_detection_net.py:92-93)
-//   * C2CNet, whole net in one CTA        (lib/models/cnns_1d.py:10-132)
+//   * C2CNet                              (lib/models/cnns_1d.py:10-132): k_proposals = whole net in one CTA per column
+//                                          (throughput form; Z = 20 / 40 through the weight ring, other Z generic),
+//                                          k_proposals_cluster = one 8-CTA cluster per column (latency form, Z = 20)
 //   * z arg-max, ProposalLayer assembly   (human_detection_net.py:44-65,95-102)
 //   * JLN crop parameters                 (lib/models/project_individual.py:110-121)
 #include "fvp_kernels.h"
