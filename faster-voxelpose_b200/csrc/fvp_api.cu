@@ -82,11 +82,12 @@ int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaSt
   return FVP_OK;
 }
 
-// depth parts per person for K3: enough CTAs for ~3 waves of (3 CTAs/SM) at small batch
+// depth parts per person for K3: enough CTAs for >= 6 waves of 4 CTAs / SM at small batch, so that the last, partly filled
+// wave costs a few per cent (batch 1: 8 parts = 5120 CTAs = 8.6 waves, 0.124 ms; with 4 parts = 4.3 waves it was 0.134 ms)
 int fvp_k3_parts(const fvp_ctx* ctx, int batch) {
   const int base = fvp_k3_patches(ctx->geom.JG) * batch * ctx->geom.P;
   int parts = 1;
-  while (parts < 8 && base * parts < 12 * ctx->num_sms) parts *= 2;   // >= 3 waves of 4 CTAs / SM
+  while (parts < 8 && base * parts < 24 * ctx->num_sms) parts *= 2;
   return parts;
 }
 
