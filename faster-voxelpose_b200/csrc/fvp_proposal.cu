@@ -34,8 +34,9 @@ __global__ void __launch_bounds__(1024) k_nms_topk(const float* __restrict__ hm,
   const int b = blockIdx.x, n = X * Y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   const float* h = hm + (size_t)b * img_stride;
   unsigned* s_keep = reinterpret_cast<unsigned*>(s_nms + n);
-  // The map is staged with independent coalesced loads first: reading the 3x3 neighbourhoods straight from global memory
-  // made every thread wait for ~60 dependent L2 round trips (ncu: 44 K warp instructions in 38 K cycles, 19 us).
+  // The map is staged with independent coalesced loads first; the 3x3 neighbourhoods are then read from shared memory.
+  // (Measured: staging + the one-warp selection below took the stage from 21 to 18 us; the rest is launch latency and the
+  // serial chain of one CTA - ncu 15 us for 49 K warp instructions.)
   for (int i = tid; i < n; i += nthreads) s_nms[i] = h[i];
   __syncthreads();
   for (int i0 = 0; i0 < n; i0 += nthreads) {     // warp-uniform trip count: every lane takes part in the ballot

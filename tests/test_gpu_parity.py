@@ -558,6 +558,8 @@ def test_error_behaviour(built_library, golden):
         eng.forward(hm[:, :2], [0])
     with pytest.raises(RuntimeError):
         eng.load_state_dict({k: v for k, v in list(g.weights.items())[:-1]})
+    with pytest.raises(capi.FvpError):                       # latency mode is -1 (automatic), 0 or 1
+        eng.set_latency_mode(2)
     eng.close()
 
 
