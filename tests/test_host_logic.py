@@ -226,6 +226,25 @@ def test_two_cta_conv_variants_do_not_spill_more_than_measured(built_library):
         assert sass.count("UTMALDG") >= 8 and "UBLKCP" in sass and "UTCHMMA" in sass
 
 
+def test_cluster_proposal_kernel_exchanges_through_distributed_shared_memory(built_library):
+    """k_proposals_cluster (C2CNet on an 8-CTA cluster per column): the layer outputs travel as 16-byte st.async stores
+    (SASS STAS.128) onto per-layer mbarriers, the weight slices arrive by bulk copies (UBLKCP), and the only cluster barriers
+    are the one after the mbarrier initialisation and the one before exit - none inside the layer loop."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "k_proposals_cluster", built_library], capture_output=True, text=True).stdout
+    if "STAS" not in sass:                      # older cuobjdump: -fun wants the mangled name; fall back to the whole file
+        full = subprocess.run(["cuobjdump", "-sass", built_library], capture_output=True, text=True).stdout
+        start = full.index("k_proposals_cluster")
+        nxt = full.find("Function :", start)
+        sass = full[start:nxt if nxt > 0 else len(full)]
+    assert sass.count("STAS.128") >= 19 and "STAS.64" in sass          # every layer sends vectors; the first layer 8-byte pairs
+    assert sass.count("UBLKCP") >= 1
+    assert sass.count("UCGABAR_ARV") == 2 and sass.count("UCGABAR_WAIT") == 2
+
+
 # ---- reference-facing module -----------------------------------------------------------------------
 def test_model_has_reference_state_dict_and_no_cpu_path(built_library, golden):
     import models
