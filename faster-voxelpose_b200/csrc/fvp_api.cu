@@ -85,7 +85,7 @@ int upload_frame_seq(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, cudaSt
 // depth parts per person for K3: enough CTAs for >= 6 waves of 4 CTAs / SM at small batch, so that the last, partly filled
 // wave costs a few per cent (batch 1: 8 parts = 5120 CTAs = 8.6 waves, 0.124 ms; with 4 parts = 4.3 waves it was 0.134 ms)
 int fvp_k3_parts(const fvp_ctx* ctx, int batch) {
-  const int base = fvp_k3_patches(ctx->geom.JG, ctx->k3_pair) * batch * ctx->geom.P;
+  const int base = fvp_k3_patches(ctx->geom.JG) * batch * ctx->geom.P;
   int parts = 1;
   while (parts < 8 && base * parts < 24 * ctx->num_sms) parts *= 2;
   return parts;
@@ -101,14 +101,7 @@ cudaError_t alloc_workspaces(fvp_ctx* ctx) {
   bool ok = true;
   auto A = [&](cudaError_t r) { if (r != cudaSuccess && ok) { ok = false; e = r; } };
   A(dalloc(&ctx->d_hm_in, (size_t)MB * g.V * g.J * P.H * P.W));
-  // staged heat maps; the pair form of K3 reads a second copy shifted by half a 128-byte line (4 float4), see k3_jln_pair
-  const size_t hm_cl4 = (size_t)MB * g.V * g.view_stride4;
-  ctx->hm_dup4 = 0;
-  if (g.JG != 4) ctx->k3_pair = 0;
-  if ((ctx->k3_pair & 3) == 1 && P.WP % 2 == 0 && (2 * hm_cl4 + 16) * 16 < ((size_t)1 << 32))
-    ctx->hm_dup4 = (hm_cl4 + 7) / 8 * 8 + 4;
-  const size_t hm_cl_total4 = ctx->hm_dup4 ? ctx->hm_dup4 + hm_cl4 : hm_cl4;
-  A(dalloc(&ctx->d_hm_cl, hm_cl_total4 * 4));
+  A(dalloc(&ctx->d_hm_cl, (size_t)MB * g.V * g.view_stride4 * 4));
   A(dalloc(&ctx->d_plane_cl, (size_t)MB * XY * JP));
   A(dalloc(&ctx->d_hmsize, (size_t)MB * 3 * XY));
   A(dalloc(&ctx->d_conf2d, (size_t)n));
@@ -145,7 +138,7 @@ cudaError_t alloc_workspaces(fvp_ctx* ctx) {
     A(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
   }
   if (ok) {
-    A(cudaMemset(ctx->d_hm_cl, 0, hm_cl_total4 * 16));                        // zero borders (never written again)
+    A(cudaMemset(ctx->d_hm_cl, 0, (size_t)MB * g.V * g.view_stride4 * 16));   // zero borders (never written again)
     A(cudaMemset(ctx->d_people, 0, (size_t)n * sizeof(FvpPerson)));
     A(cudaMemset(ctx->d_img_valid, 0, (size_t)3 * n * sizeof(int)));
     A(cudaMemset(ctx->d_feat, 0, (size_t)3 * n * g.J * 4096 * sizeof(float)));
@@ -251,8 +244,7 @@ int run_pipeline(fvp_ctx* ctx, int batch, float* d_fused_poses, float* d_plane_p
     fvp_launch_proposals(a, ctx->w_c2c, n, prefer_latency(ctx), st); ++*launches;
   }
   T.mark(5);
-  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->k3_pair, ctx->hm_dup4, ctx->d_people, ctx->d_planes_cl, batch,
-                         fvp_k3_parts(ctx, batch), st);
+  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, batch, fvp_k3_parts(ctx, batch), st);
   ++*launches;                                   // (+ one memset node)
   T.mark(6);
   fvp_run_trunk2d(ctx->w_p2p, ctx->d_planes_cl, g.proj.JP, 3 * n, 64, 64, ctx->p2p_buf, ctx->d_img_valid, false,
@@ -346,7 +338,6 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out) {
   ctx->device = device;
   ctx->h_status = h_status;
   if (const char* sa = std::getenv("FVP_SPLIT_ACT")) ctx->split_activations = std::atoi(sa) != 0;   // A/B switch (tools only)
-  if (const char* kp = std::getenv("FVP_K3_PAIR")) ctx->k3_pair = std::atoi(kp);                    // A/B switch (tools only)
   fvp_build_param_table(ctx);
 
   FvpGeom& g = ctx->geom;
@@ -445,7 +436,6 @@ int fvp_create_lane(fvp_ctx* root, int max_batch, fvp_ctx** out) {
   ctx->num_sms = root->num_sms;
   ctx->conv_mode = root->conv_mode;
   ctx->split_activations = root->split_activations;
-  ctx->k3_pair = root->k3_pair;
   ctx->root = root;
   ctx->shared_gen = -1;                            // mirrors nothing yet: the first forward copies the root's tables
   ctx->geom = root->geom;
@@ -681,7 +671,7 @@ static int forward_device(fvp_ctx* ctx, const float* d_heatmaps, int batch, cons
   int launches = 0;
   StageTimer T{ctx, st};
   T.mark(0);
-  fvp_launch_stage_heatmaps(g, d_heatmaps, ctx->d_hm_cl, ctx->hm_dup4, batch, st); ++launches;
+  fvp_launch_stage_heatmaps(g, d_heatmaps, ctx->d_hm_cl, batch, st); ++launches;
   if (ctx->k0_done) FVP_CUDA_OK(cudaEventRecord(ctx->k0_done, st));   // the input buffer is free again
 
   // Stream capture is illegal on the legacy default stream: in graph mode run on the context's own
@@ -833,7 +823,7 @@ int fvp_stage_heatmaps(fvp_ctx* ctx, const float* d_heatmaps, int batch, uintptr
   int rc = check_stage_entry(ctx, batch);
   if (rc != FVP_OK) return rc;
   cudaSetDevice(ctx->device);
-  fvp_launch_stage_heatmaps(ctx->geom, d_heatmaps, ctx->d_hm_cl, ctx->hm_dup4, batch, (cudaStream_t)stream);
+  fvp_launch_stage_heatmaps(ctx->geom, d_heatmaps, ctx->d_hm_cl, batch, (cudaStream_t)stream);
   FVP_CUDA_OK(cudaGetLastError());
   return FVP_OK;
 }
@@ -956,8 +946,7 @@ int fvp_jln_project(fvp_ctx* ctx, int batch, const int32_t* h_seq_slots, const f
   FvpPropArgs a = prop_args(ctx);
   a.people = ctx->d_people; a.img_valid = ctx->d_img_valid; a.n_slots = n;
   fvp_launch_people_from_centers(a, d_centers, n, st);
-  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->k3_pair, ctx->hm_dup4, ctx->d_people, ctx->d_planes_cl, batch,
-                         fvp_k3_parts(ctx, batch), st);
+  fvp_launch_jln_project(g, ctx->d_hm_cl, ctx->d_people, ctx->d_planes_cl, batch, fvp_k3_parts(ctx, batch), st);
   if (d_planes) fvp_launch_nhwc_to_nchw(ctx->d_planes_cl, d_planes, 3 * n, 4096, g.proj.JP, g.J, st);
   if (d_offset) {
     FVP_CUDA_OK(cudaMemcpy2DAsync(d_offset, 3 * sizeof(float), (const char*)ctx->d_people + offsetof(FvpPerson, offset),

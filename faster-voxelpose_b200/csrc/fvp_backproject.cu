@@ -28,7 +28,7 @@
 template <int JG>
 __global__ void __launch_bounds__(256) k0_stage_heatmaps(const float* __restrict__ hm, float4* __restrict__ out,
                                                           int J, int H, int W, int WP, int PADX, int PADY,
-                                                          size_t view_stride4, size_t dup4) {
+                                                          size_t view_stride4) {
   const int bv = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   if (pix >= H * W) return;
@@ -40,22 +40,15 @@ __global__ void __launch_bounds__(256) k0_stage_heatmaps(const float* __restrict
   float4* dst = out + (size_t)bv * view_stride4 + ((size_t)(y + PADY) * WP + (x + PADX)) * JG;
 #pragma unroll
   for (int g = 0; g < JG; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-  // second, half-a-line-shifted copy for the pair kernel of K3 (dup4 = float4 distance between the copies, 0 = none):
-  // in it the records of the ODD pixels start a 128-byte line, so every west/east pair of a footprint is one line in
-  // one of the two copies
-  if (dup4) {
-#pragma unroll
-    for (int g = 0; g < JG; ++g) dst[dup4 + g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-  }
 }
 
-void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_cl, size_t dup4, int batch, cudaStream_t st) {
+void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_cl, int batch, cudaStream_t st) {
   const FvpProj& P = g.proj;
   dim3 grid(fvp_cdiv(P.H * P.W, 256), batch * g.V);
   if (g.JG == 4)
-    k0_stage_heatmaps<4><<<grid, 256, 0, st>>>(d_hm, (float4*)d_hm_cl, g.J, P.H, P.W, P.WP, P.PADX, P.PADY, g.view_stride4, dup4);
+    k0_stage_heatmaps<4><<<grid, 256, 0, st>>>(d_hm, (float4*)d_hm_cl, g.J, P.H, P.W, P.WP, P.PADX, P.PADY, g.view_stride4);
   else
-    k0_stage_heatmaps<5><<<grid, 256, 0, st>>>(d_hm, (float4*)d_hm_cl, g.J, P.H, P.W, P.WP, P.PADX, P.PADY, g.view_stride4, 0);
+    k0_stage_heatmaps<5><<<grid, 256, 0, st>>>(d_hm, (float4*)d_hm_cl, g.J, P.H, P.W, P.WP, P.PADX, P.PADY, g.view_stride4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,168 +331,14 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3, pair form (JG == 4 only: 64-byte records, Panoptic's 15 joints).  The patch kernel above spends one L1 line
-// wavefront per TAP: a record is half a 128-byte line and the west and east taps of a footprint row are two load
-// instructions.  Here EIGHT lanes own a voxel column - lane s = (east << 2) | channel group - and load the 128
-// contiguous bytes of the (west, east) record pair of a footprint row with ONE instruction: 2 line wavefronts per
-// voxel-view instead of 4 when the pair starts a line.  K0 keeps a second copy of the staged heat maps shifted by half
-// a line (dup4 float4 further on), so that the pair of an odd west pixel starts a line there; each lane group picks the
-// copy by the parity of its west pixel.  Each half of the group (4 lanes) looks up 4 depths of the column redundantly
-// and pre-selects ITS x weights, so a depth costs 3 shuffles (offset, north weight, south weight) inside the half.
-// West and east partial sums are accumulated separately over the views and added once per depth (one xor-shuffle per
-// component) - a different summation order from the tap-by-tap chain of the patch kernel, within the plane tolerance
-// (1e-6, tests/test_gpu_parity.py).  A warp is 4 columns b, the CTA 8 rows a x 4 columns: 128 patches per person.
-// ------------------------------------------------------------------------------------------------
-struct FvpPairRegs {
-  int off;
-  float4 n, s;
-};
-__device__ __forceinline__ void fvp_pair_accumulate_vote(float4& acc, FvpPairRegs& tr, const float4* __restrict__ base,
-                                                         int off, int row_stride4, float wn, float ws) {
-  if (__any_sync(0xffffffffu, off != tr.off)) {
-    const unsigned o0 = (unsigned)off << 4, o2 = o0 + ((unsigned)row_stride4 << 4);
-    tr.n = fvp_ldg_at(base, o0);
-    tr.s = fvp_ldg_at(base, o2);
-  }
-  tr.off = off;
-  const float4 n = tr.n, s = tr.s;
-  acc.x = fmaf(s.x, ws, fmaf(n.x, wn, acc.x));
-  acc.y = fmaf(s.y, ws, fmaf(n.y, wn, acc.y));
-  acc.z = fmaf(s.z, ws, fmaf(n.z, wn, acc.z));
-  acc.w = fmaf(s.w, ws, fmaf(n.w, wn, acc.w));
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB)
-k3_jln_pair(FvpGeom g, const float4* __restrict__ hm_cl, int dup4, const FvpPerson* __restrict__ people,
-            float4* __restrict__ planes_cl, int n_people, int ncpart) {
-  constexpr int JG = 4;                          // channel groups (this kernel exists for 64-byte records only)
-  constexpr int BPW = 4;                         // cube columns b per warp
-  constexpr int NBB = 64 / BPW;                  // b-blocks per cube
-  constexpr int NAB = 8;                         // a-blocks per cube (8 rows each, one row per warp)
-  constexpr int CCH = 4;                         // depths per chunk: one lookup round of a half group
-  __shared__ float4 s_yz[2][CCH][8][BPW * JG];   // [buffer][depth][warp = row][(b, channel group)]
-
-  const int person = blockIdx.y;
-  const int patch = blockIdx.x % (NAB * NBB), cpart = blockIdx.x / (NAB * NBB);
-  const int ablk = patch / NBB, bblk = patch - ablk * NBB;
-  const int c_begin = cpart * (64 / ncpart), c_end = c_begin + 64 / ncpart;
-  const FvpPerson pd = people[person];
-  const FvpProj& P = g.proj;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = lane & 7;                        // float4 of the 128-byte record pair this lane loads
-  const int half = s & 4, cg = s & 3;            // east flag (as a lane offset), channel group
-  const int half_base = lane - cg;               // first lane of my half group
-  const int a = ablk * 8 + warp;                 // cube row, warp-uniform
-  const int b = bblk * BPW + (lane >> 3);        // cube column
-  const size_t img4 = (size_t)64 * 64 * JG;
-  float4* xy_img = planes_cl + ((size_t)0 * n_people + person) * img4;
-  float4* xz_img = planes_cl + ((size_t)1 * n_people + person) * img4;
-  float4* yz_img = planes_cl + ((size_t)2 * n_people + person) * img4;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  const bool live = pd.valid && !pd.empty;
-  const bool any = live && max(ablk * 8, pd.lo[0]) < min(ablk * 8 + 8, pd.hi[0]) &&
-                   max(bblk * BPW, pd.lo[1]) < min(bblk * BPW + BPW, pd.hi[1]) &&
-                   max(c_begin, pd.lo[2]) < min(c_end, pd.hi[2]);
-  if (!any) return;                              // nothing to sample in this patch: the planes are already zero
-
-  const bool a_ok = a >= pd.lo[0] && a < pd.hi[0];           // warp-uniform
-  const bool b_ok = b >= pd.lo[1] && b < pd.hi[1];
-  const int F1 = g.fine[1], F2 = g.fine[2], nfine = g.fine[0] * F1 * F2;
-  const float2* grid_s = g.fine_grid + (size_t)pd.seq * nfine * g.V;
-  const int col = ((pd.tl[0] + a) * F1 + pd.tl[1] + b) * F2 + pd.tl[2];     // + view * nfine + c
-  const int V = g.V;
-  const float fV = (float)V, rV = 1.0f / fV;
-  const int row4 = P.WP * JG;
-  const int vs4 = (int)g.view_stride4, frame_off = (person / g.P) * V * vs4;
-  const bool sample_ok = b_ok && a_ok;
-
-  float4 xy_m = zero4;
-  int it = 0;
-  for (int cc = c_begin; cc < c_end; cc += CCH, ++it) {
-    float4 acc[CCH];
-#pragma unroll
-    for (int c = 0; c < CCH; ++c) acc[c] = zero4;
-    // every branch of the sampling loop is a vote (warp-uniform), as in the patch kernel
-    const bool row_live = __any_sync(0xffffffffu, a_ok && max(cc, pd.lo[2]) < min(cc + CCH, pd.hi[2]));
-    if (row_live) {
-      const int cz = cc + cg;                    // the depth this lane looks up (both halves look up the same four)
-      const bool q_ok = b_ok && cz >= pd.lo[2] && cz < pd.hi[2];
-      float2 q_next = make_float2(0.f, 0.f);
-      if (q_ok) q_next = __ldg(grid_s + col + cz);
-      for (int v = 0; v < V; ++v) {
-        FvpPairRegs tr;
-        tr.off = -1;
-        tr.n = tr.s = zero4;
-        const float2 q = q_next;
-        if (q_ok && v + 1 < V) q_next = __ldg(grid_s + (size_t)(v + 1) * nfine + col + cz);
-        const FvpTaps t = fvp_taps(P, q.x, q.y);
-        int my_off = t.off + frame_off + v * vs4;            // float4 index of the west record (a multiple of 4)
-        my_off += ((my_off >> 2) & 1) * dup4;                // odd west pixel: the pair is line-aligned in the second copy
-        const float my_wn = half ? t.w01 : t.w00, my_ws = half ? t.w11 : t.w10;
-#pragma unroll
-        for (int k = 0; k < CCH; ++k) {
-          const int off = __shfl_sync(0xffffffffu, my_off, half_base + k);
-          const float wn = __shfl_sync(0xffffffffu, my_wn, half_base + k);
-          const float ws = __shfl_sync(0xffffffffu, my_ws, half_base + k);
-          if (__any_sync(0xffffffffu, (cc + k) >= pd.lo[2] && (cc + k) < pd.hi[2]))
-            fvp_pair_accumulate_vote(acc[k], tr, hm_cl, off + s, row4, wn, ws);
-        }
-      }
-    }
-    float4(*yzb)[8][BPW * JG] = s_yz[it & 1];
-#pragma unroll
-    for (int c = 0; c < CCH; ++c) {
-      // west + east partial sums: a + b == b + a, so both halves of the group hold the same total
-      float4 tot = acc[c];
-      tot.x += __shfl_xor_sync(0xffffffffu, tot.x, 4);
-      tot.y += __shfl_xor_sync(0xffffffffu, tot.y, 4);
-      tot.z += __shfl_xor_sync(0xffffffffu, tot.z, 4);
-      tot.w += __shfl_xor_sync(0xffffffffu, tot.w, 4);
-      const bool c_in = (cc + c) >= pd.lo[2] && (cc + c) < pd.hi[2];
-      const float4 val = (sample_ok && c_in) ? fvp_mean_clamp4(tot, fV, rV) : zero4;      // outside the crop: 0
-      xy_m = fvp_max4(xy_m, val);
-      if (!half) yzb[c][warp][(lane >> 3) * JG + cg] = val;
-    }
-    __syncthreads();
-    // yz[b][cc + c] = max over the 8 rows (64 outputs), xz[a][cc + c] = max over the 4 columns (128 outputs): one pass
-    constexpr int N_YZ = CCH * BPW * JG, N_XZ = 8 * CCH * JG;
-    if (tid < N_YZ) {
-      const int c = tid >> 4, l = tid & 15;
-      float4 m = yzb[c][0][l];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) m = fvp_max4(m, yzb[c][w][l]);
-      fvp_red_max4(yz_img + ((size_t)(bblk * BPW + (l >> 2)) * 64 + cc + c) * JG + (l & 3), m);
-    } else if (tid < N_YZ + N_XZ) {
-      const int x = tid - N_YZ, ss = x & 3, c = (x >> 2) & 3, w = x >> 4;
-      float4 m = yzb[c][w][ss];
-#pragma unroll
-      for (int i = 1; i < BPW; ++i) m = fvp_max4(m, yzb[c][w][i * JG + ss]);
-      fvp_red_max4(xz_img + ((size_t)(ablk * 8 + w) * 64 + cc + c) * JG + ss, m);
-    }
-    // two buffers: the stores of chunk it + 1 go to the other image, and a thread reaches the stores of chunk it + 2
-    // only after the barrier of chunk it + 1, which every reader of chunk it has passed its reads to arrive at
-  }
-  if (!half) {
-    if (ncpart == 1) xy_img[((size_t)a * 64 + b) * JG + cg] = xy_m;          // complete: plain store
-    else fvp_red_max4(xy_img + ((size_t)a * 64 + b) * JG + cg, xy_m);         // partial over the depth parts
-  }
-}
-
-void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, int pair, size_t dup4, const FvpPerson* d_people,
-                            float* d_planes_cl, int batch, int ncpart, cudaStream_t st) {
+void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
+                            int batch, int ncpart, cudaStream_t st) {
   const int n_people = batch * g.P;
   const int img4 = 64 * 64 * g.JG;
   // partial maxima are RED-folded into the planes, which therefore start from zero
   cudaMemsetAsync(d_planes_cl, 0, (size_t)3 * n_people * img4 * sizeof(float4), st);
-  dim3 grid(fvp_k3_patches(g.JG, pair) * ncpart, n_people);
-  if (pair && g.JG == 4 && (pair & 4))          // A/B: 5 CTAs per SM (48 registers)
-    k3_jln_pair<5><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, (int)dup4, d_people, (float4*)d_planes_cl, n_people, ncpart);
-  else if (pair && g.JG == 4)
-    k3_jln_pair<4><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, (int)dup4, d_people, (float4*)d_planes_cl, n_people, ncpart);
-  else if (g.JG == 4)
+  dim3 grid(fvp_k3_patches(g.JG) * ncpart, n_people);
+  if (g.JG == 4)
     k3_jln_patch<4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
   else if (g.JG < 4)
     k3_jln_patch<4, 4, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);

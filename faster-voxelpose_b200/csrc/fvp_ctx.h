@@ -80,8 +80,6 @@ struct fvp_ctx {
   int conv_mode = 2;                  // 0 = fp32 CUDA cores, 1 = tcgen05 3xTF32 (7x7 on CUDA cores), 2 = tcgen05 fp16 split
   int latency_mode = -1;              // fvp_set_latency_mode: -1 auto (on when the context has no lanes), 0 off, 1 on
   int launch_error = 0;               // set by a conv launcher that could not prepare its launch (FvpLaunchEnv::error)
-  int k3_pair = 0;                    // K3 pair form (JG == 4): 0 off, 1 with the shifted second heat-map copy, 2 without it; +4 = 5 CTAs per SM (A/B)
-  size_t hm_dup4 = 0;                 // float4 distance from d_hm_cl to its half-a-line-shifted second copy (0 = none)
   int split_activations = 1;          // engine 2: split (fp16 hi / lo) activations between layers, TMA-fed convolutions
   int fp16_fallback_layers = 0;       // conv layers packed without an fp16 image (weights outside the fp16 range)
   int* h_status = nullptr;            // range-guard word of this device (mapped pinned host memory, owned by fvp_api.cu)

@@ -22,8 +22,7 @@ struct FvpGeom {
 };
 
 // K0: [B][V][J][H][W] -> channel-last, zero-bordered [B][V][HP][WP][JP]
-// dup4 != 0: also write the half-a-line-shifted second copy dup4 float4 further on (pair form of K3)
-void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_cl, size_t dup4, int batch, cudaStream_t st);
+void fvp_launch_stage_heatmaps(const FvpGeom& g, const float* d_hm, float* d_hm_cl, int batch, cudaStream_t st);
 
 // (re)build both sample grids of calibration slot `slot`
 void fvp_launch_build_sample_grids(const FvpGeom& g, int slot, cudaStream_t st);
@@ -41,11 +40,9 @@ void fvp_launch_nchw_to_nhwc(const float* d_in, float* d_out, int n, int hw, int
 
 // K3: per-person back-projection + three-plane max -> planes_cl [3][B*P][64][64][JP] (zeroed, then RED.MAX-folded).
 // A person is 64 (JG <= 4) or 128 column patches, times ncpart depth parts (1, 2, 4 or 8) - one CTA each.
-// pair != 0 (JG == 4 only): the pair form - 8 lanes per column, 128 patches, west/east records in one load (dup4 = float4
-// distance of the shifted second heat-map copy, 0 = none).
-static inline int fvp_k3_patches(int JG, int pair) { return (JG <= 4 && !(pair && JG == 4)) ? 64 : 128; }
-void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, int pair, size_t dup4, const FvpPerson* d_people,
-                            float* d_planes_cl, int batch, int ncpart, cudaStream_t st);
+static inline int fvp_k3_patches(int JG) { return JG <= 4 ? 64 : 128; }
+void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPerson* d_people, float* d_planes_cl,
+                            int batch, int ncpart, cudaStream_t st);
 
 // N1 heat-map renderer (JointsDataset.generate_input_heatmap): joints [views][max_people][J][2] float64 in IMAGE_SIZE pixels,
 // num [views], vis [views][max_people][J] or NULL -> out [views][J][H][W]; d_patches = fvp_render_patch_bytes(...) bytes
