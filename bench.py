@@ -274,7 +274,9 @@ def main():
     from fvp.engine import EngineLanes
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    my_cores = fdist.pin_rank_to_cores(local, local_world) if world > 1 else []
+    # ranks pin themselves to physical cores of their GPU's NUMA node BEFORE any pinned buffer is allocated (first touch)
+    gpu_nodes = fdist.local_gpu_numa_nodes(local_world) if world > 1 else []
+    my_cores = fdist.pin_rank_to_cores(local, local_world, gpu_nodes) if world > 1 else []
     if world > 1:
         fdist.init_from_env("nccl")
     B = args.batch
@@ -624,7 +626,7 @@ def main():
             "per_shard_frames": S * B, "count_in_timed_region": len(coll_ms),
             "ms_mean": float(np.mean(coll_ms)) if coll_ms else None, "ms_max": float(np.max(coll_ms)) if coll_ms else None,
             "ms_per_step_amortised": float(np.sum(coll_ms) / max(1, reps * args.steps)) if coll_ms else None,
-            "cores_of_rank0": len(my_cores)},
+            "cores_of_rank0": len(my_cores), "gpu_numa_nodes": gpu_nodes},
     }
     if gpu_port and "value" in gpu_port:
         line["vs_gpu_reference_port"] = {"pipelined": fps / gpu_port["value"], "serial": (B / (serial_ms * 1e-3)) / gpu_port["value"]}

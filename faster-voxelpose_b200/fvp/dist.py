@@ -7,7 +7,7 @@ the final ``fused_poses`` rows ([B/R,P,J,5] fp32, 3 KB per frame) - the multi-GP
 from __future__ import annotations
 
 import os
-from typing import Callable, List, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -67,18 +67,115 @@ def gather_frames(local_rows: torch.Tensor, num_frames: int, rank: int, world: i
     return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 
-def pin_rank_to_cores(local_rank: int, local_world: int) -> list:
-    """Give every rank of a node its own block of host cores (8 ranks x 7 pinned-copy pipelines otherwise migrate over
-    all cores and contend).  Returns the cores this process may now run on ([] when affinity is not available)."""
+def _parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' (sysfs cpulist format) -> [0, 1, 2, 3, 8, 10, 11]."""
+    out: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.extend(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def _read(path: str) -> Optional[str]:
+    try:
+        with open(path) as f:
+            return f.read()
+    except OSError:
+        return None
+
+
+def gpu_numa_node(pci_bus_id: str, sysfs: str = "/sys") -> Optional[int]:
+    """NUMA node the GPU at ``pci_bus_id`` ('0000:1b:00.0') hangs off, None when the kernel does not say (-1, no file)."""
+    txt = _read(os.path.join(sysfs, "bus/pci/devices", pci_bus_id.lower(), "numa_node"))
+    try:
+        node = int(txt) if txt is not None else -1
+    except ValueError:
+        node = -1
+    return node if node >= 0 else None
+
+
+def local_gpu_numa_nodes(local_world: int, sysfs: str = "/sys") -> List[Optional[int]]:
+    """NUMA node of cuda:0 .. cuda:local_world-1 (local rank i drives cuda:i), None where unknown."""
+    nodes: List[Optional[int]] = []
+    for i in range(local_world):
+        try:
+            p = torch.cuda.get_device_properties(i)
+            nodes.append(gpu_numa_node("%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id), sysfs))
+        except Exception:       # no such device / attributes missing: unknown
+            nodes.append(None)
+    return nodes
+
+
+def _physical_cores(cpus: Sequence[int], sysfs: str) -> List[List[int]]:
+    """Group logical CPUs into physical cores (hyper-thread siblings stay together), ordered by lowest CPU id."""
+    allowed, seen, cores = set(cpus), set(), []
+    for c in sorted(allowed):
+        if c in seen:
+            continue
+        txt = _read(os.path.join(sysfs, "devices/system/cpu/cpu%d/topology/thread_siblings_list" % c))
+        sib = [x for x in (_parse_cpulist(txt) if txt else [c]) if x in allowed] or [c]
+        if c not in sib:
+            sib.append(c)
+        seen.update(sib)
+        cores.append(sorted(sib))
+    return cores
+
+
+def plan_rank_cores(allowed: Sequence[int], local_world: int, rank_nodes: Sequence[Optional[int]],
+                    sysfs: str = "/sys") -> List[List[int]]:
+    """Disjoint host-core sets for the ``local_world`` ranks of a node, whole physical cores each.
+
+    NUMA-aware when every rank's GPU node is known and owns at least half an even share of ``allowed`` per rank: the ranks of
+    a node share that node's cores, so a rank's pinned staging buffers (first touch) and its copy threads sit next to
+    the PCIe root of its GPU - H2D traffic does not cross the socket interconnect.  Otherwise an even split of all
+    allowed cores in rank order.  Returns [] per rank when there are fewer physical cores than ranks."""
+    def split(cores: List[List[int]], n: int) -> List[List[int]]:
+        per = len(cores) // n
+        return [sorted(c for core in cores[i * per:(i + 1) * per] for c in core) for i in range(n)]
+
+    phys = _physical_cores(allowed, sysfs)
+    if local_world < 1 or len(phys) < local_world:
+        return [[] for _ in range(max(0, local_world))]
+    min_share = max(1, len(phys) // local_world // 2)       # a rank never gets less than half the even share
+    if len(rank_nodes) == local_world and all(n is not None for n in rank_nodes):
+        plan: List[Optional[List[int]]] = [None] * local_world
+        ok = True
+        for node in sorted(set(rank_nodes)):
+            ranks = [r for r in range(local_world) if rank_nodes[r] == node]
+            txt = _read(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node))
+            node_cpus = set(_parse_cpulist(txt)) if txt else set()
+            cores = [core for core in phys if core[0] in node_cpus]
+            if len(cores) // len(ranks) < min_share:        # e.g. a cpuset that leaves one socket a handful of cores
+                ok = False
+                break
+            for r, mine in zip(ranks, split(cores, len(ranks))):
+                plan[r] = mine
+        if ok:
+            return [p or [] for p in plan]
+    return split(phys, local_world)
+
+
+def pin_rank_to_cores(local_rank: int, local_world: int, rank_nodes: Optional[Sequence[Optional[int]]] = None,
+                      sysfs: str = "/sys") -> list:
+    """Give every rank of a node its own block of host cores, next to its GPU when the topology is known
+    (:func:`plan_rank_cores`; 8 ranks x 7 pinned-copy pipelines otherwise migrate over all cores, contend, and their
+    pinned buffers land on whichever socket the process started on).  Call it BEFORE allocating pinned memory.
+    ``rank_nodes``: NUMA node of every local rank's GPU (default: asked from the driver / sysfs when CUDA is available).
+    Returns the cores this process may now run on ([] when affinity is not available)."""
     try:
         cores = sorted(os.sched_getaffinity(0))
-        per = len(cores) // max(1, local_world)
-        if local_world > 1 and per >= 2:
-            mine = cores[local_rank * per:(local_rank + 1) * per]
+        if local_world <= 1:
+            return cores
+        if rank_nodes is None:
+            rank_nodes = local_gpu_numa_nodes(local_world, sysfs) if torch.cuda.is_available() else [None] * local_world
+        mine = plan_rank_cores(cores, local_world, rank_nodes, sysfs)[local_rank]
+        if len(mine) >= 1 and len(cores) // local_world >= 2:
             os.sched_setaffinity(0, mine)
             return mine
         return cores
-    except (AttributeError, OSError):
+    except (AttributeError, OSError, IndexError):
         return []
 
 

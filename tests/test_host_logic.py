@@ -355,3 +355,52 @@ def test_frame_sharded_gather_world2_gloo(tmp_path, nframes):
                         "--master-addr", "127.0.0.1", "--master-port", str(29700 + nframes), str(script), PKG,
                         str(nframes)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "GATHER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _fake_sysfs(root, node_cpus, siblings, gpus):
+    """node_cpus {node: 'cpulist'}, siblings {cpu: 'cpulist'}, gpus {pci id: node} -> a sysfs-shaped tree under root."""
+    for node, cl in node_cpus.items():
+        d = root / "devices/system/node" / ("node%d" % node)
+        d.mkdir(parents=True)
+        (d / "cpulist").write_text(cl + "\n")
+    for cpu, cl in siblings.items():
+        d = root / "devices/system/cpu" / ("cpu%d" % cpu) / "topology"
+        d.mkdir(parents=True)
+        (d / "thread_siblings_list").write_text(cl + "\n")
+    for pci, node in gpus.items():
+        d = root / "bus/pci/devices" / pci
+        d.mkdir(parents=True)
+        (d / "numa_node").write_text("%d\n" % node)
+    return str(root)
+
+
+def test_rank_core_plan_is_numa_aware_and_keeps_hyperthreads_together(tmp_path):
+    """Two sockets of 8 physical cores with hyper-threads numbered after the first threads (0-7,16-23 | 8-15,24-31), eight
+    GPUs, four per socket: every rank gets two whole physical cores of its GPU's socket; unknown topology, a lopsided
+    cpuset or too few cores fall back to the even split / no pinning."""
+    from fvp import dist as fdist
+    sib = {c: "%d,%d" % (c % 16, c % 16 + 16) for c in range(32)}
+    gpus = {"0000:%02x:00.0" % (0x10 + i): (0 if i < 4 else 1) for i in range(8)}
+    sysfs = _fake_sysfs(tmp_path, {0: "0-7,16-23", 1: "8-15,24-31"}, sib, gpus)
+    assert fdist._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert fdist.gpu_numa_node("0000:14:00.0", sysfs) == 1 and fdist.gpu_numa_node("0000:99:00.0", sysfs) is None
+    nodes = [0, 0, 0, 0, 1, 1, 1, 1]
+    plan = fdist.plan_rank_cores(list(range(32)), 8, nodes, sysfs)
+    assert plan[0] == [0, 1, 16, 17] and plan[3] == [6, 7, 22, 23] and plan[4] == [8, 9, 24, 25] and plan[7] == [14, 15, 30, 31]
+    flat = [c for p in plan for c in p]
+    assert sorted(flat) == list(range(32))                                   # disjoint, complete
+    # GPUs enumerated socket 1 first: the plan follows the GPUs, not the rank order
+    plan = fdist.plan_rank_cores(list(range(32)), 8, nodes[::-1], sysfs)
+    assert plan[0] == [8, 9, 24, 25] and plan[7] == [6, 7, 22, 23]
+    # unknown node of one GPU -> even split of physical cores in rank order (siblings still together)
+    plan = fdist.plan_rank_cores(list(range(32)), 8, [0, 0, 0, None, 1, 1, 1, 1], sysfs)
+    assert plan[0] == [0, 1, 16, 17] and plan[4] == [8, 9, 24, 25]
+    # a cpuset that leaves socket 1 two cores for four ranks -> even split over everything allowed
+    allowed = list(range(8)) + [8, 9] + list(range(16, 24)) + [24, 25]
+    plan = fdist.plan_rank_cores(allowed, 8, nodes, sysfs)
+    assert plan[0] == [0, 16] and plan[7] == [7, 23]                         # 10 physical cores // 8 ranks = 1 core each
+    assert len({c for p in plan for c in p}) == sum(len(p) for p in plan) and {c for p in plan for c in p} <= set(allowed)
+    # fewer physical cores than ranks -> nobody is pinned
+    assert fdist.plan_rank_cores([0, 16], 2, [0, 0], sysfs) == [[], []]
+    # no topology files at all (a bare container): every CPU is its own core, even split
+    assert fdist.plan_rank_cores(list(range(8)), 2, [None, None], str(tmp_path / "nothing")) == [[0, 1, 2, 3], [4, 5, 6, 7]]
