@@ -127,7 +127,7 @@ def plan_rank_cores(allowed: Sequence[int], local_world: int, rank_nodes: Sequen
                     sysfs: str = "/sys") -> List[List[int]]:
     """Disjoint host-core sets for the ``local_world`` ranks of a node, whole physical cores each.
 
-    NUMA-aware when every rank's GPU node is known and owns at least half an even share of ``allowed`` per rank: the ranks of
+    NUMA-aware when every rank's GPU node is known and owns at least 3/4 of an even share of ``allowed`` per rank: the ranks of
     a node share that node's cores, so a rank's pinned staging buffers (first touch) and its copy threads sit next to
     the PCIe root of its GPU - H2D traffic does not cross the socket interconnect.  Otherwise an even split of all
     allowed cores in rank order.  Returns [] per rank when there are fewer physical cores than ranks."""
@@ -138,7 +138,7 @@ def plan_rank_cores(allowed: Sequence[int], local_world: int, rank_nodes: Sequen
     phys = _physical_cores(allowed, sysfs)
     if local_world < 1 or len(phys) < local_world:
         return [[] for _ in range(max(0, local_world))]
-    min_share = max(1, len(phys) // local_world // 2)       # a rank never gets less than half the even share
+    min_share = max(1, (len(phys) // local_world) * 3 // 4)  # locality must not cost a rank more than a quarter of its even share
     if len(rank_nodes) == local_world and all(n is not None for n in rank_nodes):
         plan: List[Optional[List[int]]] = [None] * local_world
         ok = True

@@ -404,3 +404,13 @@ def test_rank_core_plan_is_numa_aware_and_keeps_hyperthreads_together(tmp_path):
     assert fdist.plan_rank_cores([0, 16], 2, [0, 0], sysfs) == [[], []]
     # no topology files at all (a bare container): every CPU is its own core, even split
     assert fdist.plan_rank_cores(list(range(8)), 2, [None, None], str(tmp_path / "nothing")) == [[0, 1, 2, 3], [4, 5, 6, 7]]
+
+
+def test_rank_core_plan_does_not_trade_cores_for_locality(tmp_path):
+    """All eight GPUs report node 0 of a two-node box: sharing node 0's 8 physical cores would halve every rank's
+    share, so the even split over both nodes stays."""
+    from fvp import dist as fdist
+    sib = {c: "%d,%d" % (c % 16, c % 16 + 16) for c in range(32)}
+    sysfs = _fake_sysfs(tmp_path, {0: "0-7,16-23", 1: "8-15,24-31"}, sib, {})
+    plan = fdist.plan_rank_cores(list(range(32)), 8, [0] * 8, sysfs)
+    assert plan[0] == [0, 1, 16, 17] and plan[7] == [14, 15, 30, 31]
