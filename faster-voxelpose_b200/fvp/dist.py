@@ -138,7 +138,7 @@ def plan_rank_cores(allowed: Sequence[int], local_world: int, rank_nodes: Sequen
     phys = _physical_cores(allowed, sysfs)
     if local_world < 1 or len(phys) < local_world:
         return [[] for _ in range(max(0, local_world))]
-    min_share = max(1, (len(phys) // local_world) * 3 // 4)  # locality must not cost a rank more than a quarter of its even share
+    even = len(phys) // local_world                         # locality must not cost a rank more than a quarter of this
     if len(rank_nodes) == local_world and all(n is not None for n in rank_nodes):
         plan: List[Optional[List[int]]] = [None] * local_world
         ok = True
@@ -147,7 +147,8 @@ def plan_rank_cores(allowed: Sequence[int], local_world: int, rank_nodes: Sequen
             txt = _read(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node))
             node_cpus = set(_parse_cpulist(txt)) if txt else set()
             cores = [core for core in phys if core[0] in node_cpus]
-            if len(cores) // len(ranks) < min_share:        # e.g. a cpuset that leaves one socket a handful of cores
+            share = len(cores) // len(ranks)
+            if share < 1 or 4 * share < 3 * even:           # e.g. a cpuset that leaves one socket a handful of cores
                 ok = False
                 break
             for r, mine in zip(ranks, split(cores, len(ranks))):
