@@ -414,3 +414,22 @@ def test_rank_core_plan_does_not_trade_cores_for_locality(tmp_path):
     sysfs = _fake_sysfs(tmp_path, {0: "0-7,16-23", 1: "8-15,24-31"}, sib, {})
     plan = fdist.plan_rank_cores(list(range(32)), 8, [0] * 8, sysfs)
     assert plan[0] == [0, 1, 16, 17] and plan[7] == [14, 15, 30, 31]
+
+
+def test_gpu_numa_nodes_from_device_properties(tmp_path, monkeypatch):
+    """PCI address formatting of torch's device properties -> sysfs lookup; a failing query reads as 'unknown'."""
+    import types
+    from fvp import dist as fdist
+    sysfs = _fake_sysfs(tmp_path, {0: "0-3", 1: "4-7"}, {}, {"0000:1b:00.0": 0, "0001:e3:00.0": 1, "0000:2a:00.0": -1})
+    props = [types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1B, pci_device_id=0),
+             types.SimpleNamespace(pci_domain_id=1, pci_bus_id=0xE3, pci_device_id=0),
+             types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x2A, pci_device_id=0)]
+
+    def fake_props(i):
+        if i >= len(props):
+            raise RuntimeError("invalid device ordinal")
+        return props[i]
+    monkeypatch.setattr(torch.cuda, "get_device_properties", fake_props)
+    assert fdist.local_gpu_numa_nodes(4, sysfs) == [0, 1, None, None]
+    import json
+    json.dumps(fdist.local_gpu_numa_nodes(4, sysfs))                         # goes into the bench line as is
