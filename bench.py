@@ -165,34 +165,50 @@ def cpu_reference_fps(cfg, cams, resize, frames: np.ndarray, sd_np, warm: int, s
 
 def gpu_reference_port_fps(cfg, cams, resize, frames: np.ndarray, sd_np, dev, warm: int = 3, steps: int = 10) -> dict:
     """Baseline leg (like cpu_baseline, never the product): the reference's own op sequence as PyTorch CUDA ops on this
-    GPU - cached sample grids, cudnn.benchmark, fp32 (tools/ref_gpu_port.py) - i.e. what `DEVICE='cuda:0'` of the
-    reference does (run/validate.py:61-63).  The north-star target "whole pipeline >= 10x the reference's 1-GPU PyTorch
-    path" is measured against this figure, in the same run, on the same GPU."""
+    GPU - cached sample grids, cudnn.benchmark (tools/ref_gpu_port.py) - i.e. what `DEVICE='cuda:0'` of the reference
+    does (run/validate.py:61-63).  Timed twice: with PyTorch's STOCK precision switches (cuDNN convolutions may use TF32,
+    `torch.backends.cudnn.allow_tf32 = True` is the default the reference never touches) = `value`, the figure the
+    north-star target "whole pipeline >= 10x the reference's 1-GPU PyTorch path" is measured against, and with TF32 off
+    (`fp32`), the arithmetic our kernels are held to."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import ref_gpu_port
+    dev = torch.device(dev)
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}
-    tf32 = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-    torch.backends.cudnn.benchmark = True
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
-    try:
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+
+    def sync():
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+
+    def timed(cudnn_tf32: bool) -> float:
+        torch.backends.cudnn.benchmark = True
+        torch.backends.cuda.matmul.allow_tf32 = False        # PyTorch's default since 1.12; the reference has no matmul on this path
+        torch.backends.cudnn.allow_tf32 = cudnn_tf32
         ref = ref_gpu_port.CachedReference(cfg, sd, cams, torch.as_tensor(resize, dtype=torch.float), dev)
         pool = [torch.from_numpy(frames[i][None]).to(dev) for i in range(min(4, frames.shape[0]))]
         for i in range(warm):
             ref.forward(pool[i % len(pool)])
-        torch.cuda.synchronize(dev)
+        sync()
         t0 = time.perf_counter()
         for i in range(steps):
             ref.forward(pool[i % len(pool)])
-        torch.cuda.synchronize(dev)
+        sync()
         dt = time.perf_counter() - t0
+        del ref
+        return dt
+
+    try:
+        dt_stock = timed(True)
+        dt_fp32 = timed(False)
     finally:
-        torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
-    del ref
-    torch.cuda.empty_cache()
-    return {"value": steps / dt, "unit": UNIT, "ms_per_step": dt / steps * 1e3, "steps": steps, "warmup": warm, "batch": 1,
-            "what": "reference op sequence (oracle port) as PyTorch %s CUDA ops on this GPU: cached sample grids, cuDNN fp32 "
-                    "(allow_tf32 off), cudnn.benchmark, per-person host syncs as in project_individual.py" % torch.__version__}
+        torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+    return {"value": steps / dt_stock, "unit": UNIT, "ms_per_step": dt_stock / steps * 1e3, "steps": steps, "warmup": warm,
+            "batch": 1, "fp32": {"value": steps / dt_fp32, "ms_per_step": dt_fp32 / steps * 1e3},
+            "what": "reference op sequence (oracle port) as PyTorch %s CUDA ops on this GPU: cached sample grids, "
+                    "cudnn.benchmark, per-person host syncs as in project_individual.py; value = PyTorch's stock switches "
+                    "(cudnn.allow_tf32 on, as the reference runs), fp32 = TF32 off" % torch.__version__}
 
 
 def conv_tensor_rooflines(stage_ms: dict, batch: int, people_per_frame: int, J: int, grid_xy, peak_tflops: float) -> dict:
