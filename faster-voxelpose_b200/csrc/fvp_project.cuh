@@ -91,6 +91,22 @@ __device__ __forceinline__ FvpTaps fvp_taps(const FvpProj& P, float ix, float iy
   return t;
 }
 
+// The same taps in exchange form: NW offset and the two fractions; fvp_tap_weights rebuilds the four weights with the
+// very operations of fvp_taps (bit-identical), so a lane can hand (off, fx, fy) to its group instead of five values.
+__device__ __forceinline__ void fvp_taps_frac(const FvpProj& P, float ix, float iy, int& off, float& fx, float& fy) {
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  fx = __fsub_rn(ix, x0f);
+  fy = __fsub_rn(iy, y0f);
+  off = (((int)y0f + P.PADY) * P.WP + ((int)x0f + P.PADX)) * (P.JP >> 2);
+}
+__device__ __forceinline__ void fvp_tap_weights(float fx, float fy, float& w00, float& w01, float& w10, float& w11) {
+  const float ex = __fsub_rn(1.0f, fx), ey = __fsub_rn(1.0f, fy);
+  w00 = __fmul_rn(ey, ex);
+  w01 = __fmul_rn(ey, fx);
+  w10 = __fmul_rn(fy, ex);
+  w11 = __fmul_rn(fy, fx);
+}
+
 // base = staged heat-map buffer (kernel-uniform); off = 32-bit float4 index of the NW tap including the (frame, view)
 // image offset and the thread's channel group.  Byte offsets stay unsigned 32-bit so that every tap address is
 // uniform base + zero-extended register (fvp_create bounds the buffer below 4 GiB).
