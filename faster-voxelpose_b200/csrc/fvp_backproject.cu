@@ -207,11 +207,13 @@ __device__ __forceinline__ void fvp_red_max4(float4* dst, float4 m) {
 // (values are >= +0, so they order like unsigned ints; max is exact and order-independent, the result is deterministic).
 // Only non-zero values are sent - heat maps are sparse, >90 % of the partial maxima are 0 - so there are no scratch
 // images and no second reduce kernel: DRAM traffic stays near the algorithmic bytes.
-// XCH: how the lane that looked up a depth hands its taps to the other lanes of its column group (A/B, FVP_K3_XCH):
+// XCH: how the lane that looked up a depth hands its taps to the other lanes of its column group.  Shuffles ride the LSU
+// pipe that bounds this kernel, so fewer of them is time (measured on B200, profiles/r02_k3_xch.txt):
 //   0 = five shuffles per depth and view (offset + four weights);
-//   1 = three shuffles (offset + the two fractions), weights rebuilt per lane with the same operations (bit-identical);
-//   2 = through shared memory: one 16-byte store per lane and view into the warp's rows of the chunk image that is idle
-//       during sampling, then one broadcast LDS.128 per depth (shuffles and loads share the LSU pipe that bounds K3).
+//   1 = three shuffles (offset + the two fractions), the weights rebuilt per lane with the very operations of fvp_taps
+//       (bit-identical): K3 3.46 -> 3.35 ms at batch 32, 0.125 -> 0.121 ms at batch 1.  Used for 64-byte records
+//       (JG == 4), the instantiation it was measured and parity-tested on.
+// (A third form - exchange through the idle shared-memory chunk image, one LDS.128 per depth - measured 3.58 ms: removed.)
 template <int CG, int MINB, int PX16, int XCH = 0>
 __global__ void __launch_bounds__(256, MINB)
 k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __restrict__ people,
@@ -299,27 +301,11 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
           float my_fx, my_fy;
           fvp_taps_frac(P, q.x, q.y, my_off, my_fx, my_fy);
           my_off += frame_off + v * vs4;
-          // XCH == 2: this warp's rows 0 / 1 (alternating per view) of the chunk image the chunk's values go to at the
-          // end of the chunk - nobody else touches buffer (it & 1) before that (see the note at the end of the loop).
-          // A row is rewritten two views later, i.e. after the __syncwarp of the view in between, which every lane
-          // reaches with its reads of this view done.
-          float4* xrow = &s_yz[NBUF == 2 ? (it & 1) : 0][v & 1][warp][0];
-          if (XCH == 2) {
-            xrow[lane] = make_float4(__int_as_float(my_off), my_fx, my_fy, 0.0f);
-            __syncwarp();
-          }
 #pragma unroll
           for (int k = 0; k < CG; ++k) {
-            int off;
-            float fx, fy;
-            if (XCH == 2) {
-              const float4 e = xrow[group_base + k];
-              off = __float_as_int(e.x); fx = e.y; fy = e.z;
-            } else {
-              off = __shfl_sync(0xffffffffu, my_off, group_base + k);
-              fx = __shfl_sync(0xffffffffu, my_fx, group_base + k);
-              fy = __shfl_sync(0xffffffffu, my_fy, group_base + k);
-            }
+            const int off = __shfl_sync(0xffffffffu, my_off, group_base + k);
+            const float fx = __shfl_sync(0xffffffffu, my_fx, group_base + k);
+            const float fy = __shfl_sync(0xffffffffu, my_fy, group_base + k);
             float w00, w01, w10, w11;
             fvp_tap_weights(fx, fy, w00, w01, w10, w11);
             if (__any_sync(0xffffffffu, (cc + k) >= pd.lo[2] && (cc + k) < pd.hi[2]))
@@ -327,7 +313,6 @@ k3_jln_patch(FvpGeom g, const float4* __restrict__ hm_cl, const FvpPerson* __res
           }
         }
       }
-      if (XCH == 2) __syncwarp();                // the last views' exchange rows are read before the values overwrite them
     }
     // mean + clamp + the three maxima of this chunk.  Both cross-thread maxima go through ONE shared-memory image of
     // the chunk ([depth][row][lane]): a partial-mask REDUX per channel group costs a serialised collective per mask
@@ -377,13 +362,8 @@ void fvp_launch_jln_project(const FvpGeom& g, const float* d_hm_cl, const FvpPer
   // partial maxima are RED-folded into the planes, which therefore start from zero
   cudaMemsetAsync(d_planes_cl, 0, (size_t)3 * n_people * img4 * sizeof(float4), st);
   dim3 grid(fvp_k3_patches(g.JG) * ncpart, n_people);
-  static const int xch = std::getenv("FVP_K3_XCH") ? std::atoi(std::getenv("FVP_K3_XCH")) : 0;    // A/B switch (tools only)
-  if (g.JG == 4 && xch == 1)
+  if (g.JG == 4)
     k3_jln_patch<4, 4, 64, 1><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
-  else if (g.JG == 4 && xch == 2)
-    k3_jln_patch<4, 4, 64, 2><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
-  else if (g.JG == 4)
-    k3_jln_patch<4, 4, 64><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
   else if (g.JG < 4)
     k3_jln_patch<4, 4, 0><<<grid, 256, 0, st>>>(g, (const float4*)d_hm_cl, d_people, (float4*)d_planes_cl, n_people, ncpart);
   else
