@@ -1,0 +1,105 @@
+"""Readers for the data formats on either side of the hot path: the calibration files and the
+2-D detection files the reference's dataset classes load, without the dataset classes themselves (they need the image
+folders, ``json_tricks`` and ``actorsGT.mat`` even when only heat maps from 2-D poses are wanted).
+
+* Campus / Shelf calibration  ``calibration_{campus,shelf}.json``  - ``{"0": {R, T, fx, fy, cx, cy, k, p}, ...}``
+  (``lib/dataset/campus.py:114-129``, ``shelf.py`` likewise) and the demo's ``{"<sequence>": [cam, ...]}`` form
+  (``demo/calibration.json``, read by the notebook) -> lists of camera dicts with NumPy values, the ``cameras[seq]``
+  the model's ``forward`` receives;
+* Panoptic ``calibration_<seq>.json`` (``{"cameras": [{panel, node, K, distCoef, R, t}, ...]}``) -> the five HD cameras in
+  the reference's convention ``x_cam = R (x - T)``, millimetres, y-up to z-up (``lib/dataset/panoptic.py:171-205``);
+* ``pred_{campus,shelf}_maskrcnn_hrnet_coco.pkl``: ``{"<view>_<frame>": [{"pred": [17][x, y, score]}, ...]}`` -> the
+  per-view, per-person arrays of one frame, i.e. ``db_rec['pred_pose2d']`` (``campus.py:92-97``), which
+  ``fvp.render.HeatmapRenderer.from_pred`` turns into ``input_heatmaps`` on the GPU.
+
+Host logic only (NumPy); pinned against the reference's own loaders by ``oracle/gen_golden_datasets.py`` /
+``tests/test_datasets.py``.
+"""
+from __future__ import annotations
+
+import json
+import pickle
+from typing import Dict, Iterable, Iterator, List, Sequence, Tuple, Union
+
+import numpy as np
+
+CAMPUS_FRAMES: List[int] = list(range(350, 471)) + list(range(650, 751))      # campus.py:55
+SHELF_FRAMES: List[int] = list(range(300, 601))                               # shelf.py:81
+PANOPTIC_CAM_LIST: List[Tuple[int, int]] = [(0, 3), (0, 6), (0, 12), (0, 13), (0, 23)]   # panoptic.py:79
+PANOPTIC_VAL_LIST: List[str] = ["160906_pizza1", "160422_haggling1", "160906_ian5", "160906_band4"]   # panoptic.py:35-40
+
+_CAM_KEYS = ("R", "T", "fx", "fy", "cx", "cy", "k", "p")
+
+
+def _as_camera(cam: dict) -> dict:
+    """Every value as a NumPy array, exactly what ``np.array(v)`` makes of the JSON value (campus.py:119-121)."""
+    missing = [k for k in _CAM_KEYS if k not in cam]
+    if missing:
+        raise KeyError("camera entry lacks %s" % missing)
+    return {k: np.array(v) for k, v in cam.items()}
+
+
+def load_calibration(path: str) -> Union[List[dict], Dict[str, List[dict]]]:
+    """Campus / Shelf file (string keys '0'..'V-1') -> list of cameras in view order; demo-style file (sequence name ->
+    list of cameras) -> ``{sequence: [camera, ...]}``."""
+    with open(path) as f:
+        doc = json.load(f)
+    if not isinstance(doc, dict) or not doc:
+        raise ValueError("%s: not a calibration file" % path)
+    if all(isinstance(v, dict) for v in doc.values()):
+        try:
+            order = sorted(doc, key=int)
+        except ValueError:
+            raise ValueError("%s: camera keys must be integers" % path)
+        if [int(k) for k in order] != list(range(len(order))):
+            raise ValueError("%s: camera keys must be 0..V-1, got %s" % (path, order))
+        return [_as_camera(doc[k]) for k in order]
+    if all(isinstance(v, list) for v in doc.values()):
+        return {seq: [_as_camera(c) for c in cams] for seq, cams in doc.items()}
+    raise ValueError("%s: neither {view: camera} nor {sequence: [camera, ...]}" % path)
+
+
+def panoptic_cameras(calib: Union[str, dict], num_views: int = 5) -> List[dict]:
+    """The reference's camera selection and conversion for one Panoptic sequence (panoptic.py:171-205): HD cameras
+    ``PANOPTIC_CAM_LIST[:num_views]`` in file order, ``R' = R M`` (y-up -> z-up), ``T = -R'^T t * 10`` (cm -> mm, camera
+    centre instead of translation), intrinsics from ``K``, ``k = distCoef[[0, 1, 4]]``, ``p = distCoef[[2, 3]]``."""
+    if isinstance(calib, str):
+        with open(calib) as f:
+            calib = json.load(f)
+    M = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, -1.0], [0.0, 1.0, 0.0]])
+    want = PANOPTIC_CAM_LIST[:num_views]
+    out = []
+    for cam in calib["cameras"]:
+        if (cam["panel"], cam["node"]) in want:
+            K, dist = np.array(cam["K"]), np.array(cam["distCoef"])
+            R = np.array(cam["R"]).dot(M)
+            t = np.array(cam["t"]).reshape((3, 1))
+            out.append({"R": R, "T": -np.dot(R.T, t) * 10.0, "fx": K[0, 0], "fy": K[1, 1], "cx": K[0, 2], "cy": K[1, 2],
+                        "k": dist[[0, 1, 4]].reshape(3, 1), "p": dist[[2, 3]].reshape(2, 1)})
+    return out
+
+
+def load_pred_pose2d(path: str) -> dict:
+    """The detection file of Campus / Shelf (campus.py:61-67): ``{"<view>_<frame>": [{"pred": ...}, ...]}``.
+    A pickle: only open files you trust (the reference does the same)."""
+    with open(path, "rb") as f:
+        return pickle.load(f)
+
+
+def frame_preds(pred2d: dict, frame: int, num_views: int) -> List[List[np.ndarray]]:
+    """``db_rec['pred_pose2d']`` of one frame (campus.py:92-97): per view the detected people as ``[J, 3]`` arrays
+    (x, y in original-image pixels, score).  A view without an entry behaves like the container does, as in the
+    reference: the shipped files unpickle to ``defaultdict(list)`` and answer with no people, a plain dict raises."""
+    return [[np.array(p["pred"]) for p in pred2d["%d_%d" % (k, frame)]] for k in range(num_views)]
+
+
+def pred_frames(pred2d: dict, frames: Iterable[int], num_views: int) -> Iterator[Tuple[int, List[List[np.ndarray]]]]:
+    """(frame, per-view detections) over a frame range, e.g. ``CAMPUS_FRAMES`` - the order the reference's ``_get_db``
+    builds its records in."""
+    for i in frames:
+        yield i, frame_preds(pred2d, i, num_views)
+
+
+def batch_preds(pred2d: dict, frames: Sequence[int], num_views: int) -> List[List[List[np.ndarray]]]:
+    """``[frame][view][person]`` for ``HeatmapRenderer.from_pred``."""
+    return [frame_preds(pred2d, i, num_views) for i in frames]

@@ -1,0 +1,159 @@
+#!/usr/bin/env python
+"""Fixtures that pin ``fvp.datasets`` (the data-format readers either side of the hot path) to the UNMODIFIED reference.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/gen_golden_datasets.py        # writes tests/golden/datasets_fixture.npz + pred_pose2d_frame400.pkl
+
+What it does
+  1. calls the reference's own ``Campus._get_cam`` / ``Shelf._get_cam`` (lib/dataset/campus.py:114-129, shelf.py) on the
+     calibration files shipped in /root/reference/data and asserts ``fvp.datasets.load_calibration`` returns the same
+     values (``==`` on every array, same dtypes); stores the calibration JSON text and the reference's arrays;
+  2. writes a synthetic Panoptic ``calibration_<seq>.json`` (eight HD / VGA cameras, five of them the reference's
+     ``cam_list``), runs the reference's ``Panoptic._get_cam`` (panoptic.py:171-205) on it and asserts
+     ``fvp.datasets.panoptic_cameras`` equal; stores the JSON text and the expected cameras;
+  3. cuts frame 400 (BASELINE configs[0], SURVEY.md 8d "Config 1") out of the shipped detection files
+     ``pred_{campus,shelf}_maskrcnn_hrnet_coco.pkl`` into a small pickle, builds ``db_rec['pred_pose2d']`` with the very
+     expression of ``Campus._get_db`` (campus.py:92-97) and asserts ``fvp.datasets.frame_preds`` equal.
+"""
+from __future__ import annotations
+
+import importlib
+import json
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "faster-voxelpose_b200"))
+sys.path.insert(0, ROOT)
+
+from fvp import datasets as D                   # noqa: E402
+from oracle import gen_golden as GG             # noqa: E402  (easydict shim + reference path)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+FRAME = 400
+
+
+def reference_dataset_modules():
+    GG._install_reference()
+    sys.modules["json_tricks"] = json           # the loaders only call json.load on plain JSON files
+    return tuple(importlib.import_module("dataset." + m) for m in ("panoptic", "campus", "shelf"))
+
+
+def cams_equal(ours, ref) -> bool:
+    if len(ours) != len(ref):
+        return False
+    for a, b in zip(ours, ref):
+        if sorted(a) != sorted(b):
+            return False
+        for k in a:
+            x, y = np.asarray(a[k]), np.asarray(b[k])
+            if x.shape != y.shape or x.dtype != y.dtype or not np.array_equal(x, y):
+                return False
+    return True
+
+
+def cams_to_arrays(cams) -> dict:
+    """{R [V,3,3], T [V,3,1], f [V,2], c [V,2], k [V,3,1], p [V,2,1]} float64."""
+    return {"R": np.stack([np.asarray(c["R"], np.float64) for c in cams]),
+            "T": np.stack([np.asarray(c["T"], np.float64).reshape(3, 1) for c in cams]),
+            "f": np.array([[float(c["fx"]), float(c["fy"])] for c in cams]),
+            "c": np.array([[float(c["cx"]), float(c["cy"])] for c in cams]),
+            "k": np.stack([np.asarray(c["k"], np.float64).reshape(3, 1) for c in cams]),
+            "p": np.stack([np.asarray(c["p"], np.float64).reshape(2, 1) for c in cams])}
+
+
+def synthetic_panoptic_calibration(rng) -> dict:
+    cams = []
+    nodes = [(0, 1), (0, 3), (5, 7), (0, 6), (0, 12), (0, 13), (3, 3), (0, 23)]       # HD panel 0 + two VGA panels
+    for panel, node in nodes:
+        a = rng.uniform(0, 2 * np.pi)
+        q = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+        q *= np.sign(np.linalg.det(q))
+        K = np.array([[rng.uniform(1300, 1700), 0.0, rng.uniform(900, 1000)], [0.0, rng.uniform(1300, 1700), rng.uniform(500, 580)],
+                      [0.0, 0.0, 1.0]])
+        cams.append({"name": "%02d_%02d" % (panel, node), "type": "hd" if panel == 0 else "vga", "panel": panel, "node": node,
+                     "resolution": [1920, 1080], "K": K.tolist(), "distCoef": rng.uniform(-0.3, 0.3, 5).tolist(),
+                     "R": q.tolist(), "t": (rng.uniform(-300, 300, (3, 1)) + np.array([[np.cos(a)], [0.0], [np.sin(a)]]) * 200).tolist()})
+    return {"calibDataSource": "synthetic", "cameras": cams}
+
+
+def main():
+    panoptic_m, campus_m, shelf_m = reference_dataset_modules()
+    store = {}
+
+    # ---- 1. Campus / Shelf calibration files through the reference's _get_cam ----------------------------------
+    for name, mod, cls, sub, fn in (("campus", campus_m, "Campus", "Campus", "calibration_campus.json"),
+                                    ("shelf", shelf_m, "Shelf", "Shelf", "calibration_shelf.json")):
+        ds = object.__new__(getattr(mod, cls))
+        ds.dataset_dir = os.path.join(GG.REF, "data", sub)
+        ref = ds._get_cam()[name]                                  # {int view: camera}
+        ref_list = [ref[i] for i in range(len(ref))]
+        path = os.path.join(ds.dataset_dir, fn)
+        ours = D.load_calibration(path)
+        assert cams_equal(ours, ref_list), "%s: load_calibration differs from the reference's _get_cam" % name
+        store[name + "_json"] = np.array(open(path).read())
+        for k, v in cams_to_arrays(ref_list).items():
+            store["%s_%s" % (name, k)] = v
+        print("%-8s calibration: %d cameras, load_calibration == reference" % (name, len(ours)))
+    demo = D.load_calibration(os.path.join(GG.REF, "demo", "calibration.json"))
+    assert list(demo) == ["customized_sequence"] and len(demo["customized_sequence"]) == 5
+    store["demo_json"] = np.array(open(os.path.join(GG.REF, "demo", "calibration.json")).read())
+
+    # ---- 2. Panoptic conversion on a synthetic calibration_<seq>.json ------------------------------------------
+    rng = np.random.default_rng(2024)
+    calib = synthetic_panoptic_calibration(rng)
+    with tempfile.TemporaryDirectory() as tmp:
+        seq = "synthetic_seq"
+        os.makedirs(os.path.join(tmp, seq))
+        with open(os.path.join(tmp, seq, "calibration_%s.json" % seq), "w") as f:
+            json.dump(calib, f)
+        for nv in (5, 3):
+            ds = object.__new__(panoptic_m.Panoptic)
+            ds.dataset_dir, ds.sequence_list, ds.num_views = tmp, [seq], nv
+            ds.cam_list = [(0, 3), (0, 6), (0, 12), (0, 13), (0, 23)][:nv]
+            ref = ds._get_cam()[seq]
+            ours = D.panoptic_cameras(os.path.join(tmp, seq, "calibration_%s.json" % seq), nv)
+            assert cams_equal(ours, ref), "panoptic_cameras differs from the reference's _get_cam (%d views)" % nv
+            if nv == 5:
+                for k, v in cams_to_arrays(ref).items():
+                    store["panoptic_%s" % k] = v
+    assert D.PANOPTIC_VAL_LIST == panoptic_m.VAL_LIST
+    store["panoptic_json"] = np.array(json.dumps(calib))
+    print("panoptic calibration: 5 / 3 of 8 cameras selected and converted, panoptic_cameras == reference")
+
+    # ---- 3. frame 400 of the shipped detection files -----------------------------------------------------------
+    small = {}
+    for name, sub, fn, V in (("campus", "Campus", "pred_campus_maskrcnn_hrnet_coco.pkl", 3),
+                             ("shelf", "Shelf", "pred_shelf_maskrcnn_hrnet_coco.pkl", 5)):
+        full = D.load_pred_pose2d(os.path.join(GG.REF, "data", sub, fn))
+        cut = {"%d_%d" % (k, FRAME): full["%d_%d" % (k, FRAME)] for k in range(V)}
+        small[name] = cut
+        all_preds = []
+        for k in range(V):                                           # campus.py:92-97
+            preds = full["{}_{}".format(k, FRAME)]
+            preds = [np.array(p["pred"]) for p in preds]
+            all_preds.append(preds)
+        ours = D.frame_preds(cut, FRAME, V)
+        assert len(ours) == V and all(len(a) == len(b) and all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a, b))
+                                      for a, b in zip(ours, all_preds))
+        store["%s_people_per_view" % name] = np.array([len(v) for v in all_preds])
+        print("%-8s frame %d: %s people per view, frame_preds == reference" % (name, FRAME, [len(v) for v in all_preds]))
+    frames = {"campus": (campus_m.Campus, "Campus"), "shelf": (shelf_m.Shelf, "Shelf")}
+    # frame ranges as the reference's constructors set them (read from the source: the constructors need the image folders)
+    import inspect
+    assert "list(range(350, 471)) + list(range(650, 751))" in inspect.getsource(frames["campus"][0].__init__)
+    assert "list(range(300, 601))" in inspect.getsource(frames["shelf"][0].__init__)
+    with open(os.path.join(OUT, "pred_pose2d_frame400.pkl"), "wb") as f:
+        pickle.dump(small, f, protocol=4)
+    np.savez_compressed(os.path.join(OUT, "datasets_fixture.npz"), **store)
+    print("wrote", os.path.join(OUT, "datasets_fixture.npz"), os.path.getsize(os.path.join(OUT, "datasets_fixture.npz")), "bytes;",
+          "pred_pose2d_frame400.pkl", os.path.getsize(os.path.join(OUT, "pred_pose2d_frame400.pkl")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""fvp.datasets (readers of the reference's calibration / detection files) against fixtures written by
+oracle/gen_golden_datasets.py, which asserted equality with the reference's own dataset loaders (Campus/Shelf/Panoptic
+``_get_cam``, ``_get_db``) when it produced them.  CPU only, no reference needed at run time."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN_DIR
+
+from fvp import datasets as D
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return np.load(os.path.join(GOLDEN_DIR, "datasets_fixture.npz"))
+
+
+def _check(cams, fx, prefix):
+    assert len(cams) == fx[prefix + "_R"].shape[0]
+    for v, c in enumerate(cams):
+        assert np.array_equal(np.asarray(c["R"], np.float64), fx[prefix + "_R"][v])
+        assert np.array_equal(np.asarray(c["T"], np.float64).reshape(3, 1), fx[prefix + "_T"][v])
+        assert [float(c["fx"]), float(c["fy"])] == list(fx[prefix + "_f"][v])
+        assert [float(c["cx"]), float(c["cy"])] == list(fx[prefix + "_c"][v])
+        assert np.array_equal(np.asarray(c["k"], np.float64).reshape(3, 1), fx[prefix + "_k"][v])
+        assert np.array_equal(np.asarray(c["p"], np.float64).reshape(2, 1), fx[prefix + "_p"][v])
+
+
+@pytest.mark.parametrize("name,views", [("campus", 3), ("shelf", 5)])
+def test_campus_shelf_calibration_files(fx, tmp_path, name, views):
+    """calibration_{campus,shelf}.json -> cameras[seq] exactly as Campus/Shelf._get_cam builds it (campus.py:114-129)."""
+    path = tmp_path / ("calibration_%s.json" % name)
+    path.write_text(str(fx[name + "_json"]))
+    cams = D.load_calibration(str(path))
+    assert isinstance(cams, list) and len(cams) == views and all(isinstance(c["R"], np.ndarray) for c in cams)
+    _check(cams, fx, name)
+
+
+def test_demo_calibration_and_rejections(fx, tmp_path):
+    path = tmp_path / "calibration.json"
+    path.write_text(str(fx["demo_json"]))
+    d = D.load_calibration(str(path))
+    assert list(d) == ["customized_sequence"] and len(d["customized_sequence"]) == 5
+    assert d["customized_sequence"][0]["R"].shape == (3, 3)
+    bad = tmp_path / "bad.json"
+    bad.write_text(json.dumps({"0": {"R": [[1, 0, 0]] * 3}}))
+    with pytest.raises(KeyError):
+        D.load_calibration(str(bad))
+    doc = json.loads(str(fx["campus_json"]))
+    bad.write_text(json.dumps({"0": doc["0"], "2": doc["2"]}))               # view 1 missing
+    with pytest.raises(ValueError):
+        D.load_calibration(str(bad))
+    bad.write_text(json.dumps([1, 2, 3]))
+    with pytest.raises(ValueError):
+        D.load_calibration(str(bad))
+
+
+def test_panoptic_camera_selection_and_conversion(fx, tmp_path):
+    """calibration_<seq>.json -> the five HD cameras, R M, T = -R'^T t * 10, k / p from distCoef (panoptic.py:171-205)."""
+    calib = json.loads(str(fx["panoptic_json"]))
+    assert len(calib["cameras"]) == 8
+    cams = D.panoptic_cameras(calib)
+    _check(cams, fx, "panoptic")
+    path = tmp_path / "calibration_seq.json"
+    path.write_text(str(fx["panoptic_json"]))
+    three = D.panoptic_cameras(str(path), 3)
+    assert len(three) == 3 and all(np.array_equal(a["T"], b["T"]) for a, b in zip(three, cams))
+    R = cams[0]["R"]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and cams[0]["T"].shape == (3, 1)
+
+
+def test_detection_file_frames(fx):
+    """pred_*_maskrcnn_hrnet_coco.pkl -> db_rec['pred_pose2d'] of a frame (campus.py:92-97); frame 400 of both files."""
+    pred = D.load_pred_pose2d(os.path.join(GOLDEN_DIR, "pred_pose2d_frame400.pkl"))
+    for name, views in (("campus", 3), ("shelf", 5)):
+        frame = D.frame_preds(pred[name], 400, views)
+        assert [len(v) for v in frame] == list(fx[name + "_people_per_view"])
+        assert all(p.shape == (17, 3) and p.dtype == np.float64 for v in frame for p in v)
+        assert D.batch_preds(pred[name], [400, 400], views)[1][0][0] is not frame[0][0]
+        assert [i for i, _ in D.pred_frames(pred[name], [400], views)] == [400]
+    with pytest.raises(KeyError):
+        D.frame_preds(pred["campus"], 401, 3)                                    # a plain dict raises on a missing frame
+    assert len(D.CAMPUS_FRAMES) == 222 and D.CAMPUS_FRAMES[0] == 350 and D.CAMPUS_FRAMES[-1] == 750 and 500 not in D.CAMPUS_FRAMES
+    assert D.SHELF_FRAMES == list(range(300, 601))
