@@ -88,7 +88,45 @@ CASES = {
     "panoptic_256x192": dict(preset="panoptic_256x192", calib="panoptic", people=[10], min_score=None, seed=14),
     "campus_b1": dict(preset="campus", calib="campus", people=[3], min_score=None, seed=15),
     "shelf_crowd": dict(preset="shelf", calib="shelf", people=[10], min_score=None, seed=16),
+    # BASELINE configs[0] / SURVEY.md 8d "Config 1" on REAL detections: frame 400 of the shipped
+    # pred_{campus,shelf}_maskrcnn_hrnet_coco.pkl (3/2/2 and 4/5/2/2/2 detected people per view), heat maps rendered by
+    # the reference's own JointsDataset.__getitem__ ('pred' source, sigma from the config), real calibration files
+    "campus_frame400": dict(preset="campus", calib="campus", people=[0], min_score=None, seed=17, frame=400),
+    "shelf_frame400": dict(preset="shelf", calib="shelf", people=[0], min_score=None, seed=18, frame=400),
 }
+_PRED_FILES = {"campus": "data/Campus/pred_campus_maskrcnn_hrnet_coco.pkl", "shelf": "data/Shelf/pred_shelf_maskrcnn_hrnet_coco.pkl"}
+
+
+def real_frame_heatmaps(cfg, calib: str, frame: int):
+    """[V,J,H,W] float32: the reference's JointsDataset.__getitem__ ('pred' heat-map source, JointsDataset.py:144-154,
+    271-337) on the detections of one frame of the shipped file, built into a record with the expression of
+    Campus._get_db (campus.py:92-97).  Returns the maps rounded to the 1/4096 lattice the goldens store, and the record's
+    detections (before the in-place resize the reference applies to them)."""
+    import copy
+    import importlib.util
+    import pickle
+    spec = importlib.util.spec_from_file_location("ref_JointsDataset", os.path.join(REF, "lib/dataset/JointsDataset.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(REF, _PRED_FILES[calib]), "rb") as f:
+        pred2d = pickle.load(f)
+    V = int(cfg.DATASET.CAMERA_NUM)
+    all_preds = []
+    for k in range(V):
+        preds = pred2d["{}_{}".format(k, frame)]
+        all_preds.append([np.array(p["pred"]) for p in preds])
+    src = cfg.DATASET.TEST_HEATMAP_SRC
+    cfg.DATASET.TEST_HEATMAP_SRC = "pred"
+    try:
+        ds = mod.JointsDataset(cfg, is_train=False)
+        ds.db = [{"pred_pose2d": copy.deepcopy(all_preds), "target": 0, "meta": {"seq": calib}, "image": ""}]
+        _, _, _, hm = ds[0]
+    finally:
+        cfg.DATASET.TEST_HEATMAP_SRC = src
+    hm = hm.numpy()
+    assert hm.dtype == np.float32 and hm.shape[0] == V
+    q = np.floor(hm.astype(np.float64) * 4096 + 0.5)
+    return (q / 4096).astype(np.float32), all_preds, hm
 
 
 def sha(a: np.ndarray) -> str:
@@ -133,7 +171,21 @@ def run_case(name: str, spec: dict, outdir: str, ref_models, ref_tf) -> dict:
     B = len(spec["people"])
     sigma = float(cfg.NETWORK.SIGMA)
     hms, skels = [], []
+    real = {}
     for b, npeople in enumerate(spec["people"]):
+        if spec.get("frame") is not None:            # real detections rendered by the reference itself
+            hm_q, preds, hm_exact = real_frame_heatmaps(cfg, spec["calib"], spec["frame"])
+            skels.append(np.zeros((0, J, 3)))
+            hms.append(hm_q)
+            nmax = max(len(v) for v in preds)
+            pp = np.zeros((V, nmax, J, 3))
+            for v in range(V):
+                pp[v, :len(preds[v])] = np.array(preds[v])
+            nz = np.flatnonzero(hm_exact)
+            real = {"frame": np.array(spec["frame"]), "preds": pp, "preds_per_view": np.array([len(v) for v in preds], np.int32),
+                    "rendered_nz_index": nz.astype(np.int64), "rendered_nz_value": hm_exact.ravel()[nz],
+                    "rendered_max_quant_error": np.array(float(np.abs(hm_q - hm_exact).max()))}
+            continue
         sk = synth.make_skeletons(cfg, npeople, seed=spec["seed"] * 100 + b)
         skels.append(sk)
         hms.append(synth.render_heatmaps(cfg, cams, sk, sigma=sigma))
@@ -241,6 +293,7 @@ def run_case(name: str, spec: dict, outdir: str, ref_models, ref_tf) -> dict:
         "idx_z": h["idx_z"].numpy(), "conf1d": h["conf1d"].numpy(), "cols": h["cols"].numpy(),
         "hm1d": h["hm1d"].numpy(),
     }
+    store.update(real)
     Kc = O.JlnConstants(cfg)
     store["axes_coarse"] = np.concatenate([O.axis_coords(cfg.CAPTURE_SPEC.SPACE_SIZE[d], cfg.CAPTURE_SPEC.SPACE_CENTER[d],
                                                          cfg.CAPTURE_SPEC.VOXELS_PER_AXIS[d]).numpy() for d in range(3)])

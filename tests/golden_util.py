@@ -17,6 +17,9 @@ from fvp import config as fcfg, synth  # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 CASES = ["panoptic_b2", "panoptic_mixed", "panoptic_none_valid", "panoptic_256x192", "campus_b1", "shelf_crowd"]
+# BASELINE configs[0] on real detections: frame 400 of the reference's shipped Campus / Shelf detection files, heat maps
+# rendered by the reference's own JointsDataset (oracle/gen_golden.py::real_frame_heatmaps)
+REAL_CASES = ["campus_frame400", "shelf_frame400"]
 
 
 def weights_sha(sd) -> str:
@@ -52,6 +55,19 @@ class Golden:
 
     def has(self, k):
         return k in self.z.files
+
+    # ---- real-detection cases only ------------------------------------------------------------------------------
+    def real_preds(self):
+        """[view][person] -> [J,3] detections of the frame (original-image pixels), as db_rec['pred_pose2d']."""
+        n = self.z["preds_per_view"]
+        return [[self.z["preds"][v, i] for i in range(int(n[v]))] for v in range(len(n))]
+
+    def rendered(self) -> np.ndarray:
+        """The maps the reference rendered from real_preds(), exact float32 ([V,J,H,W]; heatmaps holds them rounded to
+        the 1/4096 lattice)."""
+        out = np.zeros(int(np.prod(self.heatmaps.shape[1:])), np.float32)
+        out[self.z["rendered_nz_index"]] = self.z["rendered_nz_value"]
+        return out.reshape(self.heatmaps.shape[1:])
 
 
 HEATMAP_CASES = ["heatmaps_panoptic_256x192_crowd", "heatmaps_panoptic_border", "heatmaps_campus_tiny",

@@ -14,7 +14,7 @@ def _sd(g):
     return {k: torch.from_numpy(np.asarray(v)) for k, v in g.weights.items()}
 
 
-@pytest.mark.parametrize("name", ["campus_b1", "panoptic_mixed", "panoptic_none_valid", "shelf_crowd"])
+@pytest.mark.parametrize("name", ["campus_b1", "panoptic_mixed", "panoptic_none_valid", "shelf_crowd", "campus_frame400"])
 def test_oracle_forward_matches_reference_golden(golden, name):
     g = golden(name)
     with torch.no_grad():
@@ -118,3 +118,24 @@ def test_heatmap_oracle_edge_cases():
     assert hm[1, :, 25:].max() > 0 and hm[1, :, :25].max() == 0             # patch cut by the right border
     masked = HO.render_input_heatmap([pose], [np.array([0, 1, 1])], (W, H), (160, 120), 3)
     assert masked[0].max() == 0 and np.array_equal(masked[1], hm[1])
+
+
+@pytest.mark.parametrize("name,views", [("campus_frame400", 3), ("shelf_frame400", 5)])
+def test_real_detections_frame400_chain(golden, name, views):
+    """BASELINE configs[0] on real data: the detection file -> fvp.datasets.frame_preds -> the heat-map oracle reproduces,
+    bit for bit, the maps the reference's JointsDataset rendered from frame 400 of its shipped detection file; the
+    golden's model input is those maps on the 1/4096 lattice (off by at most half a step)."""
+    import os
+    from golden_util import GOLDEN_DIR
+    from fvp import datasets as D
+    g = golden(name)
+    pred = D.load_pred_pose2d(os.path.join(GOLDEN_DIR, "pred_pose2d_frame400.pkl"))[name.split("_")[0]]
+    frame = D.frame_preds(pred, int(g["frame"]), views)
+    stored = g.real_preds()
+    assert [len(v) for v in frame] == [len(v) for v in stored]
+    assert all(np.array_equal(a, b) for va, vb in zip(frame, stored) for a, b in zip(va, vb))
+    ds = g.cfg.DATASET
+    hm = HO.pred_heatmaps(frame, g.resize, ds.HEATMAP_SIZE, ds.IMAGE_SIZE, g.cfg.NETWORK.SIGMA)
+    ref = g.rendered()
+    assert np.array_equal(hm.view(np.int32), ref.view(np.int32))
+    assert hm.max() == 1.0 and float(np.abs(g.heatmaps[0] - ref).max()) <= 0.5 / 4096 + 1e-9
