@@ -316,8 +316,12 @@ def test_end_to_end_plugin_forward(case):
     bit-exact; joint coordinates: the reference's own fp32-vs-float64 noise floor is measured in the same run
     (oracle.jln_fp64) - ours must be at most that far from the float64 result, and within 1.5 x the floor of the
     reference's fp32 result (1e-4 mm, the north-star figure, is 20-200x below what the reference itself achieves)."""
-    import models
     g, _, _ = case
+    _check_plugin_forward(g)
+
+
+def _check_plugin_forward(g):
+    import models
     cfg = g.cfg
     cfg.DEVICE = "cuda:0"
     model = models.faster_voxelpose.get(cfg)
