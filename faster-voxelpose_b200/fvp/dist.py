@@ -176,7 +176,7 @@ def pin_rank_to_cores(local_rank: int, local_world: int, rank_nodes: Optional[Se
             os.sched_setaffinity(0, mine)
             return mine
         return cores
-    except (AttributeError, OSError, IndexError):
+    except Exception:       # affinity unsupported, odd sysfs contents, ...: pinning is an optimisation, never an error
         return []
 
 

@@ -433,3 +433,15 @@ def test_gpu_numa_nodes_from_device_properties(tmp_path, monkeypatch):
     assert fdist.local_gpu_numa_nodes(4, sysfs) == [0, 1, None, None]
     import json
     json.dumps(fdist.local_gpu_numa_nodes(4, sysfs))                         # goes into the bench line as is
+
+
+def test_pinning_never_raises_on_odd_sysfs(tmp_path):
+    """Pinning is an optimisation: malformed topology files must not take a multi-GPU run down."""
+    from fvp import dist as fdist
+    root = tmp_path
+    d = root / "devices/system/node/node0"
+    d.mkdir(parents=True)
+    (d / "cpulist").write_text("0-,x\n")                                     # garbage
+    before = os.sched_getaffinity(0)
+    assert fdist.pin_rank_to_cores(0, 2, [0, 0], str(root)) == []
+    assert os.sched_getaffinity(0) == before
