@@ -8,6 +8,9 @@ folders, ``json_tricks`` and ``actorsGT.mat`` even when only heat maps from 2-D 
   the model's ``forward`` receives;
 * Panoptic ``calibration_<seq>.json`` (``{"cameras": [{panel, node, K, distCoef, R, t}, ...]}``) -> the five HD cameras in
   the reference's convention ``x_cam = R (x - T)``, millimetres, y-up to z-up (``lib/dataset/panoptic.py:171-205``);
+* Panoptic ``hdPose3d_stage1_coco19/body3DScene_*.json`` -> the ground-truth poses and visibilities of a frame as
+  ``Panoptic._get_db`` stores them (``panoptic.py:109-163``), i.e. what ``fvp.evaluate.evaluate_panoptic`` and
+  ``HeatmapRenderer.from_gt`` take;
 * ``pred_{campus,shelf}_maskrcnn_hrnet_coco.pkl``: ``{"<view>_<frame>": [{"pred": [17][x, y, score]}, ...]}`` -> the
   per-view, per-person arrays of one frame, i.e. ``db_rec['pred_pose2d']`` (``campus.py:92-97``), which
   ``fvp.render.HeatmapRenderer.from_pred`` turns into ``input_heatmaps`` on the GPU.
@@ -77,6 +80,47 @@ def panoptic_cameras(calib: Union[str, dict], num_views: int = 5) -> List[dict]:
             out.append({"R": R, "T": -np.dot(R.T, t) * 10.0, "fx": K[0, 0], "fy": K[1, 1], "cx": K[0, 2], "cy": K[1, 2],
                         "k": dist[[0, 1, 4]].reshape(3, 1), "p": dist[[2, 3]].reshape(2, 1)})
     return out
+
+
+def panoptic_annotation_files(seq_dir: str, interval: int = 12) -> List[str]:
+    """The ``hdPose3d_stage1_coco19/*.json`` files of a sequence the reference visits (panoptic.py:111-116): sorted, every
+    ``interval``-th (12 for validation, 3 for training, panoptic.py:81-88)."""
+    import glob
+    import os
+    files = sorted(glob.iglob("{:s}/*.json".format(os.path.join(seq_dir, "hdPose3d_stage1_coco19"))))
+    return [f for i, f in enumerate(files) if i % interval == 0]
+
+
+def panoptic_image_paths(dataset_dir: str, seq: str, anno_file: str, num_views: int = 5) -> List[str]:
+    """The HD images that belong to an annotation file (panoptic.py:122-133), existing or not."""
+    import os
+    out = []
+    for k in range(num_views):
+        suffix = os.path.basename(anno_file).replace("body3DScene", "")
+        prefix = "{:02d}_{:02d}".format(PANOPTIC_CAM_LIST[k][0], PANOPTIC_CAM_LIST[k][1])
+        out.append(os.path.join(dataset_dir, seq, "hdImgs", prefix, prefix + suffix).replace("json", "jpg"))
+    return out
+
+
+def panoptic_frame_gt(anno: Union[str, dict], num_joints: int = 15, root_id: int = 2) -> Tuple[List[np.ndarray], List[np.ndarray]]:
+    """Ground truth of one ``body3DScene_*.json`` as the reference's ``_get_db`` stores it (panoptic.py:138-157):
+    per body the first ``num_joints`` of ``joints19`` -> ``[J,3]`` world millimetres (y-up centimetres times ``M``, times
+    10) and ``[J]`` visibilities clipped at 0; bodies whose root joint has visibility <= 0.1 are dropped."""
+    if isinstance(anno, str):
+        with open(anno, "r") as f:
+            anno = json.load(f)
+    M = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, -1.0], [0.0, 1.0, 0.0]])
+    joints, vis = [], []
+    for body in anno["bodies"]:
+        pose3d = np.array(body["joints19"]).reshape((-1, 4))
+        pose3d = pose3d[:num_joints]
+        joints_vis = np.maximum(pose3d[:, -1], 0.0)
+        if joints_vis[root_id] <= 0.1:
+            continue
+        pose3d[:, 0:3] = pose3d[:, 0:3].dot(M)
+        joints.append(pose3d[:, 0:3] * 10.0)
+        vis.append(joints_vis)
+    return joints, vis
 
 
 def load_pred_pose2d(path: str) -> dict:

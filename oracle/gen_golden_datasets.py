@@ -12,6 +12,9 @@ What it does
   2. writes a synthetic Panoptic ``calibration_<seq>.json`` (eight HD / VGA cameras, five of them the reference's
      ``cam_list``), runs the reference's ``Panoptic._get_cam`` (panoptic.py:171-205) on it and asserts
      ``fvp.datasets.panoptic_cameras`` equal; stores the JSON text and the expected cameras;
+  2b. builds a synthetic Panoptic sequence folder (annotation files, empty image files), runs the reference's
+     ``Panoptic._get_db`` (panoptic.py:109-167, with the unmodified ``JointsDataset`` constructor and ``_rebuild_db``) and
+     asserts ``fvp.datasets.panoptic_annotation_files`` / ``panoptic_image_paths`` / ``panoptic_frame_gt`` equal;
   3. cuts frame 400 (BASELINE configs[0], SURVEY.md 8d "Config 1") out of the shipped detection files
      ``pred_{campus,shelf}_maskrcnn_hrnet_coco.pkl`` into a small pickle, builds ``db_rec['pred_pose2d']`` with the very
      expression of ``Campus._get_db`` (campus.py:92-97) and asserts ``fvp.datasets.frame_preds`` equal.
@@ -125,6 +128,66 @@ def main():
     assert D.PANOPTIC_VAL_LIST == panoptic_m.VAL_LIST
     store["panoptic_json"] = np.array(json.dumps(calib))
     print("panoptic calibration: 5 / 3 of 8 cameras selected and converted, panoptic_cameras == reference")
+
+    # ---- 2b. Panoptic annotations through the reference's _get_db on a synthetic sequence folder ---------------------
+    from fvp import config as fcfg
+    cfg = fcfg.preset("panoptic")
+    seq = "synthetic_seq"
+    with tempfile.TemporaryDirectory() as tmp:
+        adir = os.path.join(tmp, seq, "hdPose3d_stage1_coco19")
+        os.makedirs(adir)
+        anno_texts = {}
+        for i in range(26):                                                    # validation interval 12 -> files 0, 12, 24
+            bodies = []
+            nb = {0: 4, 12: 0, 24: 3}.get(i, 1)
+            for b in range(nb):
+                # centimetres, y up; the root must fall inside the capture space (JointsDataset.generate_target asserts it):
+                # world = (x, z, -y) * 10 mm with z in [-200, 1800] mm
+                j19 = np.concatenate([rng.uniform(-200, 200, (19, 1)), rng.uniform(-170, 10, (19, 1)), rng.uniform(-200, 200, (19, 1)),
+                                      rng.uniform(-0.3, 1.0, (19, 1))], axis=1)
+                j19[2, 3] = max(j19[2, 3], 0.5)
+                if i == 0 and b == 1:
+                    j19[2, 3] = 0.05                                           # root visibility <= 0.1: body dropped
+                if i == 0 and b == 2:
+                    j19[5, 3] = -1.0                                           # negative visibility clipped to 0
+                bodies.append({"id": b, "joints19": j19.reshape(-1).tolist()})
+            name = "body3DScene_%08d.json" % (100 + i)
+            text = json.dumps({"version": 0.7, "univTime": 0.0, "bodies": bodies})
+            with open(os.path.join(adir, name), "w") as f:
+                f.write(text)
+            if i in (0, 12, 24):
+                anno_texts[name] = text
+            for (panel, node) in D.PANOPTIC_CAM_LIST:
+                idir = os.path.join(tmp, seq, "hdImgs", "%02d_%02d" % (panel, node))
+                os.makedirs(idir, exist_ok=True)
+                open(os.path.join(idir, "%02d_%02d_%08d.jpg" % (panel, node, 100 + i)), "w").close()
+        cfg.DATASET.DATADIR = tmp
+        ds = object.__new__(panoptic_m.Panoptic)
+        panoptic_m.JointsDataset.__init__(ds, cfg, False, None)                # the parent constructor, unmodified
+        ds.num_joints, ds.num_views, ds.root_id = 15, 5, cfg.DATASET.ROOT_JOINT_ID
+        ds.cam_list, ds.sequence_list, ds._interval = [(0, 3), (0, 6), (0, 12), (0, 13), (0, 23)], [seq], 12
+        ds._get_db()                                                            # panoptic.py:109-167 + JointsDataset._rebuild_db
+        files = D.panoptic_annotation_files(os.path.join(tmp, seq), 12)
+        assert [os.path.basename(f) for f in files] == sorted(anno_texts)
+        recs = []
+        for f in files:
+            j, v = D.panoptic_frame_gt(f, 15, cfg.DATASET.ROOT_JOINT_ID)
+            if len(j) > 0:                                                      # panoptic.py:118-119,159: empty frames are skipped
+                recs.append((f, j, v))
+        assert len(recs) == len(ds.db) == 2
+        for (f, j, v), rec in zip(recs, ds.db):
+            m = rec["meta"]
+            n = m["num_person"]
+            assert n == len(j) and m["all_image_path"] == D.panoptic_image_paths(tmp, seq, f, 5)
+            assert np.array_equal(m["joints_3d"][:n], np.array(j)) and np.array_equal(m["joints_3d_vis"][:n], np.array(v))
+            assert not m["joints_3d"][n:].any()
+        store["panoptic_anno_names"] = np.array(sorted(anno_texts))
+        store["panoptic_anno_texts"] = np.array([anno_texts[k] for k in sorted(anno_texts)])
+        store["panoptic_gt_counts"] = np.array([len(D.panoptic_frame_gt(json.loads(anno_texts[k]))[0]) for k in sorted(anno_texts)])
+        store["panoptic_gt_joints_first"] = np.array(recs[0][1])
+        store["panoptic_gt_vis_first"] = np.array(recs[0][2])
+    print("panoptic annotations: 3 visited files (1 empty), %s people kept, panoptic_frame_gt == reference _get_db"
+          % list(store["panoptic_gt_counts"]))
 
     # ---- 3. frame 400 of the shipped detection files -----------------------------------------------------------
     small = {}

@@ -85,3 +85,26 @@ def test_detection_file_frames(fx):
         D.frame_preds(pred["campus"], 401, 3)                                    # a plain dict raises on a missing frame
     assert len(D.CAMPUS_FRAMES) == 222 and D.CAMPUS_FRAMES[0] == 350 and D.CAMPUS_FRAMES[-1] == 750 and 500 not in D.CAMPUS_FRAMES
     assert D.SHELF_FRAMES == list(range(300, 601))
+
+
+def test_panoptic_annotation_files(fx, tmp_path):
+    """body3DScene_*.json -> per-frame ground truth as Panoptic._get_db stores it (panoptic.py:109-163): y-up centimetres to
+    z-up millimetres, visibilities clipped at 0, bodies with an invisible root dropped, every 12th file visited."""
+    names, texts = [str(n) for n in fx["panoptic_anno_names"]], [str(t) for t in fx["panoptic_anno_texts"]]
+    adir = tmp_path / "seq" / "hdPose3d_stage1_coco19"
+    adir.mkdir(parents=True)
+    for i in range(26):
+        name = "body3DScene_%08d.json" % (100 + i)
+        (adir / name).write_text(texts[names.index(name)] if name in names else json.dumps({"bodies": []}))
+    files = D.panoptic_annotation_files(str(tmp_path / "seq"), 12)
+    assert [os.path.basename(f) for f in files] == names
+    assert len(D.panoptic_annotation_files(str(tmp_path / "seq"), 3)) == 9
+    counts = [len(D.panoptic_frame_gt(f)[0]) for f in files]
+    assert counts == list(fx["panoptic_gt_counts"]) == [3, 0, 3]
+    j, v = D.panoptic_frame_gt(json.loads(texts[0]))
+    assert np.array_equal(np.array(j), fx["panoptic_gt_joints_first"]) and np.array_equal(np.array(v), fx["panoptic_gt_vis_first"])
+    assert all(a.shape == (15, 3) and b.shape == (15,) and b.min() >= 0.0 for a, b in zip(j, v))
+    raw = np.array(json.loads(texts[0])["bodies"][0]["joints19"]).reshape(-1, 4)
+    assert np.allclose(j[0][4], [raw[4, 0] * 10, raw[4, 2] * 10, -raw[4, 1] * 10])          # (x, y, z) cm y-up -> (x, z, -y) mm
+    paths = D.panoptic_image_paths("/data/panoptic", "160906_pizza1", files[0], 5)
+    assert paths[0] == "/data/panoptic/160906_pizza1/hdImgs/00_03/00_03_00000100.jpg" and paths[4].endswith("00_23/00_23_00000100.jpg")
