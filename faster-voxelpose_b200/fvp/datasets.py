@@ -123,6 +123,52 @@ def panoptic_frame_gt(anno: Union[str, dict], num_joints: int = 15, root_id: int
     return joints, vis
 
 
+def panoptic_records(dataset_dir: str, sequences: Sequence[str] = tuple(PANOPTIC_VAL_LIST), interval: int = 12,
+                     num_views: int = 5, num_joints: int = 15, root_id: int = 2) -> List[dict]:
+    """The database ``Panoptic._get_db`` builds (panoptic.py:109-163), one record per visited annotation file that has at
+    least one kept body and all its HD images on disk: ``{'seq', 'all_image_path', 'joints_3d', 'joints_3d_vis'}``."""
+    import os
+    db = []
+    for seq in sequences:
+        for anno_file in panoptic_annotation_files(os.path.join(dataset_dir, seq), interval):
+            with open(anno_file, "r") as f:
+                anno = json.load(f)
+            if len(anno["bodies"]) == 0:
+                continue
+            paths = panoptic_image_paths(dataset_dir, seq, anno_file, num_views)
+            if not all(os.path.exists(p) for p in paths):
+                continue
+            joints, vis = panoptic_frame_gt(anno, num_joints, root_id)
+            if len(joints) > 0:
+                db.append({"seq": seq, "all_image_path": paths, "joints_3d": joints, "joints_3d_vis": vis})
+    return db
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # run/validate.py:45-46
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def load_views(paths: Sequence[str], color_rgb: bool = True) -> np.ndarray:
+    """The ``views`` of one frame as the reference's loader produces them (JointsDataset.py:124-134 with the transform
+    of run/validate.py:44-52): ``cv2.imread`` (colour, EXIF orientation ignored) -> BGR to RGB when ``COLOR_RGB`` ->
+    ``ToTensor`` (uint8 HWC -> float32 CHW / 255) -> ``Normalize(mean, std)``; float32 arithmetic like torchvision's.
+    Returns ``[V, 3, h, w]`` float32.  The reference does not resize here: Panoptic frames are resized once by its
+    ``preprocess.py``."""
+    import cv2
+    mean = np.array(IMAGENET_MEAN, np.float32).reshape(3, 1, 1)
+    std = np.array(IMAGENET_STD, np.float32).reshape(3, 1, 1)
+    out = []
+    for p in paths:
+        img = cv2.imread(p, cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        if img is None:
+            raise FileNotFoundError(p)
+        if color_rgb:
+            img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+        x = np.ascontiguousarray(img.transpose(2, 0, 1)).astype(np.float32) / np.float32(255)
+        out.append((x - mean) / std)
+    return np.stack(out)
+
+
 def load_pred_pose2d(path: str) -> dict:
     """The detection file of Campus / Shelf (campus.py:61-67): ``{"<view>_<frame>": [{"pred": ...}, ...]}``.
     A pickle: only open files you trust (the reference does the same)."""

@@ -1,8 +1,10 @@
-"""The caller of the hot path for the 'pred' heat-map source: ``run/validate.py:92-118`` without the reference's dataset
-classes and DataLoader (Campus / Shelf: ``TEST_HEATMAP_SRC = 'pred'``, ``configs/{campus,shelf}/jln64.yaml``).
+"""The caller of the hot path, ``run/validate.py:92-118``, without the reference's dataset classes and DataLoader.
 
+``validate_pred``      Campus / Shelf, ``TEST_HEATMAP_SRC = 'pred'`` (``configs/{campus,shelf}/jln64.yaml``):
     detections of a frame block (fvp.datasets)  ->  heat maps on the GPU (fvp.render, N1)  ->  model(...) (the hot path)
     ->  torch.cat(all_fused_poses)  ->  PCP (fvp.evaluate, N3)
+``validate_panoptic``  Panoptic, ``TEST_HEATMAP_SRC = 'image'`` (``configs/panoptic/jln64.yaml``: images -> backbone (N2)
+    inside ``model(views=...)``) or ``'gt'`` (3-D ground truth -> heat maps on the GPU):  ->  AP / recall / MPJPE
 
 The loop is the reference's: batches of ``cfg.TEST.BATCH_SIZE`` consecutive frames in ``frame_range`` order, no shuffling,
 the poses of every call appended and concatenated once at the end (run/validate.py:95-114).  Nothing here computes: the
@@ -55,3 +57,51 @@ def validate_pred(cfg, model: Callable, renderer, cameras: Sequence[dict], pred2
         preds = fused_all.detach().cpu().numpy()
         out["metric"], out["msg"], out["detail"] = evaluate.evaluate_pcp(preds, actors, list(frames), seq)
     return out
+
+
+def validate_panoptic(cfg, model: Callable, cameras: dict, records: Sequence[dict], source: Optional[str] = None, renderer=None,
+                      backbone=None, batch_size: Optional[int] = None, load_views: Callable = datasets.load_views,
+                      progress: Optional[Callable] = None) -> dict:
+    """Run ``model`` over Panoptic ``records`` (``fvp.datasets.panoptic_records``) and evaluate.
+
+    cameras   ``{sequence: fvp.datasets.panoptic_cameras(calibration_<sequence>.json)}``; batches may mix sequences
+    source    ``'image'`` (``model(backbone=backbone, views=...)``, run/validate.py:97-101; backbone =
+              ``models.resnet.get(cfg)``) or ``'gt'`` (``renderer.from_gt`` -> ``input_heatmaps``); default
+              ``cfg.DATASET.TEST_HEATMAP_SRC``
+    Returns ``{'fused_poses', 'metric', 'msg', 'detail'}`` with the metric of ``Panoptic.evaluate`` (panoptic.py:214-266).
+    """
+    source = source or str(cfg.DATASET.TEST_HEATMAP_SRC)
+    if source not in ("image", "gt"):
+        raise ValueError("source must be 'image' or 'gt' (use validate_pred for 'pred'), got %r" % source)
+    if source == "image" and backbone is None:
+        raise ValueError("the 'image' source needs the backbone (models.resnet.get(cfg))")
+    if source == "gt" and renderer is None:
+        raise ValueError("the 'gt' source needs a HeatmapRenderer")
+    B = int(batch_size if batch_size is not None else cfg.TEST.BATCH_SIZE)
+    if B < 1:
+        raise ValueError("batch size must be >= 1")
+    resize = synth.resize_transform(cfg.DATASET.ORI_IMAGE_SIZE, cfg.DATASET.IMAGE_SIZE)
+    device = torch.device(cfg.DEVICE)
+    resize_t = torch.as_tensor(resize, dtype=torch.float, device=device)
+    color_rgb = bool(cfg.DATASET.COLOR_RGB)
+    all_fused = []
+    with torch.no_grad():
+        for lo in range(0, len(records), B):
+            block = records[lo:lo + B]
+            meta = {"seq": [r["seq"] for r in block]}
+            if source == "image":
+                views = torch.from_numpy(np.stack([load_views(r["all_image_path"], color_rgb) for r in block])).to(device)
+                fused, _, _, _, _ = model(backbone=backbone, views=views, meta=meta, cameras=cameras, resize_transform=resize_t)
+            else:
+                hm = renderer.from_gt([r["joints_3d"] for r in block], [r["joints_3d_vis"] for r in block],
+                                      [cameras[r["seq"]] for r in block], resize)
+                fused, _, _, _, _ = model(backbone=None, meta=meta, input_heatmaps=hm, cameras=cameras,
+                                          resize_transform=resize_t.to(hm.device))
+            all_fused.append(fused)
+            if progress is not None:
+                progress(lo + len(block), len(records))
+        fused_all = torch.cat(all_fused, dim=0) if all_fused else torch.zeros((0,))
+    preds = fused_all.detach().cpu().numpy()
+    metric, msg, detail = evaluate.evaluate_panoptic(preds, [np.asarray(r["joints_3d"]) for r in records],
+                                                     [np.asarray(r["joints_3d_vis"]) for r in records])
+    return {"fused_poses": fused_all, "metric": metric, "msg": msg, "detail": detail}

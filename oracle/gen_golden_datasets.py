@@ -181,6 +181,23 @@ def main():
             assert n == len(j) and m["all_image_path"] == D.panoptic_image_paths(tmp, seq, f, 5)
             assert np.array_equal(m["joints_3d"][:n], np.array(j)) and np.array_equal(m["joints_3d_vis"][:n], np.array(v))
             assert not m["joints_3d"][n:].any()
+        # the whole record list, and the missing-image rule (panoptic.py:128-136): drop one HD image of the last frame
+        def reference_db():
+            d2 = object.__new__(panoptic_m.Panoptic)
+            panoptic_m.JointsDataset.__init__(d2, cfg, False, None)
+            d2.num_joints, d2.num_views, d2.root_id = 15, 5, cfg.DATASET.ROOT_JOINT_ID
+            d2.cam_list, d2.sequence_list, d2._interval = [(0, 3), (0, 6), (0, 12), (0, 13), (0, 23)], [seq], 12
+            d2._get_db()
+            return d2.db
+        for round_ in range(2):
+            ref_db, ours_db = reference_db(), D.panoptic_records(tmp, [seq])
+            assert len(ref_db) == len(ours_db) == 2 - round_
+            for a, b in zip(ours_db, ref_db):
+                n = b["meta"]["num_person"]
+                assert a["seq"] == b["meta"]["seq"] and a["all_image_path"] == b["meta"]["all_image_path"]
+                assert np.array_equal(np.array(a["joints_3d"]), b["meta"]["joints_3d"][:n])
+                assert np.array_equal(np.array(a["joints_3d_vis"]), b["meta"]["joints_3d_vis"][:n])
+            os.remove(ours_db[-1]["all_image_path"][2])
         store["panoptic_anno_names"] = np.array(sorted(anno_texts))
         store["panoptic_anno_texts"] = np.array([anno_texts[k] for k in sorted(anno_texts)])
         store["panoptic_gt_counts"] = np.array([len(D.panoptic_frame_gt(json.loads(anno_texts[k]))[0]) for k in sorted(anno_texts)])

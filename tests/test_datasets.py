@@ -108,3 +108,54 @@ def test_panoptic_annotation_files(fx, tmp_path):
     assert np.allclose(j[0][4], [raw[4, 0] * 10, raw[4, 2] * 10, -raw[4, 1] * 10])          # (x, y, z) cm y-up -> (x, z, -y) mm
     paths = D.panoptic_image_paths("/data/panoptic", "160906_pizza1", files[0], 5)
     assert paths[0] == "/data/panoptic/160906_pizza1/hdImgs/00_03/00_03_00000100.jpg" and paths[4].endswith("00_23/00_23_00000100.jpg")
+
+
+def test_load_views_equals_torchvision_transform(tmp_path):
+    """imread -> BGR2RGB -> ToTensor -> Normalize (JointsDataset.py:124-134 + run/validate.py:44-52), bit for bit against
+    torchvision, the library the reference calls."""
+    cv2 = pytest.importorskip("cv2")
+    tv = pytest.importorskip("torchvision.transforms")
+    import torch
+    rng = np.random.default_rng(5)
+    paths = []
+    for v in range(3):
+        img = rng.integers(0, 256, (24, 40, 3), dtype=np.uint8)
+        p = str(tmp_path / ("v%d.png" % v))
+        assert cv2.imwrite(p, img)
+        paths.append(p)
+    tf = tv.Compose([tv.ToTensor(), tv.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    ref = []
+    for p in paths:
+        inp = cv2.imread(p, cv2.IMREAD_COLOR | cv2.IMREAD_IGNORE_ORIENTATION)
+        inp = cv2.cvtColor(inp, cv2.COLOR_BGR2RGB)
+        ref.append(tf(inp))
+    ref = torch.stack(ref, dim=0).numpy()
+    got = D.load_views(paths)
+    assert got.dtype == np.float32 and got.shape == (3, 3, 24, 40)
+    assert np.array_equal(got.view(np.int32), ref.view(np.int32))
+    bgr = D.load_views(paths, color_rgb=False)
+    assert np.array_equal(bgr[:, 1], got[:, 1]) and not np.array_equal(bgr[:, 0], got[:, 0])     # green stays, red / blue swap
+    with pytest.raises(FileNotFoundError):
+        D.load_views([str(tmp_path / "missing.png")])
+
+
+def test_panoptic_records_skip_rules(fx, tmp_path):
+    """panoptic.py:116-163: every 12th annotation file; files without bodies, with a missing HD image or without a kept body
+    give no record."""
+    names, texts = [str(n) for n in fx["panoptic_anno_names"]], [str(t) for t in fx["panoptic_anno_texts"]]
+    seq = "160906_pizza1"
+    adir = tmp_path / seq / "hdPose3d_stage1_coco19"
+    adir.mkdir(parents=True)
+    for i in range(26):
+        name = "body3DScene_%08d.json" % (100 + i)
+        (adir / name).write_text(texts[names.index(name)] if name in names else json.dumps({"bodies": []}))
+        for panel, node in D.PANOPTIC_CAM_LIST:
+            idir = tmp_path / seq / "hdImgs" / ("%02d_%02d" % (panel, node))
+            idir.mkdir(parents=True, exist_ok=True)
+            (idir / ("%02d_%02d_%08d.jpg" % (panel, node, 100 + i))).write_bytes(b"")
+    db = D.panoptic_records(str(tmp_path), [seq])
+    assert [os.path.basename(r["all_image_path"][0]) for r in db] == ["00_03_00000100.jpg", "00_03_00000124.jpg"]
+    assert [len(r["joints_3d"]) for r in db] == [3, 3] and db[0]["seq"] == seq and len(db[0]["all_image_path"]) == 5
+    os.remove(db[1]["all_image_path"][2])                                         # one HD image of the last frame missing
+    assert len(D.panoptic_records(str(tmp_path), [seq])) == 1
+    assert len(D.panoptic_records(str(tmp_path), [seq], num_views=2)) == 2        # ... which a 2-view run does not need

@@ -87,3 +87,80 @@ def test_validation_loop_batches_frames_in_order_and_hands_over_to_the_metric():
     assert out["detail"]["total_gt"] == 15
     with pytest.raises(AssertionError):
         validate_pred(cfg, _Model(cfg), _Renderer(cfg), cams[:3], pred, frames, "shelf")
+
+
+class _GtRenderer:
+    def __init__(self, cfg):
+        self.cfg, self.calls = cfg, []
+
+    def from_gt(self, joints, vis, cams, resize):
+        ds = self.cfg.DATASET
+        assert len(joints) == len(vis) == len(cams) and all(len(c) == int(ds.CAMERA_NUM) for c in cams)
+        self.calls.append(len(joints))
+        hm = torch.zeros((len(joints), int(ds.CAMERA_NUM), int(ds.NUM_JOINTS), 4, 4))
+        for b, people in enumerate(joints):
+            hm[b, 0, 0, 0, 0] = float(people[0][0, 0])
+        return hm
+
+
+class _PanopticModel:
+    """Returns, per frame, the frame's ground truth itself (passed through the stand-in inputs) as P slots."""
+
+    def __init__(self, cfg, gt_by_marker):
+        self.P, self.J, self.gt, self.calls = int(cfg.CAPTURE_SPEC.MAX_PEOPLE), int(cfg.DATASET.NUM_JOINTS), gt_by_marker, []
+
+    def __call__(self, backbone=None, views=None, meta=None, targets=None, input_heatmaps=None, cameras=None, resize_transform=None):
+        x = views if views is not None else input_heatmaps
+        self.calls.append((list(meta["seq"]), backbone, views is not None))
+        fused = torch.zeros((x.shape[0], self.P, self.J, 5))
+        fused[..., 3] = -1.0
+        for b in range(x.shape[0]):
+            marker = round(float(x[b].reshape(-1)[0]), 3)
+            for n, pose in enumerate(self.gt[marker]):
+                fused[b, n, :, :3] = torch.from_numpy(pose).float()
+                fused[b, n, :, 3] = 0.0
+                fused[b, n, :, 4] = 0.9
+        return fused, None, None, x, None
+
+
+def test_panoptic_validation_loop_gt_and_image_sources():
+    from fvp.validate import validate_panoptic
+    cfg = fcfg.preset("panoptic")
+    cfg.DEVICE = "cpu"
+    rng = np.random.default_rng(1)
+    cam = dict(R=np.eye(3), T=np.zeros((3, 1)), fx=1.0, fy=1.0, cx=0.0, cy=0.0, k=np.zeros((3, 1)), p=np.zeros((2, 1)))
+    cameras = {"seqA": [cam] * 5, "seqB": [cam] * 5}
+    records, gt_by_marker = [], {}
+    for i in range(5):
+        people = [rng.uniform(-1000, 1000, (15, 3)) for _ in range(1 + i % 3)]
+        people[0][0, 0] = 10.0 + i                                                   # marks the frame
+        gt_by_marker[round(10.0 + i, 3)] = people
+        records.append({"seq": "seqA" if i < 3 else "seqB", "all_image_path": ["f%d_v%d" % (i, v) for v in range(5)],
+                        "joints_3d": people, "joints_3d_vis": [np.ones(15) for _ in people]})
+    # 'gt' source: heat maps from the renderer
+    R, M = _GtRenderer(cfg), _PanopticModel(cfg, gt_by_marker)
+    out = validate_panoptic(cfg, M, cameras, records, source="gt", renderer=R, batch_size=2)
+    assert R.calls == [2, 2, 1] and [c[0] for c in M.calls] == [["seqA", "seqA"], ["seqA", "seqB"], ["seqB"]]
+    assert all(c[1] is None and not c[2] for c in M.calls)
+    assert tuple(out["fused_poses"].shape) == (5, 10, 15, 5)
+    assert out["detail"]["total_gt"] == sum(len(r["joints_3d"]) for r in records) and out["detail"]["mpjpe"] < 1e-3
+    assert out["metric"] == pytest.approx(1.0, abs=1e-4) and "ap@25" in out["msg"]              # predictions == ground truth
+    # 'image' source: views loaded per frame and handed to model(backbone=..., views=...)
+    loaded = []
+
+    def fake_views(paths, color_rgb):
+        loaded.append((tuple(paths), color_rgb))
+        i = int(paths[0][1])
+        v = np.zeros((5, 3, 8, 8), np.float32)
+        v[0, 0, 0, 0] = 10.0 + i
+        return v
+    backbone = object()
+    M2 = _PanopticModel(cfg, gt_by_marker)
+    out2 = validate_panoptic(cfg, M2, cameras, records, source="image", backbone=backbone, batch_size=4, load_views=fake_views)
+    assert [len(c[0]) for c in M2.calls] == [4, 1] and all(c[1] is backbone and c[2] for c in M2.calls)
+    assert [p[0][0] for p in loaded] == ["f%d_v0" % i for i in range(5)] and all(p[1] == bool(cfg.DATASET.COLOR_RGB) for p in loaded)
+    assert torch.equal(out2["fused_poses"], out["fused_poses"])
+    with pytest.raises(ValueError):
+        validate_panoptic(cfg, M, cameras, records, source="pred", renderer=R)
+    with pytest.raises(ValueError):
+        validate_panoptic(cfg, M, cameras, records, source="image")
