@@ -245,6 +245,26 @@ def test_cluster_proposal_kernel_exchanges_through_distributed_shared_memory(bui
     assert sass.count("UCGABAR_ARV") == 2 and sass.count("UCGABAR_WAIT") == 2
 
 
+def test_k3_ships_the_three_shuffle_tap_exchange(built_library):
+    """The per-person back-projection kernel of 64-byte records (J = 13..16) hands a depth's taps to its lane group with
+    three shuffles (offset + two fractions) per depth and view, 12 per unrolled view iteration - the form measured 3 %
+    faster than five (profiles/r02_k3_xch.txt); the J = 17 instantiation keeps the five-shuffle form (20)."""
+    import re
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    full = subprocess.run(["cuobjdump", "-sass", built_library], capture_output=True, text=True).stdout
+    counts = {}
+    for m in re.finditer(r"Function : (\S*k3_jln_patch\S*)", full):
+        end = full.find("Function :", m.end())
+        counts[m.group(1)] = full[m.end():end if end > 0 else len(full)].count("SHFL.IDX")
+    by = lambda tag: [n for k, n in counts.items() if tag in k]
+    assert by("ILi4ELi4ELi64ELi1E") == [12]                      # <CG 4, 4 CTAs/SM, 64-byte pixel stride, XCH 1>: shipped for JG == 4
+    assert by("ILi8ELi2ELi0ELi0E") == [40]                       # <CG 8, XCH 0>: 5 shuffles x 8 depths
+    assert not by("ILi4ELi4ELi64ELi0E")                          # the five-shuffle 64-byte variant is no longer instantiated
+
+
 # ---- reference-facing module -----------------------------------------------------------------------
 def test_model_has_reference_state_dict_and_no_cpu_path(built_library, golden):
     import models
