@@ -73,6 +73,7 @@ int fvp_create(const fvp_config* cfg, int device, fvp_ctx** out);
  * while forwards of any lane are in flight.  Destroy lanes before their root (fvp_destroy(root) refuses otherwise -
  * it then returns without freeing and fvp_last_error(root) explains). */
 int fvp_create_lane(fvp_ctx* root, int max_batch, fvp_ctx** out);
+/* end of life of the model object (the reference relies on Python garbage collection); frees device memory */
 void fvp_destroy(fvp_ctx* ctx);
 const char* fvp_last_error(const fvp_ctx* ctx);   /* ctx may be NULL: error of the last failed fvp_create */
 int fvp_abi_version(void);
@@ -82,7 +83,8 @@ int fvp_abi_version(void);
 int fvp_param_count(const fvp_ctx* ctx);
 const char* fvp_param_name(const fvp_ctx* ctx, int index);
 int64_t fvp_param_numel(const fvp_ctx* ctx, int index);
-/* copy one fp32 state_dict tensor (host memory, contiguous, reference shape); the int64
+/* replaces model.load_state_dict(torch.load(model_file)) (run/validate.py:78-81), one tensor at a time:
+ * copy one fp32 state_dict tensor (host memory, contiguous, reference shape); the int64
  * num_batches_tracked entries are accepted and ignored (numel 1, pass NULL or anything). */
 int fvp_set_param(fvp_ctx* ctx, const char* name, const float* h_data, int64_t numel);
 /* fold eval-mode BatchNorm (eps 1e-5) into the convolutions, repack for the kernels, upload.
@@ -115,7 +117,8 @@ int fvp_set_sequence(fvp_ctx* ctx, int slot, const float* h_cameras, int num_vie
 int fvp_forward(fvp_ctx* ctx, const float* d_heatmaps, int batch, const int32_t* h_seq_slots,
                 float* d_fused_poses, float* d_plane_poses, float* d_proposal_centers, uintptr_t stream);
 
-/* Same call with HOST buffers (pinned or pageable): H2D of the heatmaps, forward, D2H of the
+/* One iteration of the reference's validation loop (run/validate.py:95-105: input_heatmaps.to(DEVICE), model(...), and
+ * the later read-back of the poses) as one call with HOST buffers (pinned or pageable): H2D of the heatmaps, forward, D2H of the
  * outputs, all on `stream`, followed by a stream synchronise.  This is the end-to-end entry the
  * benchmark's `e2e` figure times. */
 int fvp_forward_host(fvp_ctx* ctx, const float* h_heatmaps, int batch, const int32_t* h_seq_slots,
